@@ -1,0 +1,452 @@
+/*
+ * oracle/cref.c -- CPU restatement of the QUITS Monte-Carlo hot path.  TEST INFRASTRUCTURE ONLY
+ * (see oracle/__init__.py: only tests/, __graft_entry__.smoke() and bench.py's CPU arms may use it;
+ * parity unpinned at the stim/ldpc boundary).
+ *
+ *   qo_sample / qo_inject   Pauli-frame propagation of the memory circuit, i.e. what the reference gets from
+ *                           stim's compile_detector_sampler().sample()   (reference src/quits/simulation.py:22-27)
+ *   qo_bp_*                 ldpc.BpOsdDecoder.decode(): flooding / serial BP (min-sum, product-sum) and OSD-0
+ *                           (called at reference src/quits/decoder/sliding_window.py:171,182)
+ *   qo_sw_decode            the per-shot window loop of reference src/quits/decoder/sliding_window.py:162-186
+ *
+ * Frame rules (standard Pauli-frame semantics): R/RX clear x,z; H swaps; CX c t: x_t ^= x_c, z_c ^= z_t;
+ * M: rec <- x; MX: rec <- z; MR: rec <- x then clear; X_ERROR: x ^= B(p); Z_ERROR: z ^= B(p);
+ * DEPOLARIZE1: with prob p one of X,Y,Z; DEPOLARIZE2: with prob p one of the 15 non-identity pairs.
+ *
+ * Randomness is counter based so that CPU and GPU agree bit for bit (stim's own RNG stream is an
+ * implementation detail and is not reproduced).  For noise site s and 64-shot word w:
+ *   level 1  r = philox(key=seed, ctr=(s>>2, w_lo, w_hi, 0));  the word has >= 1 fault iff r[s&3] < T1(p),
+ *            T1 = floor(2^32 (1-(1-p)^64))
+ *   level 2  r = philox(ctr=(s, w_lo, w_hi, 1));  u = r0<<32|r1;  n = 1 + #{k>=1 : u >= C_k(p)},
+ *            C_k = floor(2^64 P(N<=k | N>=1)),  N ~ Binomial(64,p)
+ *   level 3  fault j<n: r = philox(ctr=(s, w_lo, w_hi, 2+j)); Pauli code = 1 + mulhi(r0, 3 or 15) (fixed for X/Z_ERROR);
+ *            position = first of the fifteen 6-bit fields of r1,r2,r3 not yet used (then linear probing)
+ * which is exactly "each of the 64 shots independently with probability p" up to the 2^-32 / 2^-64 threshold rounding.
+ * Sites are numbered in flattened circuit order; every noise instruction starts at a multiple of 4.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+enum { OP_R = 0, OP_RX, OP_H, OP_CX, OP_M, OP_MX, OP_MR, OP_XERR, OP_ZERR, OP_DEP1, OP_DEP2, OP_DET, OP_OBS };
+
+typedef struct { uint32_t v[4]; } ph4;
+
+static inline ph4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3)
+{
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    ph4 o = {{c0, c1, c2, c3}};
+    return o;
+}
+
+/* known-answer hook for tests (Random123 KAT vectors) */
+void qo_philox(uint32_t k0, uint32_t k1, const uint32_t* ctr, uint32_t* out)
+{
+    ph4 r = philox4x32_10(k0, k1, ctr[0], ctr[1], ctr[2], ctr[3]);
+    memcpy(out, r.v, 16);
+}
+
+/* thresholds for probability p:  out32[0] = T1,  out64[1..63] = C_k  (out64[0] unused = 0) */
+void qo_noise_tables(double p, uint32_t* t1, uint64_t* c)
+{
+    memset(c, 0, 64 * sizeof(uint64_t));
+    if (!(p > 0.0)) { *t1 = 0; return; }
+    double lq = log1p(-p);
+    double pany = -expm1(64.0 * lq);
+    double s = pany * 4294967296.0;
+    *t1 = s >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)s;
+    double pmf = exp(64.0 * lq);
+    double odds = p / (1.0 - p);
+    double acc = 0.0;
+    for (int k = 1; k < 64; ++k) {
+        pmf = pmf * (double)(64 - k + 1) / (double)k * odds;
+        acc += pmf;
+        double ratio = acc / pany;
+        c[k] = ratio >= 1.0 ? UINT64_MAX : (uint64_t)(ratio * 18446744073709551616.0);
+        if (k > 1 && c[k] < c[k - 1]) c[k] = c[k - 1];
+    }
+}
+
+typedef struct {
+    int n_ops;
+    const int32_t* kind;
+    const double* arg;
+    const int64_t* tstart;      /* n_ops + 1 */
+    const int32_t* targets;
+    int n_qubits, n_meas, n_det, n_obs;
+} flatc;
+
+static inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+
+/* apply the faults of site s in word w (level 2+3); returns via callback-free inline writes */
+static inline void site_faults(uint32_t k0, uint32_t k1, uint32_t s, uint64_t w, const uint64_t* ctab, int npauli,
+                               int fixed_code, uint64_t* m /* m[0..3]: x_a, z_a, x_b, z_b masks */)
+{
+    uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
+    ph4 r = philox4x32_10(k0, k1, s, wl, wh, 1u);
+    uint64_t u = ((uint64_t)r.v[0] << 32) | r.v[1];
+    int n = 1;
+    while (n < 64 && u >= ctab[n]) ++n;
+    uint64_t used = 0;
+    m[0] = m[1] = m[2] = m[3] = 0;
+    for (int j = 0; j < n; ++j) {
+        ph4 q = philox4x32_10(k0, k1, s, wl, wh, 2u + (uint32_t)j);
+        int code = fixed_code ? fixed_code : 1 + (int)mulhi32(q.v[0], (uint32_t)npauli);
+        int pos = -1, last = 0;
+        for (int i = 0; i < 15; ++i) {
+            int cand = (int)((q.v[1 + i / 5] >> (6 * (i % 5))) & 63u);
+            last = cand;
+            if (!((used >> cand) & 1u)) { pos = cand; break; }
+        }
+        if (pos < 0) { pos = last; while ((used >> pos) & 1u) pos = (pos + 1) & 63; }
+        used |= 1ull << pos;
+        for (int b = 0; b < 4; ++b) if ((code >> b) & 1) m[b] |= 1ull << pos;
+    }
+}
+
+/*
+ * Sample words [word0, word0+nwords) of 64 shots each.  det: [n_det][nwords], obs: [n_obs][nwords] (bit-sliced).
+ * inj_*: optional explicit fault list replacing the noise (noise instructions are then skipped):
+ *        fault f flips Pauli code inj_code[f] on target/pair inj_tgt[f] of flat op inj_op[f] in shot inj_shot[f]
+ *        (shot index local to this call).  Faults must be sorted by inj_op.
+ */
+int qo_run(int n_ops, const int32_t* kind, const double* arg, const int64_t* tstart, const int32_t* targets,
+           int n_qubits, int n_meas, int n_det, int n_obs,
+           uint64_t seed, uint64_t word0, uint64_t nwords, uint64_t* det, uint64_t* obs,
+           int64_t n_inj, const int32_t* inj_op, const int32_t* inj_tgt, const int32_t* inj_code, const int64_t* inj_shot,
+           int nthreads)
+{
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    /* per-op noise tables and site bases */
+    uint32_t* t1 = (uint32_t*)calloc((size_t)n_ops, sizeof(uint32_t));
+    uint64_t* ctab = (uint64_t*)calloc((size_t)n_ops * 64, sizeof(uint64_t));
+    uint32_t* sbase = (uint32_t*)calloc((size_t)n_ops, sizeof(uint32_t));
+    int64_t* mbase = (int64_t*)calloc((size_t)n_ops, sizeof(int64_t));
+    uint64_t site = 0; int64_t mc = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        int k = kind[i]; int64_t nt = tstart[i + 1] - tstart[i];
+        if (k >= OP_XERR && k <= OP_DEP2) {
+            if (arg[i] < 0.0 || arg[i] > 0.5) { free(t1); free(ctab); free(sbase); free(mbase); return -2; }
+            site = (site + 3) & ~3ull;
+            sbase[i] = (uint32_t)site;
+            site += (uint64_t)(k == OP_DEP2 ? nt / 2 : nt);
+            qo_noise_tables(arg[i], &t1[i], &ctab[(size_t)i * 64]);
+        }
+        if (k == OP_M || k == OP_MX || k == OP_MR) { mbase[i] = mc; mc += nt; }
+    }
+    if (site >= 0xFFFFFFFFull) { free(t1); free(ctab); free(sbase); free(mbase); return -3; }
+    memset(det, 0, (size_t)n_det * nwords * 8);
+    memset(obs, 0, (size_t)n_obs * nwords * 8);
+    int err = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel
+#endif
+    {
+        uint64_t* x = (uint64_t*)malloc((size_t)n_qubits * 8);
+        uint64_t* z = (uint64_t*)malloc((size_t)n_qubits * 8);
+        uint64_t* rec = (uint64_t*)malloc((size_t)(n_meas > 0 ? n_meas : 1) * 8);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+        for (int64_t wi = 0; wi < (int64_t)nwords; ++wi) {
+            uint64_t w = word0 + (uint64_t)wi;
+            uint32_t wl = (uint32_t)w, wh = (uint32_t)(w >> 32);
+            memset(x, 0, (size_t)n_qubits * 8);
+            memset(z, 0, (size_t)n_qubits * 8);
+            int64_t fi = 0;   /* cursor into the injection list */
+            for (int i = 0; i < n_ops; ++i) {
+                const int32_t* t = targets + tstart[i];
+                int64_t nt = tstart[i + 1] - tstart[i];
+                switch (kind[i]) {
+                case OP_R: case OP_RX: for (int64_t j = 0; j < nt; ++j) { x[t[j]] = 0; z[t[j]] = 0; } break;
+                case OP_H: for (int64_t j = 0; j < nt; ++j) { uint64_t a = x[t[j]]; x[t[j]] = z[t[j]]; z[t[j]] = a; } break;
+                case OP_CX: for (int64_t j = 0; j + 1 < nt; j += 2) { x[t[j + 1]] ^= x[t[j]]; z[t[j]] ^= z[t[j + 1]]; } break;
+                case OP_M: for (int64_t j = 0; j < nt; ++j) rec[mbase[i] + j] = x[t[j]]; break;
+                case OP_MX: for (int64_t j = 0; j < nt; ++j) rec[mbase[i] + j] = z[t[j]]; break;
+                case OP_MR: for (int64_t j = 0; j < nt; ++j) { rec[mbase[i] + j] = x[t[j]]; x[t[j]] = 0; z[t[j]] = 0; } break;
+                case OP_DET: { uint64_t a = 0; for (int64_t j = 0; j < nt; ++j) a ^= rec[t[j]];
+                               det[(size_t)(int64_t)arg[i] * nwords + wi] ^= a; } break;
+                case OP_OBS: { uint64_t a = 0; for (int64_t j = 0; j < nt; ++j) a ^= rec[t[j]];
+                               obs[(size_t)(int64_t)arg[i] * nwords + wi] ^= a; } break;
+                default: {
+                    int k = kind[i];
+                    int two = (k == OP_DEP2);
+                    if (n_inj >= 0) {
+                        while (fi < n_inj && inj_op[fi] < i) ++fi;
+                        for (; fi < n_inj && inj_op[fi] == i; ++fi) {
+                            int64_t sh = inj_shot[fi];
+                            if ((uint64_t)(sh >> 6) != (uint64_t)wi) continue;
+                            uint64_t bit = 1ull << (sh & 63);
+                            int code = inj_code[fi]; int j = inj_tgt[fi];
+                            int a = two ? t[2 * j] : t[j];
+                            if (code & 1) x[a] ^= bit;
+                            if (code & 2) z[a] ^= bit;
+                            if (two) { int b = t[2 * j + 1]; if (code & 4) x[b] ^= bit; if (code & 8) z[b] ^= bit; }
+                        }
+                        /* rewind is unnecessary: ops are visited in increasing order and the list is sorted */
+                        break;
+                    }
+                    int64_t ns = two ? nt / 2 : nt;
+                    uint32_t thr = t1[i];
+                    if (thr == 0) break;
+                    int npauli = k == OP_DEP1 ? 3 : (k == OP_DEP2 ? 15 : 0);
+                    int fixed = k == OP_XERR ? 1 : (k == OP_ZERR ? 2 : 0);
+                    for (int64_t g = 0; g < ns; g += 4) {
+                        uint32_t s0 = sbase[i] + (uint32_t)g;
+                        ph4 r = philox4x32_10(k0, k1, s0 >> 2, wl, wh, 0u);
+                        for (int l = 0; l < 4 && g + l < ns; ++l) {
+                            if (!(r.v[l] < thr || thr == 0xFFFFFFFFu)) continue;
+                            uint64_t m[4];
+                            site_faults(k0, k1, s0 + (uint32_t)l, w, &ctab[(size_t)i * 64], npauli, fixed, m);
+                            int64_t j = g + l;
+                            int a = two ? t[2 * j] : t[j];
+                            x[a] ^= m[0]; z[a] ^= m[1];
+                            if (two) { int b = t[2 * j + 1]; x[b] ^= m[2]; z[b] ^= m[3]; }
+                        }
+                    }
+                } break;
+                }
+            }
+        }
+        free(x); free(z); free(rec);
+    }
+    free(t1); free(ctab); free(sbase); free(mbase);
+    return err;
+}
+
+/* ============================================================================================
+ * BP (+OSD-0).  Restated from the published ldpc v2 algorithm (bp.hpp: bp_decode_parallel /
+ * bp_decode_serial; osd.hpp: OSD-0 = LLR-ordered row reduction + solve).  ldpc is not vendored.
+ *   - messages start at llr0_j = log((1-p_j)/p_j)
+ *   - flooding check update: forward/backward running min (min-sum) or tanh product (product-sum)
+ *     over the row in ascending column order; sign from syndrome + #{v<=0}
+ *   - bit update: forward prefix sums over the column in ascending row order give v[e] and the
+ *     posterior; hard decision e_j = [LLR_j <= 0]; stop as soon as H e == s; otherwise the
+ *     backward suffix pass completes v[e]
+ *   - OSD-0: columns by ascending posterior LLR (stable: ties by column index -- ldpc's own tie order
+ *     comes from std::sort and is unspecified), row-reduce choosing as pivot row the first row at or
+ *     below the current rank that has a 1 (rows swapped into place), solve on the pivots, rest 0.
+ * Two precisions: f64 (what ldpc computes in) and f32 (what the CUDA kernels compute in; the GPU is
+ * held bit-exact to this one, and within 1e-4 of the f64 posteriors).
+ * ============================================================================================ */
+typedef struct {
+    int m, n, nnz;
+    int* rowptr; int* colidx;         /* CSR, ascending column inside a row; edge id = CSR position */
+    int* colptr; int* coledge; int* colrow;   /* CSC view: edge ids / rows of column j in ascending row order */
+    double* prior;
+    int max_iter; int method;         /* 0 = min-sum, 1 = product-sum */
+    int schedule;                     /* 0 = parallel (flooding), 1 = serial */
+    double alpha;                     /* ms_scaling_factor; 0 => 1 - 2^-it */
+    int precision;                    /* 64 or 32 */
+    int osd;                          /* 1: OSD-0 when BP fails; 0: return BP output */
+} qo_bp;
+
+qo_bp* qo_bp_create(int m, int n, const int64_t* indptr /*csc n+1*/, const int32_t* indices /*rows, ascending*/,
+                    const double* priors, int max_iter, int method, int schedule, double alpha, int precision, int osd)
+{
+    qo_bp* d = (qo_bp*)calloc(1, sizeof(qo_bp));
+    int nnz = (int)indptr[n];
+    d->m = m; d->n = n; d->nnz = nnz;
+    d->rowptr = (int*)calloc((size_t)m + 1, sizeof(int));
+    d->colidx = (int*)malloc((size_t)nnz * sizeof(int) + 4);
+    d->colptr = (int*)malloc(((size_t)n + 1) * sizeof(int));
+    d->coledge = (int*)malloc((size_t)nnz * sizeof(int) + 4);
+    d->colrow = (int*)malloc((size_t)nnz * sizeof(int) + 4);
+    d->prior = (double*)malloc((size_t)n * sizeof(double) + 8);
+    for (int j = 0; j < n; ++j) { d->prior[j] = priors[j]; d->colptr[j] = (int)indptr[j]; }
+    d->colptr[n] = nnz;
+    for (int e = 0; e < nnz; ++e) d->rowptr[indices[e] + 1]++;
+    for (int i = 0; i < m; ++i) d->rowptr[i + 1] += d->rowptr[i];
+    int* fill = (int*)malloc((size_t)m * sizeof(int) + 4);
+    for (int i = 0; i < m; ++i) fill[i] = d->rowptr[i];
+    for (int j = 0; j < n; ++j)                       /* columns ascending => ascending column inside each row */
+        for (int64_t q = indptr[j]; q < indptr[j + 1]; ++q) {
+            int r = indices[q]; int e = fill[r]++;
+            d->colidx[e] = j; d->coledge[q] = e; d->colrow[q] = r;
+        }
+    free(fill);
+    d->max_iter = max_iter; d->method = method; d->schedule = schedule; d->alpha = alpha;
+    d->precision = precision; d->osd = osd;
+    return d;
+}
+
+void qo_bp_free(qo_bp* d)
+{
+    if (!d) return;
+    free(d->rowptr); free(d->colidx); free(d->colptr); free(d->coledge); free(d->colrow); free(d->prior); free(d);
+}
+
+#define REAL double
+#define RMAX DBL_MAX
+#define RTANH tanh
+#define RLOG log
+#define RFABS fabs
+#define BPFN(x) x##_f64
+#include "bp_impl.inc"
+#undef REAL
+#undef RMAX
+#undef RTANH
+#undef RLOG
+#undef RFABS
+#undef BPFN
+#define REAL float
+#define RMAX FLT_MAX
+#define RTANH tanhf
+#define RLOG logf
+#define RFABS fabsf
+#define BPFN(x) x##_f32
+#include "bp_impl.inc"
+
+/* OSD-0 on posterior LLRs (as doubles; f32 posteriors are widened exactly, so the order is unchanged). */
+static void osd0(const qo_bp* d, const uint8_t* syn, const double* llr, uint8_t* ehat)
+{
+    int m = d->m, n = d->n;
+    int* order = (int*)malloc((size_t)n * sizeof(int));
+    /* stable merge sort on (llr, index) */
+    int* tmp = (int*)malloc((size_t)n * sizeof(int));
+    for (int j = 0; j < n; ++j) order[j] = j;
+    for (int width = 1; width < n; width *= 2) {
+        for (int lo = 0; lo < n; lo += 2 * width) {
+            int mid = lo + width < n ? lo + width : n, hi = lo + 2 * width < n ? lo + 2 * width : n;
+            int a = lo, b = mid, o = lo;
+            while (a < mid && b < hi) tmp[o++] = (llr[order[b]] < llr[order[a]]) ? order[b++] : order[a++];
+            while (a < mid) tmp[o++] = order[a++];
+            while (b < hi) tmp[o++] = order[b++];
+        }
+        int* sw = order; order = tmp; tmp = sw;
+    }
+    int nw = (n + 1 + 63) / 64;                       /* +1: augmented syndrome column at bit n */
+    uint64_t* A = (uint64_t*)calloc((size_t)m * nw, 8);
+    for (int k = 0; k < n; ++k) {                      /* permuted column k = original column order[k] */
+        int j = order[k];
+        for (int q = d->colptr[j]; q < d->colptr[j + 1]; ++q)
+            A[(size_t)d->colrow[q] * nw + (k >> 6)] |= 1ull << (k & 63);
+    }
+    for (int i = 0; i < m; ++i) if (syn[i] & 1) A[(size_t)i * nw + (n >> 6)] |= 1ull << (n & 63);
+    int* pivcol = (int*)malloc((size_t)m * sizeof(int));
+    int rank = 0;
+    uint64_t* swp = (uint64_t*)malloc((size_t)nw * 8);
+    for (int k = 0; k < n && rank < m; ++k) {
+        int w = k >> 6; uint64_t bit = 1ull << (k & 63);
+        int p = -1;
+        for (int i = rank; i < m; ++i) if (A[(size_t)i * nw + w] & bit) { p = i; break; }
+        if (p < 0) continue;
+        if (p != rank) {
+            memcpy(swp, &A[(size_t)p * nw], (size_t)nw * 8);
+            memcpy(&A[(size_t)p * nw], &A[(size_t)rank * nw], (size_t)nw * 8);
+            memcpy(&A[(size_t)rank * nw], swp, (size_t)nw * 8);
+        }
+        const uint64_t* pr = &A[(size_t)rank * nw];
+        for (int i = 0; i < m; ++i) {
+            if (i == rank || !(A[(size_t)i * nw + w] & bit)) continue;
+            uint64_t* ri = &A[(size_t)i * nw];
+            for (int q = w; q < nw; ++q) ri[q] ^= pr[q];
+        }
+        pivcol[rank++] = k;
+    }
+    memset(ehat, 0, (size_t)n);
+    for (int r = 0; r < rank; ++r)
+        if (A[(size_t)r * nw + (n >> 6)] & (1ull << (n & 63))) ehat[order[pivcol[r]]] = 1;
+    free(order); free(tmp); free(A); free(pivcol); free(swp);
+}
+
+/* decode one syndrome.  Returns 1 if BP converged.  llr_out (n doubles) = BP posteriors; iters_out = iterations run;
+ * used_osd_out = 1 if the returned ehat came from OSD. */
+int qo_bp_decode(const qo_bp* d, const uint8_t* syn, uint8_t* ehat, double* llr_out, int* iters_out, int* used_osd_out)
+{
+    int conv;
+    double* llr = llr_out ? llr_out : (double*)malloc((size_t)d->n * sizeof(double));
+    if (d->precision == 32) conv = bp_run_f32(d, syn, ehat, llr, iters_out);
+    else conv = bp_run_f64(d, syn, ehat, llr, iters_out);
+    int used = 0;
+    if (!conv && d->osd) { osd0(d, syn, llr, ehat); used = 1; }
+    if (used_osd_out) *used_osd_out = used;
+    if (!llr_out) free(llr);
+    return conv;
+}
+
+/* ============================================================================================
+ * Sliding-window loop: restates reference src/quits/decoder/sliding_window.py:162-186.
+ *   per shot: acc = 0, carry = 0; for window k: s = det[F k m : (F k + W) m]; s[:m] ^= carry   (:168-169)
+ *             e = decode_k(s)                                                                (:171)
+ *             acc ^= L_k e[:ncommit_k] ; carry = U_k e[:ncommit_k]                          (:172-175)
+ *             last window: s = det[F n_win m :]; s[:m] ^= carry; acc ^= L_last e             (:179-184)
+ * L_k / U_k are given in CSC over the committed columns.
+ * ============================================================================================ */
+int qo_sw_decode(int n_windows, qo_bp* const* dec, const int32_t* row0 /*first detector of window*/,
+                 const int32_t* ncommit,
+                 const int64_t* const* Lptr, const int32_t* const* Lidx,      /* per window CSC of L (K x ncommit) */
+                 const int64_t* const* Uptr, const int32_t* const* Uidx,      /* per window CSC of U (m x ncommit); NULL for last */
+                 int m, int K, int D,
+                 const uint8_t* det /*[N][D]*/, int64_t N, uint8_t* pred /*[N][K]*/,
+                 int64_t* stats /* [n_windows][3]: converged windows, BP iterations, OSD calls */, int nthreads)
+{
+    int64_t* st = (int64_t*)calloc((size_t)n_windows * 3, sizeof(int64_t));
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel
+#endif
+    {
+        int maxn = 0, maxm = 0;
+        for (int k = 0; k < n_windows; ++k) { if (dec[k]->n > maxn) maxn = dec[k]->n; if (dec[k]->m > maxm) maxm = dec[k]->m; }
+        uint8_t* e = (uint8_t*)malloc((size_t)maxn + 8);
+        uint8_t* s = (uint8_t*)malloc((size_t)maxm + 8);
+        uint8_t* carry = (uint8_t*)malloc((size_t)m + 8);
+        double* llr = (double*)malloc((size_t)maxn * sizeof(double) + 8);
+        int64_t* lst = (int64_t*)calloc((size_t)n_windows * 3, sizeof(int64_t));
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 8)
+#endif
+        for (int64_t i = 0; i < N; ++i) {
+            uint8_t* acc = pred + (size_t)i * K;
+            memset(acc, 0, (size_t)K);
+            memset(carry, 0, (size_t)m);
+            for (int k = 0; k < n_windows; ++k) {
+                const qo_bp* d = dec[k];
+                for (int r = 0; r < d->m; ++r) s[r] = det[(size_t)i * D + row0[k] + r] & 1;
+                for (int r = 0; r < m && r < d->m; ++r) s[r] ^= carry[r];
+                int it = 0, used = 0;
+                int conv = qo_bp_decode(d, s, e, llr, &it, &used);
+                lst[3 * k + 0] += conv; lst[3 * k + 1] += it; lst[3 * k + 2] += used;
+                memset(carry, 0, (size_t)m);
+                for (int j = 0; j < ncommit[k]; ++j) {
+                    if (!e[j]) continue;
+                    for (int64_t q = Lptr[k][j]; q < Lptr[k][j + 1]; ++q) acc[Lidx[k][q]] ^= 1;
+                    if (Uptr[k]) for (int64_t q = Uptr[k][j]; q < Uptr[k][j + 1]; ++q) carry[Uidx[k][q]] ^= 1;
+                }
+            }
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        for (int q = 0; q < n_windows * 3; ++q) st[q] += lst[q];
+        free(e); free(s); free(carry); free(llr); free(lst);
+    }
+    if (stats) memcpy(stats, st, (size_t)n_windows * 3 * sizeof(int64_t));
+    free(st);
+    return 0;
+}
+
+int qo_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
