@@ -1,0 +1,153 @@
+/*
+ * include/quits_b200.h -- C ABI of the B200-native QUITS Monte-Carlo engine (libquits_b200.so).
+ *
+ * The reference (mkangquantum/quits @ b8b3b44) has no FFI of its own on this path: its seams are Python call
+ * signatures into the C++ wheels stim and ldpc.  Each entry point below names the reference interface it
+ * replaces (file:line relative to the reference tree).  Plain C: opaque handles, caller-owned buffers, int
+ * status codes, qb_last_error() for the message.  One context per (process, device); a context and the objects
+ * created from it must not be used from two threads at once.
+ *
+ * Status codes: 0 ok | 1 value error (Python ValueError) | 2 not implemented (NotImplementedError)
+ *               3 CUDA / runtime error | 4 bad argument.
+ * Bit order everywhere: bit b of a packed row lives in word b/64 at position b%64.
+ */
+#ifndef QUITS_B200_H
+#define QUITS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB_OK 0
+#define QB_EVALUE 1
+#define QB_ENOTIMPL 2
+#define QB_ECUDA 3
+#define QB_EARG 4
+
+typedef struct qb_ctx qb_ctx;
+typedef struct qb_circuit qb_circuit;
+typedef struct qb_dem qb_dem;
+typedef struct qb_plan qb_plan;
+typedef struct qb_sw qb_sw;
+
+const char* qb_last_error(void);
+int qb_version(void);
+/* number of CUDA devices visible (0 without a GPU; never fails) */
+int qb_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------ context */
+int qb_ctx_create(int device, qb_ctx** out);
+void qb_ctx_destroy(qb_ctx* ctx);
+int qb_ctx_synchronize(qb_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------ circuit
+ * Replaces stim.Circuit(text) as the reference's builders call it (src/quits/qldpc_code/bb.py:301,
+ * circuit_construction/cardinal.py:267, zxcoloration.py:270).  Host only; accepts the Stim-text dialect emitted
+ * by src/quits/circuit.py:58-279 (R RX H CX M MX MR, X_ERROR Z_ERROR DEPOLARIZE1 DEPOLARIZE2, DETECTOR,
+ * OBSERVABLE_INCLUDE, TICK, REPEAT), also in stim's canonical (fused) printing.  PAULI_CHANNEL_1/2 -> QB_ENOTIMPL. */
+typedef struct {
+    int32_t n_qubits, n_measurements, n_detectors, n_observables;
+    int64_t n_flat_ops;        /* instructions after REPEAT unrolling (TICK dropped) */
+    int64_t n_tape_ops;        /* conflict-free slices executed by the frame kernel */
+    int64_t n_noise_sites;
+    int32_t ring;              /* measurement ring size used on the device */
+} qb_circuit_info;
+
+int qb_circuit_parse(const char* stim_text, size_t len, qb_circuit** out);
+void qb_circuit_free(qb_circuit* c);
+int qb_circuit_get_info(const qb_circuit* c, qb_circuit_info* info);
+/* flattened op list (for tests and for addressing faults): kind per op, CSR of targets.  Pass NULL to skip. */
+int qb_circuit_flat(const qb_circuit* c, int32_t* kind, double* arg, int64_t* tstart /*[n_flat_ops+1]*/, int32_t* targets,
+                    int64_t* n_targets_out);
+
+/* ------------------------------------------------------------------------------------------------ sampler
+ * Replaces circuit.compile_detector_sampler(seed).sample(shots, separate_observables=True)
+ * (src/quits/simulation.py:22-27).  Shots are numbered globally: shot s of a run with a given seed is the same
+ * bits whatever the batch split or the GPU.  shot0 must be a multiple of 64.
+ * qb_sample        -> det[n_shots][n_detectors], obs[n_shots][n_observables] as 0/1 bytes (numpy bool_ layout)
+ * qb_sample_packed -> det_rows[n_shots][ceil(D/64)], obs_rows[n_shots][ceil(K/64)] as u64 bit rows            */
+int qb_sample(qb_ctx* ctx, qb_circuit* c, uint64_t seed, uint64_t shot0, uint64_t n_shots, uint8_t* det, uint8_t* obs);
+int qb_sample_packed(qb_ctx* ctx, qb_circuit* c, uint64_t seed, uint64_t shot0, uint64_t n_shots, uint64_t* det_rows,
+                     uint64_t* obs_rows);
+/* Explicit-fault mode (parity tests): the noise instructions are replaced by the listed faults.  Fault f flips
+ * Pauli code[f] (bit0 X_a, bit1 Z_a, bit2 X_b, bit3 Z_b) on target/pair tgt[f] of flat op op[f] in shot shot[f]. */
+int qb_sample_faults(qb_ctx* ctx, qb_circuit* c, int64_t n_faults, const int32_t* op, const int32_t* tgt, const int32_t* code,
+                     const int64_t* shot, uint64_t n_shots, uint8_t* det, uint8_t* obs);
+
+/* ------------------------------------------------------------------------------------------------ DEM
+ * Replaces circuit.detector_error_model(decompose_errors=False) (src/quits/decoder/base.py:151) and, through
+ * qb_dem_matrix, detector_error_model_to_matrix (base.py:74-127).  Host only. */
+int qb_dem_from_circuit(const qb_circuit* c, qb_dem** out);
+/* a DEM produced elsewhere (e.g. by stim itself): errors in the order given, CSR of detector / observable ids */
+int qb_dem_from_errors(int32_t n_detectors, int32_t n_observables, int64_t n_errors, const double* probs, const int64_t* det_ptr,
+                       const int32_t* det_idx, const int64_t* obs_ptr, const int32_t* obs_idx, qb_dem** out);
+void qb_dem_free(qb_dem* d);
+/* sizes: [n_detectors, n_observables, n_errors, nnz_det, nnz_obs, n_columns, nnz_H, nnz_L, n_detectorless] */
+int qb_dem_sizes(const qb_dem* d, int64_t sizes[9]);
+/* stim-ordered error list (CSR) + one representative circuit fault per error */
+int qb_dem_errors(const qb_dem* d, double* probs, int64_t* det_ptr, int32_t* det_idx, int64_t* obs_ptr, int32_t* obs_idx,
+                  int32_t* rep_op, int32_t* rep_tgt, int32_t* rep_code);
+/* merged check matrix H (CSC, sorted rows), observable matrix L (CSC) and priors, columns in first-sighting order */
+int qb_dem_matrix(const qb_dem* d, int64_t* h_ptr, int32_t* h_idx, int64_t* l_ptr, int32_t* l_idx, double* priors);
+
+/* ------------------------------------------------------------------------------------------------ decoder
+ * Replaces the body of sliding_window_circuit_mem (src/quits/decoder/sliding_window.py:130-188): window plan
+ * (:130-141 + decoder/base.py:149-188), one BP(+OSD) decoder per window (:146-153) and the per-shot loop (:162-186)
+ * with ldpc.BpOsdDecoder.decode inside (:171,182).  Option names follow the reference's kwargs (decoder/bposd.py:74-83). */
+typedef struct {
+    int32_t bp_method;          /* 0 'minimum_sum' | 1 'product_sum' */
+    int32_t schedule;           /* 0 'parallel' | 1 'serial' */
+    int32_t max_iter;           /* 0 => number of columns (ldpc convention) */
+    double ms_scaling_factor;   /* 0.0 => 1 - 2^-iteration */
+    int32_t osd_method;         /* 0 'osd_0' | 1 'osd_e' | 2 'osd_cs' | -1 no post-processing */
+    int32_t osd_order;
+    int32_t capacity;           /* shots per device batch; 0 => default */
+    int32_t profile;            /* 1: time the kernel classes with CUDA events on the launching stream */
+} qb_bp_opts;
+
+typedef struct {
+    int64_t shots;
+    int64_t windows;            /* shot-windows decoded */
+    int64_t bp_converged;       /* ... of which BP converged */
+    int64_t bp_iterations;      /* total BP iterations run */
+    int64_t osd_calls;
+    int64_t bp_launches, osd_launches, frame_launches, other_launches;
+    double frame_ms, bp_ms, osd_ms, total_ms;     /* CUDA-event time on the launching stream (profile = 1) */
+} qb_stats;
+
+/* Window plan (host only): spacetime() of decoder/base.py:134-190.  n_cor < 0 derives the number of sliding windows
+ * from D, m, W, F as sliding_window.py:130-141 does; n_cor >= 0 takes the caller's num_cor_rounds. */
+int qb_plan_create(const qb_dem* d, int32_t m /* hz.shape[0] */, int32_t W, int32_t F, int32_t n_cor, qb_plan** out);
+void qb_plan_free(qb_plan* p);
+/* info: [n_windows, m, K, D, W, F, num_rounds, whole_history] */
+int qb_plan_info(const qb_plan* p, int64_t info[8]);
+/* window k: dims = [row0, rows, col0, ncols, ncommit, nnz, nnz_L, nnz_U, urow0, urows]; arrays may be NULL */
+int qb_plan_window(const qb_plan* p, int32_t k, int64_t dims[10], int64_t* h_ptr, int32_t* h_idx, double* priors, int64_t* l_ptr,
+                   int32_t* l_idx, int64_t* u_ptr, int32_t* u_idx);
+
+int qb_sw_create(qb_ctx* ctx, const qb_plan* plan, const qb_bp_opts* opts, qb_sw** out);
+/* one window given explicitly: ldpc.BpOsdDecoder(pcm, channel_probs=priors, ...) as built at sliding_window.py:146-153 */
+int qb_sw_create_single(qb_ctx* ctx, int32_t rows, int32_t cols, const int64_t* indptr, const int32_t* indices, const double* priors,
+                        const qb_bp_opts* opts, qb_sw** out);
+void qb_sw_free(qb_sw* sw);
+/* det[n][D] 0/1 bytes (host) -> pred[n][K] int64 (host), the dtype the reference returns (sliding_window.py:160) */
+int qb_sw_decode(qb_sw* sw, const uint8_t* det, uint64_t n, int64_t* pred, qb_stats* stats);
+int qb_sw_decode_packed(qb_sw* sw, const uint64_t* det_rows, uint64_t n, uint64_t* pred_rows, qb_stats* stats);
+/* seam B3 (one decode per syndrome, batched): syndromes[n][rows] bytes -> ehat[n][cols] bytes, posteriors, iterations */
+int qb_bp_decode_batch(qb_sw* single, const uint8_t* syndromes, uint64_t n, uint8_t* ehat, float* llr, int32_t* iters,
+                       uint8_t* converged);
+
+/* ------------------------------------------------------------------------------------------------ fused run
+ * sample -> sliding-window decode -> compare, entirely on the device (get_stim_mem_result + sliding_window_*_mem +
+ * the caller's pL reduction, reference tests/test_sliding_window.py:83).  counts[0] += shots with any observable
+ * mispredicted, counts[1+k] += mispredictions of observable k. */
+int qb_mc_run(qb_ctx* ctx, qb_circuit* c, qb_sw* sw, uint64_t seed, uint64_t shot0, uint64_t n_shots, uint64_t* counts /*[1+K]*/,
+              qb_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

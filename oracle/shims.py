@@ -180,6 +180,9 @@ class Circuit:
         return DetectorErrorModel(odem.analyze(self.flat))
 
 
+DEFAULT_PRECISION = "f64"      # tools/make_golden.py switches this to "f32" for the fixtures the GPU is held to
+
+
 class _OracleBpDecoderBase:
     """ldpc-shaped per-shot decoder over the oracle's C BP(+OSD) (seam B3)."""
     _order_key = "osd_order"
@@ -205,7 +208,7 @@ class _OracleBpDecoderBase:
             raise NotImplementedError("oracle implements order-0 post-processing only (got %s order %d)" % (method, order))
         self._dec = cref.BpOsd(pcm, priors, max_iter=max_iter if max_iter > 0 else n, bp_method=bp_method,
                                ms_scaling_factor=ms_scaling_factor, schedule=schedule,
-                               precision=kw.get("precision", "f64"))
+                               precision=kw.get("precision", DEFAULT_PRECISION))
         self.log_prob_ratios = None
         self.converge = None
         self.iter = None

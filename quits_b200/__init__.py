@@ -1,0 +1,20 @@
+"""quits_b200 -- B200-native engine for the QUITS Monte-Carlo hot path.
+
+Pauli-frame sampling of the syndrome-extraction circuit and sliding-window BP(+OSD) decoding over the
+circuit-level detector error matrix, as hand-written sm_100a CUDA behind a C ABI (include/quits_b200.h).
+The Python layer mirrors the reference's interface for this path: ``get_stim_mem_result``
+(reference src/quits/simulation.py:8) and ``quits.decoder`` (src/quits/decoder/__init__.py:13-24).
+Importing this package loads libquits_b200.so; there is no CPU fallback.
+"""
+from . import _native
+
+_native.lib()          # fail loudly at import time if the CUDA library is missing
+
+from .circuit import Circuit, Context, DetectorErrorModel  # noqa: E402
+from .decoder import (BpLsdDecoder, BpOsdDecoder, detector_error_model_to_matrix, sliding_window_bplsd_circuit_mem,  # noqa: E402
+                      sliding_window_bplsd_phenom_mem, sliding_window_bposd_circuit_mem, sliding_window_bposd_phenom_mem,
+                      sliding_window_circuit_mem, sliding_window_phenom_mem, spacetime)
+from .engine import MonteCarlo, SlidingWindowDecoder, run_sharded, shard_range  # noqa: E402
+from .simulation import get_stim_mem_result  # noqa: E402
+
+__version__ = "0.1.0"

@@ -1,0 +1,890 @@
+// quits_b200/csrc/api.cu -- the C ABI (include/quits_b200.h): contexts, device residency, batching, launches.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/quits_b200.h"
+#include "qb_device.h"
+#include "qb_host.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+struct cuda_error : std::runtime_error { using std::runtime_error::runtime_error; };
+struct arg_error : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define CK(expr)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            throw cuda_error(std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+template <typename F>
+int guard(F&& f) {
+    try {
+        f();
+        return QB_OK;
+    } catch (const qb::value_error& e) { g_err = e.what(); return QB_EVALUE;
+    } catch (const qb::unsupported_error& e) { g_err = e.what(); return QB_ENOTIMPL;
+    } catch (const cuda_error& e) { g_err = e.what(); return QB_ECUDA;
+    } catch (const arg_error& e) { g_err = e.what(); return QB_EARG;
+    } catch (const std::bad_alloc&) { g_err = "out of host memory"; return QB_ECUDA;
+    } catch (const std::exception& e) { g_err = e.what(); return QB_ECUDA; }
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        CK(cudaMalloc(&p, bytes));
+        cap = bytes;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+template <typename T>
+void upload(DevBuf& b, const std::vector<T>& v, cudaStream_t st, size_t min_elems = 1) {
+    b.ensure(std::max(v.size(), min_elems) * sizeof(T) + 16);
+    if (!v.empty()) CK(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+
+struct EventTimer {          // accumulates CUDA-event time of one kernel class on the launching stream
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans;
+    size_t used = 0;
+    void begin(cudaStream_t st) {
+        if (used == spans.size()) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            spans.emplace_back(a, b);
+        }
+        CK(cudaEventRecord(spans[used].first, st));
+    }
+    void end(cudaStream_t st) { CK(cudaEventRecord(spans[used].second, st)); ++used; }
+    double collect() {       // call after the stream has been synchronised
+        double ms = 0;
+        for (size_t i = 0; i < used; ++i) {
+            float t = 0;
+            CK(cudaEventElapsedTime(&t, spans[i].first, spans[i].second));
+            ms += t;
+        }
+        used = 0;
+        return ms;
+    }
+    ~EventTimer() { for (auto& s : spans) { cudaEventDestroy(s.first); cudaEventDestroy(s.second); } }
+};
+
+}  // namespace
+
+struct qb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // sampler scratch
+    DevBuf det_rows, obs_rows, det_bytes, obs_bytes, inj_start, inj_tgt, inj_code, inj_shot, counts;
+    EventTimer t_frame, t_total;
+};
+
+struct qb_circuit {
+    qb::FlatCircuit fc;
+    qb::Tape tape;
+    std::vector<int32_t> noise_tape_of_flat;      // flat op -> tape op (noise ops only, else -1)
+    // device copies (created on first use with a context)
+    int dev = -1;
+    DevBuf d_ops, d_targets, d_detptr, d_detidx, d_ctab;
+};
+
+struct qb_dem {
+    qb::Dem dem;
+    qb::CheckMatrix cm;
+};
+
+struct qb_plan {
+    qb::WindowPlan plan;
+};
+
+namespace {
+
+struct WinOwned {
+    qb::WinDev dev{};
+    DevBuf colE, llr0, lmask, uptr, uidx, cptr, crow;
+    size_t bp_smem = 0, osd_smem = 0;
+    int osd_grid = 0;
+};
+
+}  // namespace
+
+struct qb_sw {
+    qb_ctx* ctx = nullptr;
+    qb::WindowPlan plan;
+    qb_bp_opts opts{};
+    bool single = false;
+    bool use_osd = true;
+    int max_iter = 0;
+    std::vector<std::unique_ptr<WinOwned>> wins;
+    DevBuf alpha;
+    // batch state
+    int cap = 0;
+    int DW = 0, KW = 0, carryW = 0, synW = 0;
+    size_t llr_stride = 0;
+    DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, counters, stats, pred, ehat, iters, conv;
+    EventTimer t_bp, t_osd;
+};
+
+namespace {
+
+void use_device(qb_ctx* ctx) { CK(cudaSetDevice(ctx->device)); }
+
+void circuit_to_device(qb_ctx* ctx, qb_circuit* c) {
+    if (c->dev == ctx->device) return;
+    upload(c->d_ops, c->tape.ops, ctx->stream);
+    upload(c->d_targets, c->tape.targets, ctx->stream, 2);
+    upload(c->d_detptr, c->tape.detptr, ctx->stream, 2);
+    upload(c->d_detidx, c->tape.detidx, ctx->stream);
+    upload(c->d_ctab, c->tape.ctab, ctx->stream, 64);
+    CK(cudaStreamSynchronize(ctx->stream));
+    c->dev = ctx->device;
+}
+
+qb::FrameArgs frame_args(qb_circuit* c, uint64_t seed) {
+    qb::FrameArgs a{};
+    a.ops = c->d_ops.as<qb::TapeOp>();
+    a.n_ops = static_cast<int>(c->tape.ops.size());
+    a.targets = c->d_targets.as<uint32_t>();
+    a.detptr = c->d_detptr.as<uint32_t>();
+    a.detidx = c->d_detidx.as<uint32_t>();
+    a.ctab = c->d_ctab.as<uint64_t>();
+    a.n_qubits = c->fc.n_qubits;
+    a.n_det = c->fc.n_det;
+    a.n_obs = c->fc.n_obs;
+    a.ring = c->tape.ring;
+    a.DW = std::max(1, (c->fc.n_det + 63) / 64);
+    a.KW = std::max(1, (c->fc.n_obs + 63) / 64);
+    a.seed = seed;
+    return a;
+}
+
+constexpr uint64_t kSampleChunk = 1ull << 18;      // shots per sampler launch when results go back to the host
+
+// ------------------------------------------------------------------------------------------------ decoder set-up
+void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, WinOwned& wo) {
+    qb::WinDev& d = wo.dev;
+    const int rows = hw.rows, ncols = hw.ncols;
+    if (rows <= 0) throw qb::value_error("a decoding window has no detector rows");
+    if (ncols <= 0) throw qb::value_error("a decoding window has no fault columns");
+    if (rows >= (1 << 16) || ncols > 8192)
+        throw qb::unsupported_error("window of " + std::to_string(rows) + " x " + std::to_string(ncols) +
+                                    " exceeds what the shared-memory BP kernel handles (rows < 65536, cols <= 8192)");
+    std::vector<int> fillr(static_cast<size_t>(rows), 0);
+    int cw = 0;
+    for (int j = 0; j < ncols; ++j) cw = std::max(cw, static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]));
+    const int cw_alloc = cw <= 6 ? 6 : (cw <= 8 ? 8 : 16);
+    if (cw > 16) throw qb::unsupported_error("column weight " + std::to_string(cw) + " > 16 is not supported by the BP kernel");
+    const int npad = (ncols + 31) / 32 * 32;
+    std::vector<uint32_t> colE(static_cast<size_t>(cw_alloc) * npad, qb::kNoEdge);
+    for (int j = 0; j < ncols; ++j) {
+        int q = 0;
+        for (int64_t e = hw.cptr[j]; e < hw.cptr[j + 1]; ++e, ++q) {
+            const int r = hw.crow[e];
+            const int slot = fillr[r]++;
+            if (slot > 255) throw qb::unsupported_error("row weight > 255 is not supported by the BP kernel");
+            colE[static_cast<size_t>(q) * npad + j] = (static_cast<uint32_t>(r) << 8) | static_cast<uint32_t>(slot);
+        }
+    }
+    int rs = 1;
+    for (int r = 0; r < rows; ++r) rs = std::max(rs, fillr[r]);
+    rs |= 1;                                             // odd row stride: conflict-free thread-per-row sweeps
+    std::vector<float> llr0(static_cast<size_t>(npad), 0.0f);
+    for (int j = 0; j < ncols; ++j) {
+        const double pr = hw.priors[j];
+        if (!(pr > 0.0 && pr < 1.0)) throw qb::value_error("fault prior outside (0, 1)");
+        llr0[j] = static_cast<float>(std::log((1.0 - pr) / pr));
+    }
+    std::vector<uint64_t> lmask(static_cast<size_t>(std::max(hw.ncommit, 1)) * KW, 0);
+    for (int j = 0; j < hw.ncommit; ++j)
+        for (int64_t e = hw.lptr[j]; e < hw.lptr[j + 1]; ++e) lmask[static_cast<size_t>(j) * KW + hw.lidx[e] / 64] ^= 1ull << (hw.lidx[e] % 64);
+    std::vector<int32_t> uptr(hw.uptr.begin(), hw.uptr.end());
+    if (uptr.empty()) uptr.assign(static_cast<size_t>(hw.ncommit) + 1, 0);
+    std::vector<uint16_t> uidx(hw.uidx.begin(), hw.uidx.end());
+    std::vector<int32_t> cptr(hw.cptr.begin(), hw.cptr.end());
+    std::vector<uint16_t> crow(hw.crow.begin(), hw.crow.end());
+    upload(wo.colE, colE, ctx->stream);
+    upload(wo.llr0, llr0, ctx->stream);
+    upload(wo.lmask, lmask, ctx->stream);
+    upload(wo.uptr, uptr, ctx->stream, 2);
+    upload(wo.uidx, uidx, ctx->stream, 2);
+    upload(wo.cptr, cptr, ctx->stream, 2);
+    upload(wo.crow, crow, ctx->stream, 2);
+    CK(cudaStreamSynchronize(ctx->stream));
+    d.rows = rows; d.ncols = ncols; d.ncols_pad = npad; d.RS = rs; d.cw = cw_alloc; d.ncommit = hw.ncommit;
+    d.row0 = hw.row0; d.carry_rows = hw.urows; d.KW = KW;
+    d.rowsW32 = (rows + 31) / 32; d.nW32 = (ncols + 31) / 32;
+    d.colE = wo.colE.as<uint32_t>(); d.llr0 = wo.llr0.as<float>(); d.lmask = wo.lmask.as<uint64_t>();
+    d.uptr = wo.uptr.as<int32_t>(); d.uidx = wo.uidx.as<uint16_t>(); d.cptr = wo.cptr.as<int32_t>(); d.crow = wo.crow.as<uint16_t>();
+    wo.bp_smem = qb::bp_smem_bytes(d);
+    if (wo.bp_smem > 227 * 1024)
+        throw qb::unsupported_error("window of " + std::to_string(rows) + " rows x row weight " + std::to_string(rs) +
+                                    " needs " + std::to_string(wo.bp_smem) + " B of shared memory for BP messages (limit 232448)");
+}
+
+void finish_decoder(qb_sw* sw) {
+    qb_ctx* ctx = sw->ctx;
+    const qb_bp_opts& o = sw->opts;
+    if (o.bp_method != 0) throw qb::unsupported_error("bp_method 'product_sum' is not implemented on the GPU path yet; use bp_method='minimum_sum'");
+    if (o.schedule != 0) throw qb::unsupported_error("schedule 'serial' is not implemented on the GPU path yet; use schedule='parallel'");
+    if (o.osd_method >= 0 && o.osd_order != 0) throw qb::unsupported_error("osd_order > 0 is not implemented on the GPU path yet; use osd_order=0");
+    if (o.ms_scaling_factor < 0) throw qb::value_error("ms_scaling_factor must be >= 0");
+    sw->use_osd = o.osd_method >= 0;
+    size_t max_bp = 0;
+    int max_cw = 0, max_npad = 0, max_rowsW = 0, max_iter = 0;
+    for (auto& w : sw->wins) {
+        max_bp = std::max(max_bp, w->bp_smem);
+        max_cw = std::max(max_cw, w->dev.cw);
+        max_npad = std::max(max_npad, w->dev.ncols_pad);
+        max_rowsW = std::max(max_rowsW, w->dev.rowsW32);
+        max_iter = std::max(max_iter, o.max_iter > 0 ? o.max_iter : w->dev.ncols);
+        if (sw->use_osd) {
+            if (!qb::osd_supported(w->dev))
+                throw qb::unsupported_error("window of " + std::to_string(w->dev.rows) + " x " + std::to_string(w->dev.ncols) +
+                                            " exceeds what the register-resident OSD kernel handles (rows <= 736)");
+            CK(qb::osd_configure(w->dev));
+            w->osd_smem = qb::osd_smem_bytes(w->dev);
+            int per_sm = static_cast<int>((227 * 1024) / (w->osd_smem + 1024));
+            per_sm = std::max(1, std::min(per_sm, 4));
+            w->osd_grid = 148 * per_sm;
+        }
+    }
+    if (o.max_iter == 0 && sw->wins.size() > 1) {
+        // ldpc's "0 => number of columns" differs per window; the kernel takes one value, so use the per-window value
+        // only when all windows agree
+        for (auto& w : sw->wins)
+            if (w->dev.ncols != sw->wins[0]->dev.ncols) throw qb::unsupported_error("max_iter = 0 with windows of different widths; pass max_iter explicitly");
+    }
+    sw->max_iter = max_iter;
+    for (int cw : {6, 8, 16})
+        if (max_cw <= cw) { CK(qb::bp_configure(max_bp, cw)); break; }
+    for (auto& w : sw->wins) CK(qb::bp_configure(max_bp, w->dev.cw));
+    std::vector<float> alpha(static_cast<size_t>(max_iter) + 1, 1.0f);
+    for (int it = 1; it <= max_iter; ++it)
+        alpha[it] = o.ms_scaling_factor == 0.0 ? static_cast<float>(1.0 - std::pow(2.0, -1.0 * it)) : static_cast<float>(o.ms_scaling_factor);
+    upload(sw->alpha, alpha, ctx->stream);
+    sw->cap = o.capacity > 0 ? o.capacity : 65536;
+    sw->DW = std::max(1, (sw->plan.D + 63) / 64);
+    sw->KW = std::max(1, (sw->plan.K + 63) / 64);
+    sw->carryW = (sw->plan.m + 31) / 32 + 1;
+    sw->synW = max_rowsW;
+    sw->llr_stride = static_cast<size_t>(max_npad);
+    CK(cudaStreamSynchronize(ctx->stream));
+}
+
+void ensure_batch(qb_sw* sw, int n) {
+    const size_t N = static_cast<size_t>(n);
+    sw->carry.ensure(N * sw->carryW * 4 + 16);
+    sw->acc.ensure(N * sw->KW * 8 + 16);
+    sw->llr.ensure(N * sw->llr_stride * 4 + 16);
+    sw->syn.ensure(N * sw->synW * 4 + 16);
+    sw->fail_list.ensure(N * 4 + 16);
+    const size_t nw = sw->wins.size();
+    sw->counters.ensure(nw * 2 * sizeof(int) + 16);
+    sw->stats.ensure(nw * 3 * sizeof(unsigned long long) + 16);
+}
+
+// decode n (<= cap) shots whose packed detector rows are on the device; leaves acc[n][KW] on the device
+void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, bool want_llr, qb_stats* stats) {
+    qb_ctx* ctx = sw->ctx;
+    cudaStream_t st = ctx->stream;
+    ensure_batch(sw, n);
+    const size_t nw = sw->wins.size();
+    CK(cudaMemsetAsync(sw->acc.p, 0, static_cast<size_t>(n) * sw->KW * 8, st));
+    CK(cudaMemsetAsync(sw->carry.p, 0, static_cast<size_t>(n) * sw->carryW * 4, st));
+    CK(cudaMemsetAsync(sw->counters.p, 0, nw * 2 * sizeof(int), st));
+    CK(cudaMemsetAsync(sw->stats.p, 0, nw * 3 * sizeof(unsigned long long), st));
+    qb::BpParams bp{};
+    bp.max_iter = sw->max_iter;
+    bp.alpha = sw->alpha.as<float>();
+    for (size_t k = 0; k < nw; ++k) {
+        WinOwned& w = *sw->wins[k];
+        qb::BatchDev b{};
+        b.n_shots = n;
+        b.det32 = reinterpret_cast<const uint32_t*>(d_det_rows);
+        b.det_stride32 = 2 * sw->DW;
+        b.in_carry_rows = k == 0 ? 0 : sw->wins[k - 1]->dev.carry_rows;
+        b.carry = sw->carry.as<uint32_t>();
+        b.carry_stride32 = sw->carryW;
+        b.acc = sw->acc.as<uint64_t>();
+        b.llr_buf = sw->llr.as<float>();
+        b.llr_stride = sw->llr_stride;
+        b.syn_buf = sw->syn.as<uint32_t>();
+        b.syn_stride32 = sw->synW;
+        b.fail_list = sw->fail_list.as<int>();
+        b.fail_count = sw->counters.as<int>() + 2 * k;
+        b.osd_next = sw->counters.as<int>() + 2 * k + 1;
+        b.stats = sw->stats.as<unsigned long long>() + 3 * k;
+        b.ehat_out = want_ehat ? sw->ehat.as<uint32_t>() : nullptr;
+        b.ehat_stride32 = w.dev.nW32;
+        b.iters_out = want_ehat ? sw->iters.as<int32_t>() : nullptr;
+        b.conv_out = want_ehat ? sw->conv.as<uint8_t>() : nullptr;
+        b.write_llr_always = want_llr ? 1 : 0;
+        if (sw->opts.profile) sw->t_bp.begin(st);
+        CK(qb::launch_bp(w.dev, b, bp, st));
+        if (sw->opts.profile) sw->t_bp.end(st);
+        if (stats) stats->bp_launches++;
+        if (sw->use_osd) {
+            if (sw->opts.profile) sw->t_osd.begin(st);
+            CK(qb::launch_osd(w.dev, b, std::min(w.osd_grid, n), st));
+            if (sw->opts.profile) sw->t_osd.end(st);
+            if (stats) stats->osd_launches++;
+        }
+    }
+}
+
+void collect_stats(qb_sw* sw, int n, qb_stats* stats) {        // stream must be synchronised
+    if (!stats) return;
+    const size_t nw = sw->wins.size();
+    std::vector<unsigned long long> h(nw * 3);
+    CK(cudaMemcpy(h.data(), sw->stats.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    stats->shots += n;
+    stats->windows += static_cast<int64_t>(nw) * n;
+    for (size_t k = 0; k < nw; ++k) {
+        stats->bp_converged += static_cast<int64_t>(h[3 * k]);
+        stats->bp_iterations += static_cast<int64_t>(h[3 * k + 1]);
+        stats->osd_calls += static_cast<int64_t>(h[3 * k + 2]);
+    }
+    if (sw->opts.profile) {
+        stats->bp_ms += sw->t_bp.collect();
+        stats->osd_ms += sw->t_osd.collect();
+    }
+}
+
+void parse_opts(const qb_bp_opts* in, qb_bp_opts& out) {
+    if (in) out = *in;
+    else {
+        out = qb_bp_opts{};
+        out.max_iter = 10;
+        out.ms_scaling_factor = 1.0;
+    }
+}
+
+}  // namespace
+
+template <typename V>
+static void export_csr(const V& lists, int64_t* ptr, int32_t* idx) {
+    int64_t pos = 0;
+    for (size_t i = 0; i < lists.size(); ++i) {
+        if (ptr) ptr[i] = pos;
+        if (idx) for (size_t j = 0; j < lists[i].size(); ++j) idx[pos + static_cast<int64_t>(j)] = lists[i][j];
+        pos += static_cast<int64_t>(lists[i].size());
+    }
+    if (ptr) ptr[lists.size()] = pos;
+}
+
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* qb_last_error(void) { return g_err.c_str(); }
+int qb_version(void) { return 100; }
+
+int qb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int qb_ctx_create(int device, qb_ctx** out) {
+    return guard([&] {
+        if (!out) throw arg_error("out is NULL");
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            cudaGetLastError();
+            throw cuda_error("no CUDA device is available: the quits_b200 engine has no CPU fallback");
+        }
+        if (device < 0 || device >= n) throw arg_error("device index out of range");
+        CK(cudaSetDevice(device));
+        std::unique_ptr<qb_ctx> ctx(new qb_ctx());
+        ctx->device = device;
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        *out = ctx.release();
+    });
+}
+
+void qb_ctx_destroy(qb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    delete ctx;
+}
+
+int qb_ctx_synchronize(qb_ctx* ctx) {
+    return guard([&] { use_device(ctx); CK(cudaStreamSynchronize(ctx->stream)); });
+}
+
+// ------------------------------------------------------------------------------------------------ circuit
+int qb_circuit_parse(const char* text, size_t len, qb_circuit** out) {
+    return guard([&] {
+        if (!text || !out) throw arg_error("NULL argument");
+        std::unique_ptr<qb_circuit> c(new qb_circuit());
+        qb::parse_flatten(text, len, c->fc);
+        qb::build_tape(c->fc, c->tape);
+        c->noise_tape_of_flat.assign(c->fc.ops.size(), -1);
+        for (size_t t = 0; t < c->tape.ops.size(); ++t) {
+            const int k = c->tape.ops[t].kind;
+            if (k >= qb::OP_XERR && k <= qb::OP_DEP2) c->noise_tape_of_flat[c->tape.ops[t].flat] = static_cast<int32_t>(t);
+        }
+        *out = c.release();
+    });
+}
+
+void qb_circuit_free(qb_circuit* c) { delete c; }
+
+int qb_circuit_get_info(const qb_circuit* c, qb_circuit_info* info) {
+    return guard([&] {
+        if (!c || !info) throw arg_error("NULL argument");
+        info->n_qubits = c->fc.n_qubits;
+        info->n_measurements = c->fc.n_meas;
+        info->n_detectors = c->fc.n_det;
+        info->n_observables = c->fc.n_obs;
+        info->n_flat_ops = static_cast<int64_t>(c->fc.ops.size());
+        info->n_tape_ops = static_cast<int64_t>(c->tape.ops.size());
+        info->n_noise_sites = c->fc.n_sites;
+        info->ring = c->tape.ring;
+    });
+}
+
+int qb_circuit_flat(const qb_circuit* c, int32_t* kind, double* arg, int64_t* tstart, int32_t* targets, int64_t* n_targets_out) {
+    return guard([&] {
+        if (!c) throw arg_error("NULL argument");
+        int64_t pos = 0;
+        for (size_t i = 0; i < c->fc.ops.size(); ++i) {
+            const qb::FlatOp& op = c->fc.ops[i];
+            if (kind) kind[i] = op.kind;
+            if (arg) arg[i] = op.arg;
+            if (tstart) tstart[i] = pos;
+            if (targets) for (size_t j = 0; j < op.targets.size(); ++j) targets[pos + static_cast<int64_t>(j)] = op.targets[j];
+            pos += static_cast<int64_t>(op.targets.size());
+        }
+        if (tstart) tstart[c->fc.ops.size()] = pos;
+        if (n_targets_out) *n_targets_out = pos;
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ sampler
+static void sample_impl(qb_ctx* ctx, qb_circuit* c, uint64_t seed, uint64_t shot0, uint64_t n_shots, uint8_t* det, uint8_t* obs,
+                        uint64_t* det_rows, uint64_t* obs_rows) {
+    if (!ctx || !c) throw arg_error("NULL argument");
+    if (shot0 & 63) throw arg_error("shot0 must be a multiple of 64");
+    use_device(ctx);
+    circuit_to_device(ctx, c);
+    qb::FrameArgs a = frame_args(c, seed);
+    if (qb::frame_smem_per_warp(a) > 200 * 1024) throw qb::unsupported_error("circuit too large for the shared-memory frame kernel");
+    const int D = c->fc.n_det, K = c->fc.n_obs;
+    for (uint64_t done = 0; done < n_shots; done += kSampleChunk) {
+        const uint64_t n = std::min(kSampleChunk, n_shots - done);
+        const uint64_t nwords = (n + 63) / 64;
+        ctx->det_rows.ensure(nwords * 64 * a.DW * 8 + 16);
+        ctx->obs_rows.ensure(nwords * 64 * a.KW * 8 + 16);
+        a.word0 = (shot0 + done) / 64;
+        a.n_words = nwords;
+        a.det_rows = ctx->det_rows.as<uint64_t>();
+        a.obs_rows = ctx->obs_rows.as<uint64_t>();
+        CK(qb::launch_frame(a, ctx->stream));
+        if (det || obs) {
+            ctx->det_bytes.ensure(n * std::max(D, 1) + 16);
+            ctx->obs_bytes.ensure(n * std::max(K, 1) + 16);
+            CK(qb::launch_unpack_bits(a.det_rows, a.DW, D, n, ctx->det_bytes.as<uint8_t>(), ctx->stream));
+            CK(qb::launch_unpack_bits(a.obs_rows, a.KW, K, n, ctx->obs_bytes.as<uint8_t>(), ctx->stream));
+            if (det && D) CK(cudaMemcpyAsync(det + done * D, ctx->det_bytes.p, n * D, cudaMemcpyDeviceToHost, ctx->stream));
+            if (obs && K) CK(cudaMemcpyAsync(obs + done * K, ctx->obs_bytes.p, n * K, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (det_rows) CK(cudaMemcpyAsync(det_rows + done * a.DW, a.det_rows, n * a.DW * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (obs_rows) CK(cudaMemcpyAsync(obs_rows + done * a.KW, a.obs_rows, n * a.KW * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+}
+
+int qb_sample(qb_ctx* ctx, qb_circuit* c, uint64_t seed, uint64_t shot0, uint64_t n_shots, uint8_t* det, uint8_t* obs) {
+    return guard([&] { sample_impl(ctx, c, seed, shot0, n_shots, det, obs, nullptr, nullptr); });
+}
+
+int qb_sample_packed(qb_ctx* ctx, qb_circuit* c, uint64_t seed, uint64_t shot0, uint64_t n_shots, uint64_t* det_rows, uint64_t* obs_rows) {
+    return guard([&] { sample_impl(ctx, c, seed, shot0, n_shots, nullptr, nullptr, det_rows, obs_rows); });
+}
+
+int qb_sample_faults(qb_ctx* ctx, qb_circuit* c, int64_t n_faults, const int32_t* op, const int32_t* tgt, const int32_t* code,
+                     const int64_t* shot, uint64_t n_shots, uint8_t* det, uint8_t* obs) {
+    return guard([&] {
+        if (!ctx || !c) throw arg_error("NULL argument");
+        if (n_faults < 0 || (n_faults > 0 && (!op || !tgt || !code || !shot))) throw arg_error("bad fault list");
+        use_device(ctx);
+        circuit_to_device(ctx, c);
+        const size_t T = c->tape.ops.size();
+        std::vector<int32_t> tape_of(static_cast<size_t>(n_faults));
+        for (int64_t f = 0; f < n_faults; ++f) {
+            if (op[f] < 0 || static_cast<size_t>(op[f]) >= c->fc.ops.size() || c->noise_tape_of_flat[op[f]] < 0)
+                throw arg_error("fault " + std::to_string(f) + " does not address a noise instruction");
+            const qb::FlatOp& fo = c->fc.ops[op[f]];
+            const int ns = fo.kind == qb::OP_DEP2 ? static_cast<int>(fo.targets.size() / 2) : static_cast<int>(fo.targets.size());
+            if (tgt[f] < 0 || tgt[f] >= ns) throw arg_error("fault " + std::to_string(f) + ": target index out of range");
+            if (shot[f] < 0 || static_cast<uint64_t>(shot[f]) >= n_shots) throw arg_error("fault " + std::to_string(f) + ": shot out of range");
+            if (code[f] < 1 || code[f] > (fo.kind == qb::OP_DEP2 ? 15 : 3)) throw arg_error("fault " + std::to_string(f) + ": bad Pauli code");
+            tape_of[f] = c->noise_tape_of_flat[op[f]];
+        }
+        std::vector<int64_t> order(static_cast<size_t>(n_faults));
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return tape_of[a] < tape_of[b]; });
+        std::vector<int32_t> start(T + 1, 0), stgt(static_cast<size_t>(n_faults)), scode(static_cast<size_t>(n_faults));
+        std::vector<int64_t> sshot(static_cast<size_t>(n_faults));
+        for (int64_t i = 0; i < n_faults; ++i) {
+            const int64_t f = order[i];
+            start[tape_of[f] + 1]++;
+            stgt[i] = tgt[f]; scode[i] = code[f]; sshot[i] = shot[f];
+        }
+        for (size_t t = 0; t < T; ++t) start[t + 1] += start[t];
+        upload(ctx->inj_start, start, ctx->stream);
+        upload(ctx->inj_tgt, stgt, ctx->stream);
+        upload(ctx->inj_code, scode, ctx->stream);
+        upload(ctx->inj_shot, sshot, ctx->stream);
+        qb::FrameArgs a = frame_args(c, 0);
+        const int D = c->fc.n_det, K = c->fc.n_obs;
+        const uint64_t nwords = (n_shots + 63) / 64;
+        ctx->det_rows.ensure(nwords * 64 * a.DW * 8 + 16);
+        ctx->obs_rows.ensure(nwords * 64 * a.KW * 8 + 16);
+        a.word0 = 0; a.n_words = nwords;
+        a.det_rows = ctx->det_rows.as<uint64_t>();
+        a.obs_rows = ctx->obs_rows.as<uint64_t>();
+        a.inject = 1;
+        a.inj_start = ctx->inj_start.as<int32_t>();
+        a.inj_tgt = ctx->inj_tgt.as<int32_t>();
+        a.inj_code = ctx->inj_code.as<int32_t>();
+        a.inj_shot = ctx->inj_shot.as<int64_t>();
+        CK(qb::launch_frame(a, ctx->stream));
+        ctx->det_bytes.ensure(n_shots * std::max(D, 1) + 16);
+        ctx->obs_bytes.ensure(n_shots * std::max(K, 1) + 16);
+        CK(qb::launch_unpack_bits(a.det_rows, a.DW, D, n_shots, ctx->det_bytes.as<uint8_t>(), ctx->stream));
+        CK(qb::launch_unpack_bits(a.obs_rows, a.KW, K, n_shots, ctx->obs_bytes.as<uint8_t>(), ctx->stream));
+        if (det && D) CK(cudaMemcpyAsync(det, ctx->det_bytes.p, n_shots * D, cudaMemcpyDeviceToHost, ctx->stream));
+        if (obs && K) CK(cudaMemcpyAsync(obs, ctx->obs_bytes.p, n_shots * K, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ DEM
+int qb_dem_from_circuit(const qb_circuit* c, qb_dem** out) {
+    return guard([&] {
+        if (!c || !out) throw arg_error("NULL argument");
+        std::unique_ptr<qb_dem> d(new qb_dem());
+        qb::analyze(c->fc, d->dem);
+        qb::dem_to_matrix(d->dem, d->cm);
+        *out = d.release();
+    });
+}
+
+int qb_dem_from_errors(int32_t n_detectors, int32_t n_observables, int64_t n_errors, const double* probs, const int64_t* det_ptr,
+                       const int32_t* det_idx, const int64_t* obs_ptr, const int32_t* obs_idx, qb_dem** out) {
+    return guard([&] {
+        if (!out || n_errors < 0 || (n_errors && (!probs || !det_ptr || !obs_ptr))) throw arg_error("NULL argument");
+        std::unique_ptr<qb_dem> d(new qb_dem());
+        d->dem.n_det = n_detectors;
+        d->dem.n_obs = n_observables;
+        for (int64_t e = 0; e < n_errors; ++e) {
+            std::vector<int32_t> dd(det_idx + det_ptr[e], det_idx + det_ptr[e + 1]), oo(obs_idx + obs_ptr[e], obs_idx + obs_ptr[e + 1]);
+            for (int32_t v : dd) if (v < 0 || v >= n_detectors) throw arg_error("detector id out of range");
+            for (int32_t v : oo) if (v < 0 || v >= n_observables) throw arg_error("observable id out of range");
+            d->dem.probs.push_back(probs[e]);
+            d->dem.dets.push_back(std::move(dd));
+            d->dem.obs.push_back(std::move(oo));
+            d->dem.rep_op.push_back(-1); d->dem.rep_tgt.push_back(-1); d->dem.rep_code.push_back(0);
+        }
+        qb::dem_to_matrix(d->dem, d->cm);
+        *out = d.release();
+    });
+}
+
+void qb_dem_free(qb_dem* d) { delete d; }
+
+int qb_dem_sizes(const qb_dem* d, int64_t sizes[9]) {
+    return guard([&] {
+        if (!d || !sizes) throw arg_error("NULL argument");
+        int64_t nd = 0, no = 0, nh = 0, nl = 0;
+        for (auto& v : d->dem.dets) nd += static_cast<int64_t>(v.size());
+        for (auto& v : d->dem.obs) no += static_cast<int64_t>(v.size());
+        for (auto& v : d->cm.col_dets) nh += static_cast<int64_t>(v.size());
+        for (auto& v : d->cm.col_obs) nl += static_cast<int64_t>(v.size());
+        sizes[0] = d->dem.n_det; sizes[1] = d->dem.n_obs; sizes[2] = static_cast<int64_t>(d->dem.probs.size());
+        sizes[3] = nd; sizes[4] = no; sizes[5] = static_cast<int64_t>(d->cm.priors.size()); sizes[6] = nh; sizes[7] = nl;
+        sizes[8] = d->cm.n_detless;
+    });
+}
+
+int qb_dem_errors(const qb_dem* d, double* probs, int64_t* det_ptr, int32_t* det_idx, int64_t* obs_ptr, int32_t* obs_idx,
+                  int32_t* rep_op, int32_t* rep_tgt, int32_t* rep_code) {
+    return guard([&] {
+        if (!d) throw arg_error("NULL argument");
+        const size_t n = d->dem.probs.size();
+        if (probs) memcpy(probs, d->dem.probs.data(), n * 8);
+        export_csr(d->dem.dets, det_ptr, det_idx);
+        export_csr(d->dem.obs, obs_ptr, obs_idx);
+        if (rep_op) memcpy(rep_op, d->dem.rep_op.data(), n * 4);
+        if (rep_tgt) memcpy(rep_tgt, d->dem.rep_tgt.data(), n * 4);
+        if (rep_code) memcpy(rep_code, d->dem.rep_code.data(), n * 4);
+    });
+}
+
+int qb_dem_matrix(const qb_dem* d, int64_t* h_ptr, int32_t* h_idx, int64_t* l_ptr, int32_t* l_idx, double* priors) {
+    return guard([&] {
+        if (!d) throw arg_error("NULL argument");
+        export_csr(d->cm.col_dets, h_ptr, h_idx);
+        export_csr(d->cm.col_obs, l_ptr, l_idx);
+        if (priors) memcpy(priors, d->cm.priors.data(), d->cm.priors.size() * 8);
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ decoder
+int qb_plan_create(const qb_dem* d, int32_t m, int32_t W, int32_t F, int32_t n_cor, qb_plan** out) {
+    return guard([&] {
+        if (!d || !out) throw arg_error("NULL argument");
+        std::unique_ptr<qb_plan> p(new qb_plan());
+        qb::plan_windows(d->cm, m, W, F, n_cor, p->plan);
+        *out = p.release();
+    });
+}
+
+void qb_plan_free(qb_plan* p) { delete p; }
+
+int qb_sw_create(qb_ctx* ctx, const qb_plan* plan, const qb_bp_opts* opts, qb_sw** out) {
+    return guard([&] {
+        if (!ctx || !plan || !out) throw arg_error("NULL argument");
+        use_device(ctx);
+        std::unique_ptr<qb_sw> sw(new qb_sw());
+        sw->ctx = ctx;
+        parse_opts(opts, sw->opts);
+        sw->plan = plan->plan;
+        const int KW = std::max(1, (sw->plan.K + 63) / 64);
+        for (const qb::Window& hw : sw->plan.windows) {
+            if (hw.urows != 0 && hw.urows != sw->plan.m) throw qb::value_error("carry block of a window is not m rows tall");
+            sw->wins.emplace_back(new WinOwned());
+            build_window(ctx, hw, KW, *sw->wins.back());
+        }
+        finish_decoder(sw.get());
+        *out = sw.release();
+    });
+}
+
+int qb_sw_create_single(qb_ctx* ctx, int32_t rows, int32_t cols, const int64_t* indptr, const int32_t* indices, const double* priors,
+                        const qb_bp_opts* opts, qb_sw** out) {
+    return guard([&] {
+        if (!ctx || !indptr || !priors || !out) throw arg_error("NULL argument");
+        use_device(ctx);
+        std::unique_ptr<qb_sw> sw(new qb_sw());
+        sw->ctx = ctx;
+        sw->single = true;
+        parse_opts(opts, sw->opts);
+        qb::Window hw;
+        hw.row0 = 0; hw.rows = rows; hw.col0 = 0; hw.ncols = cols; hw.ncommit = 0; hw.urow0 = 0; hw.urows = 0;
+        hw.cptr.assign(indptr, indptr + cols + 1);
+        if (hw.cptr[0] != 0) throw arg_error("indptr[0] must be 0");
+        for (int j = 0; j < cols; ++j) {
+            if (hw.cptr[j + 1] < hw.cptr[j]) throw arg_error("indptr must be non-decreasing");
+            std::vector<int32_t> r(indices + hw.cptr[j], indices + hw.cptr[j + 1]);
+            std::sort(r.begin(), r.end());
+            for (size_t i = 0; i < r.size(); ++i) {
+                if (r[i] < 0 || r[i] >= rows) throw arg_error("row index out of range");
+                if (i && r[i] == r[i - 1]) throw arg_error("duplicate entry in a column");
+                hw.crow.push_back(r[i]);
+            }
+        }
+        hw.priors.assign(priors, priors + cols);
+        hw.lptr.assign(1, 0);
+        hw.uptr.assign(1, 0);
+        sw->plan.m = rows; sw->plan.K = 0; sw->plan.D = rows; sw->plan.W = 1; sw->plan.F = 1; sw->plan.n_cor = 0;
+        sw->plan.windows.push_back(hw);
+        sw->wins.emplace_back(new WinOwned());
+        build_window(ctx, sw->plan.windows[0], 1, *sw->wins.back());
+        finish_decoder(sw.get());
+        *out = sw.release();
+    });
+}
+
+void qb_sw_free(qb_sw* sw) {
+    if (!sw) return;
+    if (sw->ctx) { cudaSetDevice(sw->ctx->device); cudaStreamSynchronize(sw->ctx->stream); }
+    delete sw;
+}
+
+int qb_plan_info(const qb_plan* sw, int64_t info[8]) {
+    return guard([&] {
+        if (!sw || !info) throw arg_error("NULL argument");
+        info[0] = static_cast<int64_t>(sw->plan.windows.size()); info[1] = sw->plan.m; info[2] = sw->plan.K; info[3] = sw->plan.D;
+        info[4] = sw->plan.W; info[5] = sw->plan.F; info[6] = sw->plan.num_rounds; info[7] = sw->plan.whole_history ? 1 : 0;
+    });
+}
+
+int qb_plan_window(const qb_plan* sw, int32_t k, int64_t dims[10], int64_t* h_ptr, int32_t* h_idx, double* priors, int64_t* l_ptr,
+                 int32_t* l_idx, int64_t* u_ptr, int32_t* u_idx) {
+    return guard([&] {
+        if (!sw) throw arg_error("NULL argument");
+        if (k < 0 || static_cast<size_t>(k) >= sw->plan.windows.size()) throw arg_error("window index out of range");
+        const qb::Window& w = sw->plan.windows[k];
+        if (dims) {
+            dims[0] = w.row0; dims[1] = w.rows; dims[2] = w.col0; dims[3] = w.ncols; dims[4] = w.ncommit;
+            dims[5] = static_cast<int64_t>(w.crow.size()); dims[6] = static_cast<int64_t>(w.lidx.size());
+            dims[7] = static_cast<int64_t>(w.uidx.size()); dims[8] = w.urow0; dims[9] = w.urows;
+        }
+        if (h_ptr) memcpy(h_ptr, w.cptr.data(), w.cptr.size() * 8);
+        if (h_idx && !w.crow.empty()) memcpy(h_idx, w.crow.data(), w.crow.size() * 4);
+        if (priors && !w.priors.empty()) memcpy(priors, w.priors.data(), w.priors.size() * 8);
+        if (l_ptr) memcpy(l_ptr, w.lptr.data(), w.lptr.size() * 8);
+        if (l_idx && !w.lidx.empty()) memcpy(l_idx, w.lidx.data(), w.lidx.size() * 4);
+        if (u_ptr) memcpy(u_ptr, w.uptr.data(), w.uptr.size() * 8);
+        if (u_idx && !w.uidx.empty()) memcpy(u_idx, w.uidx.data(), w.uidx.size() * 4);
+    });
+}
+
+int qb_sw_decode(qb_sw* sw, const uint8_t* det, uint64_t n, int64_t* pred, qb_stats* stats) {
+    return guard([&] {
+        if (!sw || (n && (!det || !pred))) throw arg_error("NULL argument");
+        if (sw->single) throw arg_error("qb_sw_decode needs a sliding-window decoder (qb_sw_create)");
+        qb_ctx* ctx = sw->ctx;
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        const int D = sw->plan.D, K = sw->plan.K;
+        for (uint64_t done = 0; done < n; done += static_cast<uint64_t>(sw->cap)) {
+            const int nb = static_cast<int>(std::min<uint64_t>(sw->cap, n - done));
+            sw->det_bytes.ensure(static_cast<size_t>(nb) * D + 16);
+            sw->det_rows.ensure(static_cast<size_t>(nb) * sw->DW * 8 + 16);
+            sw->pred.ensure(static_cast<size_t>(nb) * std::max(K, 1) * 8 + 16);
+            CK(cudaMemcpyAsync(sw->det_bytes.p, det + done * D, static_cast<size_t>(nb) * D, cudaMemcpyHostToDevice, st));
+            CK(qb::launch_pack_bits(sw->det_bytes.as<uint8_t>(), D, nb, sw->det_rows.as<uint64_t>(), sw->DW, st));
+            decode_batch(sw, sw->det_rows.as<uint64_t>(), nb, false, false, stats);
+            CK(qb::launch_expand_pred(sw->acc.as<uint64_t>(), sw->KW, K, nb, sw->pred.as<int64_t>(), st));
+            if (K) CK(cudaMemcpyAsync(pred + done * K, sw->pred.p, static_cast<size_t>(nb) * K * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (stats) stats->other_launches += 2;
+            collect_stats(sw, nb, stats);
+        }
+    });
+}
+
+int qb_sw_decode_packed(qb_sw* sw, const uint64_t* det_rows, uint64_t n, uint64_t* pred_rows, qb_stats* stats) {
+    return guard([&] {
+        if (!sw || (n && (!det_rows || !pred_rows))) throw arg_error("NULL argument");
+        if (sw->single) throw arg_error("qb_sw_decode_packed needs a sliding-window decoder (qb_sw_create)");
+        qb_ctx* ctx = sw->ctx;
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        for (uint64_t done = 0; done < n; done += static_cast<uint64_t>(sw->cap)) {
+            const int nb = static_cast<int>(std::min<uint64_t>(sw->cap, n - done));
+            sw->det_rows.ensure(static_cast<size_t>(nb) * sw->DW * 8 + 16);
+            CK(cudaMemcpyAsync(sw->det_rows.p, det_rows + done * sw->DW, static_cast<size_t>(nb) * sw->DW * 8, cudaMemcpyHostToDevice, st));
+            decode_batch(sw, sw->det_rows.as<uint64_t>(), nb, false, false, stats);
+            CK(cudaMemcpyAsync(pred_rows + done * sw->KW, sw->acc.p, static_cast<size_t>(nb) * sw->KW * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            collect_stats(sw, nb, stats);
+        }
+    });
+}
+
+int qb_bp_decode_batch(qb_sw* sw, const uint8_t* syndromes, uint64_t n, uint8_t* ehat, float* llr, int32_t* iters, uint8_t* converged) {
+    return guard([&] {
+        if (!sw || (n && !syndromes)) throw arg_error("NULL argument");
+        if (!sw->single) throw arg_error("qb_bp_decode_batch needs a single-window decoder (qb_sw_create_single)");
+        qb_ctx* ctx = sw->ctx;
+        use_device(ctx);
+        cudaStream_t st = ctx->stream;
+        const qb::WinDev& w = sw->wins[0]->dev;
+        const int rows = w.rows, cols = w.ncols;
+        for (uint64_t done = 0; done < n; done += static_cast<uint64_t>(sw->cap)) {
+            const int nb = static_cast<int>(std::min<uint64_t>(sw->cap, n - done));
+            sw->det_bytes.ensure(static_cast<size_t>(nb) * std::max(rows, cols) + 16);
+            sw->det_rows.ensure(static_cast<size_t>(nb) * sw->DW * 8 + 16);
+            sw->ehat.ensure(static_cast<size_t>(nb) * w.nW32 * 4 + 16);
+            sw->iters.ensure(static_cast<size_t>(nb) * 4 + 16);
+            sw->conv.ensure(static_cast<size_t>(nb) + 16);
+            CK(cudaMemcpyAsync(sw->det_bytes.p, syndromes + done * rows, static_cast<size_t>(nb) * rows, cudaMemcpyHostToDevice, st));
+            CK(qb::launch_pack_bits(sw->det_bytes.as<uint8_t>(), rows, nb, sw->det_rows.as<uint64_t>(), sw->DW, st));
+            CK(cudaMemsetAsync(sw->ehat.p, 0, static_cast<size_t>(nb) * w.nW32 * 4, st));
+            decode_batch(sw, sw->det_rows.as<uint64_t>(), nb, true, true, nullptr);
+            if (ehat) {
+                // ehat bit rows are u32 words; widen through the u64 unpacker when the stride is even, else via a u32 view
+                // (nW32 words per shot) -> unpack treats rows as u64 with words_per_row = nW32/2 only if even; use byte path below
+                std::vector<uint32_t> h(static_cast<size_t>(nb) * w.nW32);
+                CK(cudaMemcpyAsync(h.data(), sw->ehat.p, h.size() * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                for (int s = 0; s < nb; ++s)
+                    for (int j = 0; j < cols; ++j)
+                        ehat[(done + s) * cols + j] = static_cast<uint8_t>((h[static_cast<size_t>(s) * w.nW32 + (j >> 5)] >> (j & 31)) & 1u);
+            }
+            if (llr)
+                CK(cudaMemcpy2DAsync(llr + done * cols, static_cast<size_t>(cols) * 4, sw->llr.p, sw->llr_stride * 4,
+                                     static_cast<size_t>(cols) * 4, nb, cudaMemcpyDeviceToHost, st));
+            if (iters) CK(cudaMemcpyAsync(iters + done, sw->iters.p, static_cast<size_t>(nb) * 4, cudaMemcpyDeviceToHost, st));
+            if (converged) CK(cudaMemcpyAsync(converged + done, sw->conv.p, static_cast<size_t>(nb), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ fused run
+int qb_mc_run(qb_ctx* ctx, qb_circuit* c, qb_sw* sw, uint64_t seed, uint64_t shot0, uint64_t n_shots, uint64_t* counts, qb_stats* stats) {
+    return guard([&] {
+        if (!ctx || !c || !sw || !counts) throw arg_error("NULL argument");
+        if (sw->ctx != ctx) throw arg_error("decoder belongs to another context");
+        if (sw->single) throw arg_error("qb_mc_run needs a sliding-window decoder");
+        if (shot0 & 63) throw arg_error("shot0 must be a multiple of 64");
+        if (c->fc.n_det != sw->plan.D || c->fc.n_obs != sw->plan.K) throw arg_error("circuit and decoder disagree on detectors/observables");
+        use_device(ctx);
+        circuit_to_device(ctx, c);
+        cudaStream_t st = ctx->stream;
+        qb::FrameArgs a = frame_args(c, seed);
+        if (qb::frame_smem_per_warp(a) > 200 * 1024) throw qb::unsupported_error("circuit too large for the shared-memory frame kernel");
+        const int K = sw->plan.K;
+        ctx->counts.ensure((1 + static_cast<size_t>(a.KW) * 64) * 8);
+        CK(cudaMemsetAsync(ctx->counts.p, 0, (1 + static_cast<size_t>(a.KW) * 64) * 8, st));
+        const bool prof = sw->opts.profile != 0;
+        if (prof) ctx->t_total.begin(st);
+        for (uint64_t done = 0; done < n_shots; done += static_cast<uint64_t>(sw->cap)) {
+            const uint64_t n = std::min<uint64_t>(sw->cap, n_shots - done);
+            const uint64_t nwords = (n + 63) / 64;
+            ctx->det_rows.ensure(nwords * 64 * a.DW * 8 + 16);
+            ctx->obs_rows.ensure(nwords * 64 * a.KW * 8 + 16);
+            a.word0 = (shot0 + done) / 64;
+            a.n_words = nwords;
+            a.det_rows = ctx->det_rows.as<uint64_t>();
+            a.obs_rows = ctx->obs_rows.as<uint64_t>();
+            if (prof) ctx->t_frame.begin(st);
+            CK(qb::launch_frame(a, st));
+            if (prof) ctx->t_frame.end(st);
+            decode_batch(sw, a.det_rows, static_cast<int>(n), false, false, stats);
+            CK(qb::launch_count(sw->acc.as<uint64_t>(), a.obs_rows, a.KW, K, n, ctx->counts.as<unsigned long long>(), st));
+            if (stats) { stats->frame_launches++; stats->other_launches++; }
+            // per-batch statistics are read back after the batch: the counters are reused by the next one
+            CK(cudaStreamSynchronize(st));
+            collect_stats(sw, static_cast<int>(n), stats);
+        }
+        if (prof) { ctx->t_total.end(st); }
+        std::vector<unsigned long long> h(1 + static_cast<size_t>(K));
+        CK(cudaMemcpyAsync(h.data(), ctx->counts.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < h.size(); ++i) counts[i] += h[i];
+        if (stats && prof) {
+            stats->frame_ms += ctx->t_frame.collect();
+            stats->total_ms += ctx->t_total.collect();
+        }
+    });
+}
+
+}  // extern "C"

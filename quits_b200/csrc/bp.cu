@@ -1,0 +1,240 @@
+// quits_b200/csrc/bp.cu -- K3 (+K2/K5 fused): flooding min-sum BP of one sliding window, one shot per CTA (sm_100a).
+//
+// Replaces the BP stage of ldpc.BpOsdDecoder.decode() as the reference calls it once per shot and window
+// (reference src/quits/decoder/sliding_window.py:171,182) together with the glue around it:
+// window syndrome slice + carry XOR (:168-169), stop test H e == s, and on convergence the commit
+// L_k e / U_k e (:172-175).
+//
+// Data layout.  The bit->check messages of the shot live in shared memory as fp32 in padded row-major order
+// V[row * RS + slot] (RS odd: a thread-per-row sweep is bank-conflict free, and consecutive columns that share
+// a row hit consecutive banks).  The check->bit messages are never materialised: the check sweep reduces each
+// row to (min1, min2, argmin slot, sign parity) and the bit sweep rebuilds its <= CW incoming messages from
+// those summaries, which gives exactly the value of the forward/backward running-min formulation
+// (min over the other edges, sign from syndrome + #{v <= 0}).  All floating-point operations are done in the
+// same order as the CPU oracle with explicit round-to-nearest intrinsics (no FMA contraction), so hard
+// decisions and posteriors agree bit for bit with the fp32 oracle.
+// The window's column structure (<= CW packed (row, slot) entries per column, stored entry-major so a warp
+// reads 128 contiguous bytes) and the prior LLRs are shared by all shots and stream from L2.
+#include <cfloat>
+
+#include "qb_device.h"
+
+namespace qb {
+
+namespace {
+
+constexpr int kBpThreads = 256;
+
+struct BpSmem {
+    float* V;
+    float2* rsum;
+    uint32_t* rmeta;
+    uint32_t* syn;
+    uint32_t* cand;
+    uint32_t* accs;
+    uint32_t* car;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline size_t bp_layout(const WinDev& w, size_t* off /*[7]*/) {
+    size_t o = 0;
+    off[0] = o; o += align_up(static_cast<size_t>(w.rows) * w.RS * 4, 16);
+    off[1] = o; o += align_up(static_cast<size_t>(w.rows) * 8, 16);
+    off[2] = o; o += align_up(static_cast<size_t>(w.rows) * 4, 16);
+    off[3] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
+    off[4] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
+    off[5] = o; o += align_up(static_cast<size_t>(w.KW) * 8, 16);
+    off[6] = o; o += align_up(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4, 16);
+    return o;
+}
+
+template <int CW>
+__global__ void __launch_bounds__(kBpThreads, (CW <= 8 ? 4 : 2)) bp_kernel(const WinDev w, const BatchDev b, const BpParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    size_t off[7];
+    bp_layout(w, off);
+    float* V = reinterpret_cast<float*>(smem_raw + off[0]);
+    float2* rsum = reinterpret_cast<float2*>(smem_raw + off[1]);
+    uint32_t* rmeta = reinterpret_cast<uint32_t*>(smem_raw + off[2]);
+    uint32_t* syn = reinterpret_cast<uint32_t*>(smem_raw + off[3]);
+    uint32_t* cand = reinterpret_cast<uint32_t*>(smem_raw + off[4]);
+    uint32_t* accs = reinterpret_cast<uint32_t*>(smem_raw + off[5]);
+    uint32_t* car = reinterpret_cast<uint32_t*>(smem_raw + off[6]);
+
+    const int tid = threadIdx.x;
+    const int shot = blockIdx.x;
+    const int rows = w.rows, ncols = w.ncols, RS = w.RS, npad = w.ncols_pad;
+    const int carryW = (w.carry_rows + 31) / 32;
+
+    // ---- syndrome of the window: detector bits [row0, row0+rows) of this shot, first rows XOR the carry
+    if (tid < w.rowsW32) {
+        const uint32_t* d = b.det32 + static_cast<size_t>(shot) * b.det_stride32;
+        const int bit = w.row0 + 32 * tid;
+        const int wd = bit >> 5, sh = bit & 31;
+        uint32_t v = __ldg(d + wd) >> sh;
+        if (sh) v |= __ldg(d + wd + 1) << (32 - sh);
+        const int left = rows - 32 * tid;
+        if (left < 32) v &= (1u << left) - 1u;
+        if (32 * tid < b.in_carry_rows) v ^= b.carry[static_cast<size_t>(shot) * b.carry_stride32 + tid];
+        syn[tid] = v;
+    }
+    if (tid < 2 * w.KW) accs[tid] = 0;
+    if (tid <= carryW) car[tid] = 0;
+    for (int i = tid; i < rows * RS; i += kBpThreads) V[i] = FLT_MAX;       // padding slots: never the minimum, never negative
+    __syncthreads();
+    for (int j = tid; j < ncols; j += kBpThreads) {
+        const float l0 = __ldg(w.llr0 + j);
+#pragma unroll
+        for (int q = 0; q < CW; ++q) {
+            const uint32_t e = __ldg(w.colE + static_cast<size_t>(q) * npad + j);
+            if (e != kNoEdge) V[(e >> 8) * RS + (e & 255u)] = l0;
+        }
+    }
+    __syncthreads();
+
+    uint32_t hmask = 0;          // hard decisions of this thread's columns (bit k <-> column tid + k*kBpThreads)
+    bool conv = false;
+    int it = 1;
+    for (; it <= p.max_iter; ++it) {
+        const float alpha = __ldg(p.alpha + it);
+        // ---- check sweep: one thread per row
+        for (int i = tid; i < rows; i += kBpThreads) {
+            const float* vr = V + i * RS;
+            float m1 = FLT_MAX, m2 = FLT_MAX;
+            uint32_t arg = 0, neg = (syn[i >> 5] >> (i & 31)) & 1u;
+#pragma unroll 5
+            for (int s = 0; s < RS; ++s) {
+                const float v = vr[s];
+                const float a = fabsf(v);
+                neg += v <= 0.0f ? 1u : 0u;
+                if (a < m1) { m2 = m1; m1 = a; arg = static_cast<uint32_t>(s); }
+                else if (a < m2) { m2 = a; }
+            }
+            rsum[i] = make_float2(m1, m2);
+            rmeta[i] = arg | (neg << 31);
+        }
+        if (tid < w.rowsW32) cand[tid] = 0;
+        __syncthreads();
+        // ---- bit sweep: one thread per column
+        hmask = 0;
+        const bool last = it == p.max_iter;
+        int k = 0;
+        for (int j = tid; j < ncols; j += kBpThreads, ++k) {
+            uint32_t e[CW];
+#pragma unroll
+            for (int q = 0; q < CW; ++q) e[q] = __ldg(w.colE + static_cast<size_t>(q) * npad + j);
+            const float l0 = __ldg(w.llr0 + j);
+            float c[CW], vn[CW];
+            int addr[CW];
+#pragma unroll
+            for (int q = 0; q < CW; ++q) {
+                c[q] = 0.0f;
+                addr[q] = 0;
+                if (e[q] != kNoEdge) {
+                    const uint32_t row = e[q] >> 8, slot = e[q] & 255u;
+                    addr[q] = static_cast<int>(row) * RS + static_cast<int>(slot);
+                    const float v = V[addr[q]];
+                    const float2 s = rsum[row];
+                    const uint32_t meta = rmeta[row];
+                    const float mag = slot == (meta & 0x7FFFFFFFu) ? s.y : s.x;
+                    const uint32_t odd = (meta >> 31) ^ (v <= 0.0f ? 1u : 0u);
+                    c[q] = __fmul_rn(mag, odd ? -alpha : alpha);
+                }
+            }
+            float t = l0;
+#pragma unroll
+            for (int q = 0; q < CW; ++q) { vn[q] = t; t = __fadd_rn(t, c[q]); }
+            const float llr = t;
+            t = 0.0f;
+#pragma unroll
+            for (int q = CW - 1; q >= 0; --q) { vn[q] = __fadd_rn(vn[q], t); t = __fadd_rn(t, c[q]); }
+#pragma unroll
+            for (int q = 0; q < CW; ++q)
+                if (e[q] != kNoEdge) V[addr[q]] = vn[q];
+            if (llr <= 0.0f) {
+                hmask |= 1u << k;
+#pragma unroll
+                for (int q = 0; q < CW; ++q)
+                    if (e[q] != kNoEdge) atomicXor(&cand[e[q] >> 13], 1u << ((e[q] >> 8) & 31u));
+            }
+            if (last || b.write_llr_always) b.llr_buf[static_cast<size_t>(shot) * b.llr_stride + j] = llr;
+        }
+        // ---- stop test H e == s
+        const int mismatch = tid < w.rowsW32 ? (cand[tid] != syn[tid]) : 0;
+        if (!__syncthreads_or(mismatch)) { conv = true; break; }
+    }
+    if (it > p.max_iter) it = p.max_iter;
+
+    if (conv) {
+        // ---- commit: acc ^= L e[:ncommit], carry = U e[:ncommit]   (sliding_window.py:172-175)
+        uint32_t hm = hmask;
+        while (hm) {
+            const int k = __ffs(hm) - 1;
+            hm &= hm - 1;
+            const int j = tid + k * kBpThreads;
+            if (b.ehat_out) atomicOr(&b.ehat_out[static_cast<size_t>(shot) * b.ehat_stride32 + (j >> 5)], 1u << (j & 31));
+            if (j < w.ncommit) {
+                for (int wd = 0; wd < w.KW; ++wd) {
+                    const uint64_t lm = __ldg(w.lmask + static_cast<size_t>(j) * w.KW + wd);
+                    if (static_cast<uint32_t>(lm)) atomicXor(&accs[2 * wd], static_cast<uint32_t>(lm));
+                    if (static_cast<uint32_t>(lm >> 32)) atomicXor(&accs[2 * wd + 1], static_cast<uint32_t>(lm >> 32));
+                }
+                if (w.carry_rows) {
+                    for (int q = __ldg(w.uptr + j); q < __ldg(w.uptr + j + 1); ++q) {
+                        const uint32_t r = __ldg(w.uidx + q);
+                        atomicXor(&car[r >> 5], 1u << (r & 31));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < w.KW) {
+            const uint64_t v = (static_cast<uint64_t>(accs[2 * tid + 1]) << 32) | accs[2 * tid];
+            b.acc[static_cast<size_t>(shot) * w.KW + tid] ^= v;
+        }
+        if (tid < carryW) b.carry[static_cast<size_t>(shot) * b.carry_stride32 + tid] = car[tid];
+    } else {
+        // ---- hand the shot to OSD: post-carry syndrome + posteriors (already in llr_buf)
+        if (tid < w.rowsW32) b.syn_buf[static_cast<size_t>(shot) * b.syn_stride32 + tid] = syn[tid];
+        if (tid == 0) {
+            const int slot = atomicAdd(b.fail_count, 1);
+            b.fail_list[slot] = shot;
+        }
+    }
+    if (tid == 0) {
+        if (conv) atomicAdd(&b.stats[0], 1ull);
+        atomicAdd(&b.stats[1], static_cast<unsigned long long>(it));
+        if (b.iters_out) b.iters_out[shot] = it;
+        if (b.conv_out) b.conv_out[shot] = conv ? 1 : 0;
+    }
+}
+
+}  // namespace
+
+size_t bp_smem_bytes(const WinDev& w) {
+    size_t off[7];
+    return bp_layout(w, off);
+}
+
+cudaError_t bp_configure(size_t smem_bytes, int cw) {
+    if (smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e;
+    if (cw <= 6) e = cudaFuncSetAttribute(bp_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
+    else if (cw <= 8) e = cudaFuncSetAttribute(bp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
+    else if (cw <= 16) e = cudaFuncSetAttribute(bp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
+    else return cudaErrorInvalidValue;
+    return e;
+}
+
+cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, cudaStream_t st) {
+    if (b.n_shots == 0) return cudaSuccess;
+    const size_t smem = bp_smem_bytes(w);
+    if (w.cw <= 6) bp_kernel<6><<<b.n_shots, kBpThreads, smem, st>>>(w, b, p);
+    else if (w.cw <= 8) bp_kernel<8><<<b.n_shots, kBpThreads, smem, st>>>(w, b, p);
+    else if (w.cw <= 16) bp_kernel<16><<<b.n_shots, kBpThreads, smem, st>>>(w, b, p);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+}  // namespace qb

@@ -1,0 +1,108 @@
+// quits_b200/csrc/qb_device.h -- argument blocks of the CUDA kernels (sm_100a) and their launch wrappers.
+//
+//   K1  frame_kernel   per-shot Pauli-frame propagation, 64 shots per bit-word      (frame.cu)
+//   K3  bp_kernel      flooding min-sum BP of one window, one shot per CTA, messages in shared memory (bp.cu)
+//   K4  osd_kernel     OSD-0: LLR radix sort + register-resident GF(2) Gauss-Jordan, one shot per CTA (osd.cu)
+//   K2/K5 are fused into K3/K4: syndrome = slice(det) ^ carry on entry, H e == s as the stop test, L e / U e on exit.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "qb_host.h"
+
+namespace qb {
+
+// ---------------------------------------------------------------------------------------------- K1
+struct FrameArgs {
+    const TapeOp* ops;
+    int n_ops;
+    const uint32_t* targets;
+    const uint32_t* detptr;
+    const uint32_t* detidx;
+    const uint64_t* ctab;
+    int n_qubits, n_det, n_obs;
+    int ring;                 // power of two
+    int DW, KW;               // u64 words per shot in det_rows / obs_rows
+    uint64_t seed;
+    uint64_t word0;           // global index of the first 64-shot word of this launch
+    uint64_t n_words;
+    uint64_t* det_rows;       // [n_words*64][DW]   bit d of shot s = det_rows[s*DW + d/64] >> (d%64)
+    uint64_t* obs_rows;       // [n_words*64][KW]
+    // explicit-fault mode (noise instructions are replaced by the listed faults)
+    int inject;
+    const int32_t* inj_start; // [n_ops+1] fault range of every tape op
+    const int32_t* inj_tgt;
+    const int32_t* inj_code;
+    const int64_t* inj_shot;  // shot index local to this launch
+};
+size_t frame_smem_per_warp(const FrameArgs& a);
+cudaError_t launch_frame(const FrameArgs& a, cudaStream_t st);
+
+// bit rows <-> byte matrices (the reference API works on numpy bool arrays)
+cudaError_t launch_unpack_bits(const uint64_t* rows, int words_per_row, int nbits, uint64_t n_rows, uint8_t* out, cudaStream_t st);
+cudaError_t launch_pack_bits(const uint8_t* in, int nbits, uint64_t n_rows, uint64_t* rows, int words_per_row, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------- K3/K4
+constexpr uint32_t kNoEdge = 0xFFFFFFFFu;
+
+struct WinDev {
+    int rows, ncols, ncols_pad, RS, cw, ncommit;
+    int row0;                 // first detector row (global) of the window
+    int carry_rows;           // rows of the carry this window emits (0 for the last window)
+    int KW;                   // u64 words per observable mask
+    int rowsW32, nW32;
+    const uint32_t* colE;     // [cw][ncols_pad]  (row << 8 | slot), kNoEdge when the column is shorter
+    const float* llr0;        // [ncols_pad]
+    const uint64_t* lmask;    // [ncommit][KW]
+    const int32_t* uptr;      // [ncommit+1]
+    const uint16_t* uidx;
+    const int32_t* cptr;      // [ncols+1] plain CSC of the window (OSD gather)
+    const uint16_t* crow;
+};
+
+struct BatchDev {
+    int n_shots;
+    const uint32_t* det32;    // packed detector rows viewed as u32; det_stride32 words per shot (>= 2*DW + 1)
+    int det_stride32;
+    int in_carry_rows;        // rows of the incoming carry (0 for the first window)
+    uint32_t* carry;          // [n][carry_stride32]
+    int carry_stride32;
+    uint64_t* acc;            // [n][KW]  accumulated observable prediction
+    float* llr_buf;           // [n][llr_stride]
+    size_t llr_stride;
+    uint32_t* syn_buf;        // [n][syn_stride32]   post-carry syndrome of the shots handed to OSD
+    int syn_stride32;
+    int* fail_list;           // [n]
+    int* fail_count;          // [1]
+    int* osd_next;            // [1] work counter of the persistent OSD grid
+    unsigned long long* stats;// [3] converged windows, BP iterations, OSD calls
+    uint32_t* ehat_out;       // optional [n][ehat_stride32]  (pre-zeroed)
+    int ehat_stride32;
+    int32_t* iters_out;       // optional [n]
+    uint8_t* conv_out;        // optional [n]
+    int write_llr_always;
+};
+
+struct BpParams {
+    int max_iter;
+    const float* alpha;       // [max_iter+1]  scaling factor of iteration it (index it)
+};
+
+size_t bp_smem_bytes(const WinDev& w);
+cudaError_t bp_configure(size_t smem_bytes, int cw);
+cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, cudaStream_t st);
+
+size_t osd_smem_bytes(const WinDev& w);
+bool osd_supported(const WinDev& w);
+cudaError_t osd_configure(const WinDev& w);
+cudaError_t launch_osd(const WinDev& w, const BatchDev& b, int grid, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------- results
+// pred[n][K] int64 from acc bits; counts[0] += shots whose prediction differs from obs_rows in any observable,
+// counts[1+k] += mismatches of observable k.
+cudaError_t launch_expand_pred(const uint64_t* acc, int KW, int K, uint64_t n, int64_t* pred, cudaStream_t st);
+cudaError_t launch_count(const uint64_t* acc, const uint64_t* obs_rows, int KW, int K, uint64_t n, unsigned long long* counts,
+                         cudaStream_t st);
+
+}  // namespace qb

@@ -1,0 +1,26 @@
+"""BP-OSD sliding-window wrappers; signatures and defaults of reference ``src/quits/decoder/bposd.py:10,54``."""
+from __future__ import annotations
+
+from .inner import BpOsdDecoder
+from .sliding_window import sliding_window_circuit_mem, sliding_window_phenom_mem
+
+
+def sliding_window_bposd_phenom_mem(zcheck_samples, hz, lz, W, F, error_rate=0.05, max_iter=2, osd_order=0,
+                                    bp_method='product_sum', schedule='serial', osd_method='osd_cs', tqdm_on=False):
+    params = lambda: {'bp_method': bp_method, 'max_iter': max_iter, 'schedule': schedule, 'osd_method': osd_method,
+                      'osd_order': osd_order, 'error_rate': float(error_rate)}
+    return sliding_window_phenom_mem(zcheck_samples, hz, lz, W, F, BpOsdDecoder, BpOsdDecoder, params(), params(), 'decode', 'decode',
+                                     tqdm_on=tqdm_on)
+
+
+def sliding_window_bposd_circuit_mem(zcheck_samples, circuit, hz, lz, W, F, max_iter=2, osd_order=0, bp_method='product_sum',
+                                     schedule='serial', osd_method='osd_cs', tqdm_on=False):
+    """Drop-in for the reference function of the same name.  The GPU kernels implement
+    ``bp_method='minimum_sum', schedule='parallel'`` with order-0 post-processing; other settings raise NotImplementedError."""
+    params = lambda: {'bp_method': bp_method, 'max_iter': max_iter, 'schedule': schedule, 'osd_method': osd_method,
+                      'osd_order': osd_order}
+    return sliding_window_circuit_mem(zcheck_samples, circuit, hz, lz, W, F, BpOsdDecoder, BpOsdDecoder, params(), params(),
+                                      'channel_probs', 'channel_probs', 'decode', 'decode', tqdm_on=tqdm_on)
+
+
+__all__ = ["sliding_window_bposd_phenom_mem", "sliding_window_bposd_circuit_mem"]

@@ -1,0 +1,93 @@
+"""Inner decoders with the ldpc call shape (seam B3 of the reference: ``decoder(pcm, **kwargs)`` then
+``decoder.decode(syndrome)``, reference ``src/quits/decoder/sliding_window.py:146-153,171,182``), running on the GPU.
+
+They exist for per-shot compatibility and parity checks; the batched sliding-window path does not call them one
+shot at a time (it recognises these classes and runs all shots through the fused kernels).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+from scipy.sparse import csc_matrix
+
+from .. import _native as N
+from ..circuit import Context
+from ..engine import bp_options
+
+
+class _GpuInnerDecoder:
+    _order_key = "osd_order"
+    _method_key = "osd_method"
+    _default_method = "osd_0"
+
+    def __init__(self, pcm, error_rate=None, error_channel=None, channel_probs=None, ctx: Context = None, **kw):
+        pcm = csc_matrix(pcm)
+        pcm.sort_indices()
+        self.m, self.n = pcm.shape
+        if channel_probs is not None and error_channel is None:
+            error_channel = channel_probs
+        if error_channel is not None:
+            priors = np.ascontiguousarray(error_channel, dtype=np.float64)
+        elif error_rate is not None:
+            priors = np.full(self.n, float(error_rate), dtype=np.float64)
+        else:
+            raise ValueError("error_rate / error_channel / channel_probs required")
+        if priors.shape != (self.n,):
+            raise ValueError("need one prior per column")
+        self.options = dict(kw)
+        opts = bp_options(osd_method=kw.pop(self._method_key, self._default_method), osd_order=kw.pop(self._order_key, 0), **kw)
+        self.ctx = ctx or Context.default()
+        indptr = np.ascontiguousarray(pcm.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(pcm.indices if pcm.nnz else [0], dtype=np.int32)
+        h = C.c_void_p()
+        N.check(N.lib().qb_sw_create_single(self.ctx._h, self.m, self.n, N.ptr(indptr), N.ptr(indices), N.ptr(priors), C.byref(opts),
+                                            C.byref(h)))
+        self._h = h
+        self.log_prob_ratios = None
+        self.converge = None
+        self.iter = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                N.lib().qb_sw_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def decode_batch(self, syndromes):
+        """syndromes [N, m] -> (ehat uint8 [N, n], llr float32 [N, n], iters int32 [N], converged bool [N])."""
+        s = np.ascontiguousarray(np.asarray(syndromes) % 2, dtype=np.uint8)
+        if s.ndim != 2 or s.shape[1] != self.m:
+            raise ValueError("expected syndromes of shape (N, %d)" % self.m)
+        n = s.shape[0]
+        ehat = np.zeros((n, self.n), dtype=np.uint8)
+        llr = np.zeros((n, self.n), dtype=np.float32)
+        iters = np.zeros(n, dtype=np.int32)
+        conv = np.zeros(n, dtype=np.uint8)
+        N.check(N.lib().qb_bp_decode_batch(self._h, N.ptr(s), n, N.ptr(ehat), N.ptr(llr), N.ptr(iters), N.ptr(conv)))
+        return ehat, llr, iters, conv.astype(np.bool_)
+
+    def decode(self, syndrome):
+        e, llr, it, conv = self.decode_batch(np.asarray(syndrome).reshape(1, -1))
+        self.log_prob_ratios, self.iter, self.converge = llr[0], int(it[0]), bool(conv[0])
+        return e[0]
+
+
+class BpOsdDecoder(_GpuInnerDecoder):
+    """ldpc.bposd_decoder.BpOsdDecoder-shaped (kwargs as in reference decoder/bposd.py:74-84)."""
+
+
+class BpLsdDecoder(_GpuInnerDecoder):
+    """ldpc.bplsd_decoder.BpLsdDecoder-shaped (kwargs as in reference decoder/bplsd.py:74-84).  LSD post-processing is
+    not implemented on the GPU yet: constructing one raises NotImplementedError unless post-processing is off."""
+    _order_key = "lsd_order"
+    _method_key = "lsd_method"
+    _default_method = "lsd_0"
+
+    def __init__(self, pcm, **kw):
+        method = str(kw.get("lsd_method", "lsd_0")).lower()
+        if method not in ("off", "none"):
+            raise NotImplementedError("BP-LSD post-processing (lsd_method=%r) is not implemented on the GPU path yet" % method)
+        super().__init__(pcm, **kw)

@@ -1,0 +1,122 @@
+"""Device-side objects: the batched sliding-window decoder and the fused Monte-Carlo runner.
+
+``SlidingWindowDecoder`` is the engine behind the drop-in ``sliding_window_*_circuit_mem`` functions
+(reference ``src/quits/decoder/sliding_window.py:104-188``); ``MonteCarlo`` chains sampling, decoding and the
+logical-error count on the device (``get_stim_mem_result`` -> ``sliding_window_bposd_circuit_mem`` -> the caller's
+``pL`` reduction, reference ``tests/test_sliding_window.py:66-84``) and shards shots across GPUs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _native as N
+from .circuit import Circuit, Context
+from .decoder.base import WindowPlan
+
+_BP_METHODS = {"minimum_sum": 0, "min_sum": 0, "ms": 0, "msl": 0, "product_sum": 1, "prod_sum": 1, "ps": 1, "psl": 1}
+_SCHEDULES = {"parallel": 0, "p": 0, "serial": 1, "s": 1}
+_OSD_METHODS = {"osd_0": 0, "osd0": 0, "osd_e": 1, "osde": 1, "exhaustive": 1, "osd_cs": 2, "osdcs": 2, "combination_sweep": 2,
+                "off": -1, "none": -1}
+
+
+def bp_options(bp_method="minimum_sum", max_iter=0, schedule="parallel", osd_method="osd_0", osd_order=0, ms_scaling_factor=1.0,
+               capacity=0, profile=False, **unknown) -> N.QbBpOpts:
+    """Translate ldpc.BpOsdDecoder-style kwargs (reference decoder/bposd.py:74-83) into the C option block."""
+    for k in unknown:
+        if k not in ("channel_probs", "error_rate", "error_channel", "input_vector_type", "omp_thread_count",
+                     "random_schedule_seed", "serial_schedule_order", "osd_on"):
+            raise TypeError("unexpected decoder option %r" % k)
+    o = N.QbBpOpts()
+    try:
+        o.bp_method = bp_method if isinstance(bp_method, int) else _BP_METHODS[str(bp_method).lower()]
+        o.schedule = schedule if isinstance(schedule, int) else _SCHEDULES[str(schedule).lower()]
+        o.osd_method = osd_method if isinstance(osd_method, int) else _OSD_METHODS[str(osd_method).lower()]
+    except KeyError as e:
+        raise ValueError("unknown decoder option value %s" % e) from None
+    o.max_iter = int(max_iter)
+    o.ms_scaling_factor = float(ms_scaling_factor)
+    o.osd_order = int(osd_order)
+    o.capacity = int(capacity)
+    o.profile = 1 if profile else 0
+    return o
+
+
+class SlidingWindowDecoder:
+    """All windows of one circuit resident on one GPU; decodes batches of shots (K3/K4 kernels)."""
+
+    def __init__(self, circuit, m: int, W: int, F: int, num_cor_rounds: int = -1, ctx: Context = None, **bp_kwargs):
+        self.ctx = ctx or Context.default()
+        self.circuit = Circuit.of(circuit)
+        self.plan = WindowPlan(self.circuit.detector_error_model(), m, W, F, num_cor_rounds)
+        self.opts = bp_options(**bp_kwargs)
+        h = C.c_void_p()
+        N.check(N.lib().qb_sw_create(self.ctx._h, self.plan._h, C.byref(self.opts), C.byref(h)))
+        self._h = h
+        self.K, self.D = self.plan.K, self.plan.D
+        self.stats = N.QbStats()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                N.lib().qb_sw_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def decode(self, det) -> np.ndarray:
+        """det: [N, D] array of 0/1 (bool or integer) on the host -> int64 [N, K] predictions."""
+        det = np.asarray(det)
+        if det.ndim != 2 or det.shape[1] != self.D:
+            raise ValueError("expected detection events of shape (N, %d), got %r" % (self.D, det.shape))
+        if det.dtype != np.bool_ and det.dtype != np.uint8:
+            det = (det % 2).astype(np.uint8)
+        det = np.ascontiguousarray(det).view(np.uint8)
+        pred = np.zeros((det.shape[0], self.K), dtype=np.int64)
+        N.check(N.lib().qb_sw_decode(self._h, N.ptr(det), det.shape[0], N.ptr(pred), C.byref(self.stats)))
+        return pred
+
+    def decode_packed(self, det_rows: np.ndarray) -> np.ndarray:
+        det_rows = np.ascontiguousarray(det_rows, dtype=np.uint64)
+        out = np.zeros((det_rows.shape[0], max(1, (self.K + 63) // 64)), dtype=np.uint64)
+        N.check(N.lib().qb_sw_decode_packed(self._h, N.ptr(det_rows), det_rows.shape[0], N.ptr(out), C.byref(self.stats)))
+        return out
+
+
+class MonteCarlo:
+    """sample -> decode -> count on one GPU; ``run`` covers global shots [shot0, shot0 + shots)."""
+
+    def __init__(self, circuit, m: int, W: int, F: int, ctx: Context = None, **bp_kwargs):
+        self.decoder = SlidingWindowDecoder(circuit, m, W, F, ctx=ctx, **bp_kwargs)
+        self.ctx = self.decoder.ctx
+        self.circuit = self.decoder.circuit
+        self.K = self.decoder.K
+
+    def run(self, shots: int, seed: int, shot0: int = 0):
+        """Returns (counts uint64 [1+K], stats dict): counts[0] = shots with any observable mispredicted."""
+        counts = np.zeros(1 + self.K, dtype=np.uint64)
+        st = N.QbStats()
+        N.check(N.lib().qb_mc_run(self.ctx._h, self.circuit._h, self.decoder._h, int(seed), int(shot0), int(shots), N.ptr(counts),
+                                  C.byref(st)))
+        return counts, st.as_dict()
+
+
+def shard_range(total: int, rank: int, world: int, align: int = 64):
+    """Global shot range of ``rank``: contiguous, aligned to 64-shot words, union = [0, total)."""
+    words = (total + align - 1) // align
+    lo = (words * rank // world) * align
+    hi = min(total, (words * (rank + 1) // world) * align)
+    return lo, max(lo, hi)
+
+
+def run_sharded(circuit, m, W, F, shots, seed, rank=None, world=None, **bp_kwargs):
+    """One process per GPU: this rank's share of ``shots``; results are identical for any world size because the
+    noise is a function of (seed, global shot index).  Returns (counts, stats, (lo, hi)); reduce counts by summing."""
+    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    lo, hi = shard_range(int(shots), rank, world)
+    mc = MonteCarlo(circuit, m, W, F, **bp_kwargs)
+    counts, stats = mc.run(hi - lo, seed, lo)
+    return counts, stats, (lo, hi)
