@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""Headline benchmark: Monte-Carlo shots/s on the [[144,12,12]] BB code (10 rounds, sliding window W=5 F=3, p=1e-3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shots S] [--precision f64|f32]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); a step is one pass of the hot path -- sample S shots,
+decode them through the sliding window, count logical errors -- with everything resident on the device.  Shots are
+partitioned by global shot index (weak scaling: S per GPU per step); there is no data-path collective, only a final
+all-reduce of the error counters and a MAX of the device times.  Rank 0 prints ONE JSON line.
+
+  value     shots/s, whole job, CUDA-event time on the launching stream (max over ranks)
+  e2e       same metric through the drop-in calls get_stim_mem_result -> sliding_window_bposd_circuit_mem with host
+            numpy buffers (D2H of the detection events, H2D again for decoding, D2H of the predictions) inside the timed region
+  roofline  dominant kernel (BP): algorithmic message bytes per launch / CUDA-event duration, against the measured HBM peak
+  cpu_baseline  the oracle's C restatement of the same path (OpenMP, all host cores) on a bounded sample, rank 0, N=1
+
+--impl reference times that CPU path alone (the reference's stim+ldpc wheels are not installable here, so the "reference
+arm" is the oracle port of its algorithm).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "bb144_r10_p1e-3"
+W, F = 5, 3
+BP_KW = dict(max_iter=10, osd_order=0, bp_method="minimum_sum", schedule="parallel", osd_method="osd_0")
+SEED = 20260101
+METRIC = "Monte-Carlo shots/sec, [[144,12,12]] BB 10-round window p=1e-3"
+
+
+def load_workload():
+    g = os.path.join(ROOT, "tests", "golden", "circuits")
+    with open(os.path.join(g, WORKLOAD + ".stim")) as f:
+        text = f.read()
+    with open(os.path.join(g, WORKLOAD + ".json")) as f:
+        meta = json.load(f)
+    hz = np.zeros(meta["hz_shape"], dtype=np.uint8)
+    for i, r in enumerate(meta["hz_rows"]):
+        hz[i, r] = 1
+    lz = np.zeros(meta["lz_shape"], dtype=np.uint8)
+    for i, r in enumerate(meta["lz_rows"]):
+        lz[i, r] = 1
+    return text, hz, lz
+
+
+def config(shots, precision):
+    return {"workload": "%s custom circuit, W=%d F=%d, min-sum flooding BP max_iter=10 + OSD-0" % (WORKLOAD, W, F),
+            "shots_per_step_per_gpu": int(shots), "precision": precision, "seed": SEED,
+            "l2": "flushed between timed steps (256 MiB write); per-step message/LLR working set also exceeds L2"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_arm(shots, nthreads=0):
+    """The oracle's C restatement of the path (frame sampler + window loop with BP/OSD-0 in fp64), OpenMP over shots."""
+    from oracle import cref, dem as odem, stimtext, windows as owin
+    text, hz, lz = load_workload()
+    fc = stimtext.parse_flat(text)
+    wins = owin.plan(odem.analyze(fc), hz.shape[0], W, F)
+    threads = nthreads or cref.num_threads()
+    t0 = time.perf_counter()
+    det, obs = cref.sample(fc, SEED, 0, shots, nthreads=threads)
+    pred, stats = cref.sw_decode(wins, hz.shape[0], lz.shape[0], det, nthreads=threads, max_iter=BP_KW["max_iter"],
+                                 bp_method=BP_KW["bp_method"], schedule=BP_KW["schedule"], precision="f64")
+    fails = int(np.any(pred != obs, axis=1).sum())
+    dt = time.perf_counter() - t0
+    return shots / dt, dt, threads, fails
+
+
+def calibrated_cpu_sample(budget_s=12.0):
+    rate, dt, threads, _ = cpu_arm(256)
+    shots = int(max(256, min(200000, rate * budget_s)) // 64 * 64)
+    return shots
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shots", type=int, default=262144, help="shots per step per GPU")
+    ap.add_argument("--e2e-shots", type=int, default=65536)
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        shots = calibrated_cpu_sample(8.0)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            rate, dt, threads, fails = cpu_arm(shots)
+            if i >= args.warmup:
+                vals.append((rate, dt))
+        rate = float(np.mean([v[0] for v in vals])) if vals else 0.0
+        ms = float(np.mean([v[1] for v in vals]) * 1e3) if vals else 0.0
+        sample = "%d shots per step of the same workload (frame sampling + sliding-window BP/OSD-0 in fp64), OpenMP over shots" % shots
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": rate, "unit": "shots/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(shots, "f64"),
+                          "cpu_baseline": {"value": rate, "unit": "shots/s", "cores": threads, "kind": "port", "sample": sample},
+                          "e2e": {"value": rate, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "note": "stim/ldpc wheels are not installable offline; this arm is the oracle's C port of the reference's CPU path"}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import quits_b200 as qb
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    text, hz, lz = load_workload()
+    ctx = qb.Context.default(local)
+    circuit = qb.Circuit(text)
+    mc = qb.MonteCarlo(circuit, hz.shape[0], W, F, ctx=ctx, precision=args.precision, profile=True, **BP_KW)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    S = args.shots
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        # global shot range of this rank for step i: disjoint across ranks and steps
+        shot0 = (i * world + rank) * S
+        return mc.run(S, SEED, shot0)
+
+    for i in range(args.warmup):
+        step(i)
+        flush.zero_()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    counts = np.zeros(1 + mc.K, dtype=np.uint64)
+    agg = {}
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        c, st = step(args.warmup + i)
+        counts += c
+        for k, v in st.items():
+            agg[k] = agg.get(k, 0) + v
+        flush.zero_()
+        torch.cuda.synchronize()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    dev_ms = agg["total_ms"]                      # CUDA events on the launching stream, summed over the K steps
+    t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor(counts.astype(np.int64), device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms_max, wall_ms_max = (float(x) for x in t.tolist())
+    total_shots = S * args.steps * world
+    value = total_shots / (dev_ms_max / 1e3)
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        bp_launches = max(1, agg["bp_launches"])
+        achieved = agg["bp_alg_bytes"] / (agg["bp_ms"] / 1e3) / 1e9 if agg["bp_ms"] > 0 else 0.0
+        line = {"metric": METRIC, "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic", "config": config(S, args.precision), "clocks": clocks,
+                "gpu_launches": int(agg["bp_launches"] + agg["osd_launches"] + agg["frame_launches"] + agg["other_launches"]),
+                "wall_ms_per_step": wall_ms_max / args.steps,
+                "logical_errors": int(cnt[0].item()), "shots_total": int(total_shots),
+                "decoder_stats": {"bp_converged_frac": agg["bp_converged"] / max(1, agg["windows"]),
+                                  "bp_iters_per_window": agg["bp_iterations"] / max(1, agg["windows"]),
+                                  "osd_calls_per_shot": agg["osd_calls"] / max(1, agg["shots"])},
+                "kernel_ms_per_step": {"frame": agg["frame_ms"] / args.steps, "bp": agg["bp_ms"] / args.steps,
+                                       "osd": agg["osd_ms"] / args.steps},
+                "roofline": {"kernel": "bp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None,
+                             "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650",
+                             "alg_bytes_per_launch": agg["bp_alg_bytes"] / bp_launches,
+                             "ms_per_launch": agg["bp_ms"] / bp_launches,
+                             "note": "message-streaming model: iterations x 4 x nnz x sizeof(msg); messages are shared-memory resident, so DRAM traffic is far below this"}}
+
+    # ---- e2e through the drop-in API with host buffers (same stream of work, smaller batch)
+    if not args.no_e2e:
+        Se = args.e2e_shots
+        def e2e_step(i):
+            shot_seed = SEED + 1000 + i * world + rank
+            det, obs = qb.get_stim_mem_result(circuit, Se, seed=shot_seed)
+            pred = qb.sliding_window_bposd_circuit_mem(det, circuit, hz, lz, W, F, **BP_KW) if args.precision == "f64" else \
+                qb.SlidingWindowDecoder(circuit, hz.shape[0], W, F, ctx=ctx, precision="f32", **BP_KW).decode(det)
+            return int(np.any((obs - pred) % 2, axis=1).sum())
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        for i in range(n_e2e):
+            e2e_step(1 + i)
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            D, K = circuit.num_detectors, circuit.num_observables
+            line["e2e"] = {"value": Se * n_e2e * world / float(te.item()), "unit": "shots/s", "h2d_bytes_per_step": Se * D,
+                           "d2h_bytes_per_step": Se * (D + K) + Se * K * 8, "shots_per_step_per_gpu": Se, "steps": n_e2e,
+                           "path": "get_stim_mem_result -> sliding_window_bposd_circuit_mem (numpy host buffers, host wall clock)"}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            shots = calibrated_cpu_sample(12.0)
+            rate, dt, threads, fails = cpu_arm(shots)
+            line["cpu_baseline"] = {"value": rate, "unit": "shots/s", "cores": threads, "kind": "port",
+                                    "sample": "%d shots of the same workload in %.1f s (oracle C port: frame sampler + window loop, fp64, OpenMP)" % (shots, dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -104,6 +104,7 @@ typedef struct {
     double ms_scaling_factor;   /* 0.0 => 1 - 2^-iteration */
     int32_t osd_method;         /* 0 'osd_0' | 1 'osd_e' | 2 'osd_cs' | -1 no post-processing */
     int32_t osd_order;
+    int32_t precision;          /* 64 (default when 0): messages in fp64 as ldpc computes; 32: fp32 messages */
     int32_t capacity;           /* shots per device batch; 0 => default */
     int32_t profile;            /* 1: time the kernel classes with CUDA events on the launching stream */
 } qb_bp_opts;
@@ -116,6 +117,9 @@ typedef struct {
     int64_t osd_calls;
     int64_t bp_launches, osd_launches, frame_launches, other_launches;
     double frame_ms, bp_ms, osd_ms, total_ms;     /* CUDA-event time on the launching stream (profile = 1) */
+    /* algorithmic bytes of the launches above: BP = iterations x 4 x nnz x sizeof(message) + syndrome in +
+     * commit/carry out; OSD = 2 x rows x 8 ceil(cols/64) per call; frame = packed detector + observable rows written */
+    double bp_alg_bytes, osd_alg_bytes, frame_alg_bytes;
 } qb_stats;
 
 /* Window plan (host only): spacetime() of decoder/base.py:134-190.  n_cor < 0 derives the number of sliding windows
@@ -137,7 +141,7 @@ void qb_sw_free(qb_sw* sw);
 int qb_sw_decode(qb_sw* sw, const uint8_t* det, uint64_t n, int64_t* pred, qb_stats* stats);
 int qb_sw_decode_packed(qb_sw* sw, const uint64_t* det_rows, uint64_t n, uint64_t* pred_rows, qb_stats* stats);
 /* seam B3 (one decode per syndrome, batched): syndromes[n][rows] bytes -> ehat[n][cols] bytes, posteriors, iterations */
-int qb_bp_decode_batch(qb_sw* single, const uint8_t* syndromes, uint64_t n, uint8_t* ehat, float* llr, int32_t* iters,
+int qb_bp_decode_batch(qb_sw* single, const uint8_t* syndromes, uint64_t n, uint8_t* ehat, double* llr, int32_t* iters,
                        uint8_t* converged);
 
 /* ------------------------------------------------------------------------------------------------ fused run

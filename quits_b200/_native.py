@@ -15,7 +15,8 @@ class QbStats(C.Structure):
     _fields_ = [("shots", C.c_int64), ("windows", C.c_int64), ("bp_converged", C.c_int64), ("bp_iterations", C.c_int64),
                 ("osd_calls", C.c_int64), ("bp_launches", C.c_int64), ("osd_launches", C.c_int64),
                 ("frame_launches", C.c_int64), ("other_launches", C.c_int64),
-                ("frame_ms", C.c_double), ("bp_ms", C.c_double), ("osd_ms", C.c_double), ("total_ms", C.c_double)]
+                ("frame_ms", C.c_double), ("bp_ms", C.c_double), ("osd_ms", C.c_double), ("total_ms", C.c_double),
+                ("bp_alg_bytes", C.c_double), ("osd_alg_bytes", C.c_double), ("frame_alg_bytes", C.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -23,7 +24,8 @@ class QbStats(C.Structure):
 
 class QbBpOpts(C.Structure):
     _fields_ = [("bp_method", C.c_int32), ("schedule", C.c_int32), ("max_iter", C.c_int32), ("ms_scaling_factor", C.c_double),
-                ("osd_method", C.c_int32), ("osd_order", C.c_int32), ("capacity", C.c_int32), ("profile", C.c_int32)]
+                ("osd_method", C.c_int32), ("osd_order", C.c_int32), ("precision", C.c_int32), ("capacity", C.c_int32),
+                ("profile", C.c_int32)]
 
 
 class QbCircuitInfo(C.Structure):

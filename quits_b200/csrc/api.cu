@@ -120,8 +120,10 @@ namespace {
 
 struct WinOwned {
     qb::WinDev dev{};
-    DevBuf colE, llr0, lmask, uptr, uidx, cptr, crow;
+    DevBuf colE, llr0f, llr0d, lmask, uptr, uidx, cptr, crow;
     size_t bp_smem = 0, osd_smem = 0;
+    bool vglobal = false;
+    int bp_grid = 0;            // persistent grid of the VGLOBAL variant (0: one CTA per shot)
     int osd_grid = 0;
 };
 
@@ -134,13 +136,14 @@ struct qb_sw {
     bool single = false;
     bool use_osd = true;
     int max_iter = 0;
+    int precision = 64;
     std::vector<std::unique_ptr<WinOwned>> wins;
     DevBuf alpha;
     // batch state
     int cap = 0;
     int DW = 0, KW = 0, carryW = 0, synW = 0;
     size_t llr_stride = 0;
-    DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, counters, stats, pred, ehat, iters, conv;
+    DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, counters, stats, pred, ehat, iters, conv, vscratch;
     EventTimer t_bp, t_osd;
 };
 
@@ -207,11 +210,13 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, WinOwned& wo) {
     int rs = 1;
     for (int r = 0; r < rows; ++r) rs = std::max(rs, fillr[r]);
     rs |= 1;                                             // odd row stride: conflict-free thread-per-row sweeps
-    std::vector<float> llr0(static_cast<size_t>(npad), 0.0f);
+    std::vector<float> llr0f(static_cast<size_t>(npad), 0.0f);
+    std::vector<double> llr0d(static_cast<size_t>(npad), 0.0);
     for (int j = 0; j < ncols; ++j) {
         const double pr = hw.priors[j];
         if (!(pr > 0.0 && pr < 1.0)) throw qb::value_error("fault prior outside (0, 1)");
-        llr0[j] = static_cast<float>(std::log((1.0 - pr) / pr));
+        llr0d[j] = std::log((1.0 - pr) / pr);
+        llr0f[j] = static_cast<float>(llr0d[j]);
     }
     std::vector<uint64_t> lmask(static_cast<size_t>(std::max(hw.ncommit, 1)) * KW, 0);
     for (int j = 0; j < hw.ncommit; ++j)
@@ -222,7 +227,8 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, WinOwned& wo) {
     std::vector<int32_t> cptr(hw.cptr.begin(), hw.cptr.end());
     std::vector<uint16_t> crow(hw.crow.begin(), hw.crow.end());
     upload(wo.colE, colE, ctx->stream);
-    upload(wo.llr0, llr0, ctx->stream);
+    upload(wo.llr0f, llr0f, ctx->stream);
+    upload(wo.llr0d, llr0d, ctx->stream);
     upload(wo.lmask, lmask, ctx->stream);
     upload(wo.uptr, uptr, ctx->stream, 2);
     upload(wo.uidx, uidx, ctx->stream, 2);
@@ -232,12 +238,8 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, WinOwned& wo) {
     d.rows = rows; d.ncols = ncols; d.ncols_pad = npad; d.RS = rs; d.cw = cw_alloc; d.ncommit = hw.ncommit;
     d.row0 = hw.row0; d.carry_rows = hw.urows; d.KW = KW;
     d.rowsW32 = (rows + 31) / 32; d.nW32 = (ncols + 31) / 32;
-    d.colE = wo.colE.as<uint32_t>(); d.llr0 = wo.llr0.as<float>(); d.lmask = wo.lmask.as<uint64_t>();
+    d.colE = wo.colE.as<uint32_t>(); d.llr0f = wo.llr0f.as<float>(); d.llr0d = wo.llr0d.as<double>(); d.lmask = wo.lmask.as<uint64_t>();
     d.uptr = wo.uptr.as<int32_t>(); d.uidx = wo.uidx.as<uint16_t>(); d.cptr = wo.cptr.as<int32_t>(); d.crow = wo.crow.as<uint16_t>();
-    wo.bp_smem = qb::bp_smem_bytes(d);
-    if (wo.bp_smem > 227 * 1024)
-        throw qb::unsupported_error("window of " + std::to_string(rows) + " rows x row weight " + std::to_string(rs) +
-                                    " needs " + std::to_string(wo.bp_smem) + " B of shared memory for BP messages (limit 232448)");
 }
 
 void finish_decoder(qb_sw* sw) {
@@ -247,39 +249,46 @@ void finish_decoder(qb_sw* sw) {
     if (o.schedule != 0) throw qb::unsupported_error("schedule 'serial' is not implemented on the GPU path yet; use schedule='parallel'");
     if (o.osd_method >= 0 && o.osd_order != 0) throw qb::unsupported_error("osd_order > 0 is not implemented on the GPU path yet; use osd_order=0");
     if (o.ms_scaling_factor < 0) throw qb::value_error("ms_scaling_factor must be >= 0");
+    if (o.precision != 0 && o.precision != 32 && o.precision != 64) throw qb::value_error("precision must be 32 or 64");
+    sw->precision = o.precision == 32 ? 32 : 64;
+    const int prec = sw->precision;
     sw->use_osd = o.osd_method >= 0;
-    size_t max_bp = 0;
-    int max_cw = 0, max_npad = 0, max_rowsW = 0, max_iter = 0;
+    int max_npad = 0, max_rowsW = 0, max_iter = 0;
+    size_t max_slab = 0;
     for (auto& w : sw->wins) {
-        max_bp = std::max(max_bp, w->bp_smem);
-        max_cw = std::max(max_cw, w->dev.cw);
+        // messages in shared memory when they fit, else in an L2-resident global slab per CTA
+        w->vglobal = qb::bp_smem_bytes(w->dev, prec, false) > 227 * 1024;
+        w->bp_smem = qb::bp_smem_bytes(w->dev, prec, w->vglobal);
+        if (w->bp_smem > 227 * 1024)
+            throw qb::unsupported_error("window of " + std::to_string(w->dev.rows) + " rows is too tall for the BP kernel's per-row shared-memory state");
+        CK(qb::bp_configure(w->dev, prec, w->vglobal));
+        if (w->vglobal) {
+            w->bp_grid = 148 * 2;
+            max_slab = std::max(max_slab, static_cast<size_t>(w->dev.rows) * w->dev.RS * (prec / 8));
+        }
         max_npad = std::max(max_npad, w->dev.ncols_pad);
         max_rowsW = std::max(max_rowsW, w->dev.rowsW32);
         max_iter = std::max(max_iter, o.max_iter > 0 ? o.max_iter : w->dev.ncols);
         if (sw->use_osd) {
-            if (!qb::osd_supported(w->dev))
+            if (!qb::osd_supported(w->dev, prec))
                 throw qb::unsupported_error("window of " + std::to_string(w->dev.rows) + " x " + std::to_string(w->dev.ncols) +
                                             " exceeds what the register-resident OSD kernel handles (rows <= 736)");
-            CK(qb::osd_configure(w->dev));
-            w->osd_smem = qb::osd_smem_bytes(w->dev);
+            CK(qb::osd_configure(w->dev, prec));
+            w->osd_smem = qb::osd_smem_bytes(w->dev, prec);
             int per_sm = static_cast<int>((227 * 1024) / (w->osd_smem + 1024));
             per_sm = std::max(1, std::min(per_sm, 4));
             w->osd_grid = 148 * per_sm;
         }
     }
+    if (max_slab) sw->vscratch.ensure(max_slab * 148 * 2 + 16);
     if (o.max_iter == 0 && sw->wins.size() > 1) {
-        // ldpc's "0 => number of columns" differs per window; the kernel takes one value, so use the per-window value
-        // only when all windows agree
+        // ldpc's "0 => number of columns" differs per window; the kernel takes one value
         for (auto& w : sw->wins)
             if (w->dev.ncols != sw->wins[0]->dev.ncols) throw qb::unsupported_error("max_iter = 0 with windows of different widths; pass max_iter explicitly");
     }
     sw->max_iter = max_iter;
-    for (int cw : {6, 8, 16})
-        if (max_cw <= cw) { CK(qb::bp_configure(max_bp, cw)); break; }
-    for (auto& w : sw->wins) CK(qb::bp_configure(max_bp, w->dev.cw));
-    std::vector<float> alpha(static_cast<size_t>(max_iter) + 1, 1.0f);
-    for (int it = 1; it <= max_iter; ++it)
-        alpha[it] = o.ms_scaling_factor == 0.0 ? static_cast<float>(1.0 - std::pow(2.0, -1.0 * it)) : static_cast<float>(o.ms_scaling_factor);
+    std::vector<double> alpha(static_cast<size_t>(max_iter) + 1, 1.0);
+    for (int it = 1; it <= max_iter; ++it) alpha[it] = o.ms_scaling_factor == 0.0 ? 1.0 - std::pow(2.0, -1.0 * it) : o.ms_scaling_factor;
     upload(sw->alpha, alpha, ctx->stream);
     sw->cap = o.capacity > 0 ? o.capacity : 65536;
     sw->DW = std::max(1, (sw->plan.D + 63) / 64);
@@ -294,7 +303,7 @@ void ensure_batch(qb_sw* sw, int n) {
     const size_t N = static_cast<size_t>(n);
     sw->carry.ensure(N * sw->carryW * 4 + 16);
     sw->acc.ensure(N * sw->KW * 8 + 16);
-    sw->llr.ensure(N * sw->llr_stride * 4 + 16);
+    sw->llr.ensure(N * sw->llr_stride * (sw->precision / 8) + 16);
     sw->syn.ensure(N * sw->synW * 4 + 16);
     sw->fail_list.ensure(N * 4 + 16);
     const size_t nw = sw->wins.size();
@@ -314,7 +323,7 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
     CK(cudaMemsetAsync(sw->stats.p, 0, nw * 3 * sizeof(unsigned long long), st));
     qb::BpParams bp{};
     bp.max_iter = sw->max_iter;
-    bp.alpha = sw->alpha.as<float>();
+    bp.alpha = sw->alpha.as<double>();
     for (size_t k = 0; k < nw; ++k) {
         WinOwned& w = *sw->wins[k];
         qb::BatchDev b{};
@@ -325,7 +334,8 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
         b.carry = sw->carry.as<uint32_t>();
         b.carry_stride32 = sw->carryW;
         b.acc = sw->acc.as<uint64_t>();
-        b.llr_buf = sw->llr.as<float>();
+        b.llr_buf = sw->llr.p;
+        b.vscratch = sw->vscratch.p;
         b.llr_stride = sw->llr_stride;
         b.syn_buf = sw->syn.as<uint32_t>();
         b.syn_stride32 = sw->synW;
@@ -339,12 +349,12 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
         b.conv_out = want_ehat ? sw->conv.as<uint8_t>() : nullptr;
         b.write_llr_always = want_llr ? 1 : 0;
         if (sw->opts.profile) sw->t_bp.begin(st);
-        CK(qb::launch_bp(w.dev, b, bp, st));
+        CK(qb::launch_bp(w.dev, b, bp, sw->precision, w.vglobal, w.vglobal ? std::min(w.bp_grid, n) : n, st));
         if (sw->opts.profile) sw->t_bp.end(st);
         if (stats) stats->bp_launches++;
         if (sw->use_osd) {
             if (sw->opts.profile) sw->t_osd.begin(st);
-            CK(qb::launch_osd(w.dev, b, std::min(w.osd_grid, n), st));
+            CK(qb::launch_osd(w.dev, b, sw->precision, std::min(w.osd_grid, n), st));
             if (sw->opts.profile) sw->t_osd.end(st);
             if (stats) stats->osd_launches++;
         }
@@ -362,6 +372,11 @@ void collect_stats(qb_sw* sw, int n, qb_stats* stats) {        // stream must be
         stats->bp_converged += static_cast<int64_t>(h[3 * k]);
         stats->bp_iterations += static_cast<int64_t>(h[3 * k + 1]);
         stats->osd_calls += static_cast<int64_t>(h[3 * k + 2]);
+        const qb::WinDev& d = sw->wins[k]->dev;
+        const double nnz = static_cast<double>(sw->plan.windows[k].crow.size());
+        const double io = 8.0 * ((d.rows + 63) / 64) + 8.0 * sw->KW + 8.0 * ((d.carry_rows + 63) / 64);
+        stats->bp_alg_bytes += static_cast<double>(h[3 * k + 1]) * 4.0 * nnz * (sw->precision / 8) + io * n;
+        stats->osd_alg_bytes += static_cast<double>(h[3 * k + 2]) * 2.0 * d.rows * 8.0 * ((d.ncols + 63) / 64);
     }
     if (sw->opts.profile) {
         stats->bp_ms += sw->t_bp.collect();
@@ -798,7 +813,7 @@ int qb_sw_decode_packed(qb_sw* sw, const uint64_t* det_rows, uint64_t n, uint64_
     });
 }
 
-int qb_bp_decode_batch(qb_sw* sw, const uint8_t* syndromes, uint64_t n, uint8_t* ehat, float* llr, int32_t* iters, uint8_t* converged) {
+int qb_bp_decode_batch(qb_sw* sw, const uint8_t* syndromes, uint64_t n, uint8_t* ehat, double* llr, int32_t* iters, uint8_t* converged) {
     return guard([&] {
         if (!sw || (n && !syndromes)) throw arg_error("NULL argument");
         if (!sw->single) throw arg_error("qb_bp_decode_batch needs a single-window decoder (qb_sw_create_single)");
@@ -828,9 +843,16 @@ int qb_bp_decode_batch(qb_sw* sw, const uint8_t* syndromes, uint64_t n, uint8_t*
                     for (int j = 0; j < cols; ++j)
                         ehat[(done + s) * cols + j] = static_cast<uint8_t>((h[static_cast<size_t>(s) * w.nW32 + (j >> 5)] >> (j & 31)) & 1u);
             }
-            if (llr)
-                CK(cudaMemcpy2DAsync(llr + done * cols, static_cast<size_t>(cols) * 4, sw->llr.p, sw->llr_stride * 4,
-                                     static_cast<size_t>(cols) * 4, nb, cudaMemcpyDeviceToHost, st));
+            if (llr) {
+                const size_t esz = sw->precision / 8;
+                std::vector<unsigned char> h(static_cast<size_t>(nb) * cols * esz);
+                CK(cudaMemcpy2DAsync(h.data(), static_cast<size_t>(cols) * esz, sw->llr.p, sw->llr_stride * esz, static_cast<size_t>(cols) * esz,
+                                     nb, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                double* out = llr + done * cols;
+                if (esz == 8) memcpy(out, h.data(), h.size());
+                else for (size_t i = 0; i < static_cast<size_t>(nb) * cols; ++i) out[i] = static_cast<double>(reinterpret_cast<const float*>(h.data())[i]);
+            }
             if (iters) CK(cudaMemcpyAsync(iters + done, sw->iters.p, static_cast<size_t>(nb) * 4, cudaMemcpyDeviceToHost, st));
             if (converged) CK(cudaMemcpyAsync(converged + done, sw->conv.p, static_cast<size_t>(nb), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -870,7 +892,7 @@ int qb_mc_run(qb_ctx* ctx, qb_circuit* c, qb_sw* sw, uint64_t seed, uint64_t sho
             if (prof) ctx->t_frame.end(st);
             decode_batch(sw, a.det_rows, static_cast<int>(n), false, false, stats);
             CK(qb::launch_count(sw->acc.as<uint64_t>(), a.obs_rows, a.KW, K, n, ctx->counts.as<unsigned long long>(), st));
-            if (stats) { stats->frame_launches++; stats->other_launches++; }
+            if (stats) { stats->frame_launches++; stats->other_launches++; stats->frame_alg_bytes += static_cast<double>(n) * 8.0 * (a.DW + a.KW); }
             // per-batch statistics are read back after the batch: the counters are reused by the next one
             CK(cudaStreamSynchronize(st));
             collect_stats(sw, static_cast<int>(n), stats);

@@ -5,16 +5,21 @@
 // window syndrome slice + carry XOR (:168-169), stop test H e == s, and on convergence the commit
 // L_k e / U_k e (:172-175).
 //
-// Data layout.  The bit->check messages of the shot live in shared memory as fp32 in padded row-major order
+// Data layout.  The bit->check messages of the shot live in shared memory in padded row-major order
 // V[row * RS + slot] (RS odd: a thread-per-row sweep is bank-conflict free, and consecutive columns that share
 // a row hit consecutive banks).  The check->bit messages are never materialised: the check sweep reduces each
 // row to (min1, min2, argmin slot, sign parity) and the bit sweep rebuilds its <= CW incoming messages from
 // those summaries, which gives exactly the value of the forward/backward running-min formulation
 // (min over the other edges, sign from syndrome + #{v <= 0}).  All floating-point operations are done in the
 // same order as the CPU oracle with explicit round-to-nearest intrinsics (no FMA contraction), so hard
-// decisions and posteriors agree bit for bit with the fp32 oracle.
+// decisions and posteriors agree bit for bit with the oracle of the same precision:
+//   R = double  what ldpc computes in (default; LLR ties -- exact cancellations are common with 9 distinct
+//               priors -- resolve as on the CPU)
+//   R = float   half the shared memory, twice the resident shots; bit-exact with the fp32 oracle
 // The window's column structure (<= CW packed (row, slot) entries per column, stored entry-major so a warp
 // reads 128 contiguous bytes) and the prior LLRs are shared by all shots and stream from L2.
+// Windows whose messages do not fit in shared memory run the same code with V in a per-CTA global scratch slab
+// that stays L2 resident (VGLOBAL).
 #include <cfloat>
 
 #include "qb_device.h"
@@ -23,24 +28,33 @@ namespace qb {
 
 namespace {
 
-constexpr int kBpThreads = 256;
-
-struct BpSmem {
-    float* V;
-    float2* rsum;
-    uint32_t* rmeta;
-    uint32_t* syn;
-    uint32_t* cand;
-    uint32_t* accs;
-    uint32_t* car;
+template <typename R> struct Real;
+template <> struct Real<float> {
+    using pair = float2;
+    static __device__ __forceinline__ float prior(const WinDev& w, int j) { return __ldg(w.llr0f + j); }
+    static __device__ __forceinline__ float big() { return FLT_MAX; }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
+    static __device__ __forceinline__ pair mk(float a, float b) { return make_float2(a, b); }
+};
+template <> struct Real<double> {
+    using pair = double2;
+    static __device__ __forceinline__ double prior(const WinDev& w, int j) { return __ldg(w.llr0d + j); }
+    static __device__ __forceinline__ double big() { return DBL_MAX; }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double abs(double a) { return fabs(a); }
+    static __device__ __forceinline__ pair mk(double a, double b) { return make_double2(a, b); }
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline size_t bp_layout(const WinDev& w, size_t* off /*[7]*/) {
+// shared-memory layout; returns the total.  off: V, rsum, rmeta, syn, cand, accs, car
+__host__ __device__ inline size_t bp_layout(const WinDev& w, int rsize, bool vglobal, size_t* off /*[7]*/) {
     size_t o = 0;
-    off[0] = o; o += align_up(static_cast<size_t>(w.rows) * w.RS * 4, 16);
-    off[1] = o; o += align_up(static_cast<size_t>(w.rows) * 8, 16);
+    off[0] = o; o += vglobal ? 0 : align_up(static_cast<size_t>(w.rows) * w.RS * rsize, 16);
+    off[1] = o; o += align_up(static_cast<size_t>(w.rows) * 2 * rsize, 16);
     off[2] = o; o += align_up(static_cast<size_t>(w.rows) * 4, 16);
     off[3] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
     off[4] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
@@ -49,13 +63,15 @@ __host__ __device__ inline size_t bp_layout(const WinDev& w, size_t* off /*[7]*/
     return o;
 }
 
-template <int CW>
-__global__ void __launch_bounds__(kBpThreads, (CW <= 8 ? 4 : 2)) bp_kernel(const WinDev w, const BatchDev b, const BpParams p) {
+template <typename R, int CW, int NT, int MINB, bool VGLOBAL>
+__global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const BatchDev b, const BpParams p) {
+    using RT = Real<R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     size_t off[7];
-    bp_layout(w, off);
-    float* V = reinterpret_cast<float*>(smem_raw + off[0]);
-    float2* rsum = reinterpret_cast<float2*>(smem_raw + off[1]);
+    bp_layout(w, sizeof(R), VGLOBAL, off);
+    R* V = VGLOBAL ? reinterpret_cast<R*>(b.vscratch) + static_cast<size_t>(blockIdx.x) * (static_cast<size_t>(w.rows) * w.RS)
+                   : reinterpret_cast<R*>(smem_raw + off[0]);
+    typename RT::pair* rsum = reinterpret_cast<typename RT::pair*>(smem_raw + off[1]);
     uint32_t* rmeta = reinterpret_cast<uint32_t*>(smem_raw + off[2]);
     uint32_t* syn = reinterpret_cast<uint32_t*>(smem_raw + off[3]);
     uint32_t* cand = reinterpret_cast<uint32_t*>(smem_raw + off[4]);
@@ -63,177 +79,212 @@ __global__ void __launch_bounds__(kBpThreads, (CW <= 8 ? 4 : 2)) bp_kernel(const
     uint32_t* car = reinterpret_cast<uint32_t*>(smem_raw + off[6]);
 
     const int tid = threadIdx.x;
-    const int shot = blockIdx.x;
     const int rows = w.rows, ncols = w.ncols, RS = w.RS, npad = w.ncols_pad;
     const int carryW = (w.carry_rows + 31) / 32;
+    R* const llr_all = reinterpret_cast<R*>(b.llr_buf);
 
-    // ---- syndrome of the window: detector bits [row0, row0+rows) of this shot, first rows XOR the carry
-    if (tid < w.rowsW32) {
-        const uint32_t* d = b.det32 + static_cast<size_t>(shot) * b.det_stride32;
-        const int bit = w.row0 + 32 * tid;
-        const int wd = bit >> 5, sh = bit & 31;
-        uint32_t v = __ldg(d + wd) >> sh;
-        if (sh) v |= __ldg(d + wd + 1) << (32 - sh);
-        const int left = rows - 32 * tid;
-        if (left < 32) v &= (1u << left) - 1u;
-        if (32 * tid < b.in_carry_rows) v ^= b.carry[static_cast<size_t>(shot) * b.carry_stride32 + tid];
-        syn[tid] = v;
-    }
-    if (tid < 2 * w.KW) accs[tid] = 0;
-    if (tid <= carryW) car[tid] = 0;
-    for (int i = tid; i < rows * RS; i += kBpThreads) V[i] = FLT_MAX;       // padding slots: never the minimum, never negative
-    __syncthreads();
-    for (int j = tid; j < ncols; j += kBpThreads) {
-        const float l0 = __ldg(w.llr0 + j);
-#pragma unroll
-        for (int q = 0; q < CW; ++q) {
-            const uint32_t e = __ldg(w.colE + static_cast<size_t>(q) * npad + j);
-            if (e != kNoEdge) V[(e >> 8) * RS + (e & 255u)] = l0;
-        }
-    }
-    __syncthreads();
-
-    uint32_t hmask = 0;          // hard decisions of this thread's columns (bit k <-> column tid + k*kBpThreads)
-    bool conv = false;
-    int it = 1;
-    for (; it <= p.max_iter; ++it) {
-        const float alpha = __ldg(p.alpha + it);
-        // ---- check sweep: one thread per row
-        for (int i = tid; i < rows; i += kBpThreads) {
-            const float* vr = V + i * RS;
-            float m1 = FLT_MAX, m2 = FLT_MAX;
-            uint32_t arg = 0, neg = (syn[i >> 5] >> (i & 31)) & 1u;
-#pragma unroll 5
-            for (int s = 0; s < RS; ++s) {
-                const float v = vr[s];
-                const float a = fabsf(v);
-                neg += v <= 0.0f ? 1u : 0u;
-                if (a < m1) { m2 = m1; m1 = a; arg = static_cast<uint32_t>(s); }
-                else if (a < m2) { m2 = a; }
-            }
-            rsum[i] = make_float2(m1, m2);
-            rmeta[i] = arg | (neg << 31);
-        }
-        if (tid < w.rowsW32) cand[tid] = 0;
+    for (int shot = blockIdx.x; shot < b.n_shots; shot += gridDim.x) {
         __syncthreads();
-        // ---- bit sweep: one thread per column
-        hmask = 0;
-        const bool last = it == p.max_iter;
-        int k = 0;
-        for (int j = tid; j < ncols; j += kBpThreads, ++k) {
-            uint32_t e[CW];
-#pragma unroll
-            for (int q = 0; q < CW; ++q) e[q] = __ldg(w.colE + static_cast<size_t>(q) * npad + j);
-            const float l0 = __ldg(w.llr0 + j);
-            float c[CW], vn[CW];
-            int addr[CW];
+        // ---- syndrome of the window: detector bits [row0, row0+rows) of this shot, first rows XOR the carry
+        if (tid < w.rowsW32) {
+            const uint32_t* d = b.det32 + static_cast<size_t>(shot) * b.det_stride32;
+            const int bit = w.row0 + 32 * tid;
+            const int wd = bit >> 5, sh = bit & 31;
+            uint32_t v = __ldg(d + wd) >> sh;
+            if (sh) v |= __ldg(d + wd + 1) << (32 - sh);
+            const int left = rows - 32 * tid;
+            if (left < 32) v &= (1u << left) - 1u;
+            if (32 * tid < b.in_carry_rows) v ^= b.carry[static_cast<size_t>(shot) * b.carry_stride32 + tid];
+            syn[tid] = v;
+        }
+        if (tid < 2 * w.KW) accs[tid] = 0;
+        if (tid <= carryW) car[tid] = 0;
+        for (int i = tid; i < rows * RS; i += NT) V[i] = RT::big();       // padding slots: never the minimum, never negative
+        __syncthreads();
+        for (int j = tid; j < ncols; j += NT) {
+            const R l0 = RT::prior(w, j);
 #pragma unroll
             for (int q = 0; q < CW; ++q) {
-                c[q] = 0.0f;
-                addr[q] = 0;
-                if (e[q] != kNoEdge) {
-                    const uint32_t row = e[q] >> 8, slot = e[q] & 255u;
-                    addr[q] = static_cast<int>(row) * RS + static_cast<int>(slot);
-                    const float v = V[addr[q]];
-                    const float2 s = rsum[row];
-                    const uint32_t meta = rmeta[row];
-                    const float mag = slot == (meta & 0x7FFFFFFFu) ? s.y : s.x;
-                    const uint32_t odd = (meta >> 31) ^ (v <= 0.0f ? 1u : 0u);
-                    c[q] = __fmul_rn(mag, odd ? -alpha : alpha);
-                }
+                const uint32_t e = __ldg(w.colE + static_cast<size_t>(q) * npad + j);
+                if (e != kNoEdge) V[(e >> 8) * RS + (e & 255u)] = l0;
             }
-            float t = l0;
+        }
+        __syncthreads();
+
+        uint32_t hmask = 0;          // hard decisions of this thread's columns (bit k <-> column tid + k*NT)
+        bool conv = false;
+        int it = 1;
+        for (; it <= p.max_iter; ++it) {
+            const R alpha = static_cast<R>(__ldg(p.alpha + it));
+            // ---- check sweep: one thread per row
+            for (int i = tid; i < rows; i += NT) {
+                const R* vr = V + i * RS;
+                R m1 = RT::big(), m2 = RT::big();
+                uint32_t arg = 0, neg = (syn[i >> 5] >> (i & 31)) & 1u;
+#pragma unroll 5
+                for (int s = 0; s < RS; ++s) {
+                    const R v = vr[s];
+                    const R a = RT::abs(v);
+                    neg += v <= R(0) ? 1u : 0u;
+                    if (a < m1) { m2 = m1; m1 = a; arg = static_cast<uint32_t>(s); }
+                    else if (a < m2) { m2 = a; }
+                }
+                rsum[i] = RT::mk(m1, m2);
+                rmeta[i] = arg | (neg << 31);
+            }
+            if (tid < w.rowsW32) cand[tid] = 0;
+            __syncthreads();
+            // ---- bit sweep: one thread per column
+            hmask = 0;
+            const bool last = it == p.max_iter;
+            int k = 0;
+            for (int j = tid; j < ncols; j += NT, ++k) {
+                uint32_t e[CW];
 #pragma unroll
-            for (int q = 0; q < CW; ++q) { vn[q] = t; t = __fadd_rn(t, c[q]); }
-            const float llr = t;
-            t = 0.0f;
+                for (int q = 0; q < CW; ++q) e[q] = __ldg(w.colE + static_cast<size_t>(q) * npad + j);
+                const R l0 = RT::prior(w, j);
+                R c[CW], vn[CW];
+                int addr[CW];
 #pragma unroll
-            for (int q = CW - 1; q >= 0; --q) { vn[q] = __fadd_rn(vn[q], t); t = __fadd_rn(t, c[q]); }
+                for (int q = 0; q < CW; ++q) {
+                    c[q] = R(0);
+                    addr[q] = 0;
+                    if (e[q] != kNoEdge) {
+                        const uint32_t row = e[q] >> 8, slot = e[q] & 255u;
+                        addr[q] = static_cast<int>(row) * RS + static_cast<int>(slot);
+                        const R v = V[addr[q]];
+                        const typename RT::pair s = rsum[row];
+                        const uint32_t meta = rmeta[row];
+                        const R mag = slot == (meta & 0x7FFFFFFFu) ? s.y : s.x;
+                        const uint32_t odd = (meta >> 31) ^ (v <= R(0) ? 1u : 0u);
+                        c[q] = RT::mul(mag, odd ? -alpha : alpha);
+                    }
+                }
+                R t = l0;
 #pragma unroll
-            for (int q = 0; q < CW; ++q)
-                if (e[q] != kNoEdge) V[addr[q]] = vn[q];
-            if (llr <= 0.0f) {
-                hmask |= 1u << k;
+                for (int q = 0; q < CW; ++q) { vn[q] = t; t = RT::add(t, c[q]); }
+                const R llr = t;
+                t = R(0);
+#pragma unroll
+                for (int q = CW - 1; q >= 0; --q) { vn[q] = RT::add(vn[q], t); t = RT::add(t, c[q]); }
 #pragma unroll
                 for (int q = 0; q < CW; ++q)
-                    if (e[q] != kNoEdge) atomicXor(&cand[e[q] >> 13], 1u << ((e[q] >> 8) & 31u));
-            }
-            if (last || b.write_llr_always) b.llr_buf[static_cast<size_t>(shot) * b.llr_stride + j] = llr;
-        }
-        // ---- stop test H e == s
-        const int mismatch = tid < w.rowsW32 ? (cand[tid] != syn[tid]) : 0;
-        if (!__syncthreads_or(mismatch)) { conv = true; break; }
-    }
-    if (it > p.max_iter) it = p.max_iter;
-
-    if (conv) {
-        // ---- commit: acc ^= L e[:ncommit], carry = U e[:ncommit]   (sliding_window.py:172-175)
-        uint32_t hm = hmask;
-        while (hm) {
-            const int k = __ffs(hm) - 1;
-            hm &= hm - 1;
-            const int j = tid + k * kBpThreads;
-            if (b.ehat_out) atomicOr(&b.ehat_out[static_cast<size_t>(shot) * b.ehat_stride32 + (j >> 5)], 1u << (j & 31));
-            if (j < w.ncommit) {
-                for (int wd = 0; wd < w.KW; ++wd) {
-                    const uint64_t lm = __ldg(w.lmask + static_cast<size_t>(j) * w.KW + wd);
-                    if (static_cast<uint32_t>(lm)) atomicXor(&accs[2 * wd], static_cast<uint32_t>(lm));
-                    if (static_cast<uint32_t>(lm >> 32)) atomicXor(&accs[2 * wd + 1], static_cast<uint32_t>(lm >> 32));
+                    if (e[q] != kNoEdge) V[addr[q]] = vn[q];
+                if (llr <= R(0)) {
+                    hmask |= 1u << k;
+#pragma unroll
+                    for (int q = 0; q < CW; ++q)
+                        if (e[q] != kNoEdge) atomicXor(&cand[e[q] >> 13], 1u << ((e[q] >> 8) & 31u));
                 }
-                if (w.carry_rows) {
-                    for (int q = __ldg(w.uptr + j); q < __ldg(w.uptr + j + 1); ++q) {
-                        const uint32_t r = __ldg(w.uidx + q);
-                        atomicXor(&car[r >> 5], 1u << (r & 31));
+                if (last || b.write_llr_always) llr_all[static_cast<size_t>(shot) * b.llr_stride + j] = llr;
+            }
+            // ---- stop test H e == s
+            const int mismatch = tid < w.rowsW32 ? (cand[tid] != syn[tid]) : 0;
+            if (!__syncthreads_or(mismatch)) { conv = true; break; }
+        }
+        if (it > p.max_iter) it = p.max_iter;
+
+        if (conv) {
+            // ---- commit: acc ^= L e[:ncommit], carry = U e[:ncommit]   (sliding_window.py:172-175)
+            uint32_t hm = hmask;
+            while (hm) {
+                const int kk = __ffs(hm) - 1;
+                hm &= hm - 1;
+                const int j = tid + kk * NT;
+                if (b.ehat_out) atomicOr(&b.ehat_out[static_cast<size_t>(shot) * b.ehat_stride32 + (j >> 5)], 1u << (j & 31));
+                if (j < w.ncommit) {
+                    for (int wd = 0; wd < w.KW; ++wd) {
+                        const uint64_t lm = __ldg(w.lmask + static_cast<size_t>(j) * w.KW + wd);
+                        if (static_cast<uint32_t>(lm)) atomicXor(&accs[2 * wd], static_cast<uint32_t>(lm));
+                        if (static_cast<uint32_t>(lm >> 32)) atomicXor(&accs[2 * wd + 1], static_cast<uint32_t>(lm >> 32));
+                    }
+                    if (w.carry_rows) {
+                        for (int q = __ldg(w.uptr + j); q < __ldg(w.uptr + j + 1); ++q) {
+                            const uint32_t r = __ldg(w.uidx + q);
+                            atomicXor(&car[r >> 5], 1u << (r & 31));
+                        }
                     }
                 }
             }
+            __syncthreads();
+            if (tid < w.KW) {
+                const uint64_t v = (static_cast<uint64_t>(accs[2 * tid + 1]) << 32) | accs[2 * tid];
+                b.acc[static_cast<size_t>(shot) * w.KW + tid] ^= v;
+            }
+            if (tid < carryW) b.carry[static_cast<size_t>(shot) * b.carry_stride32 + tid] = car[tid];
+        } else {
+            // ---- hand the shot to OSD: post-carry syndrome + posteriors (already in llr_buf)
+            if (tid < w.rowsW32) b.syn_buf[static_cast<size_t>(shot) * b.syn_stride32 + tid] = syn[tid];
+            if (tid == 0) {
+                const int slot = atomicAdd(b.fail_count, 1);
+                b.fail_list[slot] = shot;
+            }
         }
-        __syncthreads();
-        if (tid < w.KW) {
-            const uint64_t v = (static_cast<uint64_t>(accs[2 * tid + 1]) << 32) | accs[2 * tid];
-            b.acc[static_cast<size_t>(shot) * w.KW + tid] ^= v;
-        }
-        if (tid < carryW) b.carry[static_cast<size_t>(shot) * b.carry_stride32 + tid] = car[tid];
-    } else {
-        // ---- hand the shot to OSD: post-carry syndrome + posteriors (already in llr_buf)
-        if (tid < w.rowsW32) b.syn_buf[static_cast<size_t>(shot) * b.syn_stride32 + tid] = syn[tid];
         if (tid == 0) {
-            const int slot = atomicAdd(b.fail_count, 1);
-            b.fail_list[slot] = shot;
+            if (conv) atomicAdd(&b.stats[0], 1ull);
+            atomicAdd(&b.stats[1], static_cast<unsigned long long>(it));
+            if (b.iters_out) b.iters_out[shot] = it;
+            if (b.conv_out) b.conv_out[shot] = conv ? 1 : 0;
         }
     }
-    if (tid == 0) {
-        if (conv) atomicAdd(&b.stats[0], 1ull);
-        atomicAdd(&b.stats[1], static_cast<unsigned long long>(it));
-        if (b.iters_out) b.iters_out[shot] = it;
-        if (b.conv_out) b.conv_out[shot] = conv ? 1 : 0;
+}
+
+// kernel variants: (precision, column-weight template, V in shared or global)
+using KernelPtr = void (*)(const WinDev, const BatchDev, const BpParams);
+
+struct Variant {
+    KernelPtr fn;
+    int threads;
+    size_t configured;
+};
+
+template <typename R, int CW, bool VG>
+KernelPtr pick_kernel(int* threads) {
+    // fp32: 256 threads x 4 CTAs/SM (64 regs); fp64: 512 threads x 2 CTAs/SM; wide columns get more registers
+    constexpr int NT = sizeof(R) == 4 ? 256 : 512;
+    constexpr int MINB = CW <= 8 ? (sizeof(R) == 4 ? 4 : 2) : 1;
+    *threads = NT;
+    return bp_kernel<R, CW, NT, MINB, VG>;
+}
+
+Variant& variant(int prec, int cw, bool vg) {
+    static Variant table[2][3][2] = {};
+    const int pi = prec == 32 ? 0 : 1, ci = cw <= 6 ? 0 : (cw <= 8 ? 1 : 2), gi = vg ? 1 : 0;
+    Variant& v = table[pi][ci][gi];
+    if (!v.fn) {
+#define QB_PICK(R, CWV) (vg ? pick_kernel<R, CWV, true>(&v.threads) : pick_kernel<R, CWV, false>(&v.threads))
+        if (pi == 0) v.fn = ci == 0 ? QB_PICK(float, 6) : (ci == 1 ? QB_PICK(float, 8) : QB_PICK(float, 16));
+        else v.fn = ci == 0 ? QB_PICK(double, 6) : (ci == 1 ? QB_PICK(double, 8) : QB_PICK(double, 16));
+#undef QB_PICK
     }
+    return v;
 }
 
 }  // namespace
 
-size_t bp_smem_bytes(const WinDev& w) {
+size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal) {
     size_t off[7];
-    return bp_layout(w, off);
+    return bp_layout(w, precision == 32 ? 4 : 8, vglobal, off);
 }
 
-cudaError_t bp_configure(size_t smem_bytes, int cw) {
-    if (smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
-    cudaError_t e;
-    if (cw <= 6) e = cudaFuncSetAttribute(bp_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
-    else if (cw <= 8) e = cudaFuncSetAttribute(bp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
-    else if (cw <= 16) e = cudaFuncSetAttribute(bp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes));
-    else return cudaErrorInvalidValue;
+int bp_threads(int precision) { return precision == 32 ? 256 : 512; }
+
+cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal) {
+    if (w.cw > 16) return cudaErrorInvalidValue;
+    const size_t smem = bp_smem_bytes(w, precision, vglobal);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    Variant& v = variant(precision, w.cw, vglobal);
+    if (smem <= v.configured) return cudaSuccess;          // the attribute only ever grows (decoders of different sizes coexist)
+    cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) v.configured = smem;
     return e;
 }
 
-cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, cudaStream_t st) {
+cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, bool vglobal, int grid, cudaStream_t st) {
     if (b.n_shots == 0) return cudaSuccess;
-    const size_t smem = bp_smem_bytes(w);
-    if (w.cw <= 6) bp_kernel<6><<<b.n_shots, kBpThreads, smem, st>>>(w, b, p);
-    else if (w.cw <= 8) bp_kernel<8><<<b.n_shots, kBpThreads, smem, st>>>(w, b, p);
-    else if (w.cw <= 16) bp_kernel<16><<<b.n_shots, kBpThreads, smem, st>>>(w, b, p);
-    else return cudaErrorInvalidValue;
+    Variant& v = variant(precision, w.cw, vglobal);
+    const size_t smem = bp_smem_bytes(w, precision, vglobal);
+    v.fn<<<grid, v.threads, smem, st>>>(w, b, p);
     return cudaGetLastError();
 }
 

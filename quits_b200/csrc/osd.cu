@@ -17,6 +17,7 @@
 // The column order comes from a stable 4-pass LSD radix sort of the posteriors' order-preserving integer image
 // (warp-private histograms + __match_any_sync ranking), which is exactly "ascending LLR, ties by index".
 #include <cfloat>
+#include <type_traits>
 
 #include "qb_device.h"
 
@@ -34,16 +35,16 @@ struct OsdLayout {
 
 __host__ __device__ inline size_t au(size_t x) { return (x + 15) / 16 * 16; }
 
-__host__ __device__ inline OsdLayout osd_layout(const WinDev& w, int MW, int CPT) {
+__host__ __device__ inline OsdLayout osd_layout(const WinDev& w, int MW, int CPT, int ksize) {
     OsdLayout L;
     L.n_pad = (w.ncols + kOsdThreads - 1) / kOsdThreads * kOsdThreads;
     L.TS = CPT * kOsdThreads;
     size_t o = 0;
     // region 0: sort keys + first index buffer; reused afterwards as the spill area of T (MW * TS words)
-    size_t sortA = au(static_cast<size_t>(L.n_pad) * 4) + au(static_cast<size_t>(L.n_pad) * 2);
+    size_t sortA = au(static_cast<size_t>(L.n_pad) * ksize) + au(static_cast<size_t>(L.n_pad) * 2);
     size_t tdump = au(static_cast<size_t>(MW) * L.TS * 4);
     L.keys = o;
-    L.idxA = o + au(static_cast<size_t>(L.n_pad) * 4);
+    L.idxA = o + au(static_cast<size_t>(L.n_pad) * ksize);
     o += sortA > tdump ? sortA : tdump;
     L.idxB = o; o += au(static_cast<size_t>(L.n_pad) * 2);
     L.hist = o; o += au(kOsdWarps * 256 * 4);
@@ -67,11 +68,23 @@ __device__ __forceinline__ uint32_t pick_word(const uint32_t (&c)[MW], int wsel)
     return r;
 }
 
-template <int MW, int CPT>
+// order-preserving unsigned image of a posterior (-0.0 is first folded into +0.0)
+__device__ __forceinline__ uint32_t order_key(float f) {
+    const uint32_t u = __float_as_uint(f + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ uint64_t order_key(double f) {
+    const uint64_t u = static_cast<uint64_t>(__double_as_longlong(f + 0.0));
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+template <typename R, int MW, int CPT>
 __global__ void __launch_bounds__(kOsdThreads) osd_kernel(const WinDev w, const BatchDev b) {
+    using KeyT = typename std::conditional<sizeof(R) == 4, uint32_t, uint64_t>::type;
+    constexpr int kPasses = static_cast<int>(sizeof(KeyT));
     extern __shared__ __align__(16) unsigned char sm[];
-    const OsdLayout L = osd_layout(w, MW, CPT);
-    uint32_t* keys = reinterpret_cast<uint32_t*>(sm + L.keys);
+    const OsdLayout L = osd_layout(w, MW, CPT, sizeof(KeyT));
+    KeyT* keys = reinterpret_cast<KeyT*>(sm + L.keys);
     uint16_t* idxA = reinterpret_cast<uint16_t*>(sm + L.idxA);
     uint16_t* idxB = reinterpret_cast<uint16_t*>(sm + L.idxB);
     uint32_t* tdump = reinterpret_cast<uint32_t*>(sm + L.keys);
@@ -98,19 +111,15 @@ __global__ void __launch_bounds__(kOsdThreads) osd_kernel(const WinDev w, const 
         const int job = s_job;
         if (job >= count) break;
         const int shot = b.fail_list[job];
-        const float* llr = b.llr_buf + static_cast<size_t>(shot) * b.llr_stride;
+        const R* llr = reinterpret_cast<const R*>(b.llr_buf) + static_cast<size_t>(shot) * b.llr_stride;
         const uint32_t* syn = b.syn_buf + static_cast<size_t>(shot) * b.syn_stride32;
 
         // ------------------------------------------------------------------ 1. sort columns by (LLR, index)
-        for (int i = tid; i < n; i += kOsdThreads) {
-            const float f = llr[i] + 0.0f;                       // -0.0 -> +0.0
-            const uint32_t u = __float_as_uint(f);
-            keys[i] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-        }
+        for (int i = tid; i < n; i += kOsdThreads) keys[i] = order_key(llr[i]);
         const int quarter = ((n + kOsdWarps - 1) / kOsdWarps + 31) / 32 * 32;
         const int wbeg = warp * quarter, wend = min(n, wbeg + quarter);
 #pragma unroll 1
-        for (int pass = 0; pass < 4; ++pass) {
+        for (int pass = 0; pass < kPasses; ++pass) {
             const int shift = 8 * pass;
             const uint16_t* src = (pass & 1) ? idxA : idxB;       // pass 0 reads the identity
             uint16_t* dst = (pass & 1) ? idxB : idxA;
@@ -120,7 +129,7 @@ __global__ void __launch_bounds__(kOsdThreads) osd_kernel(const WinDev w, const 
                 const int i = i0 + lane;
                 if (i < wend) {
                     const int id = pass == 0 ? i : src[i];
-                    atomicAdd(&hist[warp * 256 + ((keys[id] >> shift) & 255u)], 1u);
+                    atomicAdd(&hist[warp * 256 + static_cast<uint32_t>((keys[id] >> shift) & 255u)], 1u);
                 }
             }
             __syncthreads();
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(kOsdThreads) osd_kernel(const WinDev w, const 
                 uint32_t dg = 256u + lane;                           // invalid lanes never match anybody
                 if (valid) {
                     id = pass == 0 ? i : src[i];
-                    dg = (keys[id] >> shift) & 255u;
+                    dg = static_cast<uint32_t>((keys[id] >> shift) & 255u);
                 }
                 const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dg);
                 const uint32_t before = peers & ((1u << lane) - 1u);
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(kOsdThreads) osd_kernel(const WinDev w, const 
             }
             __syncthreads();
         }
-        const uint16_t* order = idxB;        // pass 3 wrote idxB
+        const uint16_t* order = idxB;        // the last (odd-numbered) pass wrote idxB
 
         // ------------------------------------------------------------------ 2. Gauss-Jordan on T (registers)
         uint32_t T[CPT][MW];
@@ -346,48 +355,60 @@ inline bool osd_shape(const WinDev& w, OsdShape& s) {
     return false;
 }
 
-template <typename F>
-inline cudaError_t osd_dispatch(const WinDev& w, F&& f) {
-    OsdShape s;
-    if (!osd_shape(w, s)) return cudaErrorInvalidValue;
-    const int key = s.MW * 10 + s.CPT;
-    switch (key) {
-    case 42: return f(osd_kernel<4, 2>, s);
-    case 62: return f(osd_kernel<6, 2>, s);
-    case 82: return f(osd_kernel<8, 2>, s);
-    case 83: return f(osd_kernel<8, 3>, s);
-    case 123: return f(osd_kernel<12, 3>, s);
-    case 124: return f(osd_kernel<12, 4>, s);
-    case 175: return f(osd_kernel<17, 5>, s);
-    case 236: return f(osd_kernel<23, 6>, s);
+template <typename R, typename F>
+inline cudaError_t osd_dispatch_r(const OsdShape& s, F&& f) {
+    switch (s.MW * 10 + s.CPT) {
+    case 42: return f(osd_kernel<R, 4, 2>);
+    case 62: return f(osd_kernel<R, 6, 2>);
+    case 82: return f(osd_kernel<R, 8, 2>);
+    case 83: return f(osd_kernel<R, 8, 3>);
+    case 123: return f(osd_kernel<R, 12, 3>);
+    case 124: return f(osd_kernel<R, 12, 4>);
+    case 175: return f(osd_kernel<R, 17, 5>);
+    case 236: return f(osd_kernel<R, 23, 6>);
     }
     return cudaErrorInvalidValue;
 }
 
+template <typename F>
+inline cudaError_t osd_dispatch(const WinDev& w, int precision, F&& f) {
+    OsdShape s;
+    if (!osd_shape(w, s)) return cudaErrorInvalidValue;
+    return precision == 32 ? osd_dispatch_r<float>(s, f) : osd_dispatch_r<double>(s, f);
+}
+
 }  // namespace
 
-bool osd_supported(const WinDev& w) {
-    OsdShape s;
-    return osd_shape(w, s) && osd_smem_bytes(w) <= 220 * 1024;
-}
-
-size_t osd_smem_bytes(const WinDev& w) {
+size_t osd_smem_bytes(const WinDev& w, int precision) {
     OsdShape s;
     if (!osd_shape(w, s)) return 0;
-    return osd_layout(w, s.MW, s.CPT).total;
+    return osd_layout(w, s.MW, s.CPT, precision == 32 ? 4 : 8).total;
 }
 
-cudaError_t osd_configure(const WinDev& w) {
-    const size_t smem = osd_smem_bytes(w);
-    return osd_dispatch(w, [&](auto kern, OsdShape) {
+bool osd_supported(const WinDev& w, int precision) {
+    OsdShape s;
+    return osd_shape(w, s) && osd_smem_bytes(w, precision) <= 220 * 1024;
+}
+
+cudaError_t osd_configure(const WinDev& w, int precision) {
+    // several windows may share one instantiation: the attribute only ever grows
+    static size_t configured[2][256] = {};
+    const size_t smem = osd_smem_bytes(w, precision);
+    OsdShape s;
+    if (!osd_shape(w, s)) return cudaErrorInvalidValue;
+    size_t& have = configured[precision == 32 ? 0 : 1][(s.MW * 10 + s.CPT) & 255];
+    if (smem <= have) return cudaSuccess;
+    cudaError_t e = osd_dispatch(w, precision, [&](auto kern) {
         return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     });
+    if (e == cudaSuccess) have = smem;
+    return e;
 }
 
-cudaError_t launch_osd(const WinDev& w, const BatchDev& b, int grid, cudaStream_t st) {
+cudaError_t launch_osd(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st) {
     if (b.n_shots == 0) return cudaSuccess;
-    const size_t smem = osd_smem_bytes(w);
-    return osd_dispatch(w, [&](auto kern, OsdShape) {
+    const size_t smem = osd_smem_bytes(w, precision);
+    return osd_dispatch(w, precision, [&](auto kern) {
         kern<<<grid, kOsdThreads, smem, st>>>(w, b);
         return cudaGetLastError();
     });

@@ -53,7 +53,8 @@ struct WinDev {
     int KW;                   // u64 words per observable mask
     int rowsW32, nW32;
     const uint32_t* colE;     // [cw][ncols_pad]  (row << 8 | slot), kNoEdge when the column is shorter
-    const float* llr0;        // [ncols_pad]
+    const float* llr0f;       // [ncols_pad]  prior LLRs log((1-p)/p), fp32 image (precision 32)
+    const double* llr0d;      // [ncols_pad]  ... fp64 (precision 64)
     const uint64_t* lmask;    // [ncommit][KW]
     const int32_t* uptr;      // [ncommit+1]
     const uint16_t* uidx;
@@ -69,8 +70,9 @@ struct BatchDev {
     uint32_t* carry;          // [n][carry_stride32]
     int carry_stride32;
     uint64_t* acc;            // [n][KW]  accumulated observable prediction
-    float* llr_buf;           // [n][llr_stride]
+    void* llr_buf;            // [n][llr_stride] posteriors, float or double according to the precision
     size_t llr_stride;
+    void* vscratch;           // VGLOBAL only: [grid][rows*RS] message slabs
     uint32_t* syn_buf;        // [n][syn_stride32]   post-carry syndrome of the shots handed to OSD
     int syn_stride32;
     int* fail_list;           // [n]
@@ -86,17 +88,19 @@ struct BatchDev {
 
 struct BpParams {
     int max_iter;
-    const float* alpha;       // [max_iter+1]  scaling factor of iteration it (index it)
+    const double* alpha;      // [max_iter+1]  scaling factor of iteration it (index it), rounded to the precision in the kernel
 };
 
-size_t bp_smem_bytes(const WinDev& w);
-cudaError_t bp_configure(size_t smem_bytes, int cw);
-cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, cudaStream_t st);
+// precision: 32 or 64 (message / posterior type).  vglobal: messages in a global scratch slab instead of shared memory.
+size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal);
+int bp_threads(int precision);
+cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal);
+cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, bool vglobal, int grid, cudaStream_t st);
 
-size_t osd_smem_bytes(const WinDev& w);
-bool osd_supported(const WinDev& w);
-cudaError_t osd_configure(const WinDev& w);
-cudaError_t launch_osd(const WinDev& w, const BatchDev& b, int grid, cudaStream_t st);
+size_t osd_smem_bytes(const WinDev& w, int precision);
+bool osd_supported(const WinDev& w, int precision);
+cudaError_t osd_configure(const WinDev& w, int precision);
+cudaError_t launch_osd(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------- results
 // pred[n][K] int64 from acc bits; counts[0] += shots whose prediction differs from obs_rows in any observable,

@@ -23,7 +23,7 @@ _OSD_METHODS = {"osd_0": 0, "osd0": 0, "osd_e": 1, "osde": 1, "exhaustive": 1, "
 
 
 def bp_options(bp_method="minimum_sum", max_iter=0, schedule="parallel", osd_method="osd_0", osd_order=0, ms_scaling_factor=1.0,
-               capacity=0, profile=False, **unknown) -> N.QbBpOpts:
+               precision="f64", capacity=0, profile=False, **unknown) -> N.QbBpOpts:
     """Translate ldpc.BpOsdDecoder-style kwargs (reference decoder/bposd.py:74-83) into the C option block."""
     for k in unknown:
         if k not in ("channel_probs", "error_rate", "error_channel", "input_vector_type", "omp_thread_count",
@@ -36,6 +36,9 @@ def bp_options(bp_method="minimum_sum", max_iter=0, schedule="parallel", osd_met
         o.osd_method = osd_method if isinstance(osd_method, int) else _OSD_METHODS[str(osd_method).lower()]
     except KeyError as e:
         raise ValueError("unknown decoder option value %s" % e) from None
+    if precision not in ("f64", "f32", 64, 32):
+        raise ValueError("precision must be 'f64' (what ldpc computes in; default) or 'f32'")
+    o.precision = 32 if precision in ("f32", 32) else 64
     o.max_iter = int(max_iter)
     o.ms_scaling_factor = float(ms_scaling_factor)
     o.osd_order = int(osd_order)

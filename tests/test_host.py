@@ -1,0 +1,190 @@
+"""CPU tests of the product's host side (C++ behind the C ABI): Stim-text front end, DEM, check matrix, window plan,
+error behaviour, and that the library exports what include/quits_b200.h declares.  No compute call needs a GPU here."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, circuit_meta, circuit_text
+from oracle import cref, dem as odem, shims, stimtext
+
+import quits_b200 as qb
+from quits_b200 import _native as N
+from quits_b200.decoder.base import WindowPlan
+
+CIRCUITS = sorted(f[:-5] for f in os.listdir(os.path.join(GOLDEN, "circuits")) if f.endswith(".stim"))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_library_exports_every_declared_symbol():
+    with open(os.path.join(ROOT, "include", "quits_b200.h")) as f:
+        header = f.read()
+    declared = sorted(set(re.findall(r"\b(qb_[a-z_0-9]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(N.SO_PATH)
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert sorted(N.SYMBOLS) == declared
+    assert lib.qb_version() == 100
+
+
+def test_no_gpu_means_loud_failure():
+    if N.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(N.QbCudaError, match="no CPU fallback"):
+        qb.get_stim_mem_result(circuit_text("toric3_zxcol_r3_p1e-3"), 10, seed=1)
+    _, hz, lz = circuit_meta("toric3_zxcol_r3_p1e-3")
+    with pytest.raises(N.QbCudaError):
+        qb.sliding_window_bposd_circuit_mem(np.zeros((4, 45), dtype=bool), circuit_text("toric3_zxcol_r3_p1e-3"), hz, lz, 3, 2,
+                                            bp_method="minimum_sum", schedule="parallel", osd_method="osd_0")
+
+
+@pytest.mark.parametrize("name", CIRCUITS)
+def test_front_end_and_dem_match_oracle(name):
+    text = circuit_text(name)
+    c = qb.Circuit(text)
+    fc = stimtext.parse_flat(text)
+    assert (c.num_qubits, c.num_measurements, c.num_detectors, c.num_observables, c.num_flat_ops) == \
+        (fc.n_qubits, fc.n_meas, fc.n_det, fc.n_obs, len(fc.ops))
+    kind, arg, ts, tg = c.flat()
+    ok, oa, ots, otg = cref.flat_arrays(fc)
+    assert np.array_equal(kind, ok) and np.array_equal(arg, oa) and np.array_equal(ts, ots) and np.array_equal(tg, otg[:len(tg)])
+    d = c.detector_error_model()
+    od = odem.analyze(fc)
+    e = d.errors()
+    assert d.num_errors == len(od.probs)
+    assert np.array_equal(e["probs"], np.array(od.probs))                   # bit-identical priors
+    assert e["det_idx"].tolist() == [x for ds in od.dets for x in ds]
+    assert e["obs_idx"].tolist() == [x for ds in od.obs for x in ds]
+    assert np.array_equal(np.diff(e["det_ptr"]), [len(x) for x in od.dets])
+    assert list(zip(e["rep_op"].tolist(), e["rep_tgt"].tolist(), e["rep_code"].tolist())) == [tuple(r) for r in od.rep]
+    gpath = os.path.join(GOLDEN, "dem", name + ".json")
+    if os.path.exists(gpath):
+        with open(gpath) as f:
+            g = json.load(f)
+        assert d.num_errors == g["n_errors"] and sha(e["probs"]) == g["probs_sha256"] and sha(e["det_idx"]) == g["det_idx_sha256"]
+        assert sha(e["obs_idx"]) == g["obs_idx_sha256"]
+
+
+def test_canonical_stim_printing_is_accepted():
+    """What str(stim.Circuit) would hand us: fused target lists, shortest-repr numbers, indented REPEAT bodies."""
+    text = circuit_text("bb72_r6_p1e-3")
+    a = qb.Circuit(text)
+    b = qb.Circuit(stimtext.canonical_text(text))
+    assert (a.num_qubits, a.num_measurements, a.num_detectors, a.num_observables) == \
+        (b.num_qubits, b.num_measurements, b.num_detectors, b.num_observables)
+    ea, eb = a.detector_error_model().errors(), b.detector_error_model().errors()
+    assert np.array_equal(ea["probs"], eb["probs"]) and np.array_equal(ea["det_idx"], eb["det_idx"])
+
+
+@pytest.mark.parametrize("case", sorted(f[:-5] for f in os.listdir(os.path.join(GOLDEN, "windows"))))
+def test_window_plan_equals_reference_spacetime(case):
+    """The digests were produced by the reference's own spacetime() (decoder/base.py:134-190), tools/make_golden.py."""
+    with open(os.path.join(GOLDEN, "windows", case + ".json")) as f:
+        g = json.load(f)
+    c = qb.Circuit(circuit_text(g["circuit"]))
+    plan = WindowPlan(c.detector_error_model(), g["m"], g["W"], g["F"])
+    assert plan.n_windows == len(g["windows"])
+    for k, e in enumerate(g["windows"]):
+        w = plan.window(k)
+        H, L = w["H"], w["L"]
+        assert list(H.shape) == e["H_shape"] and H.nnz == e["H_nnz"]
+        assert sha(H.indptr.astype(np.int64)) == e["H_indptr"] and sha(H.indices.astype(np.int32)) == e["H_indices"]
+        assert list(L.shape) == e["L_shape"] and sha(L.indptr.astype(np.int64)) == e["L_indptr"]
+        assert sha(L.indices.astype(np.int32)) == e["L_indices"]
+        assert sha(w["priors"]) == e["priors"]
+        if "U_shape" in e:
+            U = w["U"]
+            assert list(U.shape) == e["U_shape"] and sha(U.indptr.astype(np.int64)) == e["U_indptr"]
+            assert sha(U.indices.astype(np.int32)) == e["U_indices"]
+    # the spacetime() drop-in returns the same four lists
+    _, hz, _ = circuit_meta(g["circuit"])
+    checks, obs, priors, updates = qb.spacetime(c, hz, g["W"], g["F"], g["num_cor_rounds"])
+    assert len(checks) == len(g["windows"]) and len(updates) == len(g["windows"]) - 1
+    assert [list(h.shape) for h in checks] == [e["H_shape"] for e in g["windows"]]
+
+
+def test_matrix_conversion_on_a_foreign_dem():
+    """detector_error_model_to_matrix on a stim-shaped object that is not ours (the oracle's shim)."""
+    text = circuit_text("toric3_zxcol_r3_p1e-3")
+    theirs = shims.Circuit(text).detector_error_model()
+    H1, L1, p1 = qb.detector_error_model_to_matrix(theirs)
+    H2, L2, p2 = qb.detector_error_model_to_matrix(qb.Circuit(text).detector_error_model())
+    assert (H1 != H2).nnz == 0 and (L1 != L2).nnz == 0 and np.array_equal(p1, p2)
+    assert H1.dtype == np.uint8 and H1.shape == (45, 234)
+
+
+def test_merge_rule_keys_on_detectors_only():
+    """base.py:93-99: equal detector sets merge (XOR-combined probability), the first sighting's observables win."""
+    class T:
+        def __init__(self, v, o): self.val, self._o = v, o
+        def is_relative_detector_id(self): return not self._o
+        def is_logical_observable_id(self): return self._o
+    class I:
+        type = "error"
+        def __init__(self, p, d, o): self._p, self._t = p, [T(x, False) for x in d] + [T(x, True) for x in o]
+        def args_copy(self): return [self._p]
+        def targets_copy(self): return self._t
+    class Dem:
+        num_detectors, num_observables = 3, 2
+        def flattened(self): return [I(0.1, [0, 1], [0]), I(0.2, [2], []), I(0.3, [1, 0], [1])]
+    H, L, p = qb.detector_error_model_to_matrix(Dem())
+    assert H.shape == (3, 2) and L.shape == (2, 2)
+    assert H.toarray().tolist() == [[1, 0], [1, 0], [0, 1]]
+    assert L.toarray().tolist() == [[1, 0], [0, 0]]
+    assert p[0] == 0.1 * (1 - 0.3) + 0.3 * (1 - 0.1) and p[1] == 0.2
+
+
+def test_error_behaviour():
+    text = circuit_text("toric3_zxcol_r3_p1e-3")
+    _, hz, lz = circuit_meta("toric3_zxcol_r3_p1e-3")
+    with pytest.raises(ValueError, match="F cannot be zero"):
+        qb.spacetime(text, hz, 3, 0, 1)
+    with pytest.raises(ZeroDivisionError):                 # the reference divides by F before spacetime() checks it
+        qb.sliding_window_bposd_circuit_mem(np.zeros((2, 45), dtype=bool), text, hz, lz, 3, 0, bp_method="minimum_sum",
+                                            schedule="parallel")
+    with pytest.raises(NotImplementedError):
+        qb.Circuit("PAULI_CHANNEL_1(0.1,0.1,0.1) 0\nM 0\n")
+    for bad in ("FOO 1 2\n", "CX 0\n", "REPEAT 3 {\nH 0\n", "}\n", "M 0\nDETECTOR rec[-2]\n", "X_ERROR(0.7) 0\n", "H -1\n"):
+        with pytest.raises(ValueError):
+            qb.Circuit(bad)
+    # a window without faults is a ValueError like in the reference (base.py:161-162)
+    quiet = "R 0 1\nM 0 1\nDETECTOR rec[-1]\nDETECTOR rec[-2]\nM 0 1\nDETECTOR rec[-1] rec[-3]\nDETECTOR rec[-2] rec[-4]\n" \
+            "M 0 1\nDETECTOR rec[-1] rec[-3]\nDETECTOR rec[-2] rec[-4]\n"
+    with pytest.raises(ValueError):
+        qb.spacetime(quiet, np.zeros((2, 2)), 2, 1, 1)
+    # W larger than the history: the reference warns and decodes the whole history (sliding_window.py:140)
+    if N.device_count() == 0:
+        with warnings.catch_warnings(record=True) as rec:
+            warnings.simplefilter("always")
+            with pytest.raises(N.QbCudaError):
+                qb.sliding_window_bposd_circuit_mem(np.zeros((2, 45), dtype=bool), text, hz, lz, 9, 2, bp_method="minimum_sum",
+                                                    schedule="parallel")
+        assert any("whole history" in str(w.message) for w in rec)
+
+
+def test_repeat_and_split_semantics():
+    """REPEAT unrolling, rec[-k] resolution, and sequential semantics inside one instruction (CX 0 1 1 2)."""
+    c = qb.Circuit("R 0 1 2\nX_ERROR(0.25) 0\nCX 0 1 1 2\nREPEAT 2 {\n    M 2\n    DETECTOR rec[-1]\n}\nOBSERVABLE_INCLUDE(1) rec[-1] rec[-2]\n")
+    assert (c.num_qubits, c.num_measurements, c.num_detectors, c.num_observables) == (3, 2, 2, 2)
+    assert c.num_tape_ops >= c.num_flat_ops - 1        # the CX was split in two, the DETECTORs are separate blocks
+    e = c.detector_error_model().errors()
+    assert e["probs"].tolist() == [0.25] and e["det_idx"].tolist() == [0, 1] and e["obs_idx"].tolist() == []
+
+
+def test_shard_ranges():
+    for total in (0, 1, 63, 64, 1000, 10**7 + 3):
+        for world in (1, 2, 3, 8):
+            spans = [qb.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            for (a, b), (c2, d) in zip(spans, spans[1:]):
+                assert b == c2 and a <= b
+            assert all(lo % 64 == 0 for lo, _ in spans)

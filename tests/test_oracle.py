@@ -1,0 +1,158 @@
+"""CPU tests of the ORACLE (test infrastructure): pinned against the only bit-exact artefact the reference holds for
+this path (the printed [[72,12,6]] circuit of doc/02A), against Random123's Philox known answers, and cross-checked
+internally (forward frame propagation <-> backward DEM analysis; BP/OSD output properties; the reference's own
+window loop, whose outputs are the committed fixtures, against the oracle's C restatement of that loop)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import BP_KW, DECODE_CASES, GOLDEN, case_circuit, circuit_text, decode_case
+from oracle import cref, dem as odem, stimtext
+
+
+def test_doc02A_printout_is_reproduced():
+    """reference doc/02A_custom_circuit_generation.ipynb:82-289 prints stim's canonical form of the [[72,12,6]] custom
+    circuit (15 rounds, p=1e-3); the oracle's parser + canonical printer must give the same 206 lines from the text the
+    reference's own BbCode.build_circuit emitted (tests/golden/circuits/bb72_r15_p1e-3.stim)."""
+    with open(os.path.join(GOLDEN, "ref_doc02A_bb72_r15_printout.txt")) as f:
+        want = [ln.rstrip() for ln in f.read().strip("\n").split("\n")]
+    got = stimtext.canonical_text(circuit_text("bb72_r15_p1e-3")).split("\n")
+    assert len(want) == 206
+    assert got == want
+
+
+def test_canonical_text_is_the_same_circuit():
+    text = circuit_text("bb72_r6_p1e-3")
+    a = stimtext.parse_flat(text)
+    b = stimtext.parse_flat(stimtext.canonical_text(text))
+    assert (a.n_qubits, a.n_meas, a.n_det, a.n_obs) == (b.n_qubits, b.n_meas, b.n_det, b.n_obs)
+    da, db = odem.analyze(a), odem.analyze(b)
+    assert da.dets == db.dets and da.obs == db.obs and da.probs == db.probs
+
+
+def test_survey_sizes():
+    """SURVEY.md appendix C (probe of the reference): gross code, 10 rounds."""
+    fc = stimtext.parse_flat(circuit_text("bb144_r10_p1e-3"))
+    assert (fc.n_qubits, fc.n_meas, fc.n_det, fc.n_obs) == (288, 1728, 864, 12)
+    d = odem.analyze(fc)
+    assert len(d.probs) == 8064 and sum(len(x) for x in d.dets) == 28152
+    assert abs(sum(d.probs) - 14.67) < 0.01
+
+
+@pytest.mark.parametrize("key,ctr,want", [
+    ((0, 0), (0, 0, 0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff, 0xffffffff), (0xffffffff,) * 4, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0xa4093822, 0x299f31d0), (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+])
+def test_philox_known_answers(key, ctr, want):
+    """Random123 kat_vectors, philox4x32 with 10 rounds."""
+    assert tuple(int(x) for x in cref.philox(key[0], key[1], ctr)) == want
+
+
+def test_noise_tables():
+    for p in (1e-4, 1e-3, 1e-2, 0.2):
+        t1, c = cref.noise_tables(p)
+        assert abs(t1 / 2**32 - (1 - (1 - p) ** 64)) < 1e-9
+        assert all(int(c[k]) <= int(c[k + 1]) for k in range(1, 62))
+        # P(N = 1 | N >= 1)
+        want = 64 * p * (1 - p) ** 63 / (1 - (1 - p) ** 64)
+        assert abs(int(c[1]) / 2**64 - want) < 1e-12
+    assert cref.noise_tables(0.0)[0] == 0
+
+
+@pytest.mark.parametrize("name", ["bb72_r6_p1e-3", "bb72_r3_p1e-3_X", "toric3_zxcol_r3_p1e-3", "hgp225_r3_p1e-2"])
+def test_forward_frame_reproduces_every_dem_column(name):
+    """Inject each error's representative fault into the frame simulator: the detectors / observables that fire must be
+    exactly that error's symptom (frame rules and backward analyser are two independent restatements)."""
+    fc = stimtext.parse_flat(circuit_text(name))
+    d = odem.analyze(fc)
+    ops = np.array([r[0] for r in d.rep]); tg = np.array([r[1] for r in d.rep]); cd = np.array([r[2] for r in d.rep])
+    det, obs = cref.inject(fc, ops, tg, cd)
+    for i in range(len(d.probs)):
+        assert np.flatnonzero(det[i]).tolist() == d.dets[i], i
+        assert np.flatnonzero(obs[i]).tolist() == d.obs[i], i
+
+
+def test_sampler_marginals_match_dem():
+    fc = stimtext.parse_flat(circuit_text("bb72_r6_p3e-3"))
+    d = odem.analyze(fc)
+    shots = 64 * 400
+    det, obs = cref.sample(fc, 99, 0, shots)
+    prod = np.ones(fc.n_det)
+    for p, ds in zip(d.probs, d.dets):
+        for x in ds:
+            prod[x] *= 1 - 2 * p
+    want = 0.5 * (1 - prod)
+    got = det.mean(axis=0)
+    sigma = np.sqrt(want * (1 - want) / shots)
+    assert np.all(np.abs(got - want) < 5.5 * sigma + 1e-9)
+    # no-noise circuits fire nothing
+    quiet = stimtext.parse_flat(circuit_text("bb72_r6_p3e-3").replace("(0.0030000000)", "(0)"))
+    det0, obs0 = cref.sample(quiet, 1, 0, 128)
+    assert det0.sum() == 0 and obs0.sum() == 0
+
+
+@pytest.mark.parametrize("case", sorted(f[:-5] for f in os.listdir(os.path.join(GOLDEN, "windows"))))
+def test_oracle_windows_equal_reference_spacetime(case):
+    """oracle/windows.py against the digests of the reference's own spacetime() output (tools/make_golden.py)."""
+    import hashlib
+    import json
+    from oracle import windows as owin
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    with open(os.path.join(GOLDEN, "windows", case + ".json")) as f:
+        g = json.load(f)
+    d = odem.analyze(stimtext.parse_flat(circuit_text(g["circuit"])))
+    wins = owin.plan(d, g["m"], g["W"], g["F"])
+    assert len(wins) == len(g["windows"])
+    for w, e in zip(wins, g["windows"]):
+        H = w["H"]; H.sort_indices()
+        L = w["L"]; L.sort_indices()
+        assert list(H.shape) == e["H_shape"] and sha(H.indptr.astype(np.int64)) == e["H_indptr"] and sha(H.indices.astype(np.int32)) == e["H_indices"]
+        assert list(L.shape) == e["L_shape"] and sha(L.indptr.astype(np.int64)) == e["L_indptr"] and sha(L.indices.astype(np.int32)) == e["L_indices"]
+        assert sha(np.asarray(w["priors"], dtype=np.float64)) == e["priors"]
+        if "U_shape" in e:
+            U = w["U"]; U.sort_indices()
+            assert list(U.shape) == e["U_shape"] and sha(U.indptr.astype(np.int64)) == e["U_indptr"] and sha(U.indices.astype(np.int32)) == e["U_indices"]
+
+
+def test_bp_osd_output_properties():
+    fc = stimtext.parse_flat(circuit_text("bb72_r6_p3e-3"))
+    d = odem.analyze(fc)
+    D, C = fc.n_det, len(d.probs)
+    rows = np.array([x for ds in d.dets for x in ds]); cols = np.array([j for j, ds in enumerate(d.dets) for _ in ds])
+    H = sp.csc_matrix((np.ones(len(rows), dtype=np.uint8), (rows, cols)), shape=(D, C))
+    pri = np.array(d.probs)
+    rng = np.random.default_rng(3)
+    dec64 = cref.BpOsd(H, pri, max_iter=10, bp_method="minimum_sum", schedule="parallel", precision="f64")
+    dec32 = cref.BpOsd(H, pri, max_iter=10, bp_method="minimum_sum", schedule="parallel", precision="f32")
+    n_osd = 0
+    for _ in range(40):
+        e = (rng.random(C) < pri * 1.5).astype(np.uint8)
+        s = (H @ e) % 2
+        e64, l64, it64, c64 = dec64.decode(s)
+        e32, l32, it32, c32 = dec32.decode(s)
+        assert np.array_equal((H @ e64) % 2, s) and np.array_equal((H @ e32) % 2, s)      # BP-converged or OSD: always a solution
+        # fp32 and fp64 follow the same trajectory unless an exactly-tied LLR (common with 9 distinct priors) resolves
+        # differently; when they do, the posteriors agree to fp32 rounding accumulated over the iterations
+        if it64 == it32 and c64 == c32:
+            assert np.max(np.abs(l64 - l32) / np.maximum(1.0, np.abs(l64))) < 1e-3
+        n_osd += dec64.used_osd
+    assert n_osd > 0        # the sample must have exercised OSD
+    # zero syndrome -> zero correction after one iteration
+    e0, _, it0, c0 = dec64.decode(np.zeros(D, dtype=np.uint8))
+    assert e0.sum() == 0 and it0 == 1 and c0
+
+
+@pytest.mark.parametrize("case", DECODE_CASES)
+def test_restated_window_loop_equals_reference_loop(case):
+    """oracle/cref.c qo_sw_decode (the C restatement of sliding_window.py:162-186) against the fixtures, which were
+    produced by the reference's own Python loop."""
+    from oracle import windows as owin
+    g = decode_case(case)
+    wins = owin.plan(odem.analyze(stimtext.parse_flat(circuit_text(case_circuit(case)))), g["m"], g["W"], g["F"])
+    for prec in ("f32", "f64"):
+        pred, stats = cref.sw_decode(wins, g["m"], g["K"], g["det"].astype(np.uint8), max_iter=BP_KW["max_iter"],
+                                     bp_method=BP_KW["bp_method"], schedule=BP_KW["schedule"], precision=prec)
+        assert np.array_equal(pred.astype(np.int64), g["pred_" + prec]), prec
