@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
                 if (last || b.write_llr_always) llr_all[static_cast<size_t>(shot) * b.llr_stride + j] = llr;
             }
             // ---- stop test H e == s
+            __syncthreads();
             const int mismatch = tid < w.rowsW32 ? (cand[tid] != syn[tid]) : 0;
             if (!__syncthreads_or(mismatch)) { conv = true; break; }
         }

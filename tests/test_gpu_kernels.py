@@ -1,0 +1,139 @@
+"""GPU kernel-level parity: single-window BP/OSD against the oracle per shot (hard decisions, iteration counts and
+posteriors), explicit-fault propagation against the DEM, and size-independent properties at the headline size."""
+import numpy as np
+import pytest
+
+from conftest import BP_KW, case_circuit, circuit_meta, circuit_text, decode_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def qb():
+    import quits_b200
+    assert quits_b200._native.device_count() > 0, "no CUDA device"
+    return quits_b200
+
+
+def _oracle_windows(name, m, W, F):
+    from oracle import dem as odem, stimtext, windows as owin
+    return owin.plan(odem.analyze(stimtext.parse_flat(circuit_text(name))), m, W, F)
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("case,window", [("bb72_r6_p3e-3_W5F3", 0), ("bb144_r10_p3e-3_W5F3", 1), ("bb144_r10_p1e-3_W5F3", 3),
+                                         ("hgp225_r3_p1e-2_W3F2", 0), ("toric3_zxcol_r3_p1e-3_W3F2", 1)])
+def test_inner_decoder_matches_oracle_per_shot(qb, case, window, precision):
+    """Seam B3: BpOsdDecoder(pcm, channel_probs=...).decode(s) on the GPU vs the oracle's C BP + OSD-0: error estimate,
+    convergence flag and iteration count bit-exact; posteriors bit-exact in the same precision (so well within the
+    1e-4 the spec asks for)."""
+    from oracle import cref
+    g = decode_case(case)
+    w = _oracle_windows(case_circuit(case), g["m"], g["W"], g["F"])[window]
+    H, pri = w["H"], w["priors"]
+    n = min(g["shots"], 96)
+    syn = g["det"][:n, w["row0"]:w["row0"] + H.shape[0]].astype(np.uint8)
+    dec = qb.BpOsdDecoder(H, channel_probs=pri, max_iter=10, bp_method="minimum_sum", schedule="parallel", osd_method="osd_0",
+                          osd_order=0, precision=precision)
+    ehat, llr, iters, conv = dec.decode_batch(syn)
+    orc = cref.BpOsd(H, pri, max_iter=10, bp_method="minimum_sum", schedule="parallel", precision=precision)
+    n_osd = 0
+    for i in range(n):
+        e, l, it, c = orc.decode(syn[i])
+        assert np.array_equal(ehat[i], e), (i, c, orc.used_osd)
+        assert bool(conv[i]) == c and int(iters[i]) == it
+        assert np.array_equal(llr[i], l), "posterior LLRs differ (max |d| = %g)" % np.max(np.abs(llr[i] - l))
+        if c:
+            assert np.array_equal((H @ ehat[i]) % 2, syn[i])      # (OSD on a rank-deficient last window may face an inconsistent raw syndrome)
+        n_osd += orc.used_osd
+    # single-shot call shape of the reference's plug-in protocol
+    one = dec.decode(syn[0])
+    assert one.shape == (H.shape[1],) and np.array_equal(one, ehat[0]) and dec.converge == bool(conv[0])
+
+
+@pytest.mark.parametrize("name", ["bb72_r6_p1e-3", "bb72_r3_p1e-3_X", "toric3_zxcol_r3_p1e-3", "hgp225_r3_p1e-2", "bb144_r10_p1e-3"])
+def test_every_dem_column_propagates_to_its_symptom(qb, name):
+    """K1 in explicit-fault mode: the representative circuit fault of every DEM error, pushed through the frame kernel,
+    fires exactly that error's detectors and observables (forward propagation on the GPU == backward analysis on the host)."""
+    c = qb.Circuit(circuit_text(name))
+    e = c.detector_error_model().errors()
+    det, obs = c.inject(e["rep_op"], e["rep_tgt"], e["rep_code"])
+    n = len(e["probs"])
+    want_det = np.zeros((n, c.num_detectors), dtype=bool)
+    want_obs = np.zeros((n, c.num_observables), dtype=bool)
+    for i in range(n):
+        want_det[i, e["det_idx"][e["det_ptr"][i]:e["det_ptr"][i + 1]]] = True
+        want_obs[i, e["obs_idx"][e["obs_ptr"][i]:e["obs_ptr"][i + 1]]] = True
+    assert np.array_equal(det, want_det) and np.array_equal(obs, want_obs)
+
+
+def test_frame_propagation_is_linear(qb):
+    """Detector bits are GF(2)-linear in the injected faults: shot(f1 + f2) == shot(f1) ^ shot(f2)."""
+    c = qb.Circuit(circuit_text("bb144_r10_p1e-3"))
+    e = c.detector_error_model().errors()
+    rng = np.random.default_rng(7)
+    n = 300
+    a, b = rng.integers(0, len(e["probs"]), n), rng.integers(0, len(e["probs"]), n)
+    ops = np.concatenate([e["rep_op"][a], e["rep_op"][b], e["rep_op"][a], e["rep_op"][b]])
+    tg = np.concatenate([e["rep_tgt"][a], e["rep_tgt"][b], e["rep_tgt"][a], e["rep_tgt"][b]])
+    cd = np.concatenate([e["rep_code"][a], e["rep_code"][b], e["rep_code"][a], e["rep_code"][b]])
+    shots = np.concatenate([np.arange(n), n + np.arange(n), 2 * n + np.arange(n), 2 * n + np.arange(n)])
+    det, obs = c.inject(ops, tg, cd, shots=shots, n_shots=3 * n)
+    assert np.array_equal(det[2 * n:], det[:n] ^ det[n:2 * n]) and np.array_equal(obs[2 * n:], obs[:n] ^ obs[n:2 * n])
+
+
+def test_full_size_against_live_oracle_and_batching(qb):
+    """Headline workload, 4096 shots: GPU pipeline == oracle pipeline run live (C restatement, fp64), and the result does
+    not depend on the device batch size or on how the shot range is split."""
+    from oracle import cref, stimtext
+    name, W, F, shots, seed = "bb144_r10_p1e-3", 5, 3, 4096, 31337
+    _, hz, lz = circuit_meta(name)
+    c = qb.Circuit(circuit_text(name))
+    det, obs = qb.get_stim_mem_result(c, shots, seed=seed)
+    odet, oobs = cref.sample(stimtext.parse_flat(circuit_text(name)), seed, 0, shots)
+    assert np.array_equal(det, odet.astype(bool)) and np.array_equal(obs, oobs.astype(bool))
+    pred = qb.sliding_window_bposd_circuit_mem(det, c, hz, lz, W, F, **BP_KW)
+    opred, ostats = cref.sw_decode(_oracle_windows(name, hz.shape[0], W, F), hz.shape[0], lz.shape[0], odet, precision="f64",
+                                   max_iter=10, bp_method="minimum_sum", schedule="parallel")
+    assert np.array_equal(pred, opred.astype(np.int64))
+    small = qb.SlidingWindowDecoder(c, hz.shape[0], W, F, capacity=1000, **BP_KW)
+    assert np.array_equal(small.decode(det), pred)
+    assert small.stats.bp_converged == int(ostats[:, 0].sum()) and small.stats.osd_calls == int(ostats[:, 2].sum())
+    assert small.stats.bp_iterations == int(ostats[:, 1].sum())
+    mc = qb.MonteCarlo(c, hz.shape[0], W, F, capacity=1536, **BP_KW)
+    wrong = np.any((obs - pred) % 2, axis=1)
+    c_all, _ = mc.run(shots, seed)
+    c_a, _ = mc.run(1024, seed, 0)
+    c_b, _ = mc.run(shots - 1024, seed, 1024)
+    assert int(c_all[0]) == int(wrong.sum()) and np.array_equal(c_all, c_a + c_b)
+
+
+def test_decoder_edge_cases(qb):
+    name = "toric3_zxcol_r3_p1e-3"
+    _, hz, lz = circuit_meta(name)
+    c = qb.Circuit(circuit_text(name))
+    empty = qb.sliding_window_bposd_circuit_mem(np.zeros((0, c.num_detectors), dtype=bool), c, hz, lz, 3, 2, **BP_KW)
+    assert empty.shape == (0, c.num_observables) and empty.dtype == np.int64
+    zeros = qb.sliding_window_bposd_circuit_mem(np.zeros((5, c.num_detectors), dtype=bool), c, hz, lz, 3, 2, **BP_KW)
+    assert zeros.sum() == 0
+    ints = qb.sliding_window_bposd_circuit_mem(np.zeros((3, c.num_detectors), dtype=np.int64) + 2, c, hz, lz, 3, 2, **BP_KW)   # % 2
+    assert ints.sum() == 0
+    det, obs = qb.get_stim_mem_result(c, 0, seed=1)
+    assert det.shape == (0, c.num_detectors) and obs.shape == (0, c.num_observables)
+    det, obs = qb.get_stim_mem_result(c, 1, seed=1)                              # ragged: a single shot of a 64-shot word
+    assert det.shape == (1, c.num_detectors)
+    with pytest.raises(NotImplementedError):
+        qb.sliding_window_bposd_circuit_mem(det, c, hz, lz, 3, 2)               # reference defaults: product_sum / serial
+    with pytest.raises(NotImplementedError):
+        qb.sliding_window_bposd_circuit_mem(det, c, hz, lz, 3, 2, max_iter=10, osd_order=1, bp_method="minimum_sum",
+                                            schedule="parallel", osd_method="osd_cs")
+    with pytest.raises(ValueError):
+        qb.sliding_window_bposd_circuit_mem(np.zeros((2, 7), dtype=bool), c, hz, lz, 3, 2, **BP_KW)
+
+
+def test_seedless_sampling_is_random(qb):
+    c = qb.Circuit(circuit_text("bb72_r6_p3e-3"))
+    a, _ = qb.get_stim_mem_result(c, 256)
+    b, _ = qb.get_stim_mem_result(c, 256)
+    assert not np.array_equal(a, b)
+    assert 0.01 < a.mean() < 0.3
