@@ -1,5 +1,6 @@
 // quits_b200/csrc/api.cu -- the C ABI (include/quits_b200.h): contexts, device residency, batching, launches.
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -120,7 +121,7 @@ namespace {
 
 struct WinOwned {
     qb::WinDev dev{};
-    DevBuf colE, llr0f, llr0d, lmask, uptr, uidx, cptr, crow;
+    DevBuf colE, llr0f, llr0d, lmask, uptr, uidx, cptr, crow, colrec, ptabf, ptabd, rlen, rsum0f, rsum0d, neg0;
     size_t bp_smem = 0, osd_smem = 0;
     bool vglobal = false;
     int bp_grid = 0;            // persistent grid of the VGLOBAL variant (0: one CTA per shot)
@@ -226,6 +227,73 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, WinOwned& wo) {
     std::vector<uint16_t> uidx(hw.uidx.begin(), hw.uidx.end());
     std::vector<int32_t> cptr(hw.cptr.begin(), hw.cptr.end());
     std::vector<uint16_t> crow(hw.crow.begin(), hw.crow.end());
+    // ---- compact form for the BP kernel's fast path (see bp.cu): columns sorted by weight, one 16-byte record each
+    d.compact = 0;
+    {
+        std::vector<double> ptab;
+        std::vector<int> pidx(static_cast<size_t>(ncols));
+        for (int j = 0; j < ncols; ++j) {
+            size_t k = 0;
+            while (k < ptab.size() && ptab[k] != llr0d[j]) ++k;
+            if (k == ptab.size()) { if (ptab.size() > 4096) break; ptab.push_back(llr0d[j]); }
+            pidx[j] = static_cast<int>(k);
+        }
+        const bool fits = cw <= 6 && static_cast<long long>(rows) * rs < 65535 && ncols < 65535 && ptab.size() <= 4096 && rs <= 255;
+        if (fits) {
+            const uint32_t magic = static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(rs)) + 1u;
+            for (uint32_t a = 0; a < static_cast<uint32_t>(rows) * rs; ++a)
+                if (static_cast<uint32_t>((static_cast<uint64_t>(a) * magic) >> 32) != a / rs) throw std::runtime_error("internal: row magic is not exact");
+            std::vector<int> order(static_cast<size_t>(ncols));
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return (hw.cptr[a + 1] - hw.cptr[a]) > (hw.cptr[b + 1] - hw.cptr[b]); });
+            std::vector<uint32_t> rec(static_cast<size_t>(npad) * 4, 0);
+            for (int r = 0; r < npad; ++r) {
+                uint32_t* o = &rec[static_cast<size_t>(r) * 4];
+                if (r >= ncols) { o[0] = o[1] = o[2] = 0xFFFFFFFFu; o[3] = 0xFFFFu; continue; }
+                const int j = order[r];
+                uint16_t e[6] = {0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF};
+                const int wt = static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]);
+                for (int q = 0; q < wt; ++q) {
+                    const uint32_t ce = colE[static_cast<size_t>(q) * npad + j];
+                    e[q] = static_cast<uint16_t>((ce >> 8) * rs + (ce & 255u));
+                }
+                o[0] = e[0] | (static_cast<uint32_t>(e[1]) << 16);
+                o[1] = e[2] | (static_cast<uint32_t>(e[3]) << 16);
+                o[2] = e[4] | (static_cast<uint32_t>(e[5]) << 16);
+                o[3] = static_cast<uint32_t>(j) | (static_cast<uint32_t>(pidx[j]) << 16) | (static_cast<uint32_t>(wt) << 28);
+            }
+            std::vector<uint8_t> rlen(static_cast<size_t>(rows)), neg0(static_cast<size_t>(rows), 0);
+            std::vector<double> s0d(static_cast<size_t>(rows) * 2, DBL_MAX);
+            std::vector<float> s0f(static_cast<size_t>(rows) * 2, FLT_MAX);
+            for (int r = 0; r < rows; ++r) rlen[r] = static_cast<uint8_t>(fillr[r]);
+            for (int j = 0; j < ncols; ++j)
+                for (int64_t e2 = hw.cptr[j]; e2 < hw.cptr[j + 1]; ++e2) {
+                    const int r = hw.crow[e2];
+                    const double ad = std::fabs(llr0d[j]);
+                    const float af = std::fabs(llr0f[j]);
+                    if (llr0d[j] <= 0.0) neg0[r] ^= 1;
+                    double& m1 = s0d[2 * r]; double& m2 = s0d[2 * r + 1];
+                    m2 = std::min(m2, std::max(m1, ad)); m1 = std::min(m1, ad);
+                    float& f1 = s0f[2 * r]; float& f2 = s0f[2 * r + 1];
+                    f2 = std::min(f2, std::max(f1, af)); f1 = std::min(f1, af);
+                }
+            std::vector<float> ptf(ptab.begin(), ptab.end());
+            upload(wo.colrec, rec, ctx->stream);
+            upload(wo.ptabd, ptab, ctx->stream);
+            upload(wo.ptabf, ptf, ctx->stream);
+            upload(wo.rlen, rlen, ctx->stream);
+            upload(wo.neg0, neg0, ctx->stream);
+            upload(wo.rsum0d, s0d, ctx->stream);
+            upload(wo.rsum0f, s0f, ctx->stream);
+            d.compact = 1;
+            d.n_ptab = static_cast<int>(ptab.size());
+            d.rs_magic = magic;
+            d.colrec = wo.colrec.as<uint4>();
+            d.ptabf = wo.ptabf.as<float>(); d.ptabd = wo.ptabd.as<double>();
+            d.rlen = wo.rlen.as<uint8_t>(); d.neg0 = wo.neg0.as<uint8_t>();
+            d.rsum0f = wo.rsum0f.as<float2>(); d.rsum0d = wo.rsum0d.as<double2>();
+        }
+    }
     upload(wo.colE, colE, ctx->stream);
     upload(wo.llr0f, llr0f, ctx->stream);
     upload(wo.llr0d, llr0d, ctx->stream);

@@ -63,6 +63,74 @@ __host__ __device__ inline size_t bp_layout(const WinDev& w, int rsize, bool vgl
     return o;
 }
 
+// ---- window syndrome: detector bits [row0, row0+rows) of this shot, first rows XOR the carry (sliding_window.py:168-169)
+__device__ __forceinline__ void load_syndrome(const WinDev& w, const BatchDev& b, int shot, int tid, uint32_t* syn, uint32_t* accs,
+                                              uint32_t* car) {
+    const int carryW = (w.carry_rows + 31) / 32;
+    if (tid < w.rowsW32) {
+        const uint32_t* d = b.det32 + static_cast<size_t>(shot) * b.det_stride32;
+        const int bit = w.row0 + 32 * tid;
+        const int wd = bit >> 5, sh = bit & 31;
+        uint32_t v = __ldg(d + wd) >> sh;
+        if (sh) v |= __ldg(d + wd + 1) << (32 - sh);
+        const int left = w.rows - 32 * tid;
+        if (left < 32) v &= (1u << left) - 1u;
+        if (32 * tid < b.in_carry_rows) v ^= b.carry[static_cast<size_t>(shot) * b.carry_stride32 + tid];
+        syn[tid] = v;
+    }
+    if (tid < 2 * w.KW) accs[tid] = 0;
+    if (tid <= carryW) car[tid] = 0;
+}
+
+// ---- after BP: commit acc ^= L e[:ncommit], carry = U e[:ncommit] (sliding_window.py:172-175), or hand the shot to OSD
+template <int NT, bool RECORDS = false>
+__device__ __forceinline__ void finish_shot(const WinDev& w, const BatchDev& b, int shot, int tid, bool conv, int it, uint32_t hmask,
+                                            const uint32_t* syn, uint32_t* accs, uint32_t* car) {
+    const int carryW = (w.carry_rows + 31) / 32;
+    if (conv) {
+        uint32_t hm = hmask;
+        while (hm) {
+            const int kk = __ffs(hm) - 1;
+            hm &= hm - 1;
+            int j = tid + kk * NT;
+            if (RECORDS) j = static_cast<int>(__ldg(&w.colrec[j].w) & 0xFFFFu);      // record -> original column
+            if (b.ehat_out) atomicOr(&b.ehat_out[static_cast<size_t>(shot) * b.ehat_stride32 + (j >> 5)], 1u << (j & 31));
+            if (j < w.ncommit) {
+                for (int wd = 0; wd < w.KW; ++wd) {
+                    const uint64_t lm = __ldg(w.lmask + static_cast<size_t>(j) * w.KW + wd);
+                    if (static_cast<uint32_t>(lm)) atomicXor(&accs[2 * wd], static_cast<uint32_t>(lm));
+                    if (static_cast<uint32_t>(lm >> 32)) atomicXor(&accs[2 * wd + 1], static_cast<uint32_t>(lm >> 32));
+                }
+                if (w.carry_rows) {
+                    for (int q = __ldg(w.uptr + j); q < __ldg(w.uptr + j + 1); ++q) {
+                        const uint32_t r = __ldg(w.uidx + q);
+                        atomicXor(&car[r >> 5], 1u << (r & 31));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < w.KW) {
+            const uint64_t v = (static_cast<uint64_t>(accs[2 * tid + 1]) << 32) | accs[2 * tid];
+            b.acc[static_cast<size_t>(shot) * w.KW + tid] ^= v;
+        }
+        if (tid < carryW) b.carry[static_cast<size_t>(shot) * b.carry_stride32 + tid] = car[tid];
+    } else {
+        // post-carry syndrome for OSD; the posteriors are already in llr_buf
+        if (tid < w.rowsW32) b.syn_buf[static_cast<size_t>(shot) * b.syn_stride32 + tid] = syn[tid];
+        if (tid == 0) {
+            const int slot = atomicAdd(b.fail_count, 1);
+            b.fail_list[slot] = shot;
+        }
+    }
+    if (tid == 0) {
+        if (conv) atomicAdd(&b.stats[0], 1ull);
+        atomicAdd(&b.stats[1], static_cast<unsigned long long>(it));
+        if (b.iters_out) b.iters_out[shot] = it;
+        if (b.conv_out) b.conv_out[shot] = conv ? 1 : 0;
+    }
+}
+
 template <typename R, int CW, int NT, int MINB, bool VGLOBAL>
 __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const BatchDev b, const BpParams p) {
     using RT = Real<R>;
@@ -80,25 +148,11 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
 
     const int tid = threadIdx.x;
     const int rows = w.rows, ncols = w.ncols, RS = w.RS, npad = w.ncols_pad;
-    const int carryW = (w.carry_rows + 31) / 32;
     R* const llr_all = reinterpret_cast<R*>(b.llr_buf);
 
     for (int shot = blockIdx.x; shot < b.n_shots; shot += gridDim.x) {
         __syncthreads();
-        // ---- syndrome of the window: detector bits [row0, row0+rows) of this shot, first rows XOR the carry
-        if (tid < w.rowsW32) {
-            const uint32_t* d = b.det32 + static_cast<size_t>(shot) * b.det_stride32;
-            const int bit = w.row0 + 32 * tid;
-            const int wd = bit >> 5, sh = bit & 31;
-            uint32_t v = __ldg(d + wd) >> sh;
-            if (sh) v |= __ldg(d + wd + 1) << (32 - sh);
-            const int left = rows - 32 * tid;
-            if (left < 32) v &= (1u << left) - 1u;
-            if (32 * tid < b.in_carry_rows) v ^= b.carry[static_cast<size_t>(shot) * b.carry_stride32 + tid];
-            syn[tid] = v;
-        }
-        if (tid < 2 * w.KW) accs[tid] = 0;
-        if (tid <= carryW) car[tid] = 0;
+        load_syndrome(w, b, shot, tid, syn, accs, car);
         for (int i = tid; i < rows * RS; i += NT) V[i] = RT::big();       // padding slots: never the minimum, never negative
         __syncthreads();
         for (int j = tid; j < ncols; j += NT) {
@@ -185,48 +239,184 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
         }
         if (it > p.max_iter) it = p.max_iter;
 
-        if (conv) {
-            // ---- commit: acc ^= L e[:ncommit], carry = U e[:ncommit]   (sliding_window.py:172-175)
-            uint32_t hm = hmask;
-            while (hm) {
-                const int kk = __ffs(hm) - 1;
-                hm &= hm - 1;
-                const int j = tid + kk * NT;
-                if (b.ehat_out) atomicOr(&b.ehat_out[static_cast<size_t>(shot) * b.ehat_stride32 + (j >> 5)], 1u << (j & 31));
-                if (j < w.ncommit) {
-                    for (int wd = 0; wd < w.KW; ++wd) {
-                        const uint64_t lm = __ldg(w.lmask + static_cast<size_t>(j) * w.KW + wd);
-                        if (static_cast<uint32_t>(lm)) atomicXor(&accs[2 * wd], static_cast<uint32_t>(lm));
-                        if (static_cast<uint32_t>(lm >> 32)) atomicXor(&accs[2 * wd + 1], static_cast<uint32_t>(lm >> 32));
+        finish_shot<NT, false>(w, b, shot, tid, conv, it, hmask, syn, accs, car);
+    }
+}
+
+// =====================================================================================================================
+// Compact variant (the one the BB / HGP windows use): same arithmetic, fewer instructions and bytes.
+//   * one 16-byte record per column (6 u16 message addresses + prior index) -> a single LDG.128 per column and sweep;
+//   * the row summary is (min1 with the row's sign parity in its sign bit, min2): the edge that holds the minimum is
+//     recognised by |v| == min1 (if two edges tie, min2 == min1 and either choice gives the same value), so no argmin;
+//   * iteration 1 needs no message array at all: every bit->check message is the column's prior, so the row summaries
+//     are precomputed per window (rsum0) and only the syndrome bit is folded in;
+//   * rows are swept to their true length (rlen), so the padding slots are never initialised or read.
+// =====================================================================================================================
+template <typename R> struct Compact;
+template <> struct Compact<float> {
+    static __device__ __forceinline__ float2 sum0(const WinDev& w, int i) { return __ldg(w.rsum0f + i); }
+    static __device__ __forceinline__ const float* ptab(const WinDev& w) { return w.ptabf; }
+    static __device__ __forceinline__ float signed_by(float m, uint32_t neg) { return __uint_as_float(__float_as_uint(m) | (neg << 31)); }
+    static __device__ __forceinline__ uint32_t sign_of(float m) { return __float_as_uint(m) >> 31; }
+    static __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
+};
+template <> struct Compact<double> {
+    static __device__ __forceinline__ double2 sum0(const WinDev& w, int i) { return __ldg(w.rsum0d + i); }
+    static __device__ __forceinline__ const double* ptab(const WinDev& w) { return w.ptabd; }
+    static __device__ __forceinline__ double signed_by(double m, uint32_t neg) {
+        return __hiloint2double(__double2hiint(m) | static_cast<int>(neg << 31), __double2loint(m));
+    }
+    static __device__ __forceinline__ uint32_t sign_of(double m) { return static_cast<uint32_t>(__double2hiint(m)) >> 31; }
+    static __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double mx(double a, double b) { return fmax(a, b); }
+};
+
+// off: V, rsum, syn, cand, accs, car, ptab
+__host__ __device__ inline size_t bpc_layout(const WinDev& w, int rsize, size_t* off /*[7]*/) {
+    size_t o = 0;
+    off[0] = o; o += align_up(static_cast<size_t>(w.rows) * w.RS * rsize, 16);
+    off[1] = o; o += align_up(static_cast<size_t>(w.rows) * 2 * rsize, 16);
+    off[2] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
+    off[3] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
+    off[4] = o; o += align_up(static_cast<size_t>(w.KW) * 8, 16);
+    off[5] = o; o += align_up(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4, 16);
+    off[6] = o; o += align_up(static_cast<size_t>(w.n_ptab) * rsize, 16);
+    return o;
+}
+
+// one column with at most W edges (lanes whose column is lighter are predicated off edge by edge)
+template <typename R, int W>
+__device__ __forceinline__ R column_update(const uint4 rec, const int wt, const R l0, const R alpha, const bool first, R* V,
+                                           const typename Real<R>::pair* rsum, uint32_t* cand, const uint32_t magic) {
+    using RT = Real<R>;
+    using CT = Compact<R>;
+    const uint32_t e[6] = {rec.x & 0xFFFFu, rec.x >> 16, rec.y & 0xFFFFu, rec.y >> 16, rec.z & 0xFFFFu, rec.z >> 16};
+    R c[W], vn[W];
+    uint32_t row[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        const bool valid = q < wt;
+        const uint32_t a = valid ? e[q] : 0u;
+        row[q] = __umulhi(a, magic);
+        const R vl = V[a];
+        const R v = first ? l0 : vl;
+        const typename RT::pair s = rsum[row[q]];
+        const R m1 = RT::abs(s.x);
+        const R mag = RT::abs(v) == m1 ? s.y : m1;
+        const uint32_t odd = CT::sign_of(s.x) ^ (v <= R(0) ? 1u : 0u);
+        const R cc = RT::mul(mag, odd ? -alpha : alpha);
+        c[q] = valid ? cc : R(0);
+    }
+    R t = l0;
+#pragma unroll
+    for (int q = 0; q < W; ++q) { vn[q] = t; t = RT::add(t, c[q]); }
+    const R llr = t;
+    t = R(0);
+#pragma unroll
+    for (int q = W - 1; q >= 0; --q) { vn[q] = RT::add(vn[q], t); t = RT::add(t, c[q]); }
+#pragma unroll
+    for (int q = 0; q < W; ++q)
+        if (q < wt) V[e[q]] = vn[q];
+    if (llr <= R(0)) {
+#pragma unroll
+        for (int q = 0; q < W; ++q)
+            if (q < wt) atomicXor(&cand[row[q] >> 5], 1u << (row[q] & 31u));
+    }
+    return llr;
+}
+
+template <typename R, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, const BatchDev b, const BpParams p) {
+    using RT = Real<R>;
+    using CT = Compact<R>;
+    using Pair = typename RT::pair;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    size_t off[7];
+    bpc_layout(w, sizeof(R), off);
+    R* V = reinterpret_cast<R*>(smem_raw + off[0]);
+    Pair* rsum = reinterpret_cast<Pair*>(smem_raw + off[1]);
+    uint32_t* syn = reinterpret_cast<uint32_t*>(smem_raw + off[2]);
+    uint32_t* cand = reinterpret_cast<uint32_t*>(smem_raw + off[3]);
+    uint32_t* accs = reinterpret_cast<uint32_t*>(smem_raw + off[4]);
+    uint32_t* car = reinterpret_cast<uint32_t*>(smem_raw + off[5]);
+    R* ptab = reinterpret_cast<R*>(smem_raw + off[6]);
+
+    const int tid = threadIdx.x;
+    const int rows = w.rows, npad = w.ncols_pad, RS = w.RS;
+    const uint32_t magic = w.rs_magic;
+    R* const llr_all = reinterpret_cast<R*>(b.llr_buf);
+    for (int i = tid; i < w.n_ptab; i += NT) ptab[i] = CT::ptab(w)[i];
+
+    for (int shot = blockIdx.x; shot < b.n_shots; shot += gridDim.x) {
+        __syncthreads();
+        load_syndrome(w, b, shot, tid, syn, accs, car);
+        __syncthreads();
+        uint32_t hmask = 0;          // bit k <-> record tid + k*NT (records are the columns sorted by weight)
+        bool conv = false;
+        int it = 1;
+        for (; it <= p.max_iter; ++it) {
+            const R alpha = static_cast<R>(__ldg(p.alpha + it));
+            const bool first = it == 1;
+            // ---- check sweep: one thread per row -> (min1 | parity sign, min2)
+            for (int i = tid; i < rows; i += NT) {
+                uint32_t neg = (syn[i >> 5] >> (i & 31)) & 1u;
+                Pair s;
+                if (first) {
+                    s = CT::sum0(w, i);
+                    neg += __ldg(w.neg0 + i);
+                } else {
+                    const R* vr = V + i * RS;
+                    const int len = __ldg(w.rlen + i);
+                    R m1 = RT::big(), m2 = RT::big();
+#pragma unroll 4
+                    for (int q = 0; q < len; ++q) {
+                        const R v = vr[q];
+                        const R a = RT::abs(v);
+                        neg += v <= R(0) ? 1u : 0u;
+                        m2 = CT::mn(m2, CT::mx(m1, a));
+                        m1 = CT::mn(m1, a);
                     }
-                    if (w.carry_rows) {
-                        for (int q = __ldg(w.uptr + j); q < __ldg(w.uptr + j + 1); ++q) {
-                            const uint32_t r = __ldg(w.uidx + q);
-                            atomicXor(&car[r >> 5], 1u << (r & 31));
-                        }
-                    }
+                    s = RT::mk(m1, m2);
+                }
+                s.x = CT::signed_by(s.x, neg & 1u);
+                rsum[i] = s;
+            }
+            if (tid < w.rowsW32) cand[tid] = 0;
+            __syncthreads();
+            // ---- bit sweep: one thread per column record; the warp runs the code path of its heaviest column
+            hmask = 0;
+            const bool last = it == p.max_iter;
+            int k = 0;
+            for (int r = tid; r < npad; r += NT, ++k) {
+                const uint4 rec = __ldg(w.colrec + r);
+                const int wt = static_cast<int>(rec.w >> 28);
+                const R l0 = ptab[(rec.w >> 16) & 0xFFFu];
+                const int wmax = static_cast<int>(__reduce_max_sync(0xFFFFFFFFu, static_cast<unsigned>(wt)));
+                R llr;
+                switch (wmax) {
+                case 0: llr = l0; break;
+                case 1: llr = column_update<R, 1>(rec, wt, l0, alpha, first, V, rsum, cand, magic); break;
+                case 2: llr = column_update<R, 2>(rec, wt, l0, alpha, first, V, rsum, cand, magic); break;
+                case 3: llr = column_update<R, 3>(rec, wt, l0, alpha, first, V, rsum, cand, magic); break;
+                case 4: llr = column_update<R, 4>(rec, wt, l0, alpha, first, V, rsum, cand, magic); break;
+                case 5: llr = column_update<R, 5>(rec, wt, l0, alpha, first, V, rsum, cand, magic); break;
+                default: llr = column_update<R, 6>(rec, wt, l0, alpha, first, V, rsum, cand, magic); break;
+                }
+                const uint32_t j = rec.w & 0xFFFFu;                    // original column; 0xFFFF marks a padding record
+                if (j != 0xFFFFu) {
+                    if (llr <= R(0)) hmask |= 1u << k;
+                    if (last || b.write_llr_always) llr_all[static_cast<size_t>(shot) * b.llr_stride + j] = llr;
                 }
             }
+            // ---- stop test H e == s
             __syncthreads();
-            if (tid < w.KW) {
-                const uint64_t v = (static_cast<uint64_t>(accs[2 * tid + 1]) << 32) | accs[2 * tid];
-                b.acc[static_cast<size_t>(shot) * w.KW + tid] ^= v;
-            }
-            if (tid < carryW) b.carry[static_cast<size_t>(shot) * b.carry_stride32 + tid] = car[tid];
-        } else {
-            // ---- hand the shot to OSD: post-carry syndrome + posteriors (already in llr_buf)
-            if (tid < w.rowsW32) b.syn_buf[static_cast<size_t>(shot) * b.syn_stride32 + tid] = syn[tid];
-            if (tid == 0) {
-                const int slot = atomicAdd(b.fail_count, 1);
-                b.fail_list[slot] = shot;
-            }
+            const int mismatch = tid < w.rowsW32 ? (cand[tid] != syn[tid]) : 0;
+            if (!__syncthreads_or(mismatch)) { conv = true; break; }
         }
-        if (tid == 0) {
-            if (conv) atomicAdd(&b.stats[0], 1ull);
-            atomicAdd(&b.stats[1], static_cast<unsigned long long>(it));
-            if (b.iters_out) b.iters_out[shot] = it;
-            if (b.conv_out) b.conv_out[shot] = conv ? 1 : 0;
-        }
+        if (it > p.max_iter) it = p.max_iter;
+        // map record bits back to columns for the commit
+        finish_shot<NT, true>(w, b, shot, tid, conv, it, hmask, syn, accs, car);
     }
 }
 
@@ -261,10 +451,23 @@ Variant& variant(int prec, int cw, bool vg) {
     return v;
 }
 
+Variant& compact_variant(int prec) {
+    static Variant table[2] = {};
+    Variant& v = table[prec == 32 ? 0 : 1];
+    if (!v.fn) {
+        if (prec == 32) { v.fn = bp_kernel_compact<float, 256, 4>; v.threads = 256; }
+        else { v.fn = bp_kernel_compact<double, 512, 2>; v.threads = 512; }
+    }
+    return v;
+}
+
+inline bool use_compact(const WinDev& w, bool vglobal) { return w.compact && !vglobal; }
+
 }  // namespace
 
 size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal) {
     size_t off[7];
+    if (use_compact(w, vglobal)) return bpc_layout(w, precision == 32 ? 4 : 8, off);
     return bp_layout(w, precision == 32 ? 4 : 8, vglobal, off);
 }
 
@@ -274,7 +477,7 @@ cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal) {
     if (w.cw > 16) return cudaErrorInvalidValue;
     const size_t smem = bp_smem_bytes(w, precision, vglobal);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    Variant& v = variant(precision, w.cw, vglobal);
+    Variant& v = use_compact(w, vglobal) ? compact_variant(precision) : variant(precision, w.cw, vglobal);
     if (smem <= v.configured) return cudaSuccess;          // the attribute only ever grows (decoders of different sizes coexist)
     cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e == cudaSuccess) v.configured = smem;
@@ -283,7 +486,7 @@ cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal) {
 
 cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, bool vglobal, int grid, cudaStream_t st) {
     if (b.n_shots == 0) return cudaSuccess;
-    Variant& v = variant(precision, w.cw, vglobal);
+    Variant& v = use_compact(w, vglobal) ? compact_variant(precision) : variant(precision, w.cw, vglobal);
     const size_t smem = bp_smem_bytes(w, precision, vglobal);
     v.fn<<<grid, v.threads, smem, st>>>(w, b, p);
     return cudaGetLastError();

@@ -60,6 +60,18 @@ struct WinDev {
     const uint16_t* uidx;
     const int32_t* cptr;      // [ncols+1] plain CSC of the window (OSD gather)
     const uint16_t* crow;
+    // compact form (cw <= 6, rows*RS < 65535, <= 1024 distinct priors): one 16-byte record per column
+    //   rec = 6 x u16 message address (row*RS + slot, 0xFFFF = none), u16 prior index, u16 unused
+    int compact;
+    int n_ptab;
+    uint32_t rs_magic;        // row = __umulhi(addr, rs_magic)  (= addr / RS exactly for addr < 65536)
+    const uint4* colrec;      // [ncols_pad]
+    const float* ptabf;       // [n_ptab] distinct prior LLRs
+    const double* ptabd;
+    const uint8_t* rlen;      // [rows] row weights
+    const float2* rsum0f;     // [rows] iteration-1 row summaries (min1, min2 of the prior LLRs along the row)
+    const double2* rsum0d;
+    const uint8_t* neg0;      // [rows] parity of #{prior LLR <= 0} along the row
 };
 
 struct BatchDev {
@@ -92,6 +104,7 @@ struct BpParams {
 };
 
 // precision: 32 or 64 (message / posterior type).  vglobal: messages in a global scratch slab instead of shared memory.
+constexpr uint32_t kNoAddr = 0xFFFFu;
 size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal);
 int bp_threads(int precision);
 cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal);
