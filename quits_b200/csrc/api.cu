@@ -184,6 +184,30 @@ qb::FrameArgs frame_args(qb_circuit* c, uint64_t seed) {
 constexpr uint64_t kSampleChunk = 1ull << 18;      // shots per sampler launch when results go back to the host
 
 // ------------------------------------------------------------------------------------------------ decoder set-up
+// GF(2) rank of a window matrix (bit-packed rows, plain elimination); once per window at set-up
+int gf2_rank(const qb::Window& hw) {
+    const int rows = hw.rows, ncols = hw.ncols, nw = (ncols + 63) / 64;
+    std::vector<uint64_t> a(static_cast<size_t>(rows) * nw, 0);
+    for (int j = 0; j < ncols; ++j)
+        for (int64_t e = hw.cptr[j]; e < hw.cptr[j + 1]; ++e) a[static_cast<size_t>(hw.crow[e]) * nw + (j >> 6)] |= 1ull << (j & 63);
+    int rank = 0;
+    for (int j = 0; j < ncols && rank < rows; ++j) {
+        const int wd = j >> 6;
+        const uint64_t bit = 1ull << (j & 63);
+        int piv = -1;
+        for (int i = rank; i < rows; ++i)
+            if (a[static_cast<size_t>(i) * nw + wd] & bit) { piv = i; break; }
+        if (piv < 0) continue;
+        if (piv != rank)
+            for (int q = 0; q < nw; ++q) std::swap(a[static_cast<size_t>(piv) * nw + q], a[static_cast<size_t>(rank) * nw + q]);
+        for (int i = rank + 1; i < rows; ++i)
+            if (a[static_cast<size_t>(i) * nw + wd] & bit)
+                for (int q = wd; q < nw; ++q) a[static_cast<size_t>(i) * nw + q] ^= a[static_cast<size_t>(rank) * nw + q];
+        ++rank;
+    }
+    return rank;
+}
+
 void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, WinOwned& wo) {
     qb::WinDev& d = wo.dev;
     const int rows = hw.rows, ncols = hw.ncols;
@@ -306,6 +330,7 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, WinOwned& wo) {
     d.rows = rows; d.ncols = ncols; d.ncols_pad = npad; d.RS = rs; d.cw = cw_alloc; d.ncommit = hw.ncommit;
     d.row0 = hw.row0; d.carry_rows = hw.urows; d.KW = KW;
     d.rowsW32 = (rows + 31) / 32; d.nW32 = (ncols + 31) / 32;
+    d.full_row_rank = gf2_rank(hw) == rows ? 1 : 0;
     d.colE = wo.colE.as<uint32_t>(); d.llr0f = wo.llr0f.as<float>(); d.llr0d = wo.llr0d.as<double>(); d.lmask = wo.lmask.as<uint64_t>();
     d.uptr = wo.uptr.as<int32_t>(); d.uidx = wo.uidx.as<uint16_t>(); d.cptr = wo.cptr.as<int32_t>(); d.crow = wo.crow.as<uint16_t>();
 }
@@ -344,7 +369,7 @@ void finish_decoder(qb_sw* sw) {
             CK(qb::osd_configure(w->dev, prec));
             w->osd_smem = qb::osd_smem_bytes(w->dev, prec);
             int per_sm = static_cast<int>((227 * 1024) / (w->osd_smem + 1024));
-            per_sm = std::max(1, std::min(per_sm, 4));
+            per_sm = std::max(1, std::min(per_sm, 5));
             w->osd_grid = 148 * per_sm;
         }
     }

@@ -60,12 +60,26 @@ __host__ __device__ inline OsdLayout osd_layout(const WinDev& w, int MW, int CPT
     return L;
 }
 
-template <int MW>
-__device__ __forceinline__ uint32_t pick_word(const uint32_t (&c)[MW], int wsel) {
-    uint32_t r = 0;
-#pragma unroll
-    for (int i = 0; i < MW; ++i) r = (i == wsel) ? c[i] : r;
-    return r;
+// Word `wsel` of every register-resident column of this thread (T columns, then the candidate), and the pivot row
+// leaves the free mask.  wsel is uniform over the CTA, so the switch is a non-divergent jump, not a select chain.
+template <int MW, int CPT>
+__device__ __forceinline__ void pivot_words(const uint32_t (&T)[CPT][MW], const uint32_t (&cand)[MW], uint32_t (&freem)[MW],
+                                            const int wsel, const uint32_t bsel, uint32_t (&out)[CPT + 1]) {
+#define QB_CASE(I)                                                   \
+    case I:                                                          \
+        if constexpr (I < MW) {                                      \
+            _Pragma("unroll") for (int c = 0; c < CPT; ++c) out[c] = T[c][I]; \
+            out[CPT] = cand[I];                                      \
+            freem[I] &= ~bsel;                                       \
+        }                                                            \
+        break;
+    switch (wsel) {
+        QB_CASE(0) QB_CASE(1) QB_CASE(2) QB_CASE(3) QB_CASE(4) QB_CASE(5) QB_CASE(6) QB_CASE(7)
+        QB_CASE(8) QB_CASE(9) QB_CASE(10) QB_CASE(11) QB_CASE(12) QB_CASE(13) QB_CASE(14) QB_CASE(15)
+        QB_CASE(16) QB_CASE(17) QB_CASE(18) QB_CASE(19) QB_CASE(20) QB_CASE(21) QB_CASE(22) QB_CASE(23)
+    default: break;
+    }
+#undef QB_CASE
 }
 
 // order-preserving unsigned image of a posterior (-0.0 is first folded into +0.0)
@@ -78,7 +92,7 @@ __device__ __forceinline__ uint64_t order_key(double f) {
     return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
-template <typename R, int MW, int CPT>
+template <typename R, int MW, int CPT, bool EXACT>
 __global__ void __launch_bounds__(kOsdThreads) osd_kernel(const WinDev w, const BatchDev b) {
     using KeyT = typename std::conditional<sizeof(R) == 4, uint32_t, uint64_t>::type;
     constexpr int kPasses = static_cast<int>(sizeof(KeyT));
@@ -251,47 +265,68 @@ __global__ void __launch_bounds__(kOsdThreads) osd_kernel(const WinDev w, const 
             }
             if (pt < 0) { refill = true; continue; }
             if (tid == pt) {
-#pragma unroll
-                for (int i = 0; i < MW; ++i) rbuf[par * MW + i] = cand[i];
                 pivcol[rank] = static_cast<uint16_t>(candcol);
+                if (EXACT) {
+#pragma unroll
+                    for (int i = 0; i < MW; ++i) rbuf[par * MW + i] = cand[i];
+                } else {
+                    // full-row-rank window: the solution does not depend on which free row becomes the pivot row, so take
+                    // the first one and publish the update vector with that bit already cleared
+                    int pr = -1;
+#pragma unroll
+                    for (int i = 0; i < MW; ++i) {
+                        const uint32_t x = cand[i] & freem[i];
+                        if (pr < 0 && x) pr = 32 * i + __ffs(x) - 1;
+                    }
+#pragma unroll
+                    for (int i = 0; i < MW; ++i) rbuf[par * MW + i] = cand[i] & ~((i == (pr >> 5)) ? (1u << (pr & 31)) : 0u);
+                    pivrow[rank] = static_cast<uint16_t>(pr);
+                }
             }
             __syncthreads();
-            // -- C: pivot row = first free row in position order with a 1; rank-1 update of every column
+            // -- C: pivot row, then the rank-1 update of every register-resident column
             const uint32_t* rb = rbuf + par * MW;
-            int p = -1;
-            for (int c0 = rank; c0 < m; c0 += 32) {
-                const int pos = c0 + lane;
-                uint32_t bit = 0;
-                if (pos < m) {
-                    const int row = seq[pos];
-                    bit = (rb[row >> 5] >> (row & 31)) & 1u;
+            int prow;
+            if (EXACT) {
+                // rank-deficient window (inconsistent syndromes are possible): follow the oracle's row order exactly,
+                // i.e. the first free row in position order that has a 1
+                int p = -1;
+                for (int c0 = rank; c0 < m; c0 += 32) {
+                    const int pos = c0 + lane;
+                    uint32_t bit = 0;
+                    if (pos < m) {
+                        const int row = seq[pos];
+                        bit = (rb[row >> 5] >> (row & 31)) & 1u;
+                    }
+                    const uint32_t bb = __ballot_sync(0xFFFFFFFFu, bit);
+                    if (bb) { p = c0 + __ffs(bb) - 1; break; }
                 }
-                const uint32_t bb = __ballot_sync(0xFFFFFFFFu, bit);
-                if (bb) { p = c0 + __ffs(bb) - 1; break; }
+                prow = seq[p];
+                if (tid == 0) {
+                    pivrow[rank] = static_cast<uint16_t>(prow);
+                    pend_p = p;
+                    pend_rank = rank;
+                }
+            } else {
+                prow = pivrow[rank];
             }
-            const int prow = seq[p];
             const int wsel = prow >> 5;
             const uint32_t bsel = 1u << (prow & 31);
             uint32_t r[MW];
 #pragma unroll
-            for (int i = 0; i < MW; ++i) r[i] = rb[i] & ~((i == wsel) ? bsel : 0u);
+            for (int i = 0; i < MW; ++i) r[i] = EXACT ? (rb[i] & ~((i == wsel) ? bsel : 0u)) : rb[i];
+            uint32_t pw[CPT + 1];
+            pivot_words<MW, CPT>(T, cand, freem, wsel, bsel, pw);
 #pragma unroll
             for (int c = 0; c < CPT; ++c) {
-                if (pick_word<MW>(T[c], wsel) & bsel) {
+                if (pw[c] & bsel) {
 #pragma unroll
                     for (int i = 0; i < MW; ++i) T[c][i] ^= r[i];
                 }
             }
-            if (pick_word<MW>(cand, wsel) & bsel) {
+            if (pw[CPT] & bsel) {
 #pragma unroll
                 for (int i = 0; i < MW; ++i) cand[i] ^= r[i];
-            }
-#pragma unroll
-            for (int i = 0; i < MW; ++i) freem[i] &= ~((i == wsel) ? bsel : 0u);
-            if (tid == 0) {
-                pivrow[rank] = static_cast<uint16_t>(prow);
-                pend_p = p;
-                pend_rank = rank;
             }
             ++rank;
             par ^= 1;
@@ -355,17 +390,17 @@ inline bool osd_shape(const WinDev& w, OsdShape& s) {
     return false;
 }
 
-template <typename R, typename F>
+template <typename R, bool EXACT, typename F>
 inline cudaError_t osd_dispatch_r(const OsdShape& s, F&& f) {
     switch (s.MW * 10 + s.CPT) {
-    case 42: return f(osd_kernel<R, 4, 2>);
-    case 62: return f(osd_kernel<R, 6, 2>);
-    case 82: return f(osd_kernel<R, 8, 2>);
-    case 83: return f(osd_kernel<R, 8, 3>);
-    case 123: return f(osd_kernel<R, 12, 3>);
-    case 124: return f(osd_kernel<R, 12, 4>);
-    case 175: return f(osd_kernel<R, 17, 5>);
-    case 236: return f(osd_kernel<R, 23, 6>);
+    case 42: return f(osd_kernel<R, 4, 2, EXACT>);
+    case 62: return f(osd_kernel<R, 6, 2, EXACT>);
+    case 82: return f(osd_kernel<R, 8, 2, EXACT>);
+    case 83: return f(osd_kernel<R, 8, 3, EXACT>);
+    case 123: return f(osd_kernel<R, 12, 3, EXACT>);
+    case 124: return f(osd_kernel<R, 12, 4, EXACT>);
+    case 175: return f(osd_kernel<R, 17, 5, EXACT>);
+    case 236: return f(osd_kernel<R, 23, 6, EXACT>);
     }
     return cudaErrorInvalidValue;
 }
@@ -374,7 +409,8 @@ template <typename F>
 inline cudaError_t osd_dispatch(const WinDev& w, int precision, F&& f) {
     OsdShape s;
     if (!osd_shape(w, s)) return cudaErrorInvalidValue;
-    return precision == 32 ? osd_dispatch_r<float>(s, f) : osd_dispatch_r<double>(s, f);
+    if (w.full_row_rank) return precision == 32 ? osd_dispatch_r<float, false>(s, f) : osd_dispatch_r<double, false>(s, f);
+    return precision == 32 ? osd_dispatch_r<float, true>(s, f) : osd_dispatch_r<double, true>(s, f);
 }
 
 }  // namespace
@@ -392,11 +428,11 @@ bool osd_supported(const WinDev& w, int precision) {
 
 cudaError_t osd_configure(const WinDev& w, int precision) {
     // several windows may share one instantiation: the attribute only ever grows
-    static size_t configured[2][256] = {};
+    static size_t configured[4][256] = {};
     const size_t smem = osd_smem_bytes(w, precision);
     OsdShape s;
     if (!osd_shape(w, s)) return cudaErrorInvalidValue;
-    size_t& have = configured[precision == 32 ? 0 : 1][(s.MW * 10 + s.CPT) & 255];
+    size_t& have = configured[(precision == 32 ? 0 : 1) + (w.full_row_rank ? 2 : 0)][(s.MW * 10 + s.CPT) & 255];
     if (smem <= have) return cudaSuccess;
     cudaError_t e = osd_dispatch(w, precision, [&](auto kern) {
         return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));

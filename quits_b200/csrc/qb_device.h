@@ -52,6 +52,7 @@ struct WinDev {
     int carry_rows;           // rows of the carry this window emits (0 for the last window)
     int KW;                   // u64 words per observable mask
     int rowsW32, nW32;
+    int full_row_rank;        // GF(2) rank of the window matrix == rows (then OSD's answer does not depend on pivot-row order)
     const uint32_t* colE;     // [cw][ncols_pad]  (row << 8 | slot), kNoEdge when the column is shorter
     const float* llr0f;       // [ncols_pad]  prior LLRs log((1-p)/p), fp32 image (precision 32)
     const double* llr0d;      // [ncols_pad]  ... fp64 (precision 64)
