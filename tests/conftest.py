@@ -11,6 +11,23 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def _ensure_built():
+    """Compile libquits_b200.so (nvcc, sm_100a) when it is absent or stale; building is not a fallback, importing
+    quits_b200 without the library still fails loudly."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_qb_build", os.path.join(ROOT, "quits_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    try:
+        mod.build()
+    except RuntimeError:
+        if not os.path.exists(mod.SO):
+            raise
+
+
+_ensure_built()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
