@@ -17,10 +17,10 @@ flooding, OSD-0) and is pinned three ways:
 
 * the only bit-exact artefact the reference holds for this path, the printed
   [[72,12,6]] circuit of ``doc/02A_custom_circuit_generation.ipynb:82-289``, is
-  reproduced through the oracle's parser/printer (tests/test_oracle_text.py);
+  reproduced through the oracle's parser/printer (tests/test_oracle.py::test_doc02A_printout_is_reproduced);
 * forward frame propagation of every detector-error-model column's
   representative fault reproduces that column (frame sim <-> DEM analyser
-  self-consistency, tests/test_oracle_dem.py);
+  self-consistency, tests/test_oracle.py::test_forward_frame_reproduces_every_dem_column);
 * the *unmodified* reference window glue (``decoder/base.py:74-190``,
   ``decoder/sliding_window.py:104-188``) is run in the build container on top
   of the oracle through stim/ldpc-shaped shims (``oracle/shims.py``); its
