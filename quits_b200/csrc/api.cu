@@ -262,29 +262,38 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, WinOwned& wo) {
             if (k == ptab.size()) { if (ptab.size() > 4096) break; ptab.push_back(llr0d[j]); }
             pidx[j] = static_cast<int>(k);
         }
-        const bool fits = cw <= 6 && static_cast<long long>(rows) * rs < 65535 && ncols < 65535 && ptab.size() <= 4096 && rs <= 255;
+        const bool fits = cw <= 6 && static_cast<long long>(rows) * rs + 1 < 65535 && ncols < 65535 && ptab.size() <= 4096 && rs <= 255;
         if (fits) {
             const uint32_t magic = static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(rs)) + 1u;
-            for (uint32_t a = 0; a < static_cast<uint32_t>(rows) * rs; ++a)
+            for (uint32_t a = 0; a <= static_cast<uint32_t>(rows) * rs; ++a)
                 if (static_cast<uint32_t>((static_cast<uint64_t>(a) * magic) >> 32) != a / rs) throw std::runtime_error("internal: row magic is not exact");
             std::vector<int> order(static_cast<size_t>(ncols));
             std::iota(order.begin(), order.end(), 0);
             std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return (hw.cptr[a + 1] - hw.cptr[a]) > (hw.cptr[b + 1] - hw.cptr[b]); });
-            std::vector<uint32_t> rec(static_cast<size_t>(npad) * 4, 0);
-            for (int r = 0; r < npad; ++r) {
+            // records: 6 x u16 message address (dummy edges point at the dummy row's slot rows*rs), then
+            // w = original column | prior index << 16 | weight of the heaviest column of the record's warp << 28
+            const uint32_t dummy = static_cast<uint32_t>(rows) * static_cast<uint32_t>(rs);
+            const int nrec = std::max(npad, 1024);           // the kernel prefetches record `tid` before it tests tid < npad
+            std::vector<uint32_t> rec(static_cast<size_t>(nrec) * 4, 0);
+            for (int r = 0; r < nrec; ++r) {
                 uint32_t* o = &rec[static_cast<size_t>(r) * 4];
-                if (r >= ncols) { o[0] = o[1] = o[2] = 0xFFFFFFFFu; o[3] = 0xFFFFu; continue; }
-                const int j = order[r];
-                uint16_t e[6] = {0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF};
-                const int wt = static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]);
-                for (int q = 0; q < wt; ++q) {
-                    const uint32_t ce = colE[static_cast<size_t>(q) * npad + j];
-                    e[q] = static_cast<uint16_t>((ce >> 8) * rs + (ce & 255u));
+                uint32_t e[6] = {dummy, dummy, dummy, dummy, dummy, dummy};
+                uint32_t word3 = 0xFFFFu;                     // padding record: no column
+                if (r < ncols) {
+                    const int j = order[r];
+                    const int wt = static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]);
+                    for (int q = 0; q < wt; ++q) {
+                        const uint32_t ce = colE[static_cast<size_t>(q) * npad + j];
+                        e[q] = (ce >> 8) * static_cast<uint32_t>(rs) + (ce & 255u);
+                    }
+                    word3 = static_cast<uint32_t>(j) | (static_cast<uint32_t>(pidx[j]) << 16);
                 }
-                o[0] = e[0] | (static_cast<uint32_t>(e[1]) << 16);
-                o[1] = e[2] | (static_cast<uint32_t>(e[3]) << 16);
-                o[2] = e[4] | (static_cast<uint32_t>(e[5]) << 16);
-                o[3] = static_cast<uint32_t>(j) | (static_cast<uint32_t>(pidx[j]) << 16) | (static_cast<uint32_t>(wt) << 28);
+                const int lead = r / 32 * 32;                 // columns are sorted by weight: the warp's first lane is its heaviest
+                const int wmax = lead < ncols ? static_cast<int>(hw.cptr[order[lead] + 1] - hw.cptr[order[lead]]) : 0;
+                o[0] = e[0] | (e[1] << 16);
+                o[1] = e[2] | (e[3] << 16);
+                o[2] = e[4] | (e[5] << 16);
+                o[3] = word3 | (static_cast<uint32_t>(wmax) << 28);
             }
             std::vector<uint8_t> rlen(static_cast<size_t>(rows)), neg0(static_cast<size_t>(rows), 0);
             std::vector<double> s0d(static_cast<size_t>(rows) * 2, DBL_MAX);

@@ -245,21 +245,30 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
 
 // =====================================================================================================================
 // Compact variant (the one the BB / HGP windows use): same arithmetic, fewer instructions and bytes.
-//   * one 16-byte record per column (6 u16 message addresses + prior index) -> a single LDG.128 per column and sweep;
+//   * one 16-byte record per column (6 u16 message addresses + prior index) -> a single LDG.128 per column and sweep,
+//     prefetched one record ahead;
+//   * records are sorted by column weight and every warp runs the code path of its heaviest column (the weight field of
+//     a record holds the warp's maximum).  Lighter columns are padded with DUMMY edges that point at a dummy row
+//     (index `rows`) whose summary is (0, 0): their check->bit message is +-0, and x + (+-0) == x exactly, so the padding
+//     needs no predication at all;
 //   * the row summary is (min1 with the row's sign parity in its sign bit, min2): the edge that holds the minimum is
 //     recognised by |v| == min1 (if two edges tie, min2 == min1 and either choice gives the same value), so no argmin;
+//     the sign of a message is applied by XOR on the sign bit (mul(m, -a) == -mul(m, a) exactly in round-to-nearest);
 //   * iteration 1 needs no message array at all: every bit->check message is the column's prior, so the row summaries
 //     are precomputed per window (rsum0) and only the syndrome bit is folded in;
-//   * rows are swept to their true length (rlen), so the padding slots are never initialised or read.
+//   * rows are swept to their true length (rlen) with two independent (min1, min2) chains and explicit compare/select
+//     (fmin/fmax on doubles expand to NaN-aware sequences several times longer).
 // =====================================================================================================================
 template <typename R> struct Compact;
 template <> struct Compact<float> {
     static __device__ __forceinline__ float2 sum0(const WinDev& w, int i) { return __ldg(w.rsum0f + i); }
     static __device__ __forceinline__ const float* ptab(const WinDev& w) { return w.ptabf; }
     static __device__ __forceinline__ float signed_by(float m, uint32_t neg) { return __uint_as_float(__float_as_uint(m) | (neg << 31)); }
-    static __device__ __forceinline__ uint32_t sign_of(float m) { return __float_as_uint(m) >> 31; }
-    static __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
-    static __device__ __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ float mag(float m) { return __uint_as_float(__float_as_uint(m) & 0x7FFFFFFFu); }
+    // x with its sign flipped when (sign bit of s) xor neg
+    static __device__ __forceinline__ float flip(float x, float s, bool neg) {
+        return __uint_as_float(__float_as_uint(x) ^ ((__float_as_uint(s) & 0x80000000u) ^ (neg ? 0x80000000u : 0u)));
+    }
 };
 template <> struct Compact<double> {
     static __device__ __forceinline__ double2 sum0(const WinDev& w, int i) { return __ldg(w.rsum0d + i); }
@@ -267,16 +276,18 @@ template <> struct Compact<double> {
     static __device__ __forceinline__ double signed_by(double m, uint32_t neg) {
         return __hiloint2double(__double2hiint(m) | static_cast<int>(neg << 31), __double2loint(m));
     }
-    static __device__ __forceinline__ uint32_t sign_of(double m) { return static_cast<uint32_t>(__double2hiint(m)) >> 31; }
-    static __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
-    static __device__ __forceinline__ double mx(double a, double b) { return fmax(a, b); }
+    static __device__ __forceinline__ double mag(double m) { return __hiloint2double(__double2hiint(m) & 0x7FFFFFFF, __double2loint(m)); }
+    static __device__ __forceinline__ double flip(double x, double s, bool neg) {
+        const uint32_t f = (static_cast<uint32_t>(__double2hiint(s)) & 0x80000000u) ^ (neg ? 0x80000000u : 0u);
+        return __hiloint2double(static_cast<int>(static_cast<uint32_t>(__double2hiint(x)) ^ f), __double2loint(x));
+    }
 };
 
-// off: V, rsum, syn, cand, accs, car, ptab
+// off: V, rsum, syn, cand, accs, car, ptab.  V and rsum carry one extra entry for the dummy row.
 __host__ __device__ inline size_t bpc_layout(const WinDev& w, int rsize, size_t* off /*[7]*/) {
     size_t o = 0;
-    off[0] = o; o += align_up(static_cast<size_t>(w.rows) * w.RS * rsize, 16);
-    off[1] = o; o += align_up(static_cast<size_t>(w.rows) * 2 * rsize, 16);
+    off[0] = o; o += align_up((static_cast<size_t>(w.rows) * w.RS + 1) * rsize, 16);
+    off[1] = o; o += align_up(static_cast<size_t>(w.rows + 1) * 2 * rsize, 16);
     off[2] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
     off[3] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
     off[4] = o; o += align_up(static_cast<size_t>(w.KW) * 8, 16);
@@ -285,28 +296,31 @@ __host__ __device__ inline size_t bpc_layout(const WinDev& w, int rsize, size_t*
     return o;
 }
 
-// one column with at most W edges (lanes whose column is lighter are predicated off edge by edge)
-template <typename R, int W>
-__device__ __forceinline__ R column_update(const uint4 rec, const int wt, const R l0, const R alpha, const bool first, R* V,
-                                           const typename Real<R>::pair* rsum, uint32_t* cand, const uint32_t magic) {
+// running two smallest magnitudes of a row
+template <typename R>
+__device__ __forceinline__ void min2_step(const R v, R& m1, R& m2, uint32_t& neg) {
+    const R a = Compact<R>::mag(v);
+    neg += v <= R(0) ? 1u : 0u;
+    const bool p = a < m1, q = a < m2;
+    m2 = p ? m1 : (q ? a : m2);
+    m1 = p ? a : m1;
+}
+
+// one column of a warp whose heaviest column has W edges (dummy edges included, no predication)
+template <typename R, int W, bool FIRST>
+__device__ __forceinline__ R column_update(const uint4 rec, const R l0, const R alpha, R* V, const typename Real<R>::pair* rsum,
+                                           uint32_t* cand, const uint32_t magic, const uint32_t rows) {
     using RT = Real<R>;
     using CT = Compact<R>;
     const uint32_t e[6] = {rec.x & 0xFFFFu, rec.x >> 16, rec.y & 0xFFFFu, rec.y >> 16, rec.z & 0xFFFFu, rec.z >> 16};
     R c[W], vn[W];
-    uint32_t row[W];
 #pragma unroll
     for (int q = 0; q < W; ++q) {
-        const bool valid = q < wt;
-        const uint32_t a = valid ? e[q] : 0u;
-        row[q] = __umulhi(a, magic);
-        const R vl = V[a];
-        const R v = first ? l0 : vl;
-        const typename RT::pair s = rsum[row[q]];
-        const R m1 = RT::abs(s.x);
-        const R mag = RT::abs(v) == m1 ? s.y : m1;
-        const uint32_t odd = CT::sign_of(s.x) ^ (v <= R(0) ? 1u : 0u);
-        const R cc = RT::mul(mag, odd ? -alpha : alpha);
-        c[q] = valid ? cc : R(0);
+        const R v = FIRST ? l0 : V[e[q]];
+        const typename RT::pair s = rsum[__umulhi(e[q], magic)];
+        const R m1 = CT::mag(s.x);
+        const R m = CT::mag(v) == m1 ? s.y : m1;
+        c[q] = CT::flip(RT::mul(m, alpha), s.x, v <= R(0));
     }
     R t = l0;
 #pragma unroll
@@ -316,14 +330,29 @@ __device__ __forceinline__ R column_update(const uint4 rec, const int wt, const 
 #pragma unroll
     for (int q = W - 1; q >= 0; --q) { vn[q] = RT::add(vn[q], t); t = RT::add(t, c[q]); }
 #pragma unroll
-    for (int q = 0; q < W; ++q)
-        if (q < wt) V[e[q]] = vn[q];
+    for (int q = 0; q < W; ++q) V[e[q]] = vn[q];
     if (llr <= R(0)) {
 #pragma unroll
-        for (int q = 0; q < W; ++q)
-            if (q < wt) atomicXor(&cand[row[q] >> 5], 1u << (row[q] & 31u));
+        for (int q = 0; q < W; ++q) {
+            const uint32_t row = __umulhi(e[q], magic);
+            if (row < rows) atomicXor(&cand[row >> 5], 1u << (row & 31u));
+        }
     }
     return llr;
+}
+
+template <typename R, bool FIRST>
+__device__ __forceinline__ R column_dispatch(const uint4 rec, const R l0, const R alpha, R* V, const typename Real<R>::pair* rsum,
+                                             uint32_t* cand, const uint32_t magic, const uint32_t rows) {
+    switch (rec.w >> 28) {                  // warp-uniform: the weight of the warp's heaviest column
+    case 0: return l0;
+    case 1: return column_update<R, 1, FIRST>(rec, l0, alpha, V, rsum, cand, magic, rows);
+    case 2: return column_update<R, 2, FIRST>(rec, l0, alpha, V, rsum, cand, magic, rows);
+    case 3: return column_update<R, 3, FIRST>(rec, l0, alpha, V, rsum, cand, magic, rows);
+    case 4: return column_update<R, 4, FIRST>(rec, l0, alpha, V, rsum, cand, magic, rows);
+    case 5: return column_update<R, 5, FIRST>(rec, l0, alpha, V, rsum, cand, magic, rows);
+    default: return column_update<R, 6, FIRST>(rec, l0, alpha, V, rsum, cand, magic, rows);
+    }
 }
 
 template <typename R, int NT, int MINB>
@@ -347,6 +376,10 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
     const uint32_t magic = w.rs_magic;
     R* const llr_all = reinterpret_cast<R*>(b.llr_buf);
     for (int i = tid; i < w.n_ptab; i += NT) ptab[i] = CT::ptab(w)[i];
+    if (tid == 0) {                          // the dummy row: summary (0, 0), one message slot
+        rsum[rows] = RT::mk(R(0), R(0));
+        V[rows * RS] = R(0);
+    }
 
     for (int shot = blockIdx.x; shot < b.n_shots; shot += gridDim.x) {
         __syncthreads();
@@ -358,6 +391,7 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
         for (; it <= p.max_iter; ++it) {
             const R alpha = static_cast<R>(__ldg(p.alpha + it));
             const bool first = it == 1;
+            uint4 rec = __ldg(w.colrec + tid);               // NT <= npad is not guaranteed: colrec is padded to a multiple of NT
             // ---- check sweep: one thread per row -> (min1 | parity sign, min2)
             for (int i = tid; i < rows; i += NT) {
                 uint32_t neg = (syn[i >> 5] >> (i & 31)) & 1u;
@@ -368,42 +402,35 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
                 } else {
                     const R* vr = V + i * RS;
                     const int len = __ldg(w.rlen + i);
-                    R m1 = RT::big(), m2 = RT::big();
-#pragma unroll 4
-                    for (int q = 0; q < len; ++q) {
-                        const R v = vr[q];
-                        const R a = RT::abs(v);
-                        neg += v <= R(0) ? 1u : 0u;
-                        m2 = CT::mn(m2, CT::mx(m1, a));
-                        m1 = CT::mn(m1, a);
+                    R m1a = RT::big(), m2a = RT::big(), m1b = RT::big(), m2b = RT::big();
+                    int q = 0;
+#pragma unroll 2
+                    for (; q + 1 < len; q += 2) {
+                        min2_step<R>(vr[q], m1a, m2a, neg);
+                        min2_step<R>(vr[q + 1], m1b, m2b, neg);
                     }
-                    s = RT::mk(m1, m2);
+                    if (q < len) min2_step<R>(vr[q], m1a, m2a, neg);
+                    const bool lo = m1b < m1a;
+                    const R m1 = lo ? m1b : m1a, mo = lo ? m1a : m1b;       // smaller / larger of the two chain minima
+                    const R m2c = m2b < m2a ? m2b : m2a;
+                    s = RT::mk(m1, m2c < mo ? m2c : mo);
                 }
                 s.x = CT::signed_by(s.x, neg & 1u);
                 rsum[i] = s;
             }
             if (tid < w.rowsW32) cand[tid] = 0;
             __syncthreads();
-            // ---- bit sweep: one thread per column record; the warp runs the code path of its heaviest column
+            // ---- bit sweep: one thread per column record
             hmask = 0;
             const bool last = it == p.max_iter;
             int k = 0;
             for (int r = tid; r < npad; r += NT, ++k) {
-                const uint4 rec = __ldg(w.colrec + r);
-                const int wt = static_cast<int>(rec.w >> 28);
-                const R l0 = ptab[(rec.w >> 16) & 0xFFFu];
-                const int wmax = static_cast<int>(__reduce_max_sync(0xFFFFFFFFu, static_cast<unsigned>(wt)));
-                R llr;
-                switch (wmax) {
-                case 0: llr = l0; break;
-                case 1: llr = column_update<R, 1>(rec, wt, l0, alpha, first, V, rsum, cand, magic); break;
-                case 2: llr = column_update<R, 2>(rec, wt, l0, alpha, first, V, rsum, cand, magic); break;
-                case 3: llr = column_update<R, 3>(rec, wt, l0, alpha, first, V, rsum, cand, magic); break;
-                case 4: llr = column_update<R, 4>(rec, wt, l0, alpha, first, V, rsum, cand, magic); break;
-                case 5: llr = column_update<R, 5>(rec, wt, l0, alpha, first, V, rsum, cand, magic); break;
-                default: llr = column_update<R, 6>(rec, wt, l0, alpha, first, V, rsum, cand, magic); break;
-                }
-                const uint32_t j = rec.w & 0xFFFFu;                    // original column; 0xFFFF marks a padding record
+                const uint4 cur = rec;
+                if (r + NT < npad) rec = __ldg(w.colrec + r + NT);
+                const R l0 = ptab[(cur.w >> 16) & 0xFFFu];
+                const R llr = first ? column_dispatch<R, true>(cur, l0, alpha, V, rsum, cand, magic, static_cast<uint32_t>(rows))
+                                    : column_dispatch<R, false>(cur, l0, alpha, V, rsum, cand, magic, static_cast<uint32_t>(rows));
+                const uint32_t j = cur.w & 0xFFFFu;                    // original column; 0xFFFF marks a padding record
                 if (j != 0xFFFFu) {
                     if (llr <= R(0)) hmask |= 1u << k;
                     if (last || b.write_llr_always) llr_all[static_cast<size_t>(shot) * b.llr_stride + j] = llr;
