@@ -132,6 +132,12 @@ int qb_plan_info(const qb_plan* p, int64_t info[8]);
 int qb_plan_window(const qb_plan* p, int32_t k, int64_t dims[10], int64_t* h_ptr, int32_t* h_idx, double* priors, int64_t* l_ptr,
                    int32_t* l_idx, int64_t* u_ptr, int32_t* u_idx);
 
+/* Diagnostic (host only): the shared-memory layout qb_sw_create would choose for window k at the given message precision
+ * (32 / 64) -- record order[ncols], slot[nnz] of every edge inside its row (CSC order of qb_plan_window) -- and the predicted
+ * shared-memory passes per request relative to the conflict-free minimum: ratios = [message gather with the naive layout,
+ * row-summary gather naive, message gather chosen, row-summary gather chosen].  No reference counterpart (ldpc has no GPU). */
+int qb_plan_layout(const qb_plan* p, int32_t k, int32_t precision, int32_t* order, int32_t* slot, double ratios[4]);
+
 int qb_sw_create(qb_ctx* ctx, const qb_plan* plan, const qb_bp_opts* opts, qb_sw** out);
 /* one window given explicitly: ldpc.BpOsdDecoder(pcm, channel_probs=priors, ...) as built at sliding_window.py:146-153 */
 int qb_sw_create_single(qb_ctx* ctx, int32_t rows, int32_t cols, const int64_t* indptr, const int32_t* indices, const double* priors,

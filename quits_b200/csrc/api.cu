@@ -208,7 +208,7 @@ int gf2_rank(const qb::Window& hw) {
     return rank;
 }
 
-void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, WinOwned& wo) {
+void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinOwned& wo) {
     qb::WinDev& d = wo.dev;
     const int rows = hw.rows, ncols = hw.ncols;
     if (rows <= 0) throw qb::value_error("a decoding window has no detector rows");
@@ -221,20 +221,31 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, WinOwned& wo) {
     for (int j = 0; j < ncols; ++j) cw = std::max(cw, static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]));
     const int cw_alloc = cw <= 6 ? 6 : (cw <= 8 ? 8 : 16);
     if (cw > 16) throw qb::unsupported_error("column weight " + std::to_string(cw) + " > 16 is not supported by the BP kernel");
+    for (int32_t r : hw.crow) fillr[r]++;
+    int rs = 1;
+    for (int r = 0; r < rows; ++r) rs = std::max(rs, fillr[r]);
+    if (rs > 255) throw qb::unsupported_error("row weight > 255 is not supported by the BP kernel");
+    rs |= 1;                                             // odd row stride: conflict-free thread-per-row sweeps
+    // slot of every edge in its row and order of the column records: chosen so that the bit sweep's shared-memory
+    // gathers are bank-conflict free (layout.cpp); any choice gives the same arithmetic
+    qb::BpLayout layout;
+    if (cw <= 6) {
+        qb::optimize_bp_layout(hw, rs, precision, layout);
+    } else {
+        layout.order.resize(static_cast<size_t>(ncols));
+        std::iota(layout.order.begin(), layout.order.end(), 0);
+        std::stable_sort(layout.order.begin(), layout.order.end(), [&](int a, int b) { return (hw.cptr[a + 1] - hw.cptr[a]) > (hw.cptr[b + 1] - hw.cptr[b]); });
+        layout.slot.resize(hw.crow.size());
+        std::vector<int> fill(static_cast<size_t>(rows), 0);
+        for (size_t e = 0; e < hw.crow.size(); ++e) layout.slot[e] = fill[hw.crow[e]]++;
+    }
     const int npad = (ncols + 31) / 32 * 32;
     std::vector<uint32_t> colE(static_cast<size_t>(cw_alloc) * npad, qb::kNoEdge);
     for (int j = 0; j < ncols; ++j) {
         int q = 0;
-        for (int64_t e = hw.cptr[j]; e < hw.cptr[j + 1]; ++e, ++q) {
-            const int r = hw.crow[e];
-            const int slot = fillr[r]++;
-            if (slot > 255) throw qb::unsupported_error("row weight > 255 is not supported by the BP kernel");
-            colE[static_cast<size_t>(q) * npad + j] = (static_cast<uint32_t>(r) << 8) | static_cast<uint32_t>(slot);
-        }
+        for (int64_t e = hw.cptr[j]; e < hw.cptr[j + 1]; ++e, ++q)
+            colE[static_cast<size_t>(q) * npad + j] = (static_cast<uint32_t>(hw.crow[e]) << 8) | static_cast<uint32_t>(layout.slot[e]);
     }
-    int rs = 1;
-    for (int r = 0; r < rows; ++r) rs = std::max(rs, fillr[r]);
-    rs |= 1;                                             // odd row stride: conflict-free thread-per-row sweeps
     std::vector<float> llr0f(static_cast<size_t>(npad), 0.0f);
     std::vector<double> llr0d(static_cast<size_t>(npad), 0.0);
     for (int j = 0; j < ncols; ++j) {
@@ -267,9 +278,7 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, WinOwned& wo) {
             const uint32_t magic = static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(rs)) + 1u;
             for (uint32_t a = 0; a <= static_cast<uint32_t>(rows) * rs; ++a)
                 if (static_cast<uint32_t>((static_cast<uint64_t>(a) * magic) >> 32) != a / rs) throw std::runtime_error("internal: row magic is not exact");
-            std::vector<int> order(static_cast<size_t>(ncols));
-            std::iota(order.begin(), order.end(), 0);
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return (hw.cptr[a + 1] - hw.cptr[a]) > (hw.cptr[b + 1] - hw.cptr[b]); });
+            const std::vector<int>& order = layout.order;
             // records: 6 x u16 message address (dummy edges point at the dummy row's slot rows*rs), then
             // w = original column | prior index << 16 | weight of the heaviest column of the record's warp << 28
             const uint32_t dummy = static_cast<uint32_t>(rows) * static_cast<uint32_t>(rs);
@@ -794,7 +803,7 @@ int qb_sw_create(qb_ctx* ctx, const qb_plan* plan, const qb_bp_opts* opts, qb_sw
         for (const qb::Window& hw : sw->plan.windows) {
             if (hw.urows != 0 && hw.urows != sw->plan.m) throw qb::value_error("carry block of a window is not m rows tall");
             sw->wins.emplace_back(new WinOwned());
-            build_window(ctx, hw, KW, *sw->wins.back());
+            build_window(ctx, hw, KW, sw->opts.precision == 32 ? 32 : 64, *sw->wins.back());
         }
         finish_decoder(sw.get());
         *out = sw.release();
@@ -830,7 +839,7 @@ int qb_sw_create_single(qb_ctx* ctx, int32_t rows, int32_t cols, const int64_t* 
         sw->plan.m = rows; sw->plan.K = 0; sw->plan.D = rows; sw->plan.W = 1; sw->plan.F = 1; sw->plan.n_cor = 0;
         sw->plan.windows.push_back(hw);
         sw->wins.emplace_back(new WinOwned());
-        build_window(ctx, sw->plan.windows[0], 1, *sw->wins.back());
+        build_window(ctx, sw->plan.windows[0], 1, sw->opts.precision == 32 ? 32 : 64, *sw->wins.back());
         finish_decoder(sw.get());
         *out = sw.release();
     });
@@ -868,6 +877,35 @@ int qb_plan_window(const qb_plan* sw, int32_t k, int64_t dims[10], int64_t* h_pt
         if (l_idx && !w.lidx.empty()) memcpy(l_idx, w.lidx.data(), w.lidx.size() * 4);
         if (u_ptr) memcpy(u_ptr, w.uptr.data(), w.uptr.size() * 8);
         if (u_idx && !w.uidx.empty()) memcpy(u_idx, w.uidx.data(), w.uidx.size() * 4);
+    });
+}
+
+int qb_plan_layout(const qb_plan* p, int32_t k, int32_t precision, int32_t* order, int32_t* slot, double ratios[4]) {
+    return guard([&] {
+        if (!p) throw arg_error("NULL argument");
+        if (k < 0 || static_cast<size_t>(k) >= p->plan.windows.size()) throw arg_error("window index out of range");
+        if (precision != 32 && precision != 64) throw arg_error("precision must be 32 or 64");
+        const qb::Window& hw = p->plan.windows[k];
+        std::vector<int> len(static_cast<size_t>(hw.rows), 0);
+        int cw = 0, rs = 1;
+        for (int32_t r : hw.crow) rs = std::max(rs, ++len[r]);
+        rs |= 1;
+        for (int j = 0; j < hw.ncols; ++j) cw = std::max(cw, static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]));
+        if (cw > 6) throw qb::unsupported_error("layout search covers column weights <= 6");
+        qb::BpLayout naive, lay;
+        naive.order.resize(static_cast<size_t>(hw.ncols));
+        std::iota(naive.order.begin(), naive.order.end(), 0);
+        std::stable_sort(naive.order.begin(), naive.order.end(), [&](int a, int b) { return (hw.cptr[a + 1] - hw.cptr[a]) > (hw.cptr[b + 1] - hw.cptr[b]); });
+        naive.slot.resize(hw.crow.size());
+        std::fill(len.begin(), len.end(), 0);
+        for (size_t e = 0; e < hw.crow.size(); ++e) naive.slot[e] = len[hw.crow[e]]++;
+        qb::optimize_bp_layout(hw, rs, precision, lay);
+        if (ratios) {
+            qb::layout_wavefronts(hw, rs, precision, naive, &ratios[0], &ratios[1]);
+            qb::layout_wavefronts(hw, rs, precision, lay, &ratios[2], &ratios[3]);
+        }
+        if (order) std::copy(lay.order.begin(), lay.order.end(), order);
+        if (slot) std::copy(lay.slot.begin(), lay.slot.end(), slot);
     });
 }
 

@@ -108,6 +108,16 @@ struct WindowPlan {
     std::vector<Window> windows;
 };
 
+// ---- shared-memory layout of a window's BP messages (layout.cpp) ---------------------------------------------
+struct BpLayout {
+    std::vector<int> order;             // record r holds column order[r]; weights non-increasing
+    std::vector<int> slot;              // slot of every edge inside its row, indexed like Window::crow
+    long rsum_excess = 0, v_excess = 0; // residual bank-class collisions after the search (0 = conflict free)
+};
+// rs: row stride of the message array; precision 32 / 64 selects the bank-class geometry
+void optimize_bp_layout(const Window& hw, int rs, int precision, BpLayout& out);
+void layout_wavefronts(const Window& hw, int rs, int precision, const BpLayout& lay, double* v_ratio, double* r_ratio);
+
 // n_cor_override < 0: derive the number of sliding windows as sliding_window.py:130-141 does
 void plan_windows(const CheckMatrix& cm, int m, int W, int F, int n_cor_override, WindowPlan& plan);
 

@@ -188,3 +188,26 @@ def test_shard_ranges():
             for (a, b), (c2, d) in zip(spans, spans[1:]):
                 assert b == c2 and a <= b
             assert all(lo % 64 == 0 for lo, _ in spans)
+
+
+@pytest.mark.parametrize("precision", [64, 32])
+def test_bp_layout_is_a_valid_conflict_free_arrangement(precision):
+    """layout.cpp: the record order is a permutation sorted by column weight, every row's slots are a permutation of
+    0..len-1, and the predicted shared-memory passes of the bit sweep are within 20 % of the conflict-free minimum
+    (the naive layout needs 1.7-2.8x)."""
+    circuit = qb.Circuit(circuit_text("bb144_r10_p1e-3"))
+    plan = WindowPlan(circuit.detector_error_model(), 72, 5, 3)
+    for k in (1, 3):
+        H = plan.window(k)["H"]
+        order = np.zeros(H.shape[1], dtype=np.int32)
+        slot = np.zeros(H.nnz, dtype=np.int32)
+        ratios = np.zeros(4)
+        N.check(N.lib().qb_plan_layout(plan._h, k, precision, N.ptr(order), N.ptr(slot), N.ptr(ratios)))
+        assert sorted(order.tolist()) == list(range(H.shape[1]))
+        wts = np.diff(H.indptr)[order]
+        assert np.all(wts[:-1] >= wts[1:])
+        for i in range(H.shape[0]):
+            s = slot[H.indices == i]
+            assert sorted(s.tolist()) == list(range(len(s)))
+        assert ratios[0] > 2.0 and ratios[1] > 1.5
+        assert ratios[2] < 1.1 and ratios[3] < 1.25, ratios
