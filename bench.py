@@ -123,6 +123,7 @@ def main():
     ap.add_argument("--shots", type=int, default=262144, help="shots per step per GPU")
     ap.add_argument("--e2e-shots", type=int, default=65536)
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--lanes", type=int, default=0, help="concurrent sub-batches per device batch (0 = engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -160,7 +161,7 @@ def main():
     text, hz, lz = load_workload()
     ctx = qb.Context.default(local)
     circuit = qb.Circuit(text)
-    mc = qb.MonteCarlo(circuit, hz.shape[0], W, F, ctx=ctx, precision=args.precision, profile=True, **BP_KW)
+    mc = qb.MonteCarlo(circuit, hz.shape[0], W, F, ctx=ctx, precision=args.precision, profile=True, lanes=args.lanes, **BP_KW)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     S = args.shots
 

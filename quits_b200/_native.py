@@ -25,7 +25,7 @@ class QbStats(C.Structure):
 class QbBpOpts(C.Structure):
     _fields_ = [("bp_method", C.c_int32), ("schedule", C.c_int32), ("max_iter", C.c_int32), ("ms_scaling_factor", C.c_double),
                 ("osd_method", C.c_int32), ("osd_order", C.c_int32), ("precision", C.c_int32), ("capacity", C.c_int32),
-                ("profile", C.c_int32)]
+                ("profile", C.c_int32), ("lanes", C.c_int32)]
 
 
 class QbCircuitInfo(C.Structure):

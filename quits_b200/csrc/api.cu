@@ -97,6 +97,20 @@ struct qb_ctx {
     // sampler scratch
     DevBuf det_rows, obs_rows, det_bytes, obs_bytes, inj_start, inj_tgt, inj_code, inj_shot, counts;
     EventTimer t_frame, t_total;
+    // side streams of the decoder: a batch is decoded as kMaxLanes independent sub-batches so that the latency-bound OSD
+    // kernel of one sub-batch shares the SMs with the BP kernel of another
+    static constexpr int kMaxLanes = 4;
+    cudaStream_t aux[kMaxLanes - 1] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes - 1] = {};
+    cudaStream_t lane_stream(int lane) {
+        if (lane == 0) return stream;
+        if (!aux[lane - 1]) {
+            CK(cudaStreamCreateWithFlags(&aux[lane - 1], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ev_join[lane - 1], cudaEventDisableTiming));
+        }
+        if (!ev_fork) CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        return aux[lane - 1];
+    }
 };
 
 struct qb_circuit {
@@ -142,6 +156,7 @@ struct qb_sw {
     DevBuf alpha;
     // batch state
     int cap = 0;
+    int lanes = 1, lanes_used = 1;    // concurrent sub-batches per batch (decode_batch)
     int DW = 0, KW = 0, carryW = 0, synW = 0;
     size_t llr_stride = 0;
     DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, counters, stats, pred, ehat, iters, conv, vscratch;
@@ -402,6 +417,8 @@ void finish_decoder(qb_sw* sw) {
     for (int it = 1; it <= max_iter; ++it) alpha[it] = o.ms_scaling_factor == 0.0 ? 1.0 - std::pow(2.0, -1.0 * it) : o.ms_scaling_factor;
     upload(sw->alpha, alpha, ctx->stream);
     sw->cap = o.capacity > 0 ? o.capacity : 65536;
+    sw->lanes = o.lanes > 0 ? std::min(o.lanes, static_cast<int32_t>(qb_ctx::kMaxLanes)) : 2;
+    if (max_slab) sw->lanes = 1;                      // the global message slabs are indexed by CTA, not by sub-batch
     sw->DW = std::max(1, (sw->plan.D + 63) / 64);
     sw->KW = std::max(1, (sw->plan.K + 63) / 64);
     sw->carryW = (sw->plan.m + 31) / 32 + 1;
@@ -417,78 +434,104 @@ void ensure_batch(qb_sw* sw, int n) {
     sw->llr.ensure(N * sw->llr_stride * (sw->precision / 8) + 16);
     sw->syn.ensure(N * sw->synW * 4 + 16);
     sw->fail_list.ensure(N * 4 + 16);
-    const size_t nw = sw->wins.size();
+    const size_t nw = sw->wins.size() * qb_ctx::kMaxLanes;
     sw->counters.ensure(nw * 2 * sizeof(int) + 16);
     sw->stats.ensure(nw * 3 * sizeof(unsigned long long) + 16);
 }
 
-// decode n (<= cap) shots whose packed detector rows are on the device; leaves acc[n][KW] on the device
+// decode n (<= cap) shots whose packed detector rows are on the device; leaves acc[n][KW] on the device.
+// The batch is cut into `lanes` contiguous sub-batches, each walking the windows on its own stream (the windows of one
+// shot are sequential -- carry dependency, sliding_window.py:169,174 -- but shots are independent).
 void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, bool want_llr, qb_stats* stats) {
     qb_ctx* ctx = sw->ctx;
     cudaStream_t st = ctx->stream;
     ensure_batch(sw, n);
     const size_t nw = sw->wins.size();
+    int lanes = sw->lanes;
+    if (want_ehat || n < 4096) lanes = 1;
+    sw->lanes_used = lanes;
     CK(cudaMemsetAsync(sw->acc.p, 0, static_cast<size_t>(n) * sw->KW * 8, st));
     CK(cudaMemsetAsync(sw->carry.p, 0, static_cast<size_t>(n) * sw->carryW * 4, st));
-    CK(cudaMemsetAsync(sw->counters.p, 0, nw * 2 * sizeof(int), st));
-    CK(cudaMemsetAsync(sw->stats.p, 0, nw * 3 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(sw->counters.p, 0, nw * lanes * 2 * sizeof(int), st));
+    CK(cudaMemsetAsync(sw->stats.p, 0, nw * lanes * 3 * sizeof(unsigned long long), st));
+    if (lanes > 1) {
+        for (int l = 1; l < lanes; ++l) ctx->lane_stream(l);
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        for (int l = 1; l < lanes; ++l) CK(cudaStreamWaitEvent(ctx->lane_stream(l), ctx->ev_fork, 0));
+    }
     qb::BpParams bp{};
     bp.max_iter = sw->max_iter;
     bp.alpha = sw->alpha.as<double>();
+    const size_t esz = static_cast<size_t>(sw->precision / 8);
     for (size_t k = 0; k < nw; ++k) {
         WinOwned& w = *sw->wins[k];
-        qb::BatchDev b{};
-        b.n_shots = n;
-        b.det32 = reinterpret_cast<const uint32_t*>(d_det_rows);
-        b.det_stride32 = 2 * sw->DW;
-        b.in_carry_rows = k == 0 ? 0 : sw->wins[k - 1]->dev.carry_rows;
-        b.carry = sw->carry.as<uint32_t>();
-        b.carry_stride32 = sw->carryW;
-        b.acc = sw->acc.as<uint64_t>();
-        b.llr_buf = sw->llr.p;
-        b.vscratch = sw->vscratch.p;
-        b.llr_stride = sw->llr_stride;
-        b.syn_buf = sw->syn.as<uint32_t>();
-        b.syn_stride32 = sw->synW;
-        b.fail_list = sw->fail_list.as<int>();
-        b.fail_count = sw->counters.as<int>() + 2 * k;
-        b.osd_next = sw->counters.as<int>() + 2 * k + 1;
-        b.stats = sw->stats.as<unsigned long long>() + 3 * k;
-        b.ehat_out = want_ehat ? sw->ehat.as<uint32_t>() : nullptr;
-        b.ehat_stride32 = w.dev.nW32;
-        b.iters_out = want_ehat ? sw->iters.as<int32_t>() : nullptr;
-        b.conv_out = want_ehat ? sw->conv.as<uint8_t>() : nullptr;
-        b.write_llr_always = want_llr ? 1 : 0;
-        if (sw->opts.profile) sw->t_bp.begin(st);
-        CK(qb::launch_bp(w.dev, b, bp, sw->precision, w.vglobal, w.vglobal ? std::min(w.bp_grid, n) : n, st));
-        if (sw->opts.profile) sw->t_bp.end(st);
-        if (stats) stats->bp_launches++;
-        if (sw->use_osd) {
-            if (sw->opts.profile) sw->t_osd.begin(st);
-            CK(qb::launch_osd(w.dev, b, sw->precision, std::min(w.osd_grid, n), st));
-            if (sw->opts.profile) sw->t_osd.end(st);
-            if (stats) stats->osd_launches++;
+        for (int l = 0; l < lanes; ++l) {
+            const size_t s0 = static_cast<size_t>(n) * l / lanes, s1 = static_cast<size_t>(n) * (l + 1) / lanes;
+            const int nl = static_cast<int>(s1 - s0);
+            if (nl == 0) continue;
+            cudaStream_t ls = ctx->lane_stream(l);
+            qb::BatchDev b{};
+            b.n_shots = nl;
+            b.det_stride32 = 2 * sw->DW;
+            b.det32 = reinterpret_cast<const uint32_t*>(d_det_rows) + s0 * b.det_stride32;
+            b.in_carry_rows = k == 0 ? 0 : sw->wins[k - 1]->dev.carry_rows;
+            b.carry_stride32 = sw->carryW;
+            b.carry = sw->carry.as<uint32_t>() + s0 * sw->carryW;
+            b.acc = sw->acc.as<uint64_t>() + s0 * sw->KW;
+            b.llr_stride = sw->llr_stride;
+            b.llr_buf = static_cast<unsigned char*>(sw->llr.p) + s0 * sw->llr_stride * esz;
+            b.vscratch = sw->vscratch.p;
+            b.syn_stride32 = sw->synW;
+            b.syn_buf = sw->syn.as<uint32_t>() + s0 * sw->synW;
+            b.fail_list = sw->fail_list.as<int>() + s0;          // shot indices local to the sub-batch
+            const size_t slot = static_cast<size_t>(l) * nw + k;
+            b.fail_count = sw->counters.as<int>() + 2 * slot;
+            b.osd_next = sw->counters.as<int>() + 2 * slot + 1;
+            b.stats = sw->stats.as<unsigned long long>() + 3 * slot;
+            b.ehat_out = want_ehat ? sw->ehat.as<uint32_t>() : nullptr;
+            b.ehat_stride32 = w.dev.nW32;
+            b.iters_out = want_ehat ? sw->iters.as<int32_t>() : nullptr;
+            b.conv_out = want_ehat ? sw->conv.as<uint8_t>() : nullptr;
+            b.write_llr_always = want_llr ? 1 : 0;
+            if (sw->opts.profile) sw->t_bp.begin(ls);
+            CK(qb::launch_bp(w.dev, b, bp, sw->precision, w.vglobal, w.vglobal ? std::min(w.bp_grid, nl) : nl, ls));
+            if (sw->opts.profile) sw->t_bp.end(ls);
+            if (stats) stats->bp_launches++;
+            if (sw->use_osd) {
+                if (sw->opts.profile) sw->t_osd.begin(ls);
+                CK(qb::launch_osd(w.dev, b, sw->precision, std::min(w.osd_grid, nl), ls));
+                if (sw->opts.profile) sw->t_osd.end(ls);
+                if (stats) stats->osd_launches++;
+            }
         }
+    }
+    for (int l = 1; l < lanes; ++l) {
+        CK(cudaEventRecord(ctx->ev_join[l - 1], ctx->lane_stream(l)));
+        CK(cudaStreamWaitEvent(st, ctx->ev_join[l - 1], 0));
     }
 }
 
 void collect_stats(qb_sw* sw, int n, qb_stats* stats) {        // stream must be synchronised
     if (!stats) return;
     const size_t nw = sw->wins.size();
-    std::vector<unsigned long long> h(nw * 3);
+    const int lanes = sw->lanes_used;
+    std::vector<unsigned long long> h(nw * lanes * 3);
     CK(cudaMemcpy(h.data(), sw->stats.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     stats->shots += n;
     stats->windows += static_cast<int64_t>(nw) * n;
-    for (size_t k = 0; k < nw; ++k) {
-        stats->bp_converged += static_cast<int64_t>(h[3 * k]);
-        stats->bp_iterations += static_cast<int64_t>(h[3 * k + 1]);
-        stats->osd_calls += static_cast<int64_t>(h[3 * k + 2]);
-        const qb::WinDev& d = sw->wins[k]->dev;
-        const double nnz = static_cast<double>(sw->plan.windows[k].crow.size());
-        const double io = 8.0 * ((d.rows + 63) / 64) + 8.0 * sw->KW + 8.0 * ((d.carry_rows + 63) / 64);
-        stats->bp_alg_bytes += static_cast<double>(h[3 * k + 1]) * 4.0 * nnz * (sw->precision / 8) + io * n;
-        stats->osd_alg_bytes += static_cast<double>(h[3 * k + 2]) * 2.0 * d.rows * 8.0 * ((d.ncols + 63) / 64);
-    }
+    for (int l = 0; l < lanes; ++l)
+        for (size_t k = 0; k < nw; ++k) {
+            const unsigned long long* hk = &h[(static_cast<size_t>(l) * nw + k) * 3];
+            stats->bp_converged += static_cast<int64_t>(hk[0]);
+            stats->bp_iterations += static_cast<int64_t>(hk[1]);
+            stats->osd_calls += static_cast<int64_t>(hk[2]);
+            const qb::WinDev& d = sw->wins[k]->dev;
+            const double nnz = static_cast<double>(sw->plan.windows[k].crow.size());
+            const size_t s0 = static_cast<size_t>(n) * l / lanes, s1 = static_cast<size_t>(n) * (l + 1) / lanes;
+            const double io = 8.0 * ((d.rows + 63) / 64) + 8.0 * sw->KW + 8.0 * ((d.carry_rows + 63) / 64);
+            stats->bp_alg_bytes += static_cast<double>(hk[1]) * 4.0 * nnz * (sw->precision / 8) + io * static_cast<double>(s1 - s0);
+            stats->osd_alg_bytes += static_cast<double>(hk[2]) * 2.0 * d.rows * 8.0 * ((d.ncols + 63) / 64);
+        }
     if (sw->opts.profile) {
         stats->bp_ms += sw->t_bp.collect();
         stats->osd_ms += sw->t_osd.collect();
@@ -552,6 +595,11 @@ void qb_ctx_destroy(qb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    for (int i = 0; i < qb_ctx::kMaxLanes - 1; ++i) {
+        if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); }
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     delete ctx;
 }
 

@@ -23,7 +23,7 @@ _OSD_METHODS = {"osd_0": 0, "osd0": 0, "osd_e": 1, "osde": 1, "exhaustive": 1, "
 
 
 def bp_options(bp_method="minimum_sum", max_iter=0, schedule="parallel", osd_method="osd_0", osd_order=0, ms_scaling_factor=1.0,
-               precision="f64", capacity=0, profile=False, **unknown) -> N.QbBpOpts:
+               precision="f64", capacity=0, profile=False, lanes=0, **unknown) -> N.QbBpOpts:
     """Translate ldpc.BpOsdDecoder-style kwargs (reference decoder/bposd.py:74-83) into the C option block."""
     for k in unknown:
         if k not in ("channel_probs", "error_rate", "error_channel", "input_vector_type", "omp_thread_count",
@@ -44,6 +44,7 @@ def bp_options(bp_method="minimum_sum", max_iter=0, schedule="parallel", osd_met
     o.osd_order = int(osd_order)
     o.capacity = int(capacity)
     o.profile = 1 if profile else 0
+    o.lanes = int(lanes)
     return o
 
 
