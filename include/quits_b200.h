@@ -107,7 +107,7 @@ typedef struct {
     int32_t precision;          /* 64 (default when 0): messages in fp64 as ldpc computes; 32: fp32 messages */
     int32_t capacity;           /* shots per device batch; 0 => default */
     int32_t profile;            /* 1: time the kernel classes with CUDA events on the launching stream */
-    int32_t lanes;              /* concurrent sub-batches per device batch (streams); 0 => default (2), 1 => serial */
+    int32_t lanes;              /* concurrent sub-batches per device batch (streams); 0 => default (1, serial) */
 } qb_bp_opts;
 
 typedef struct {

@@ -136,10 +136,10 @@ namespace {
 struct WinOwned {
     qb::WinDev dev{};
     DevBuf colE, llr0f, llr0d, lmask, uptr, uidx, cptr, crow, colrec, ptabf, ptabd, rlen, rsum0f, rsum0d, neg0;
-    size_t bp_smem = 0, osd_smem = 0;
+    size_t bp_smem = 0;
     bool vglobal = false;
     int bp_grid = 0;            // persistent grid of the VGLOBAL variant (0: one CTA per shot)
-    int osd_grid = 0;
+    int sort_grid = 0, elim_grid = 0;
 };
 
 }  // namespace
@@ -158,8 +158,8 @@ struct qb_sw {
     int cap = 0;
     int lanes = 1, lanes_used = 1;    // concurrent sub-batches per batch (decode_batch)
     int DW = 0, KW = 0, carryW = 0, synW = 0;
-    size_t llr_stride = 0;
-    DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, counters, stats, pred, ehat, iters, conv, vscratch;
+    size_t llr_stride = 0, order_stride = 0;
+    DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, order, counters, stats, pred, ehat, iters, conv, vscratch;
     EventTimer t_bp, t_osd;
 };
 
@@ -380,7 +380,7 @@ void finish_decoder(qb_sw* sw) {
     const int prec = sw->precision;
     sw->use_osd = o.osd_method >= 0;
     int max_npad = 0, max_rowsW = 0, max_iter = 0;
-    size_t max_slab = 0;
+    size_t max_slab = 0, max_order = 0;
     for (auto& w : sw->wins) {
         // messages in shared memory when they fit, else in an L2-resident global slab per CTA
         w->vglobal = qb::bp_smem_bytes(w->dev, prec, false) > 227 * 1024;
@@ -398,12 +398,13 @@ void finish_decoder(qb_sw* sw) {
         if (sw->use_osd) {
             if (!qb::osd_supported(w->dev, prec))
                 throw qb::unsupported_error("window of " + std::to_string(w->dev.rows) + " x " + std::to_string(w->dev.ncols) +
-                                            " exceeds what the register-resident OSD kernel handles (rows <= 736)");
+                                            " exceeds what the OSD kernels handle (rows <= 768)");
             CK(qb::osd_configure(w->dev, prec));
-            w->osd_smem = qb::osd_smem_bytes(w->dev, prec);
-            int per_sm = static_cast<int>((227 * 1024) / (w->osd_smem + 1024));
-            per_sm = std::max(1, std::min(per_sm, 5));
-            w->osd_grid = 148 * per_sm;
+            const int sort_per_sm = static_cast<int>((227 * 1024) / (qb::osd_sort_smem_bytes(w->dev, prec) + 1024));
+            const int elim_per_sm = static_cast<int>((227 * 1024) / (qb::osd_elim_smem_bytes(w->dev) + 1024));
+            w->sort_grid = 148 * std::max(1, std::min(sort_per_sm, 6));
+            w->elim_grid = 148 * std::max(1, std::min(elim_per_sm, 16));
+            max_order = std::max(max_order, static_cast<size_t>((w->dev.ncols + 63) / 64 * 64));
         }
     }
     if (max_slab) sw->vscratch.ensure(max_slab * 148 * 2 + 16);
@@ -417,13 +418,14 @@ void finish_decoder(qb_sw* sw) {
     for (int it = 1; it <= max_iter; ++it) alpha[it] = o.ms_scaling_factor == 0.0 ? 1.0 - std::pow(2.0, -1.0 * it) : o.ms_scaling_factor;
     upload(sw->alpha, alpha, ctx->stream);
     sw->cap = o.capacity > 0 ? o.capacity : 65536;
-    sw->lanes = o.lanes > 0 ? std::min(o.lanes, static_cast<int32_t>(qb_ctx::kMaxLanes)) : 2;
+    sw->lanes = o.lanes > 0 ? std::min(o.lanes, static_cast<int32_t>(qb_ctx::kMaxLanes)) : 1;
     if (max_slab) sw->lanes = 1;                      // the global message slabs are indexed by CTA, not by sub-batch
     sw->DW = std::max(1, (sw->plan.D + 63) / 64);
     sw->KW = std::max(1, (sw->plan.K + 63) / 64);
     sw->carryW = (sw->plan.m + 31) / 32 + 1;
     sw->synW = max_rowsW;
     sw->llr_stride = static_cast<size_t>(max_npad);
+    sw->order_stride = max_order;
     CK(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -434,8 +436,9 @@ void ensure_batch(qb_sw* sw, int n) {
     sw->llr.ensure(N * sw->llr_stride * (sw->precision / 8) + 16);
     sw->syn.ensure(N * sw->synW * 4 + 16);
     sw->fail_list.ensure(N * 4 + 16);
+    if (sw->use_osd) sw->order.ensure(N * sw->order_stride * 2 + 16);
     const size_t nw = sw->wins.size() * qb_ctx::kMaxLanes;
-    sw->counters.ensure(nw * 2 * sizeof(int) + 16);
+    sw->counters.ensure(nw * 4 * sizeof(int) + 16);
     sw->stats.ensure(nw * 3 * sizeof(unsigned long long) + 16);
 }
 
@@ -452,7 +455,7 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
     sw->lanes_used = lanes;
     CK(cudaMemsetAsync(sw->acc.p, 0, static_cast<size_t>(n) * sw->KW * 8, st));
     CK(cudaMemsetAsync(sw->carry.p, 0, static_cast<size_t>(n) * sw->carryW * 4, st));
-    CK(cudaMemsetAsync(sw->counters.p, 0, nw * lanes * 2 * sizeof(int), st));
+    CK(cudaMemsetAsync(sw->counters.p, 0, nw * lanes * 4 * sizeof(int), st));
     CK(cudaMemsetAsync(sw->stats.p, 0, nw * lanes * 3 * sizeof(unsigned long long), st));
     if (lanes > 1) {
         for (int l = 1; l < lanes; ++l) ctx->lane_stream(l);
@@ -485,8 +488,11 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.syn_buf = sw->syn.as<uint32_t>() + s0 * sw->synW;
             b.fail_list = sw->fail_list.as<int>() + s0;          // shot indices local to the sub-batch
             const size_t slot = static_cast<size_t>(l) * nw + k;
-            b.fail_count = sw->counters.as<int>() + 2 * slot;
-            b.osd_next = sw->counters.as<int>() + 2 * slot + 1;
+            b.fail_count = sw->counters.as<int>() + 4 * slot;
+            b.sort_next = sw->counters.as<int>() + 4 * slot + 1;
+            b.osd_next = sw->counters.as<int>() + 4 * slot + 2;
+            b.order_buf = sw->order.as<uint16_t>() + s0 * sw->order_stride;     // fail slots of a sub-batch are < its shot count
+            b.order_stride = sw->order_stride;
             b.stats = sw->stats.as<unsigned long long>() + 3 * slot;
             b.ehat_out = want_ehat ? sw->ehat.as<uint32_t>() : nullptr;
             b.ehat_stride32 = w.dev.nW32;
@@ -499,9 +505,10 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             if (stats) stats->bp_launches++;
             if (sw->use_osd) {
                 if (sw->opts.profile) sw->t_osd.begin(ls);
-                CK(qb::launch_osd(w.dev, b, sw->precision, std::min(w.osd_grid, nl), ls));
+                CK(qb::launch_osd_sort(w.dev, b, sw->precision, std::min(w.sort_grid, nl), ls));
+                CK(qb::launch_osd_elim(w.dev, b, std::min(w.elim_grid, nl), ls));
                 if (sw->opts.profile) sw->t_osd.end(ls);
-                if (stats) stats->osd_launches++;
+                if (stats) stats->osd_launches += 2;
             }
         }
     }

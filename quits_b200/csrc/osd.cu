@@ -1,4 +1,4 @@
-// quits_b200/csrc/osd.cu -- K4: OSD-0 for the windows BP left unconverged, one shot per 128-thread CTA (sm_100a).
+// quits_b200/csrc/osd.cu -- K4: OSD-0 for the windows BP left unconverged (sm_100a).
 //
 // Replaces the OSD stage of ldpc.BpOsdDecoder.decode() (reference call site src/quits/decoder/sliding_window.py:171,182;
 // osd_method 'osd_0', or 'osd_cs'/'osd_e' with osd_order = 0 which are the same thing).  Definition it is held to
@@ -6,16 +6,22 @@
 // column order picking as pivot row the first row at or below the current rank that has a 1 and swapping it into
 // place; the solution is the reduced syndrome on the pivot columns, 0 elsewhere.
 //
-// How it is computed here.  Instead of reducing the m x n matrix, the kernel keeps only the accumulated row
-// transformation T (m x m over GF(2), plus the syndrome as an extra column), one column per thread-slot IN
-// REGISTERS as MW 32-bit words over the physical rows.  A candidate column of H is sparse (<= 6 rows), so its
-// reduced form is the XOR of <= 6 columns of T; 128 candidates (the next 128 columns in sorted order) are carried
-// in registers and receive the same rank-1 updates as T, so T only has to be spilled to shared memory when a new
-// batch of candidates is fetched.  Row swaps are virtual: `seq` lists the free rows in the oracle's position order
-// and a pivot only moves the head of that list into the vacated slot.  Work per pivot is one rank-1 update of
-// (m + 1 + 128) register-resident bit-columns; no m x n traffic at all.
-// The column order comes from a stable 4-pass LSD radix sort of the posteriors' order-preserving integer image
-// (warp-private histograms + __match_any_sync ranking), which is exactly "ascending LLR, ties by index".
+// Two kernels per window, both persistent grids pulling failed shots from the list the BP kernel wrote:
+//
+//   osd_sort_kernel   one 128-thread CTA per shot: stable LSD radix sort (8-bit digits) of the posteriors' order-preserving
+//                     integer image in shared memory (warp-private histograms + __match_any_sync ranking), which is exactly
+//                     "ascending LLR, ties by index"; the column order goes to HBM as u16.
+//   osd_elim_kernel   ONE WARP per shot, ~10 shots resident per SM, no block barrier anywhere.  Instead of reducing the
+//                     m x n matrix the warp keeps the accumulated row transformation T (m x m over GF(2)) in shared
+//                     memory, one 128-bit-packed column per pivot found so far (the columns of rows that are not yet pivot
+//                     rows are unit vectors and stay implicit).  A candidate column of H is sparse (<= 6 rows), so its
+//                     reduced form is the XOR of <= 6 columns of T; 32 candidates (the next 32 columns in sorted order) sit
+//                     in registers, one per lane.  Per pivot: ballot for the first live candidate, publish its vector r,
+//                     pick the pivot row, XOR r into every candidate and every stored column of T that has the pivot
+//                     row's bit, and into the syndrome column.  Row swaps are virtual: `seq` lists the free rows in the
+//                     oracle's position order and a pivot only moves the head of that list into the vacated slot.
+//                     Full-row-rank windows skip `seq`: with all rows eventually pivots and consistent syndromes the
+//                     solution does not depend on which free row a pivot takes, so the first set bit is used.
 #include <cfloat>
 #include <type_traits>
 
@@ -25,61 +31,28 @@ namespace qb {
 
 namespace {
 
-constexpr int kOsdThreads = 128;
-constexpr int kOsdWarps = 4;
-
-struct OsdLayout {
-    size_t keys, idxA, idxB, hist, rbuf, flags, seq, pivcol, pivrow, sprime, accs, car, total;
-    int n_pad, TS;
-};
+constexpr int kSortThreads = 128;
+constexpr int kSortWarps = 4;
+constexpr uint32_t kFull = 0xFFFFFFFFu;
 
 __host__ __device__ inline size_t au(size_t x) { return (x + 15) / 16 * 16; }
 
-__host__ __device__ inline OsdLayout osd_layout(const WinDev& w, int MW, int CPT, int ksize) {
-    OsdLayout L;
-    L.n_pad = (w.ncols + kOsdThreads - 1) / kOsdThreads * kOsdThreads;
-    L.TS = CPT * kOsdThreads;
+// ====================================================================================================== sort
+struct SortLayout {
+    size_t keys, idxA, idxB, hist, total;
+    int n_pad;
+};
+
+__host__ __device__ inline SortLayout sort_layout(const WinDev& w, int ksize) {
+    SortLayout L;
+    L.n_pad = (w.ncols + kSortThreads - 1) / kSortThreads * kSortThreads;
     size_t o = 0;
-    // region 0: sort keys + first index buffer; reused afterwards as the spill area of T (MW * TS words)
-    size_t sortA = au(static_cast<size_t>(L.n_pad) * ksize) + au(static_cast<size_t>(L.n_pad) * 2);
-    size_t tdump = au(static_cast<size_t>(MW) * L.TS * 4);
-    L.keys = o;
-    L.idxA = o + au(static_cast<size_t>(L.n_pad) * ksize);
-    o += sortA > tdump ? sortA : tdump;
+    L.keys = o; o += au(static_cast<size_t>(L.n_pad) * ksize);
+    L.idxA = o; o += au(static_cast<size_t>(L.n_pad) * 2);
     L.idxB = o; o += au(static_cast<size_t>(L.n_pad) * 2);
-    L.hist = o; o += au(kOsdWarps * 256 * 4);
-    L.rbuf = o; o += au(2 * static_cast<size_t>(MW) * 4);
-    L.flags = o; o += au(2 * kOsdWarps * 4);
-    L.seq = o; o += au(static_cast<size_t>(w.rows) * 2);
-    L.pivcol = o; o += au(static_cast<size_t>(w.rows) * 2);
-    L.pivrow = o; o += au(static_cast<size_t>(w.rows) * 2);
-    L.sprime = o; o += au(static_cast<size_t>(MW) * 4);
-    L.accs = o; o += au(static_cast<size_t>(w.KW) * 8);
-    L.car = o; o += au(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4);
+    L.hist = o; o += au(kSortWarps * 256 * 4);
     L.total = o;
     return L;
-}
-
-// Word `wsel` of every register-resident column of this thread (T columns, then the candidate), and the pivot row
-// leaves the free mask.  wsel is uniform over the CTA, so the switch is a non-divergent jump, not a select chain.
-template <int MW, int CPT>
-__device__ __forceinline__ void pivot_words(const uint32_t (&T)[CPT][MW], const uint32_t (&cand)[MW], uint32_t (&freem)[MW],
-                                            const int wsel, const uint32_t bsel, uint32_t (&out)[CPT + 1]) {
-#define QB_CASE(I)                                                   \
-    case I:                                                          \
-        if constexpr (I < MW) {                                      \
-            _Pragma("unroll") for (int c = 0; c < CPT; ++c) out[c] = T[c][I]; \
-            out[CPT] = cand[I];                                      \
-            freem[I] &= ~bsel;                                       \
-        }                                                            \
-        break;
-    switch (wsel) {
-        QB_CASE(0) QB_CASE(1) QB_CASE(2) QB_CASE(3) QB_CASE(4) QB_CASE(5) QB_CASE(6) QB_CASE(7)
-        QB_CASE(8) QB_CASE(9) QB_CASE(10) QB_CASE(11) QB_CASE(12) QB_CASE(13) QB_CASE(14) QB_CASE(15)
-        QB_CASE(16) QB_CASE(17) QB_CASE(18) QB_CASE(19) QB_CASE(20) QB_CASE(21) QB_CASE(22) QB_CASE(23)
-    default: break;
-    }
-#undef QB_CASE
 }
 
 // order-preserving unsigned image of a posterior (-0.0 is first folded into +0.0)
@@ -92,52 +65,42 @@ __device__ __forceinline__ uint64_t order_key(double f) {
     return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
-template <typename R, int MW, int CPT, bool EXACT>
-__global__ void __launch_bounds__(kOsdThreads) osd_kernel(const WinDev w, const BatchDev b) {
+template <typename R>
+__global__ void __launch_bounds__(kSortThreads) osd_sort_kernel(const WinDev w, const BatchDev b) {
     using KeyT = typename std::conditional<sizeof(R) == 4, uint32_t, uint64_t>::type;
     constexpr int kPasses = static_cast<int>(sizeof(KeyT));
     extern __shared__ __align__(16) unsigned char sm[];
-    const OsdLayout L = osd_layout(w, MW, CPT, sizeof(KeyT));
+    const SortLayout L = sort_layout(w, sizeof(KeyT));
     KeyT* keys = reinterpret_cast<KeyT*>(sm + L.keys);
     uint16_t* idxA = reinterpret_cast<uint16_t*>(sm + L.idxA);
     uint16_t* idxB = reinterpret_cast<uint16_t*>(sm + L.idxB);
-    uint32_t* tdump = reinterpret_cast<uint32_t*>(sm + L.keys);
     uint32_t* hist = reinterpret_cast<uint32_t*>(sm + L.hist);
-    uint32_t* rbuf = reinterpret_cast<uint32_t*>(sm + L.rbuf);
-    uint32_t* flags = reinterpret_cast<uint32_t*>(sm + L.flags);
-    uint16_t* seq = reinterpret_cast<uint16_t*>(sm + L.seq);
-    uint16_t* pivcol = reinterpret_cast<uint16_t*>(sm + L.pivcol);
-    uint16_t* pivrow = reinterpret_cast<uint16_t*>(sm + L.pivrow);
-    uint32_t* sprime = reinterpret_cast<uint32_t*>(sm + L.sprime);
-    uint32_t* accs = reinterpret_cast<uint32_t*>(sm + L.accs);
-    uint32_t* car = reinterpret_cast<uint32_t*>(sm + L.car);
     __shared__ int s_job;
+    __shared__ uint32_t wsum[kSortWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m = w.rows, n = w.ncols, TS = L.TS;
-    const int carryW = (w.carry_rows + 31) / 32;
+    const int n = w.ncols;
     const int count = *b.fail_count;
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_job = atomicAdd(b.osd_next, 1);
+        if (tid == 0) s_job = atomicAdd(b.sort_next, 1);
         __syncthreads();
         const int job = s_job;
         if (job >= count) break;
         const int shot = b.fail_list[job];
         const R* llr = reinterpret_cast<const R*>(b.llr_buf) + static_cast<size_t>(shot) * b.llr_stride;
-        const uint32_t* syn = b.syn_buf + static_cast<size_t>(shot) * b.syn_stride32;
+        uint16_t* out = b.order_buf + static_cast<size_t>(job) * b.order_stride;
 
-        // ------------------------------------------------------------------ 1. sort columns by (LLR, index)
-        for (int i = tid; i < n; i += kOsdThreads) keys[i] = order_key(llr[i]);
-        const int quarter = ((n + kOsdWarps - 1) / kOsdWarps + 31) / 32 * 32;
+        for (int i = tid; i < n; i += kSortThreads) keys[i] = order_key(llr[i]);
+        const int quarter = ((n + kSortWarps - 1) / kSortWarps + 31) / 32 * 32;
         const int wbeg = warp * quarter, wend = min(n, wbeg + quarter);
 #pragma unroll 1
         for (int pass = 0; pass < kPasses; ++pass) {
             const int shift = 8 * pass;
             const uint16_t* src = (pass & 1) ? idxA : idxB;       // pass 0 reads the identity
-            uint16_t* dst = (pass & 1) ? idxB : idxA;
-            for (int i = tid; i < kOsdWarps * 256; i += kOsdThreads) hist[i] = 0;
+            uint16_t* dst = pass == kPasses - 1 ? out : ((pass & 1) ? idxB : idxA);
+            for (int i = tid; i < kSortWarps * 256; i += kSortThreads) hist[i] = 0;
             __syncthreads();
             for (int i0 = wbeg; i0 < wend; i0 += 32) {
                 const int i = i0 + lane;
@@ -148,28 +111,27 @@ __global__ void __launch_bounds__(kOsdThreads) osd_kernel(const WinDev w, const 
             }
             __syncthreads();
             {   // exclusive scan over (digit major, warp minor): thread t owns digits 2t, 2t+1
-                uint32_t loc[2 * kOsdWarps];
+                uint32_t loc[2 * kSortWarps];
                 uint32_t sum = 0;
 #pragma unroll
-                for (int q = 0; q < 2 * kOsdWarps; ++q) {
-                    const int d = 2 * tid + q / kOsdWarps, wq = q % kOsdWarps;
+                for (int q = 0; q < 2 * kSortWarps; ++q) {
+                    const int d = 2 * tid + q / kSortWarps, wq = q % kSortWarps;
                     loc[q] = sum;
                     sum += hist[wq * 256 + d];
                 }
                 uint32_t inc = sum;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    const uint32_t t = __shfl_up_sync(kFull, inc, o);
                     if (lane >= o) inc += t;
                 }
-                __shared__ uint32_t wsum[kOsdWarps];
                 if (lane == 31) wsum[warp] = inc;
                 __syncthreads();
                 uint32_t base = inc - sum;
                 for (int q = 0; q < warp; ++q) base += wsum[q];
 #pragma unroll
-                for (int q = 0; q < 2 * kOsdWarps; ++q) {
-                    const int d = 2 * tid + q / kOsdWarps, wq = q % kOsdWarps;
+                for (int q = 0; q < 2 * kSortWarps; ++q) {
+                    const int d = 2 * tid + q / kSortWarps, wq = q % kSortWarps;
                     hist[wq * 256 + d] = base + loc[q];
                 }
             }
@@ -183,7 +145,7 @@ __global__ void __launch_bounds__(kOsdThreads) osd_kernel(const WinDev w, const 
                     id = pass == 0 ? i : src[i];
                     dg = static_cast<uint32_t>((keys[id] >> shift) & 255u);
                 }
-                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, dg);
+                const uint32_t peers = __match_any_sync(kFull, dg);
                 const uint32_t before = peers & ((1u << lane) - 1u);
                 if (valid) {
                     const uint32_t pos = hist[warp * 256 + dg] + __popc(before);
@@ -195,159 +157,215 @@ __global__ void __launch_bounds__(kOsdThreads) osd_kernel(const WinDev w, const 
             }
             __syncthreads();
         }
-        const uint16_t* order = idxB;        // the last (odd-numbered) pass wrote idxB
+    }
+}
 
-        // ------------------------------------------------------------------ 2. Gauss-Jordan on T (registers)
-        uint32_t T[CPT][MW];
-        uint32_t cand[MW];
-        uint32_t freem[MW];
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const int k = tid + c * kOsdThreads;
-#pragma unroll
-            for (int i = 0; i < MW; ++i) {
-                uint32_t v = 0;
-                if (k < m && (k >> 5) == i) v = 1u << (k & 31);
-                if (k == m && i < w.rowsW32) v = syn[i];
-                T[c][i] = v;
-            }
+// ====================================================================================================== elimination
+struct ElimLayout {
+    size_t T, rvec, freem, svec, seq, pivcol, pivrow, slot, accs, car, total;
+    int TS;
+};
+
+__host__ __device__ inline ElimLayout elim_layout(const WinDev& w, int NQ, bool exact) {
+    ElimLayout L;
+    L.TS = (w.rows + 31) / 32 * 32;
+    size_t o = 0;
+    L.T = o; o += static_cast<size_t>(NQ) * L.TS * 16;
+    L.rvec = o; o += static_cast<size_t>(NQ) * 16;
+    L.freem = o; o += static_cast<size_t>(NQ) * 16;
+    L.svec = o; o += static_cast<size_t>(NQ) * 16;
+    L.seq = o; o += exact ? au(static_cast<size_t>(w.rows) * 2) : 0;
+    L.pivcol = o; o += au(static_cast<size_t>(w.rows) * 2);
+    L.pivrow = o; o += au(static_cast<size_t>(w.rows) * 2);
+    L.slot = o; o += au(static_cast<size_t>(w.rows) * 2);
+    L.accs = o; o += au(static_cast<size_t>(w.KW) * 8);
+    L.car = o; o += au(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4);
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ uint32_t comp(const uint4& v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void xor4(uint4& a, const uint4& b) { a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w; }
+__device__ __forceinline__ uint32_t and_any(const uint4& a, const uint4& b) { return (a.x & b.x) | (a.y & b.y) | (a.z & b.z) | (a.w & b.w); }
+
+template <int NQ, bool EXACT>
+__global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const BatchDev b) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const ElimLayout L = elim_layout(w, NQ, EXACT);
+    uint4* T4 = reinterpret_cast<uint4*>(sm + L.T);
+    const uint32_t* T32 = reinterpret_cast<const uint32_t*>(sm + L.T);
+    uint4* rvec = reinterpret_cast<uint4*>(sm + L.rvec);
+    uint4* freem = reinterpret_cast<uint4*>(sm + L.freem);
+    uint4* svec = reinterpret_cast<uint4*>(sm + L.svec);
+    uint32_t* rvec32 = reinterpret_cast<uint32_t*>(rvec);
+    uint32_t* freem32 = reinterpret_cast<uint32_t*>(freem);
+    uint32_t* svec32 = reinterpret_cast<uint32_t*>(svec);
+    uint16_t* seq = reinterpret_cast<uint16_t*>(sm + L.seq);
+    uint16_t* pivcol = reinterpret_cast<uint16_t*>(sm + L.pivcol);
+    uint16_t* pivrow = reinterpret_cast<uint16_t*>(sm + L.pivrow);
+    uint16_t* slot_of_row = reinterpret_cast<uint16_t*>(sm + L.slot);
+    uint32_t* accs = reinterpret_cast<uint32_t*>(sm + L.accs);
+    uint32_t* car = reinterpret_cast<uint32_t*>(sm + L.car);
+
+    const int lane = threadIdx.x;
+    const int m = w.rows, n = w.ncols, TS = L.TS;
+    const int carryW = (w.carry_rows + 31) / 32;
+    const int count = *b.fail_count;
+
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = atomicAdd(b.osd_next, 1);
+        job = __shfl_sync(kFull, job, 0);
+        if (job >= count) break;
+        const int shot = b.fail_list[job];
+        const uint32_t* syn = b.syn_buf + static_cast<size_t>(shot) * b.syn_stride32;
+        const uint16_t* order = b.order_buf + static_cast<size_t>(job) * b.order_stride;
+
+        __syncwarp();
+        for (int i = lane; i < m; i += 32) {
+            slot_of_row[i] = 0xFFFFu;
+            if (EXACT) seq[i] = static_cast<uint16_t>(i);
         }
-#pragma unroll
-        for (int i = 0; i < MW; ++i) {
+        for (int i = lane; i < 4 * NQ; i += 32) {
             const int left = m - 32 * i;
-            freem[i] = left >= 32 ? 0xFFFFFFFFu : (left > 0 ? (1u << left) - 1u : 0u);
-            cand[i] = 0;
+            freem32[i] = left >= 32 ? 0xFFFFFFFFu : (left > 0 ? (1u << left) - 1u : 0u);
+            svec32[i] = i < w.rowsW32 ? syn[i] : 0u;
         }
-        for (int i = tid; i < m; i += kOsdThreads) seq[i] = static_cast<uint16_t>(i);
-        if (tid < 2 * w.KW) accs[tid] = 0;
-        if (tid <= carryW) car[tid] = 0;
-        int rank = 0, base = 0, par = 0, candcol = -1;
-        int pend_p = -1, pend_rank = 0;          // deferred seq update (thread 0)
-        bool refill = true;
-        while (rank < m) {
-            if (refill) {
-                if (base >= n) break;
-                __syncthreads();
+        for (int i = lane; i < 2 * w.KW; i += 32) accs[i] = 0;
+        for (int i = lane; i <= carryW; i += 32) car[i] = 0;
+        __syncwarp();
+
+        int rank = 0, base = 0;
+        while (rank < m && base < n) {
+            // ---- next 32 columns in sorted order, reduced by the transformation so far: one per lane
+            uint4 cand[NQ];
 #pragma unroll
-                for (int c = 0; c < CPT; ++c)
+            for (int i = 0; i < NQ; ++i) cand[i] = make_uint4(0u, 0u, 0u, 0u);
+            int candcol = -1;
+            if (base + lane < n) {
+                candcol = order[base + lane];
+                const int qb = __ldg(w.cptr + candcol), qe = __ldg(w.cptr + candcol + 1);
+                for (int q = qb; q < qe; ++q) {
+                    const int row = __ldg(w.crow + q);
+                    const uint32_t s = slot_of_row[row];
+                    if (s != 0xFFFFu) {
 #pragma unroll
-                    for (int i = 0; i < MW; ++i) tdump[i * TS + tid + c * kOsdThreads] = T[c][i];
-                __syncthreads();
-                const int pos = base + tid;
+                        for (int i = 0; i < NQ; ++i) xor4(cand[i], T4[i * TS + s]);
+                    } else {                                     // the row is not a pivot row yet: its column of T is a unit vector
+                        const uint32_t bit = 1u << (row & 31);
+                        const int c = (row >> 5) & 3;
 #pragma unroll
-                for (int i = 0; i < MW; ++i) cand[i] = 0;
-                candcol = -1;
-                if (pos < n) {
-                    candcol = order[pos];
-                    const int qb = __ldg(w.cptr + candcol), qe = __ldg(w.cptr + candcol + 1);
-                    for (int q = qb; q < qe; ++q) {
-                        const int row = __ldg(w.crow + q);
-#pragma unroll
-                        for (int i = 0; i < MW; ++i) cand[i] ^= tdump[i * TS + row];
+                        for (int i = 0; i < NQ; ++i) {
+                            if (i == (row >> 7)) {
+                                cand[i].x ^= c == 0 ? bit : 0u;
+                                cand[i].y ^= c == 1 ? bit : 0u;
+                                cand[i].z ^= c == 2 ? bit : 0u;
+                                cand[i].w ^= c == 3 ? bit : 0u;
+                            }
+                        }
                     }
                 }
-                base += kOsdThreads;
-                refill = false;
             }
-            // -- A: first candidate (in sorted order) that still has a 1 in a free row
-            uint32_t any = 0;
+            base += 32;
+            uint32_t live = 0;
 #pragma unroll
-            for (int i = 0; i < MW; ++i) any |= cand[i] & freem[i];
-            const uint32_t ball = __ballot_sync(0xFFFFFFFFu, any != 0);
-            if (lane == 0) flags[par * kOsdWarps + warp] = ball;
-            __syncthreads();
-            if (tid == 0 && pend_p >= 0) { seq[pend_p] = seq[pend_rank]; pend_p = -1; }
-            int pt = -1;
+            for (int i = 0; i < NQ; ++i) live |= and_any(cand[i], freem[i]);
+            bool alive = live != 0;
+
+            // ---- consume the panel: every live candidate becomes a pivot, in sorted order
+            for (;;) {
+                const uint32_t mask = __ballot_sync(kFull, alive);
+                if (!mask) break;
+                const int pl = __ffs(mask) - 1;
+                if (lane == pl) {
 #pragma unroll
-            for (int q = kOsdWarps - 1; q >= 0; --q) {
-                const uint32_t f = flags[par * kOsdWarps + q];
-                if (f) pt = q * 32 + __ffs(f) - 1;
-            }
-            if (pt < 0) { refill = true; continue; }
-            if (tid == pt) {
-                pivcol[rank] = static_cast<uint16_t>(candcol);
-                if (EXACT) {
-#pragma unroll
-                    for (int i = 0; i < MW; ++i) rbuf[par * MW + i] = cand[i];
+                    for (int i = 0; i < NQ; ++i) {
+                        rvec[i] = cand[i];
+                        T4[i * TS + rank] = cand[i];             // column of T of the new pivot row: e_prow ^ r = the candidate itself
+                        cand[i] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    alive = false;
+                }
+                __syncwarp();
+                int prow;
+                if (!EXACT) {
+                    const uint32_t x = lane < 4 * NQ ? (rvec32[lane] & freem32[lane]) : 0u;
+                    const uint32_t bal = __ballot_sync(kFull, x != 0u);
+                    const int wl = __ffs(bal) - 1;
+                    prow = 32 * wl + __shfl_sync(kFull, __ffs(x) - 1, wl);
                 } else {
-                    // full-row-rank window: the solution does not depend on which free row becomes the pivot row, so take
-                    // the first one and publish the update vector with that bit already cleared
-                    int pr = -1;
-#pragma unroll
-                    for (int i = 0; i < MW; ++i) {
-                        const uint32_t x = cand[i] & freem[i];
-                        if (pr < 0 && x) pr = 32 * i + __ffs(x) - 1;
+                    // rank-deficient window (inconsistent syndromes are possible): follow the oracle's row order exactly,
+                    // i.e. the first free row in position order that has a 1
+                    int p = -1;
+                    for (int c0 = rank; c0 < m; c0 += 32) {
+                        const int pos = c0 + lane;
+                        uint32_t bit = 0;
+                        if (pos < m) {
+                            const int row = seq[pos];
+                            bit = (rvec32[row >> 5] >> (row & 31)) & 1u;
+                        }
+                        const uint32_t bb = __ballot_sync(kFull, bit);
+                        if (bb) { p = c0 + __ffs(bb) - 1; break; }
                     }
-#pragma unroll
-                    for (int i = 0; i < MW; ++i) rbuf[par * MW + i] = cand[i] & ~((i == (pr >> 5)) ? (1u << (pr & 31)) : 0u);
-                    pivrow[rank] = static_cast<uint16_t>(pr);
+                    prow = seq[p];
+                    __syncwarp();
+                    if (lane == 0) seq[p] = seq[rank];
                 }
-            }
-            __syncthreads();
-            // -- C: pivot row, then the rank-1 update of every register-resident column
-            const uint32_t* rb = rbuf + par * MW;
-            int prow;
-            if (EXACT) {
-                // rank-deficient window (inconsistent syndromes are possible): follow the oracle's row order exactly,
-                // i.e. the first free row in position order that has a 1
-                int p = -1;
-                for (int c0 = rank; c0 < m; c0 += 32) {
-                    const int pos = c0 + lane;
-                    uint32_t bit = 0;
-                    if (pos < m) {
-                        const int row = seq[pos];
-                        bit = (rb[row >> 5] >> (row & 31)) & 1u;
-                    }
-                    const uint32_t bb = __ballot_sync(0xFFFFFFFFu, bit);
-                    if (bb) { p = c0 + __ffs(bb) - 1; break; }
-                }
-                prow = seq[p];
-                if (tid == 0) {
+                const int wsel = prow >> 5;
+                const uint32_t bsel = 1u << (prow & 31);
+                const uint32_t sbit = svec32[wsel] & bsel;
+                const int pcol = __shfl_sync(kFull, candcol, pl);
+                __syncwarp();
+                if (lane == 0) {
+                    rvec32[wsel] &= ~bsel;                       // r = the candidate without the pivot bit
+                    freem32[wsel] &= ~bsel;
+                    pivcol[rank] = static_cast<uint16_t>(pcol);
                     pivrow[rank] = static_cast<uint16_t>(prow);
-                    pend_p = p;
-                    pend_rank = rank;
+                    slot_of_row[prow] = static_cast<uint16_t>(rank);
                 }
-            } else {
-                prow = pivrow[rank];
-            }
-            const int wsel = prow >> 5;
-            const uint32_t bsel = 1u << (prow & 31);
-            uint32_t r[MW];
+                __syncwarp();
+                if (sbit && lane < 4 * NQ) svec32[lane] ^= rvec32[lane];
+                uint4 r[NQ];
 #pragma unroll
-            for (int i = 0; i < MW; ++i) r[i] = EXACT ? (rb[i] & ~((i == wsel) ? bsel : 0u)) : rb[i];
-            uint32_t pw[CPT + 1];
-            pivot_words<MW, CPT>(T, cand, freem, wsel, bsel, pw);
+                for (int i = 0; i < NQ; ++i) r[i] = rvec[i];
+                // own candidate
+                {
+                    uint4 v = cand[0];
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                if (pw[c] & bsel) {
+                    for (int i = 1; i < NQ; ++i)
+                        if (i == (wsel >> 2)) v = cand[i];
+                    if (comp(v, wsel & 3) & bsel) {
+                        uint32_t lv = 0;
 #pragma unroll
-                    for (int i = 0; i < MW; ++i) T[c][i] ^= r[i];
-                }
-            }
-            if (pw[CPT] & bsel) {
-#pragma unroll
-                for (int i = 0; i < MW; ++i) cand[i] ^= r[i];
-            }
-            ++rank;
-            par ^= 1;
-        }
-        // ------------------------------------------------------------------ 3. solution on the pivots, commit
-        __syncthreads();
-        {
-            const int ks = m % kOsdThreads, cs = m / kOsdThreads;       // owner of the syndrome column
-            if (tid == ks) {
-#pragma unroll
-                for (int c = 0; c < CPT; ++c)
-                    if (c == cs) {
-#pragma unroll
-                        for (int i = 0; i < MW; ++i) sprime[i] = T[c][i];
+                        for (int i = 0; i < NQ; ++i) {
+                            xor4(cand[i], r[i]);
+                            lv |= and_any(cand[i], freem[i]);
+                        }
+                        alive = lv != 0;
                     }
+                }
+                // stored columns of T (pivot slots found before this one)
+                const int tword = ((wsel >> 2) * TS) * 4 + (wsel & 3);
+                for (int s = lane; s < rank; s += 32) {
+                    if (T32[tword + 4 * s] & bsel) {
+#pragma unroll
+                        for (int i = 0; i < NQ; ++i) {
+                            uint4 t = T4[i * TS + s];
+                            xor4(t, r[i]);
+                            T4[i * TS + s] = t;
+                        }
+                    }
+                }
+                ++rank;
+                __syncwarp();
+                if (rank == m) break;
             }
         }
-        __syncthreads();
-        for (int rr = tid; rr < rank; rr += kOsdThreads) {
+        // ---- solution on the pivots (reduced syndrome), commit
+        __syncwarp();
+        for (int rr = lane; rr < rank; rr += 32) {
             const int row = pivrow[rr];
-            if (!((sprime[row >> 5] >> (row & 31)) & 1u)) continue;
+            if (!((svec32[row >> 5] >> (row & 31)) & 1u)) continue;
             const int j = pivcol[rr];
             if (b.ehat_out) atomicOr(&b.ehat_out[static_cast<size_t>(shot) * b.ehat_stride32 + (j >> 5)], 1u << (j & 31));
             if (j < w.ncommit) {
@@ -364,88 +382,77 @@ __global__ void __launch_bounds__(kOsdThreads) osd_kernel(const WinDev w, const 
                 }
             }
         }
-        __syncthreads();
-        if (tid < w.KW) {
-            const uint64_t v = (static_cast<uint64_t>(accs[2 * tid + 1]) << 32) | accs[2 * tid];
-            b.acc[static_cast<size_t>(shot) * w.KW + tid] ^= v;
+        __syncwarp();
+        for (int i = lane; i < w.KW; i += 32) {
+            const uint64_t v = (static_cast<uint64_t>(accs[2 * i + 1]) << 32) | accs[2 * i];
+            b.acc[static_cast<size_t>(shot) * w.KW + i] ^= v;
         }
-        if (tid < carryW) b.carry[static_cast<size_t>(shot) * b.carry_stride32 + tid] = car[tid];
-        if (tid == 0) atomicAdd(&b.stats[2], 1ull);
+        for (int i = lane; i < carryW; i += 32) b.carry[static_cast<size_t>(shot) * b.carry_stride32 + i] = car[i];
+        if (lane == 0) atomicAdd(&b.stats[2], 1ull);
     }
 }
 
-struct OsdShape { int MW, CPT; };
+inline int elim_nq(const WinDev& w) { return (w.rows + 127) / 128; }
 
-// instantiated (MW, CPT) shapes: MW 32-bit words cover the rows, CPT*128 thread-slots cover the rows+1 columns of T
-inline bool osd_shape(const WinDev& w, OsdShape& s) {
-    static const int shapes[][2] = {{4, 2}, {6, 2}, {8, 2}, {8, 3}, {12, 3}, {12, 4}, {17, 5}, {23, 6}};
-    if (w.ncols > 65535 || w.rows > 65535) return false;
-    for (auto& sh : shapes) {
-        if (w.rows <= sh[0] * 32 && w.rows + 1 <= sh[1] * kOsdThreads) {
-            s.MW = sh[0];
-            s.CPT = sh[1];
-            return true;
-        }
-    }
-    return false;
-}
-
-template <typename R, bool EXACT, typename F>
-inline cudaError_t osd_dispatch_r(const OsdShape& s, F&& f) {
-    switch (s.MW * 10 + s.CPT) {
-    case 42: return f(osd_kernel<R, 4, 2, EXACT>);
-    case 62: return f(osd_kernel<R, 6, 2, EXACT>);
-    case 82: return f(osd_kernel<R, 8, 2, EXACT>);
-    case 83: return f(osd_kernel<R, 8, 3, EXACT>);
-    case 123: return f(osd_kernel<R, 12, 3, EXACT>);
-    case 124: return f(osd_kernel<R, 12, 4, EXACT>);
-    case 175: return f(osd_kernel<R, 17, 5, EXACT>);
-    case 236: return f(osd_kernel<R, 23, 6, EXACT>);
+template <typename F>
+inline cudaError_t elim_dispatch(const WinDev& w, F&& f) {
+    const bool exact = !w.full_row_rank;
+    switch (elim_nq(w)) {
+    case 1: return exact ? f(osd_elim_kernel<1, true>) : f(osd_elim_kernel<1, false>);
+    case 2: return exact ? f(osd_elim_kernel<2, true>) : f(osd_elim_kernel<2, false>);
+    case 3: return exact ? f(osd_elim_kernel<3, true>) : f(osd_elim_kernel<3, false>);
+    case 4: return exact ? f(osd_elim_kernel<4, true>) : f(osd_elim_kernel<4, false>);
+    case 5: return exact ? f(osd_elim_kernel<5, true>) : f(osd_elim_kernel<5, false>);
+    case 6: return exact ? f(osd_elim_kernel<6, true>) : f(osd_elim_kernel<6, false>);
     }
     return cudaErrorInvalidValue;
 }
 
-template <typename F>
-inline cudaError_t osd_dispatch(const WinDev& w, int precision, F&& f) {
-    OsdShape s;
-    if (!osd_shape(w, s)) return cudaErrorInvalidValue;
-    if (w.full_row_rank) return precision == 32 ? osd_dispatch_r<float, false>(s, f) : osd_dispatch_r<double, false>(s, f);
-    return precision == 32 ? osd_dispatch_r<float, true>(s, f) : osd_dispatch_r<double, true>(s, f);
-}
-
 }  // namespace
 
-size_t osd_smem_bytes(const WinDev& w, int precision) {
-    OsdShape s;
-    if (!osd_shape(w, s)) return 0;
-    return osd_layout(w, s.MW, s.CPT, precision == 32 ? 4 : 8).total;
-}
+size_t osd_sort_smem_bytes(const WinDev& w, int precision) { return sort_layout(w, precision == 32 ? 4 : 8).total; }
+size_t osd_elim_smem_bytes(const WinDev& w) { return elim_layout(w, elim_nq(w), !w.full_row_rank).total; }
 
 bool osd_supported(const WinDev& w, int precision) {
-    OsdShape s;
-    return osd_shape(w, s) && osd_smem_bytes(w, precision) <= 220 * 1024;
+    return w.rows <= 768 && w.ncols <= 65535 && osd_sort_smem_bytes(w, precision) <= 220 * 1024 && osd_elim_smem_bytes(w) <= 220 * 1024;
 }
 
 cudaError_t osd_configure(const WinDev& w, int precision) {
-    // several windows may share one instantiation: the attribute only ever grows
-    static size_t configured[4][256] = {};
-    const size_t smem = osd_smem_bytes(w, precision);
-    OsdShape s;
-    if (!osd_shape(w, s)) return cudaErrorInvalidValue;
-    size_t& have = configured[(precision == 32 ? 0 : 1) + (w.full_row_rank ? 2 : 0)][(s.MW * 10 + s.CPT) & 255];
-    if (smem <= have) return cudaSuccess;
-    cudaError_t e = osd_dispatch(w, precision, [&](auto kern) {
-        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    });
-    if (e == cudaSuccess) have = smem;
-    return e;
+    // several windows may share one instantiation: the attributes only ever grow
+    static size_t sort_have[2] = {}, elim_have[2][8] = {};
+    const size_t ss = osd_sort_smem_bytes(w, precision), es = osd_elim_smem_bytes(w);
+    size_t& sh = sort_have[precision == 32 ? 0 : 1];
+    if (ss > sh) {
+        cudaError_t e = precision == 32
+            ? cudaFuncSetAttribute(osd_sort_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ss))
+            : cudaFuncSetAttribute(osd_sort_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ss));
+        if (e != cudaSuccess) return e;
+        sh = ss;
+    }
+    size_t& eh = elim_have[w.full_row_rank ? 0 : 1][elim_nq(w) & 7];
+    if (es > eh) {
+        cudaError_t e = elim_dispatch(w, [&](auto kern) {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(es));
+        });
+        if (e != cudaSuccess) return e;
+        eh = es;
+    }
+    return cudaSuccess;
 }
 
-cudaError_t launch_osd(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st) {
+cudaError_t launch_osd_sort(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st) {
     if (b.n_shots == 0) return cudaSuccess;
-    const size_t smem = osd_smem_bytes(w, precision);
-    return osd_dispatch(w, precision, [&](auto kern) {
-        kern<<<grid, kOsdThreads, smem, st>>>(w, b);
+    const size_t smem = osd_sort_smem_bytes(w, precision);
+    if (precision == 32) osd_sort_kernel<float><<<grid, kSortThreads, smem, st>>>(w, b);
+    else osd_sort_kernel<double><<<grid, kSortThreads, smem, st>>>(w, b);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_osd_elim(const WinDev& w, const BatchDev& b, int grid, cudaStream_t st) {
+    if (b.n_shots == 0) return cudaSuccess;
+    const size_t smem = osd_elim_smem_bytes(w);
+    return elim_dispatch(w, [&](auto kern) {
+        kern<<<grid, 32, smem, st>>>(w, b);
         return cudaGetLastError();
     });
 }

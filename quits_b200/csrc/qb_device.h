@@ -2,7 +2,7 @@
 //
 //   K1  frame_kernel   per-shot Pauli-frame propagation, 64 shots per bit-word      (frame.cu)
 //   K3  bp_kernel      flooding min-sum BP of one window, one shot per CTA, messages in shared memory (bp.cu)
-//   K4  osd_kernel     OSD-0: LLR radix sort + register-resident GF(2) Gauss-Jordan, one shot per CTA (osd.cu)
+//   K4  osd_sort_kernel / osd_elim_kernel   OSD-0: LLR radix sort (CTA per shot), GF(2) Gauss-Jordan (warp per shot) (osd.cu)
 //   K2/K5 are fused into K3/K4: syndrome = slice(det) ^ carry on entry, H e == s as the stop test, L e / U e on exit.
 #pragma once
 #include <cuda_runtime.h>
@@ -90,7 +90,10 @@ struct BatchDev {
     int syn_stride32;
     int* fail_list;           // [n]
     int* fail_count;          // [1]
-    int* osd_next;            // [1] work counter of the persistent OSD grid
+    int* sort_next;           // [1] work counter of the persistent OSD sort grid
+    int* osd_next;            // [1] work counter of the persistent OSD elimination grid
+    uint16_t* order_buf;      // [fail slot][order_stride] columns in OSD order (sort kernel -> elimination kernel)
+    size_t order_stride;
     unsigned long long* stats;// [3] converged windows, BP iterations, OSD calls
     uint32_t* ehat_out;       // optional [n][ehat_stride32]  (pre-zeroed)
     int ehat_stride32;
@@ -111,10 +114,12 @@ int bp_threads(int precision);
 cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal);
 cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, bool vglobal, int grid, cudaStream_t st);
 
-size_t osd_smem_bytes(const WinDev& w, int precision);
+size_t osd_sort_smem_bytes(const WinDev& w, int precision);
+size_t osd_elim_smem_bytes(const WinDev& w);
 bool osd_supported(const WinDev& w, int precision);
 cudaError_t osd_configure(const WinDev& w, int precision);
-cudaError_t launch_osd(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
+cudaError_t launch_osd_sort(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
+cudaError_t launch_osd_elim(const WinDev& w, const BatchDev& b, int grid, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------- results
 // pred[n][K] int64 from acc bits; counts[0] += shots whose prediction differs from obs_rows in any observable,
