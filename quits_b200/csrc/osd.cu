@@ -20,6 +20,8 @@
 //                     pick the pivot row, XOR r into every candidate and every stored column of T that has the pivot
 //                     row's bit, and into the syndrome column.  Row swaps are virtual: `seq` lists the free rows in the
 //                     oracle's position order and a pivot only moves the head of that list into the vacated slot.
+//                     The elimination stops as soon as the reduced syndrome vanishes on all free rows: from then on no
+//                     pivot can touch it, so the answer is final (typically after a few hundred of the ~3600 columns).
 //                     Full-row-rank windows skip `seq`: with all rows eventually pivots and consistent syndromes the
 //                     solution does not depend on which free row a pivot takes, so the first set bit is used.
 #include <cfloat>
@@ -236,7 +238,8 @@ __global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const Batc
         __syncwarp();
 
         int rank = 0, base = 0;
-        while (rank < m && base < n) {
+        bool done = false;
+        while (rank < m && base < n && !done) {
             // ---- next 32 columns in sorted order, reduced by the transformation so far: one per lane
             uint4 cand[NQ];
 #pragma unroll
@@ -359,6 +362,13 @@ __global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const Batc
                 ++rank;
                 __syncwarp();
                 if (rank == m) break;
+                // Early exit (exact): once the reduced syndrome is zero on every free row, no later pivot can change it
+                // (an operation only acts on a vector that has the pivot row's bit, and pivot rows are taken from the
+                // free rows), and every later pivot gets solution bit 0.
+                {
+                    const uint32_t y = lane < 4 * NQ ? (svec32[lane] & freem32[lane]) : 0u;
+                    if (!__any_sync(kFull, y != 0u)) { done = true; break; }
+                }
             }
         }
         // ---- solution on the pivots (reduced syndrome), commit
