@@ -188,7 +188,7 @@ def main():
         c, st = step(args.warmup + i)
         counts += c
         for k, v in st.items():
-            agg[k] = agg.get(k, 0) + v
+            agg[k] = max(agg.get(k, 0), v) if k == "osd_max_columns" else agg.get(k, 0) + v
         flush.zero_()
         torch.cuda.synchronize()
     barrier()
@@ -223,7 +223,10 @@ def main():
                 "logical_errors": int(cnt[0].item()), "shots_total": int(total_shots),
                 "decoder_stats": {"bp_converged_frac": agg["bp_converged"] / max(1, agg["windows"]),
                                   "bp_iters_per_window": agg["bp_iterations"] / max(1, agg["windows"]),
-                                  "osd_calls_per_shot": agg["osd_calls"] / max(1, agg["shots"])},
+                                  "osd_calls_per_shot": agg["osd_calls"] / max(1, agg["shots"]),
+                                  "osd_columns_per_call": agg["osd_columns"] / max(1, agg["osd_calls"]),
+                                  "osd_pivots_per_call": agg["osd_pivots"] / max(1, agg["osd_calls"]),
+                                  "osd_max_columns": agg["osd_max_columns"], "osd_fast_path_overflows": agg["osd_overflows"]},
                 "kernel_ms_per_step": {"frame": agg["frame_ms"] / args.steps, "bp": agg["bp_ms"] / args.steps,
                                        "osd": agg["osd_ms"] / args.steps},
                 "roofline": {"kernel": "bp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

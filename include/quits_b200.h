@@ -121,6 +121,9 @@ typedef struct {
     /* algorithmic bytes of the launches above: BP = iterations x 4 x nnz x sizeof(message) + syndrome in +
      * commit/carry out; OSD = 2 x rows x 8 ceil(cols/64) per call; frame = packed detector + observable rows written */
     double bp_alg_bytes, osd_alg_bytes, frame_alg_bytes;
+    /* OSD work actually done (the elimination stops early, osd.cu): columns examined, pivots taken, worst case */
+    int64_t osd_columns, osd_pivots, osd_max_columns;
+    int64_t osd_overflows;      /* shots the fast OSD path handed to the full sort */
 } qb_stats;
 
 /* Window plan (host only): spacetime() of decoder/base.py:134-190.  n_cor < 0 derives the number of sliding windows

@@ -139,7 +139,7 @@ struct WinOwned {
     size_t bp_smem = 0;
     bool vglobal = false;
     int bp_grid = 0;            // persistent grid of the VGLOBAL variant (0: one CTA per shot)
-    int sort_grid = 0, elim_grid = 0;
+    int sort_grid = 0, elim_grid = 0, fast_grid = 0;
 };
 
 }  // namespace
@@ -159,11 +159,14 @@ struct qb_sw {
     int lanes = 1, lanes_used = 1;    // concurrent sub-batches per batch (decode_batch)
     int DW = 0, KW = 0, carryW = 0, synW = 0;
     size_t llr_stride = 0, order_stride = 0;
-    DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, order, counters, stats, pred, ehat, iters, conv, vscratch;
+    DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, ovf_list, order, counters, stats, pred, ehat, iters, conv, vscratch;
     EventTimer t_bp, t_osd;
 };
 
 namespace {
+
+constexpr size_t kStatSlots = 8;
+constexpr size_t kCounterSlots = 8;
 
 void use_device(qb_ctx* ctx) { CK(cudaSetDevice(ctx->device)); }
 
@@ -364,6 +367,11 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
     d.row0 = hw.row0; d.carry_rows = hw.urows; d.KW = KW;
     d.rowsW32 = (rows + 31) / 32; d.nW32 = (ncols + 31) / 32;
     d.full_row_rank = gf2_rank(hw) == rows ? 1 : 0;
+    {
+        double lmin = DBL_MAX;
+        for (int j = 0; j < ncols; ++j) lmin = std::min(lmin, llr0d[j]);
+        d.bin_scale = lmin > 1e-3 ? 24.0 / lmin : 24.0;
+    }
     d.colE = wo.colE.as<uint32_t>(); d.llr0f = wo.llr0f.as<float>(); d.llr0d = wo.llr0d.as<double>(); d.lmask = wo.lmask.as<uint64_t>();
     d.uptr = wo.uptr.as<int32_t>(); d.uidx = wo.uidx.as<uint16_t>(); d.cptr = wo.cptr.as<int32_t>(); d.crow = wo.crow.as<uint16_t>();
 }
@@ -404,6 +412,8 @@ void finish_decoder(qb_sw* sw) {
             const int elim_per_sm = static_cast<int>((227 * 1024) / (qb::osd_elim_smem_bytes(w->dev) + 1024));
             w->sort_grid = 148 * std::max(1, std::min(sort_per_sm, 6));
             w->elim_grid = 148 * std::max(1, std::min(elim_per_sm, 16));
+            const int fast_per_sm = static_cast<int>((227 * 1024) / (qb::osd_fast_smem_bytes(w->dev) + 1024));
+            w->fast_grid = 148 * std::max(1, std::min(fast_per_sm, 16));
             max_order = std::max(max_order, static_cast<size_t>((w->dev.ncols + 63) / 64 * 64));
         }
     }
@@ -436,10 +446,11 @@ void ensure_batch(qb_sw* sw, int n) {
     sw->llr.ensure(N * sw->llr_stride * (sw->precision / 8) + 16);
     sw->syn.ensure(N * sw->synW * 4 + 16);
     sw->fail_list.ensure(N * 4 + 16);
+    if (sw->use_osd) sw->ovf_list.ensure(N * 4 + 16);
     if (sw->use_osd) sw->order.ensure(N * sw->order_stride * 2 + 16);
     const size_t nw = sw->wins.size() * qb_ctx::kMaxLanes;
-    sw->counters.ensure(nw * 4 * sizeof(int) + 16);
-    sw->stats.ensure(nw * 3 * sizeof(unsigned long long) + 16);
+    sw->counters.ensure(nw * kCounterSlots * sizeof(int) + 16);
+    sw->stats.ensure(nw * kStatSlots * sizeof(unsigned long long) + 16);
 }
 
 // decode n (<= cap) shots whose packed detector rows are on the device; leaves acc[n][KW] on the device.
@@ -455,8 +466,8 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
     sw->lanes_used = lanes;
     CK(cudaMemsetAsync(sw->acc.p, 0, static_cast<size_t>(n) * sw->KW * 8, st));
     CK(cudaMemsetAsync(sw->carry.p, 0, static_cast<size_t>(n) * sw->carryW * 4, st));
-    CK(cudaMemsetAsync(sw->counters.p, 0, nw * lanes * 4 * sizeof(int), st));
-    CK(cudaMemsetAsync(sw->stats.p, 0, nw * lanes * 3 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(sw->counters.p, 0, nw * lanes * kCounterSlots * sizeof(int), st));
+    CK(cudaMemsetAsync(sw->stats.p, 0, nw * lanes * kStatSlots * sizeof(unsigned long long), st));
     if (lanes > 1) {
         for (int l = 1; l < lanes; ++l) ctx->lane_stream(l);
         CK(cudaEventRecord(ctx->ev_fork, st));
@@ -488,12 +499,16 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.syn_buf = sw->syn.as<uint32_t>() + s0 * sw->synW;
             b.fail_list = sw->fail_list.as<int>() + s0;          // shot indices local to the sub-batch
             const size_t slot = static_cast<size_t>(l) * nw + k;
-            b.fail_count = sw->counters.as<int>() + 4 * slot;
-            b.sort_next = sw->counters.as<int>() + 4 * slot + 1;
-            b.osd_next = sw->counters.as<int>() + 4 * slot + 2;
+            int* ctr = sw->counters.as<int>() + kCounterSlots * slot;
+            b.fail_count = ctr;
+            b.fast_next = ctr + 1;
+            b.ovf_count = ctr + 2;
+            b.sort_next = ctr + 3;
+            b.osd_next = ctr + 4;
+            b.ovf_list = sw->use_osd ? sw->ovf_list.as<int>() + s0 : nullptr;
             b.order_buf = sw->order.as<uint16_t>() + s0 * sw->order_stride;     // fail slots of a sub-batch are < its shot count
             b.order_stride = sw->order_stride;
-            b.stats = sw->stats.as<unsigned long long>() + 3 * slot;
+            b.stats = sw->stats.as<unsigned long long>() + kStatSlots * slot;
             b.ehat_out = want_ehat ? sw->ehat.as<uint32_t>() : nullptr;
             b.ehat_stride32 = w.dev.nW32;
             b.iters_out = want_ehat ? sw->iters.as<int32_t>() : nullptr;
@@ -505,10 +520,16 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             if (stats) stats->bp_launches++;
             if (sw->use_osd) {
                 if (sw->opts.profile) sw->t_osd.begin(ls);
-                CK(qb::launch_osd_sort(w.dev, b, sw->precision, std::min(w.sort_grid, nl), ls));
-                CK(qb::launch_osd_elim(w.dev, b, std::min(w.elim_grid, nl), ls));
+                // fast path: per-warp selection of the least reliable columns + elimination; the (rare) shots it cannot finish
+                // go through the full sort + elimination, which read the overflow list instead of the fail list
+                CK(qb::launch_osd_fast(w.dev, b, sw->precision, std::min(w.fast_grid, nl), ls));
+                qb::BatchDev bo = b;
+                bo.fail_list = b.ovf_list;
+                bo.fail_count = b.ovf_count;
+                CK(qb::launch_osd_sort(w.dev, bo, sw->precision, std::min(w.sort_grid, std::max(1, nl / 64)), ls));
+                CK(qb::launch_osd_elim(w.dev, bo, std::min(w.elim_grid, std::max(1, nl / 64)), ls));
                 if (sw->opts.profile) sw->t_osd.end(ls);
-                if (stats) stats->osd_launches += 2;
+                if (stats) stats->osd_launches += 3;
             }
         }
     }
@@ -522,16 +543,20 @@ void collect_stats(qb_sw* sw, int n, qb_stats* stats) {        // stream must be
     if (!stats) return;
     const size_t nw = sw->wins.size();
     const int lanes = sw->lanes_used;
-    std::vector<unsigned long long> h(nw * lanes * 3);
+    std::vector<unsigned long long> h(nw * lanes * kStatSlots);
     CK(cudaMemcpy(h.data(), sw->stats.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     stats->shots += n;
     stats->windows += static_cast<int64_t>(nw) * n;
     for (int l = 0; l < lanes; ++l)
         for (size_t k = 0; k < nw; ++k) {
-            const unsigned long long* hk = &h[(static_cast<size_t>(l) * nw + k) * 3];
+            const unsigned long long* hk = &h[(static_cast<size_t>(l) * nw + k) * kStatSlots];
             stats->bp_converged += static_cast<int64_t>(hk[0]);
             stats->bp_iterations += static_cast<int64_t>(hk[1]);
             stats->osd_calls += static_cast<int64_t>(hk[2]);
+            stats->osd_columns += static_cast<int64_t>(hk[3]);
+            stats->osd_pivots += static_cast<int64_t>(hk[4]);
+            stats->osd_max_columns = std::max(stats->osd_max_columns, static_cast<int64_t>(hk[5]));
+            stats->osd_overflows += static_cast<int64_t>(hk[6]);
             const qb::WinDev& d = sw->wins[k]->dev;
             const double nnz = static_cast<double>(sw->plan.windows[k].crow.size());
             const size_t s0 = static_cast<size_t>(n) * l / lanes, s1 = static_cast<size_t>(n) * (l + 1) / lanes;

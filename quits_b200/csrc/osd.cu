@@ -164,11 +164,11 @@ __global__ void __launch_bounds__(kSortThreads) osd_sort_kernel(const WinDev w, 
 
 // ====================================================================================================== elimination
 struct ElimLayout {
-    size_t T, rvec, freem, svec, seq, pivcol, pivrow, slot, accs, car, total;
+    size_t T, rvec, freem, svec, seq, pivcol, pivrow, slot, accs, car, selkey, selidx, sorted, bins, total;
     int TS;
 };
 
-__host__ __device__ inline ElimLayout elim_layout(const WinDev& w, int NQ, bool exact) {
+__host__ __device__ inline ElimLayout elim_layout(const WinDev& w, int NQ, bool exact, int selcap) {
     ElimLayout L;
     L.TS = (w.rows + 31) / 32 * 32;
     size_t o = 0;
@@ -182,6 +182,10 @@ __host__ __device__ inline ElimLayout elim_layout(const WinDev& w, int NQ, bool 
     L.slot = o; o += au(static_cast<size_t>(w.rows) * 2);
     L.accs = o; o += au(static_cast<size_t>(w.KW) * 8);
     L.car = o; o += au(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4);
+    L.selkey = o; o += au(static_cast<size_t>(selcap) * 8);
+    L.selidx = o; o += au(static_cast<size_t>(selcap) * 2);
+    L.sorted = o; o += au(static_cast<size_t>(selcap) * 2);
+    L.bins = o; o += selcap ? 128 : 0;
     L.total = o;
     return L;
 }
@@ -190,10 +194,11 @@ __device__ __forceinline__ uint32_t comp(const uint4& v, int c) { return c == 0 
 __device__ __forceinline__ void xor4(uint4& a, const uint4& b) { a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w; }
 __device__ __forceinline__ uint32_t and_any(const uint4& a, const uint4& b) { return (a.x & b.x) | (a.y & b.y) | (a.z & b.z) | (a.w & b.w); }
 
+// One shot, one warp: eliminate over `order[0 .. n_avail)` (the first n_avail columns of the OSD order out of n).  Returns
+// false -- and commits nothing -- when those columns ran out before the answer was final although more columns exist.
 template <int NQ, bool EXACT>
-__global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const BatchDev b) {
-    extern __shared__ __align__(16) unsigned char sm[];
-    const ElimLayout L = elim_layout(w, NQ, EXACT);
+__device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, unsigned char* sm, const ElimLayout& L, const int shot,
+                                         const uint16_t* order, const int n, const int n_total) {
     uint4* T4 = reinterpret_cast<uint4*>(sm + L.T);
     const uint32_t* T32 = reinterpret_cast<const uint32_t*>(sm + L.T);
     uint4* rvec = reinterpret_cast<uint4*>(sm + L.rvec);
@@ -208,21 +213,11 @@ __global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const Batc
     uint16_t* slot_of_row = reinterpret_cast<uint16_t*>(sm + L.slot);
     uint32_t* accs = reinterpret_cast<uint32_t*>(sm + L.accs);
     uint32_t* car = reinterpret_cast<uint32_t*>(sm + L.car);
-
-    const int lane = threadIdx.x;
-    const int m = w.rows, n = w.ncols, TS = L.TS;
+    const int lane = threadIdx.x & 31;
+    const int m = w.rows, TS = L.TS;
     const int carryW = (w.carry_rows + 31) / 32;
-    const int count = *b.fail_count;
-
-    for (;;) {
-        int job = 0;
-        if (lane == 0) job = atomicAdd(b.osd_next, 1);
-        job = __shfl_sync(kFull, job, 0);
-        if (job >= count) break;
-        const int shot = b.fail_list[job];
-        const uint32_t* syn = b.syn_buf + static_cast<size_t>(shot) * b.syn_stride32;
-        const uint16_t* order = b.order_buf + static_cast<size_t>(job) * b.order_stride;
-
+    const uint32_t* syn = b.syn_buf + static_cast<size_t>(shot) * b.syn_stride32;
+    {
         __syncwarp();
         for (int i = lane; i < m; i += 32) {
             slot_of_row[i] = 0xFFFFu;
@@ -371,6 +366,7 @@ __global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const Batc
                 }
             }
         }
+        if (!done && rank < m && n < n_total) return false;      // ran out of sorted columns: the caller retries with the full order
         // ---- solution on the pivots (reduced syndrome), commit
         __syncwarp();
         for (int rr = lane; rr < rank; rr += 32) {
@@ -398,7 +394,125 @@ __global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const Batc
             b.acc[static_cast<size_t>(shot) * w.KW + i] ^= v;
         }
         for (int i = lane; i < carryW; i += 32) b.carry[static_cast<size_t>(shot) * b.carry_stride32 + i] = car[i];
-        if (lane == 0) atomicAdd(&b.stats[2], 1ull);
+        if (lane == 0) {
+            atomicAdd(&b.stats[2], 1ull);
+            atomicAdd(&b.stats[3], static_cast<unsigned long long>(min(base, n)));
+            atomicAdd(&b.stats[4], static_cast<unsigned long long>(rank));
+            atomicMax(&b.stats[5], static_cast<unsigned long long>(min(base, n)));
+        }
+    }
+    return true;
+}
+
+template <int NQ, bool EXACT>
+__global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const BatchDev b) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const ElimLayout L = elim_layout(w, NQ, EXACT, 0);
+    const int lane = threadIdx.x;
+    const int count = *b.fail_count;
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = atomicAdd(b.osd_next, 1);
+        job = __shfl_sync(kFull, job, 0);
+        if (job >= count) break;
+        const int shot = b.fail_list[job];
+        elim_job<NQ, EXACT>(w, b, sm, L, shot, b.order_buf + static_cast<size_t>(job) * b.order_stride, w.ncols, w.ncols);
+    }
+}
+
+// Fast path: the elimination almost always ends within the few dozen least reliable columns (see the early exit), so the
+// warp selects just those itself instead of waiting for a full sort: a 32-bin histogram of the posteriors (bins are monotone
+// in the LLR, width = 1/24 of the window's smallest prior LLR), the smallest bin prefix holding >= kSelTarget columns, a stable
+// ballot compaction of those columns in index order, and a rank-by-counting sort on (key, index).  Shots whose elimination
+// outruns the selection are appended to the overflow list and redone by osd_sort_kernel + osd_elim_kernel.
+constexpr int kSelCap = 256, kSelTarget = 64;
+
+template <typename R, int NQ, bool EXACT>
+__global__ void __launch_bounds__(32) osd_fast_kernel(const WinDev w, const BatchDev b) {
+    using KeyT = typename std::conditional<sizeof(R) == 4, uint32_t, uint64_t>::type;
+    extern __shared__ __align__(16) unsigned char sm[];
+    const ElimLayout L = elim_layout(w, NQ, EXACT, kSelCap);
+    KeyT* selkey = reinterpret_cast<KeyT*>(sm + L.selkey);
+    uint16_t* selidx = reinterpret_cast<uint16_t*>(sm + L.selidx);
+    uint16_t* sorted = reinterpret_cast<uint16_t*>(sm + L.sorted);
+    uint32_t* bins = reinterpret_cast<uint32_t*>(sm + L.bins);
+    const int lane = threadIdx.x;
+    const int n = w.ncols;
+    const int count = *b.fail_count;
+    const R scale = static_cast<R>(w.bin_scale);
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = atomicAdd(b.fast_next, 1);
+        job = __shfl_sync(kFull, job, 0);
+        if (job >= count) break;
+        const int shot = b.fail_list[job];
+        const R* llr = reinterpret_cast<const R*>(b.llr_buf) + static_cast<size_t>(shot) * b.llr_stride;
+        // ---- histogram: lane b ends up with the number of columns in bin b
+        bins[lane] = 0;
+        __syncwarp();
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < n) {
+                const R v = llr[i];
+                const int bin = v > R(0) ? 1 + static_cast<int>(fmin(static_cast<double>(v * scale), 30.0)) : 0;
+                atomicAdd(&bins[bin], 1u);
+            }
+        }
+        __syncwarp();
+        const uint32_t mycount = bins[lane];
+        uint32_t cum = mycount;                                            // inclusive prefix over bins
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, cum, o);
+            if (lane >= o) cum += t;
+        }
+        const uint32_t enough = __ballot_sync(kFull, cum >= static_cast<uint32_t>(kSelTarget));
+        int bsel = enough ? __ffs(enough) - 1 : 31;
+        if (__shfl_sync(kFull, cum, bsel) > static_cast<uint32_t>(kSelCap)) {
+            const uint32_t fits = __ballot_sync(kFull, cum <= static_cast<uint32_t>(kSelCap));
+            bsel = fits ? 31 - __clz(fits) : -1;
+        }
+        const int S = bsel >= 0 ? static_cast<int>(__shfl_sync(kFull, cum, bsel)) : 0;
+        bool finished = false;
+        if (S > 0) {
+            // ---- compaction in index order
+            int offset = 0;
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                bool sel = false;
+                KeyT key = 0;
+                if (i < n) {
+                    const R v = llr[i];
+                    const int bin = v > R(0) ? 1 + static_cast<int>(fmin(static_cast<double>(v * scale), 30.0)) : 0;
+                    sel = bin <= bsel;
+                    key = order_key(v);
+                }
+                const uint32_t mask = __ballot_sync(kFull, sel);
+                if (sel) {
+                    const int pos = offset + __popc(mask & ((1u << lane) - 1u));
+                    selkey[pos] = key;
+                    selidx[pos] = static_cast<uint16_t>(i);
+                }
+                offset += __popc(mask);
+            }
+            __syncwarp();
+            // ---- rank by counting on (key, position); positions are in index order, so ties resolve by column index
+            for (int e = lane; e < S; e += 32) {
+                const KeyT ke = selkey[e];
+                int rank = 0;
+                for (int f = 0; f < S; ++f) {
+                    const KeyT kf = selkey[f];
+                    rank += (kf < ke || (kf == ke && f < e)) ? 1 : 0;
+                }
+                sorted[rank] = selidx[e];
+            }
+            __syncwarp();
+            finished = elim_job<NQ, EXACT>(w, b, sm, L, shot, sorted, S, n);
+        }
+        if (!finished && lane == 0) {
+            b.ovf_list[atomicAdd(b.ovf_count, 1)] = shot;
+            atomicAdd(&b.stats[6], 1ull);
+        }
     }
 }
 
@@ -418,19 +532,40 @@ inline cudaError_t elim_dispatch(const WinDev& w, F&& f) {
     return cudaErrorInvalidValue;
 }
 
+
+template <typename R, typename F>
+inline cudaError_t fast_dispatch_r(const WinDev& w, F&& f) {
+    const bool exact = !w.full_row_rank;
+    switch (elim_nq(w)) {
+    case 1: return exact ? f(osd_fast_kernel<R, 1, true>) : f(osd_fast_kernel<R, 1, false>);
+    case 2: return exact ? f(osd_fast_kernel<R, 2, true>) : f(osd_fast_kernel<R, 2, false>);
+    case 3: return exact ? f(osd_fast_kernel<R, 3, true>) : f(osd_fast_kernel<R, 3, false>);
+    case 4: return exact ? f(osd_fast_kernel<R, 4, true>) : f(osd_fast_kernel<R, 4, false>);
+    case 5: return exact ? f(osd_fast_kernel<R, 5, true>) : f(osd_fast_kernel<R, 5, false>);
+    case 6: return exact ? f(osd_fast_kernel<R, 6, true>) : f(osd_fast_kernel<R, 6, false>);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <typename F>
+inline cudaError_t fast_dispatch(const WinDev& w, int precision, F&& f) {
+    return precision == 32 ? fast_dispatch_r<float>(w, f) : fast_dispatch_r<double>(w, f);
+}
+
 }  // namespace
 
 size_t osd_sort_smem_bytes(const WinDev& w, int precision) { return sort_layout(w, precision == 32 ? 4 : 8).total; }
-size_t osd_elim_smem_bytes(const WinDev& w) { return elim_layout(w, elim_nq(w), !w.full_row_rank).total; }
+size_t osd_elim_smem_bytes(const WinDev& w) { return elim_layout(w, elim_nq(w), !w.full_row_rank, 0).total; }
+size_t osd_fast_smem_bytes(const WinDev& w) { return elim_layout(w, elim_nq(w), !w.full_row_rank, kSelCap).total; }
 
 bool osd_supported(const WinDev& w, int precision) {
-    return w.rows <= 768 && w.ncols <= 65535 && osd_sort_smem_bytes(w, precision) <= 220 * 1024 && osd_elim_smem_bytes(w) <= 220 * 1024;
+    return w.rows <= 768 && w.ncols <= 65535 && osd_sort_smem_bytes(w, precision) <= 220 * 1024 && osd_fast_smem_bytes(w) <= 220 * 1024;
 }
 
 cudaError_t osd_configure(const WinDev& w, int precision) {
     // several windows may share one instantiation: the attributes only ever grow
-    static size_t sort_have[2] = {}, elim_have[2][8] = {};
-    const size_t ss = osd_sort_smem_bytes(w, precision), es = osd_elim_smem_bytes(w);
+    static size_t sort_have[2] = {}, elim_have[2][8] = {}, fast_have[2][2][8] = {};
+    const size_t ss = osd_sort_smem_bytes(w, precision), es = osd_elim_smem_bytes(w), fs = osd_fast_smem_bytes(w);
     size_t& sh = sort_have[precision == 32 ? 0 : 1];
     if (ss > sh) {
         cudaError_t e = precision == 32
@@ -447,7 +582,24 @@ cudaError_t osd_configure(const WinDev& w, int precision) {
         if (e != cudaSuccess) return e;
         eh = es;
     }
+    size_t& fh = fast_have[precision == 32 ? 0 : 1][w.full_row_rank ? 0 : 1][elim_nq(w) & 7];
+    if (fs > fh) {
+        cudaError_t e = fast_dispatch(w, precision, [&](auto kern) {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fs));
+        });
+        if (e != cudaSuccess) return e;
+        fh = fs;
+    }
     return cudaSuccess;
+}
+
+cudaError_t launch_osd_fast(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st) {
+    if (b.n_shots == 0) return cudaSuccess;
+    const size_t smem = osd_fast_smem_bytes(w);
+    return fast_dispatch(w, precision, [&](auto kern) {
+        kern<<<grid, 32, smem, st>>>(w, b);
+        return cudaGetLastError();
+    });
 }
 
 cudaError_t launch_osd_sort(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st) {

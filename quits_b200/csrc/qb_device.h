@@ -52,6 +52,7 @@ struct WinDev {
     int carry_rows;           // rows of the carry this window emits (0 for the last window)
     int KW;                   // u64 words per observable mask
     int rowsW32, nW32;
+    double bin_scale;         // OSD fast path: 24 / (smallest prior LLR of the window)
     int full_row_rank;        // GF(2) rank of the window matrix == rows (then OSD's answer does not depend on pivot-row order)
     const uint32_t* colE;     // [cw][ncols_pad]  (row << 8 | slot), kNoEdge when the column is shorter
     const float* llr0f;       // [ncols_pad]  prior LLRs log((1-p)/p), fp32 image (precision 32)
@@ -90,11 +91,14 @@ struct BatchDev {
     int syn_stride32;
     int* fail_list;           // [n]
     int* fail_count;          // [1]
+    int* fast_next;           // [1] work counter of the persistent OSD fast-path grid
+    int* ovf_list;            // [n] shots the fast path hands to the full sort + elimination
+    int* ovf_count;           // [1]
     int* sort_next;           // [1] work counter of the persistent OSD sort grid
     int* osd_next;            // [1] work counter of the persistent OSD elimination grid
     uint16_t* order_buf;      // [fail slot][order_stride] columns in OSD order (sort kernel -> elimination kernel)
     size_t order_stride;
-    unsigned long long* stats;// [3] converged windows, BP iterations, OSD calls
+    unsigned long long* stats;// [8] converged windows, BP iterations, OSD calls, OSD columns examined, OSD pivots, max OSD columns, fast-path overflows
     uint32_t* ehat_out;       // optional [n][ehat_stride32]  (pre-zeroed)
     int ehat_stride32;
     int32_t* iters_out;       // optional [n]
@@ -116,8 +120,10 @@ cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int
 
 size_t osd_sort_smem_bytes(const WinDev& w, int precision);
 size_t osd_elim_smem_bytes(const WinDev& w);
+size_t osd_fast_smem_bytes(const WinDev& w);
 bool osd_supported(const WinDev& w, int precision);
 cudaError_t osd_configure(const WinDev& w, int precision);
+cudaError_t launch_osd_fast(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
 cudaError_t launch_osd_sort(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
 cudaError_t launch_osd_elim(const WinDev& w, const BatchDev& b, int grid, cudaStream_t st);
 
