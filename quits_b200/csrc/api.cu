@@ -159,7 +159,7 @@ struct qb_sw {
     int lanes = 1, lanes_used = 1;    // concurrent sub-batches per batch (decode_batch)
     int DW = 0, KW = 0, carryW = 0, synW = 0;
     size_t llr_stride = 0, order_stride = 0;
-    DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, ovf_list, order, counters, stats, pred, ehat, iters, conv, vscratch;
+    DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, ovf_list, order, sel_key, sel_idx, sel_cnt, counters, stats, pred, ehat, iters, conv, vscratch;
     EventTimer t_bp, t_osd;
 };
 
@@ -370,7 +370,7 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
     {
         double lmin = DBL_MAX;
         for (int j = 0; j < ncols; ++j) lmin = std::min(lmin, llr0d[j]);
-        d.bin_scale = lmin > 1e-3 ? 24.0 / lmin : 24.0;
+        d.bin_scale = lmin > 1e-3 ? 10.0 / lmin : 10.0;
     }
     d.colE = wo.colE.as<uint32_t>(); d.llr0f = wo.llr0f.as<float>(); d.llr0d = wo.llr0d.as<double>(); d.lmask = wo.lmask.as<uint64_t>();
     d.uptr = wo.uptr.as<int32_t>(); d.uidx = wo.uidx.as<uint16_t>(); d.cptr = wo.cptr.as<int32_t>(); d.crow = wo.crow.as<uint16_t>();
@@ -446,7 +446,12 @@ void ensure_batch(qb_sw* sw, int n) {
     sw->llr.ensure(N * sw->llr_stride * (sw->precision / 8) + 16);
     sw->syn.ensure(N * sw->synW * 4 + 16);
     sw->fail_list.ensure(N * 4 + 16);
-    if (sw->use_osd) sw->ovf_list.ensure(N * 4 + 16);
+    if (sw->use_osd) {
+        sw->ovf_list.ensure(N * 4 + 16);
+        sw->sel_key.ensure(N * qb::kOsdSelCap * (sw->precision / 8) + 16);
+        sw->sel_idx.ensure(N * qb::kOsdSelCap * 2 + 16);
+        sw->sel_cnt.ensure(N * 4 + 16);
+    }
     if (sw->use_osd) sw->order.ensure(N * sw->order_stride * 2 + 16);
     const size_t nw = sw->wins.size() * qb_ctx::kMaxLanes;
     sw->counters.ensure(nw * kCounterSlots * sizeof(int) + 16);
@@ -506,6 +511,11 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.sort_next = ctr + 3;
             b.osd_next = ctr + 4;
             b.ovf_list = sw->use_osd ? sw->ovf_list.as<int>() + s0 : nullptr;
+            if (sw->use_osd) {
+                b.sel_key = static_cast<unsigned char*>(sw->sel_key.p) + s0 * qb::kOsdSelCap * esz;
+                b.sel_idx = sw->sel_idx.as<uint16_t>() + s0 * qb::kOsdSelCap;
+                b.sel_cnt = sw->sel_cnt.as<int>() + s0;
+            }
             b.order_buf = sw->order.as<uint16_t>() + s0 * sw->order_stride;     // fail slots of a sub-batch are < its shot count
             b.order_stride = sw->order_stride;
             b.stats = sw->stats.as<unsigned long long>() + kStatSlots * slot;

@@ -50,8 +50,61 @@ template <> struct Real<double> {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// ---- hand-off to OSD: the posteriors' 32-bin histogram (built while the last iteration stores them) selects the least
+// reliable columns -- the smallest bin prefix with >= kSelTarget columns, at most kSelCap -- and the CTA writes their
+// (order key, column) pairs to HBM, so the OSD warp never scans the full posterior vector (osd.cu, fast path).
+constexpr int kSelWords = 36;        // 32 bins, selected count, boundary bin, 2 spare
+
+template <typename R>
+__device__ __forceinline__ int llr_bin(const R v, const R scale) {
+    return v > R(0) ? 1 + static_cast<int>(fmin(static_cast<double>(v * scale), 30.0)) : 0;
+}
+__device__ __forceinline__ uint32_t order_key_of(float f) {
+    const uint32_t u = __float_as_uint(f + 0.0f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ uint64_t order_key_of(double f) {
+    const uint64_t u = static_cast<uint64_t>(__double_as_longlong(f + 0.0));
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+template <typename R, int NT>
+__device__ __forceinline__ void select_for_osd(const WinDev& w, const BatchDev& b, int shot, int tid, uint32_t* hist) {
+    using KeyT = decltype(order_key_of(R(0)));
+    if (tid < 32) {
+        uint32_t cum = hist[tid];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, cum, o);
+            if (tid >= o) cum += t;
+        }
+        const uint32_t enough = __ballot_sync(0xFFFFFFFFu, cum >= static_cast<uint32_t>(kOsdSelTarget));
+        int bsel = enough ? __ffs(enough) - 1 : 31;
+        if (__shfl_sync(0xFFFFFFFFu, cum, bsel) > static_cast<uint32_t>(kOsdSelCap)) {
+            const uint32_t fits = __ballot_sync(0xFFFFFFFFu, cum <= static_cast<uint32_t>(kOsdSelCap));
+            bsel = fits ? 31 - __clz(fits) : -1;
+        }
+        if (tid == 0) { hist[32] = 0; hist[33] = static_cast<uint32_t>(bsel); }
+    }
+    __syncthreads();
+    const int bsel = static_cast<int>(hist[33]);
+    const R scale = static_cast<R>(w.bin_scale);
+    const R* llr = reinterpret_cast<const R*>(b.llr_buf) + static_cast<size_t>(shot) * b.llr_stride;
+    KeyT* gkey = reinterpret_cast<KeyT*>(b.sel_key) + static_cast<size_t>(shot) * kOsdSelCap;
+    uint16_t* gidx = b.sel_idx + static_cast<size_t>(shot) * kOsdSelCap;
+    for (int j = tid; j < w.ncols; j += NT) {
+        const R v = llr[j];
+        if (llr_bin<R>(v, scale) <= bsel) {
+            const uint32_t pos = atomicAdd(&hist[32], 1u);
+            if (pos < static_cast<uint32_t>(kOsdSelCap)) { gkey[pos] = order_key_of(v); gidx[pos] = static_cast<uint16_t>(j); }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) b.sel_cnt[shot] = static_cast<int>(hist[32]);
+}
+
 // shared-memory layout; returns the total.  off: V, rsum, rmeta, syn, cand, accs, car
-__host__ __device__ inline size_t bp_layout(const WinDev& w, int rsize, bool vglobal, size_t* off /*[7]*/) {
+__host__ __device__ inline size_t bp_layout(const WinDev& w, int rsize, bool vglobal, size_t* off /*[8]*/) {
     size_t o = 0;
     off[0] = o; o += vglobal ? 0 : align_up(static_cast<size_t>(w.rows) * w.RS * rsize, 16);
     off[1] = o; o += align_up(static_cast<size_t>(w.rows) * 2 * rsize, 16);
@@ -60,6 +113,7 @@ __host__ __device__ inline size_t bp_layout(const WinDev& w, int rsize, bool vgl
     off[4] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
     off[5] = o; o += align_up(static_cast<size_t>(w.KW) * 8, 16);
     off[6] = o; o += align_up(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4, 16);
+    off[7] = o; o += kSelWords * 4;
     return o;
 }
 
@@ -83,9 +137,9 @@ __device__ __forceinline__ void load_syndrome(const WinDev& w, const BatchDev& b
 }
 
 // ---- after BP: commit acc ^= L e[:ncommit], carry = U e[:ncommit] (sliding_window.py:172-175), or hand the shot to OSD
-template <int NT, bool RECORDS = false>
+template <typename R, int NT, bool RECORDS = false>
 __device__ __forceinline__ void finish_shot(const WinDev& w, const BatchDev& b, int shot, int tid, bool conv, int it, uint32_t hmask,
-                                            const uint32_t* syn, uint32_t* accs, uint32_t* car) {
+                                            const uint32_t* syn, uint32_t* accs, uint32_t* car, uint32_t* hist) {
     const int carryW = (w.carry_rows + 31) / 32;
     if (conv) {
         uint32_t hm = hmask;
@@ -122,6 +176,11 @@ __device__ __forceinline__ void finish_shot(const WinDev& w, const BatchDev& b, 
             const int slot = atomicAdd(b.fail_count, 1);
             b.fail_list[slot] = shot;
         }
+        if (b.sel_cnt) {
+            __threadfence_block();
+            __syncthreads();                                  // the posteriors of this shot are complete
+            select_for_osd<R, NT>(w, b, shot, tid, hist);
+        }
     }
     if (tid == 0) {
         if (conv) atomicAdd(&b.stats[0], 1ull);
@@ -135,7 +194,7 @@ template <typename R, int CW, int NT, int MINB, bool VGLOBAL>
 __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const BatchDev b, const BpParams p) {
     using RT = Real<R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    size_t off[7];
+    size_t off[8];
     bp_layout(w, sizeof(R), VGLOBAL, off);
     R* V = VGLOBAL ? reinterpret_cast<R*>(b.vscratch) + static_cast<size_t>(blockIdx.x) * (static_cast<size_t>(w.rows) * w.RS)
                    : reinterpret_cast<R*>(smem_raw + off[0]);
@@ -145,6 +204,7 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
     uint32_t* cand = reinterpret_cast<uint32_t*>(smem_raw + off[4]);
     uint32_t* accs = reinterpret_cast<uint32_t*>(smem_raw + off[5]);
     uint32_t* car = reinterpret_cast<uint32_t*>(smem_raw + off[6]);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + off[7]);
 
     const int tid = threadIdx.x;
     const int rows = w.rows, ncols = w.ncols, RS = w.RS, npad = w.ncols_pad;
@@ -187,10 +247,11 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
                 rmeta[i] = arg | (neg << 31);
             }
             if (tid < w.rowsW32) cand[tid] = 0;
+            const bool last = it == p.max_iter;
+            if (last && tid < 32) hist[tid] = 0;
             __syncthreads();
             // ---- bit sweep: one thread per column
             hmask = 0;
-            const bool last = it == p.max_iter;
             int k = 0;
             for (int j = tid; j < ncols; j += NT, ++k) {
                 uint32_t e[CW];
@@ -231,6 +292,7 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
                         if (e[q] != kNoEdge) atomicXor(&cand[e[q] >> 13], 1u << ((e[q] >> 8) & 31u));
                 }
                 if (last || b.write_llr_always) llr_all[static_cast<size_t>(shot) * b.llr_stride + j] = llr;
+                if (last) atomicAdd(&hist[llr_bin<R>(llr, static_cast<R>(w.bin_scale))], 1u);
             }
             // ---- stop test H e == s
             __syncthreads();
@@ -239,7 +301,7 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
         }
         if (it > p.max_iter) it = p.max_iter;
 
-        finish_shot<NT, false>(w, b, shot, tid, conv, it, hmask, syn, accs, car);
+        finish_shot<R, NT, false>(w, b, shot, tid, conv, it, hmask, syn, accs, car, hist);
     }
 }
 
@@ -284,7 +346,7 @@ template <> struct Compact<double> {
 };
 
 // off: V, rsum, syn, cand, accs, car, ptab.  V and rsum carry one extra entry for the dummy row.
-__host__ __device__ inline size_t bpc_layout(const WinDev& w, int rsize, size_t* off /*[7]*/) {
+__host__ __device__ inline size_t bpc_layout(const WinDev& w, int rsize, size_t* off /*[8]*/) {
     size_t o = 0;
     off[0] = o; o += align_up((static_cast<size_t>(w.rows) * w.RS + 1) * rsize, 16);
     off[1] = o; o += align_up(static_cast<size_t>(w.rows + 1) * 2 * rsize, 16);
@@ -293,6 +355,7 @@ __host__ __device__ inline size_t bpc_layout(const WinDev& w, int rsize, size_t*
     off[4] = o; o += align_up(static_cast<size_t>(w.KW) * 8, 16);
     off[5] = o; o += align_up(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4, 16);
     off[6] = o; o += align_up(static_cast<size_t>(w.n_ptab) * rsize, 16);
+    off[7] = o; o += kSelWords * 4;
     return o;
 }
 
@@ -361,7 +424,7 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
     using CT = Compact<R>;
     using Pair = typename RT::pair;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    size_t off[7];
+    size_t off[8];
     bpc_layout(w, sizeof(R), off);
     R* V = reinterpret_cast<R*>(smem_raw + off[0]);
     Pair* rsum = reinterpret_cast<Pair*>(smem_raw + off[1]);
@@ -370,6 +433,7 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
     uint32_t* accs = reinterpret_cast<uint32_t*>(smem_raw + off[4]);
     uint32_t* car = reinterpret_cast<uint32_t*>(smem_raw + off[5]);
     R* ptab = reinterpret_cast<R*>(smem_raw + off[6]);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + off[7]);
 
     const int tid = threadIdx.x;
     const int rows = w.rows, npad = w.ncols_pad, RS = w.RS;
@@ -419,10 +483,11 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
                 rsum[i] = s;
             }
             if (tid < w.rowsW32) cand[tid] = 0;
+            const bool last = it == p.max_iter;
+            if (last && tid < 32) hist[tid] = 0;
             __syncthreads();
             // ---- bit sweep: one thread per column record
             hmask = 0;
-            const bool last = it == p.max_iter;
             int k = 0;
             for (int r = tid; r < npad; r += NT, ++k) {
                 const uint4 cur = rec;
@@ -434,6 +499,7 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
                 if (j != 0xFFFFu) {
                     if (llr <= R(0)) hmask |= 1u << k;
                     if (last || b.write_llr_always) llr_all[static_cast<size_t>(shot) * b.llr_stride + j] = llr;
+                    if (last) atomicAdd(&hist[llr_bin<R>(llr, static_cast<R>(w.bin_scale))], 1u);
                 }
             }
             // ---- stop test H e == s
@@ -443,7 +509,7 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
         }
         if (it > p.max_iter) it = p.max_iter;
         // map record bits back to columns for the commit
-        finish_shot<NT, true>(w, b, shot, tid, conv, it, hmask, syn, accs, car);
+        finish_shot<R, NT, true>(w, b, shot, tid, conv, it, hmask, syn, accs, car, hist);
     }
 }
 
@@ -493,7 +559,7 @@ inline bool use_compact(const WinDev& w, bool vglobal) { return w.compact && !vg
 }  // namespace
 
 size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal) {
-    size_t off[7];
+    size_t off[8];
     if (use_compact(w, vglobal)) return bpc_layout(w, precision == 32 ? 4 : 8, off);
     return bp_layout(w, precision == 32 ? 4 : 8, vglobal, off);
 }

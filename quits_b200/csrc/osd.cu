@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kSortThreads) osd_sort_kernel(const WinDev w, 
 
 // ====================================================================================================== elimination
 struct ElimLayout {
-    size_t T, rvec, freem, svec, seq, pivcol, pivrow, slot, accs, car, selkey, selidx, sorted, bins, total;
+    size_t T, rvec, freem, svec, seq, pivcol, pivrow, slot, accs, car, selkey, selidx, bins, total;
     int TS;
 };
 
@@ -184,7 +184,6 @@ __host__ __device__ inline ElimLayout elim_layout(const WinDev& w, int NQ, bool 
     L.car = o; o += au(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4);
     L.selkey = o; o += au(static_cast<size_t>(selcap) * 8);
     L.selidx = o; o += au(static_cast<size_t>(selcap) * 2);
-    L.sorted = o; o += au(static_cast<size_t>(selcap) * 2);
     L.bins = o; o += selcap ? 128 : 0;
     L.total = o;
     return L;
@@ -421,11 +420,11 @@ __global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const Batc
 }
 
 // Fast path: the elimination almost always ends within the few dozen least reliable columns (see the early exit), so the
-// warp selects just those itself instead of waiting for a full sort: a 32-bin histogram of the posteriors (bins are monotone
-// in the LLR, width = 1/24 of the window's smallest prior LLR), the smallest bin prefix holding >= kSelTarget columns, a stable
-// ballot compaction of those columns in index order, and a rank-by-counting sort on (key, index).  Shots whose elimination
-// outruns the selection are appended to the overflow list and redone by osd_sort_kernel + osd_elim_kernel.
-constexpr int kSelCap = 256, kSelTarget = 64;
+// BP kernel hands over just those (bp.cu select_for_osd: a 32-bin histogram of the posteriors, bins monotone in the LLR with
+// width 1/10 of the window's smallest prior LLR, the smallest bin prefix holding >= kOsdSelTarget columns, at most kOsdSelCap)
+// and the warp only has to order them: a bitonic sort on (key, index) in shared memory.  Shots whose elimination outruns the
+// selection are appended to the overflow list and redone by osd_sort_kernel + osd_elim_kernel on the full posterior vector.
+constexpr int kSelCap = kOsdSelCap;
 
 template <typename R, int NQ, bool EXACT>
 __global__ void __launch_bounds__(32) osd_fast_kernel(const WinDev w, const BatchDev b) {
@@ -434,80 +433,40 @@ __global__ void __launch_bounds__(32) osd_fast_kernel(const WinDev w, const Batc
     const ElimLayout L = elim_layout(w, NQ, EXACT, kSelCap);
     KeyT* selkey = reinterpret_cast<KeyT*>(sm + L.selkey);
     uint16_t* selidx = reinterpret_cast<uint16_t*>(sm + L.selidx);
-    uint16_t* sorted = reinterpret_cast<uint16_t*>(sm + L.sorted);
-    uint32_t* bins = reinterpret_cast<uint32_t*>(sm + L.bins);
     const int lane = threadIdx.x;
     const int n = w.ncols;
     const int count = *b.fail_count;
-    const R scale = static_cast<R>(w.bin_scale);
     for (;;) {
         int job = 0;
         if (lane == 0) job = atomicAdd(b.fast_next, 1);
         job = __shfl_sync(kFull, job, 0);
         if (job >= count) break;
         const int shot = b.fail_list[job];
-        const R* llr = reinterpret_cast<const R*>(b.llr_buf) + static_cast<size_t>(shot) * b.llr_stride;
-        // ---- histogram: lane b ends up with the number of columns in bin b
-        bins[lane] = 0;
-        __syncwarp();
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            if (i < n) {
-                const R v = llr[i];
-                const int bin = v > R(0) ? 1 + static_cast<int>(fmin(static_cast<double>(v * scale), 30.0)) : 0;
-                atomicAdd(&bins[bin], 1u);
-            }
-        }
-        __syncwarp();
-        const uint32_t mycount = bins[lane];
-        uint32_t cum = mycount;                                            // inclusive prefix over bins
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(kFull, cum, o);
-            if (lane >= o) cum += t;
-        }
-        const uint32_t enough = __ballot_sync(kFull, cum >= static_cast<uint32_t>(kSelTarget));
-        int bsel = enough ? __ffs(enough) - 1 : 31;
-        if (__shfl_sync(kFull, cum, bsel) > static_cast<uint32_t>(kSelCap)) {
-            const uint32_t fits = __ballot_sync(kFull, cum <= static_cast<uint32_t>(kSelCap));
-            bsel = fits ? 31 - __clz(fits) : -1;
-        }
-        const int S = bsel >= 0 ? static_cast<int>(__shfl_sync(kFull, cum, bsel)) : 0;
+        const int S = b.sel_cnt[shot];                       // selection made by the BP kernel (bp.cu, select_for_osd)
         bool finished = false;
-        if (S > 0) {
-            // ---- compaction in index order
-            int offset = 0;
-            for (int i0 = 0; i0 < n; i0 += 32) {
-                const int i = i0 + lane;
-                bool sel = false;
-                KeyT key = 0;
-                if (i < n) {
-                    const R v = llr[i];
-                    const int bin = v > R(0) ? 1 + static_cast<int>(fmin(static_cast<double>(v * scale), 30.0)) : 0;
-                    sel = bin <= bsel;
-                    key = order_key(v);
-                }
-                const uint32_t mask = __ballot_sync(kFull, sel);
-                if (sel) {
-                    const int pos = offset + __popc(mask & ((1u << lane) - 1u));
-                    selkey[pos] = key;
-                    selidx[pos] = static_cast<uint16_t>(i);
-                }
-                offset += __popc(mask);
-            }
+        if (S > 0 && S <= kOsdSelCap) {
+            const KeyT* gkey = reinterpret_cast<const KeyT*>(b.sel_key) + static_cast<size_t>(shot) * kOsdSelCap;
+            const uint16_t* gidx = b.sel_idx + static_cast<size_t>(shot) * kOsdSelCap;
+            for (int i = lane; i < S; i += 32) { selkey[i] = gkey[i]; selidx[i] = gidx[i]; }
+            // ---- bitonic sort on (key, column index) in shared memory, padded to a power of two with +inf entries
+            int P = 32;
+            while (P < S) P <<= 1;
+            for (int i = S + lane; i < P; i += 32) { selkey[i] = ~static_cast<KeyT>(0); selidx[i] = 0xFFFFu; }
             __syncwarp();
-            // ---- rank by counting on (key, position); positions are in index order, so ties resolve by column index
-            for (int e = lane; e < S; e += 32) {
-                const KeyT ke = selkey[e];
-                int rank = 0;
-                for (int f = 0; f < S; ++f) {
-                    const KeyT kf = selkey[f];
-                    rank += (kf < ke || (kf == ke && f < e)) ? 1 : 0;
+            for (int k = 2; k <= P; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = lane; t < (P >> 1); t += 32) {
+                        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));       // index with bit j clear
+                        const int l = i | j;
+                        const KeyT ki = selkey[i], kl = selkey[l];
+                        const uint16_t xi = selidx[i], xl = selidx[l];
+                        const bool gt = ki > kl || (ki == kl && xi > xl);
+                        if (gt == ((i & k) == 0)) { selkey[i] = kl; selkey[l] = ki; selidx[i] = xl; selidx[l] = xi; }
+                    }
+                    __syncwarp();
                 }
-                sorted[rank] = selidx[e];
             }
-            __syncwarp();
-            finished = elim_job<NQ, EXACT>(w, b, sm, L, shot, sorted, S, n);
+            finished = elim_job<NQ, EXACT>(w, b, sm, L, shot, selidx, S, n);
         }
         if (!finished && lane == 0) {
             b.ovf_list[atomicAdd(b.ovf_count, 1)] = shot;

@@ -45,6 +45,8 @@ cudaError_t launch_pack_bits(const uint8_t* in, int nbits, uint64_t n_rows, uint
 
 // ---------------------------------------------------------------------------------------------- K3/K4
 constexpr uint32_t kNoEdge = 0xFFFFFFFFu;
+constexpr int kOsdSelCap = 512;      // columns handed to the OSD fast path per failed shot (at most)
+constexpr int kOsdSelTarget = 96;    // ... and the count the selection aims for
 
 struct WinDev {
     int rows, ncols, ncols_pad, RS, cw, ncommit;
@@ -52,7 +54,7 @@ struct WinDev {
     int carry_rows;           // rows of the carry this window emits (0 for the last window)
     int KW;                   // u64 words per observable mask
     int rowsW32, nW32;
-    double bin_scale;         // OSD fast path: 24 / (smallest prior LLR of the window)
+    double bin_scale;         // OSD fast path: LLR -> selection bin scale, 10 / (smallest prior LLR of the window)
     int full_row_rank;        // GF(2) rank of the window matrix == rows (then OSD's answer does not depend on pivot-row order)
     const uint32_t* colE;     // [cw][ncols_pad]  (row << 8 | slot), kNoEdge when the column is shorter
     const float* llr0f;       // [ncols_pad]  prior LLRs log((1-p)/p), fp32 image (precision 32)
@@ -91,6 +93,9 @@ struct BatchDev {
     int syn_stride32;
     int* fail_list;           // [n]
     int* fail_count;          // [1]
+    void* sel_key;            // [n][kOsdSelCap] order keys (u32 / u64 by precision) of the least reliable columns of a failed shot
+    uint16_t* sel_idx;        // [n][kOsdSelCap] their column indices (unordered; the OSD warp sorts them)
+    int* sel_cnt;             // [n] how many (0 .. kOsdSelCap); NULL when OSD is off
     int* fast_next;           // [1] work counter of the persistent OSD fast-path grid
     int* ovf_list;            // [n] shots the fast path hands to the full sort + elimination
     int* ovf_count;           // [1]
