@@ -121,7 +121,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shots", type=int, default=262144, help="shots per step per GPU")
-    ap.add_argument("--e2e-shots", type=int, default=65536)
+    ap.add_argument("--e2e-shots", type=int, default=262144)
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--lanes", type=int, default=0, help="concurrent sub-batches per device batch (0 = engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -239,11 +239,12 @@ def main():
     # ---- e2e through the drop-in API with host buffers (same stream of work, smaller batch)
     if not args.no_e2e:
         Se = args.e2e_shots
+        dec32 = qb.SlidingWindowDecoder(circuit, hz.shape[0], W, F, ctx=ctx, precision="f32", **BP_KW) if args.precision == "f32" else None
+
         def e2e_step(i):
             shot_seed = SEED + 1000 + i * world + rank
             det, obs = qb.get_stim_mem_result(circuit, Se, seed=shot_seed)
-            pred = qb.sliding_window_bposd_circuit_mem(det, circuit, hz, lz, W, F, **BP_KW) if args.precision == "f64" else \
-                qb.SlidingWindowDecoder(circuit, hz.shape[0], W, F, ctx=ctx, precision="f32", **BP_KW).decode(det)
+            pred = qb.sliding_window_bposd_circuit_mem(det, circuit, hz, lz, W, F, **BP_KW) if dec32 is None else dec32.decode(det)
             return int(np.any((obs - pred) % 2, axis=1).sum())
         e2e_step(0)
         barrier()

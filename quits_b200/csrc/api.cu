@@ -158,7 +158,7 @@ struct qb_sw {
     int cap = 0;
     int lanes = 1, lanes_used = 1;    // concurrent sub-batches per batch (decode_batch)
     int DW = 0, KW = 0, carryW = 0, synW = 0;
-    size_t llr_stride = 0, order_stride = 0;
+    size_t llr_stride = 0;
     DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, ovf_list, order, sel_key, sel_idx, sel_cnt, counters, stats, pred, ehat, iters, conv, vscratch;
     EventTimer t_bp, t_osd;
 };
@@ -388,7 +388,7 @@ void finish_decoder(qb_sw* sw) {
     const int prec = sw->precision;
     sw->use_osd = o.osd_method >= 0;
     int max_npad = 0, max_rowsW = 0, max_iter = 0;
-    size_t max_slab = 0, max_order = 0;
+    size_t max_slab = 0;
     for (auto& w : sw->wins) {
         // messages in shared memory when they fit, else in an L2-resident global slab per CTA
         w->vglobal = qb::bp_smem_bytes(w->dev, prec, false) > 227 * 1024;
@@ -414,7 +414,6 @@ void finish_decoder(qb_sw* sw) {
             w->elim_grid = 148 * std::max(1, std::min(elim_per_sm, 16));
             const int fast_per_sm = static_cast<int>((227 * 1024) / (qb::osd_fast_smem_bytes(w->dev) + 1024));
             w->fast_grid = 148 * std::max(1, std::min(fast_per_sm, 16));
-            max_order = std::max(max_order, static_cast<size_t>((w->dev.ncols + 63) / 64 * 64));
         }
     }
     if (max_slab) sw->vscratch.ensure(max_slab * 148 * 2 + 16);
@@ -435,7 +434,6 @@ void finish_decoder(qb_sw* sw) {
     sw->carryW = (sw->plan.m + 31) / 32 + 1;
     sw->synW = max_rowsW;
     sw->llr_stride = static_cast<size_t>(max_npad);
-    sw->order_stride = max_order;
     CK(cudaStreamSynchronize(ctx->stream));
 }
 
@@ -452,7 +450,6 @@ void ensure_batch(qb_sw* sw, int n) {
         sw->sel_idx.ensure(N * qb::kOsdSelCap * 2 + 16);
         sw->sel_cnt.ensure(N * 4 + 16);
     }
-    if (sw->use_osd) sw->order.ensure(N * sw->order_stride * 2 + 16);
     const size_t nw = sw->wins.size() * qb_ctx::kMaxLanes;
     sw->counters.ensure(nw * kCounterSlots * sizeof(int) + 16);
     sw->stats.ensure(nw * kStatSlots * sizeof(unsigned long long) + 16);
@@ -465,6 +462,7 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
     qb_ctx* ctx = sw->ctx;
     cudaStream_t st = ctx->stream;
     ensure_batch(sw, n);
+    if (want_llr && sw->use_osd) sw->order.ensure(static_cast<size_t>(n) * sw->llr_stride * 2 + 16);
     const size_t nw = sw->wins.size();
     int lanes = sw->lanes;
     if (want_ehat || n < 4096) lanes = 1;
@@ -498,6 +496,8 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.carry = sw->carry.as<uint32_t>() + s0 * sw->carryW;
             b.acc = sw->acc.as<uint64_t>() + s0 * sw->KW;
             b.llr_stride = sw->llr_stride;
+            b.llr_esize = sw->precision / 8;
+            b.order_alt = (want_llr && sw->use_osd) ? sw->order.as<uint16_t>() + s0 * sw->llr_stride : nullptr;   // keep the posteriors intact for the caller
             b.llr_buf = static_cast<unsigned char*>(sw->llr.p) + s0 * sw->llr_stride * esz;
             b.vscratch = sw->vscratch.p;
             b.syn_stride32 = sw->synW;
@@ -516,8 +516,6 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
                 b.sel_idx = sw->sel_idx.as<uint16_t>() + s0 * qb::kOsdSelCap;
                 b.sel_cnt = sw->sel_cnt.as<int>() + s0;
             }
-            b.order_buf = sw->order.as<uint16_t>() + s0 * sw->order_stride;     // fail slots of a sub-batch are < its shot count
-            b.order_stride = sw->order_stride;
             b.stats = sw->stats.as<unsigned long long>() + kStatSlots * slot;
             b.ehat_out = want_ehat ? sw->ehat.as<uint32_t>() : nullptr;
             b.ehat_stride32 = w.dev.nW32;

@@ -10,7 +10,7 @@
 //
 //   osd_sort_kernel   one 128-thread CTA per shot: stable LSD radix sort (8-bit digits) of the posteriors' order-preserving
 //                     integer image in shared memory (warp-private histograms + __match_any_sync ranking), which is exactly
-//                     "ascending LLR, ties by index"; the column order goes to HBM as u16.
+//                     "ascending LLR, ties by index"; the column order goes to HBM as u16 (over the shot's posterior row, which is dead by then).
 //   osd_elim_kernel   ONE WARP per shot, ~10 shots resident per SM, no block barrier anywhere.  Instead of reducing the
 //                     m x n matrix the warp keeps the accumulated row transformation T (m x m over GF(2)) in shared
 //                     memory, one 128-bit-packed column per pivot found so far (the columns of rows that are not yet pivot
@@ -92,9 +92,11 @@ __global__ void __launch_bounds__(kSortThreads) osd_sort_kernel(const WinDev w, 
         if (job >= count) break;
         const int shot = b.fail_list[job];
         const R* llr = reinterpret_cast<const R*>(b.llr_buf) + static_cast<size_t>(shot) * b.llr_stride;
-        uint16_t* out = b.order_buf + static_cast<size_t>(job) * b.order_stride;
+        // the column order overwrites the head of this shot's posterior row: the keys are in shared memory by then
+        uint16_t* out = b.order_alt ? b.order_alt + static_cast<size_t>(shot) * b.llr_stride : reinterpret_cast<uint16_t*>(const_cast<R*>(llr));
 
         for (int i = tid; i < n; i += kSortThreads) keys[i] = order_key(llr[i]);
+        __syncthreads();
         const int quarter = ((n + kSortWarps - 1) / kSortWarps + 31) / 32 * 32;
         const int wbeg = warp * quarter, wend = min(n, wbeg + quarter);
 #pragma unroll 1
@@ -415,7 +417,10 @@ __global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const Batc
         job = __shfl_sync(kFull, job, 0);
         if (job >= count) break;
         const int shot = b.fail_list[job];
-        elim_job<NQ, EXACT>(w, b, sm, L, shot, b.order_buf + static_cast<size_t>(job) * b.order_stride, w.ncols, w.ncols);
+        const uint16_t* order = b.order_alt ? b.order_alt + static_cast<size_t>(shot) * b.llr_stride
+                                            : reinterpret_cast<const uint16_t*>(static_cast<const unsigned char*>(b.llr_buf) +
+                                                                                static_cast<size_t>(shot) * b.llr_stride * b.llr_esize);
+        elim_job<NQ, EXACT>(w, b, sm, L, shot, order, w.ncols, w.ncols);
     }
 }
 

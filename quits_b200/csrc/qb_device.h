@@ -88,6 +88,8 @@ struct BatchDev {
     uint64_t* acc;            // [n][KW]  accumulated observable prediction
     void* llr_buf;            // [n][llr_stride] posteriors, float or double according to the precision
     size_t llr_stride;
+    int llr_esize;            // 4 or 8
+    uint16_t* order_alt;      // optional [n][llr_stride]: where the full OSD sort puts the column order; NULL => over the posterior row
     void* vscratch;           // VGLOBAL only: [grid][rows*RS] message slabs
     uint32_t* syn_buf;        // [n][syn_stride32]   post-carry syndrome of the shots handed to OSD
     int syn_stride32;
@@ -101,8 +103,6 @@ struct BatchDev {
     int* ovf_count;           // [1]
     int* sort_next;           // [1] work counter of the persistent OSD sort grid
     int* osd_next;            // [1] work counter of the persistent OSD elimination grid
-    uint16_t* order_buf;      // [fail slot][order_stride] columns in OSD order (sort kernel -> elimination kernel)
-    size_t order_stride;
     unsigned long long* stats;// [8] converged windows, BP iterations, OSD calls, OSD columns examined, OSD pivots, max OSD columns, fast-path overflows
     uint32_t* ehat_out;       // optional [n][ehat_stride32]  (pre-zeroed)
     int ehat_stride32;

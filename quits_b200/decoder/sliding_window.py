@@ -6,6 +6,8 @@ loop (:162-186) is replaced by the CUDA kernels in quits_b200/csrc (one launch s
 """
 from __future__ import annotations
 
+import collections
+import hashlib
 import warnings
 
 import numpy as np
@@ -13,6 +15,28 @@ import numpy as np
 from ..circuit import Circuit
 from ..engine import SlidingWindowDecoder
 from .inner import BpLsdDecoder, BpOsdDecoder, _GpuInnerDecoder
+
+
+# Decoders are set up once per (circuit text, window geometry, options) and reused by later calls of the drop-in functions:
+# the reference rebuilds its ldpc decoders on every call (sliding_window.py:146-153), here that would mean re-analysing the
+# circuit and re-allocating the device batch buffers each time.  Small LRU; keyed by content, not identity.
+_DECODER_CACHE: "collections.OrderedDict" = collections.OrderedDict()
+_DECODER_CACHE_SIZE = 4
+
+
+def _cached_decoder(circuit, m, W, F, num_cor_rounds, kw) -> SlidingWindowDecoder:
+    c = Circuit.of(circuit)
+    key = (hashlib.sha1(c.text.encode()).hexdigest(), int(m), int(W), int(F), int(num_cor_rounds),
+           tuple(sorted((k, repr(v)) for k, v in kw.items())))
+    dec = _DECODER_CACHE.get(key)
+    if dec is None:
+        dec = SlidingWindowDecoder(c, m, W, F, num_cor_rounds, **kw)
+        _DECODER_CACHE[key] = dec
+        while len(_DECODER_CACHE) > _DECODER_CACHE_SIZE:
+            _DECODER_CACHE.popitem(last=False)
+    else:
+        _DECODER_CACHE.move_to_end(key)
+    return dec
 
 
 def _engine_kwargs(decoder_cls, params: dict, rate_name: str) -> dict:
@@ -56,7 +80,7 @@ def sliding_window_circuit_mem(zcheck_samples, circuit, hz, lz, W, F, decoder1, 
     kw2 = _engine_kwargs(decoder2, dict2, error_rate_name2)
     if kw1 != kw2 or function_name1 != "decode" or function_name2 != "decode":
         raise NotImplementedError("different inner decoders for the sliding windows and the last window are not supported on the GPU path")
-    dec = SlidingWindowDecoder(Circuit.of(circuit), m, W, F, num_cor_rounds, **kw1)
+    dec = _cached_decoder(circuit, m, W, F, num_cor_rounds, kw1)
     # the reference leaves the priors of the last constructed decoders in the caller's dicts (sliding_window.py:148,151)
     if dec.plan.n_windows > 1:
         dict1[error_rate_name1] = dec.plan.window(dec.plan.n_windows - 2)["priors"]
