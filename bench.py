@@ -67,7 +67,8 @@ def cpu_arm(shots, nthreads=0):
     text, hz, lz = load_workload()
     fc = stimtext.parse_flat(text)
     wins = owin.plan(odem.analyze(fc), hz.shape[0], W, F)
-    threads = nthreads or cref.num_threads()
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for its workers)
+    threads = nthreads or max(cref.num_threads(), os.cpu_count() or 1)
     t0 = time.perf_counter()
     det, obs = cref.sample(fc, SEED, 0, shots, nthreads=threads)
     pred, stats = cref.sw_decode(wins, hz.shape[0], lz.shape[0], det, nthreads=threads, max_iter=BP_KW["max_iter"],

@@ -129,6 +129,15 @@ typedef struct {
 /* Window plan (host only): spacetime() of decoder/base.py:134-190.  n_cor < 0 derives the number of sliding windows
  * from D, m, W, F as sliding_window.py:130-141 does; n_cor >= 0 takes the caller's num_cor_rounds. */
 int qb_plan_create(const qb_dem* d, int32_t m /* hz.shape[0] */, int32_t W, int32_t F, int32_t n_cor, qb_plan** out);
+/* A window plan given explicitly (host only) -- used for the phenomenological sliding window, whose windows are built from
+ * hz by Kronecker products instead of from a circuit DEM (src/quits/decoder/sliding_window.py:14-101, matrices :56-69).
+ * dims[k] = [row0, rows, (unused), ncols, ncommit, nnz, nnz_L, nnz_U, urow0, urows] as returned by qb_plan_window; the CSC
+ * arrays are the windows' arrays concatenated in order (each window's pointer array starts at 0 and has ncols+1 resp.
+ * ncommit+1 entries).  Window k decodes detector rows [row0, row0+rows), XORs the carry of window k-1 into its first urows
+ * rows, commits L e[:ncommit] into the observable prediction and hands U e[:ncommit] (urows rows) to window k+1. */
+int qb_plan_create_explicit(int32_t m, int32_t K, int32_t D, int32_t n_windows, const int64_t* dims, const int64_t* h_ptr,
+                            const int32_t* h_idx, const double* priors, const int64_t* l_ptr, const int32_t* l_idx,
+                            const int64_t* u_ptr, const int32_t* u_idx, qb_plan** out);
 void qb_plan_free(qb_plan* p);
 /* info: [n_windows, m, K, D, W, F, num_rounds, whole_history] */
 int qb_plan_info(const qb_plan* p, int64_t info[8]);

@@ -38,7 +38,7 @@ class QbCircuitInfo(C.Structure):
 SYMBOLS = ["qb_last_error", "qb_version", "qb_device_count", "qb_ctx_create", "qb_ctx_destroy", "qb_ctx_synchronize",
            "qb_circuit_parse", "qb_circuit_free", "qb_circuit_get_info", "qb_circuit_flat", "qb_sample", "qb_sample_packed",
            "qb_sample_faults", "qb_dem_from_circuit", "qb_dem_free", "qb_dem_sizes", "qb_dem_errors", "qb_dem_matrix",
-           "qb_dem_from_errors", "qb_plan_create", "qb_plan_free", "qb_plan_info", "qb_plan_window", "qb_plan_layout",
+           "qb_dem_from_errors", "qb_plan_create", "qb_plan_create_explicit", "qb_plan_free", "qb_plan_info", "qb_plan_window", "qb_plan_layout",
            "qb_sw_create", "qb_sw_create_single", "qb_sw_free", "qb_sw_decode",
            "qb_sw_decode_packed", "qb_bp_decode_batch", "qb_mc_run"]
 
@@ -78,6 +78,7 @@ def lib():
     L.qb_dem_matrix.argtypes = [vp] + [vp] * 5
     L.qb_dem_from_errors.argtypes = [i32, i32, i64, vp, vp, vp, vp, vp, C.POINTER(vp)]
     L.qb_plan_create.argtypes = [vp, i32, i32, i32, i32, C.POINTER(vp)]
+    L.qb_plan_create_explicit.argtypes = [i32, i32, i32, i32] + [vp] * 8 + [C.POINTER(vp)]
     L.qb_plan_free.argtypes = [vp]
     L.qb_plan_free.restype = None
     L.qb_plan_info.argtypes = [vp, vp]

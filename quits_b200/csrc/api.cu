@@ -877,6 +877,52 @@ int qb_plan_create(const qb_dem* d, int32_t m, int32_t W, int32_t F, int32_t n_c
     });
 }
 
+int qb_plan_create_explicit(int32_t m, int32_t K, int32_t D, int32_t n_windows, const int64_t* dims, const int64_t* h_ptr,
+                            const int32_t* h_idx, const double* priors, const int64_t* l_ptr, const int32_t* l_idx,
+                            const int64_t* u_ptr, const int32_t* u_idx, qb_plan** out) {
+    return guard([&] {
+        if (!out || !dims || !h_ptr || !h_idx || !priors || !l_ptr || !u_ptr) throw arg_error("NULL argument");
+        if (m <= 0 || K < 0 || D <= 0 || n_windows <= 0) throw arg_error("bad plan dimensions");
+        std::unique_ptr<qb_plan> p(new qb_plan());
+        qb::WindowPlan& plan = p->plan;
+        plan.m = m; plan.K = K; plan.D = D; plan.W = 0; plan.F = 0; plan.num_rounds = D / m - 2; plan.n_cor = n_windows - 1;
+        size_t hp = 0, hi = 0, pp = 0, lp = 0, li = 0, up = 0, ui = 0;
+        for (int k = 0; k < n_windows; ++k) {
+            const int64_t* d = dims + 10 * static_cast<size_t>(k);
+            qb::Window w;
+            w.row0 = static_cast<int>(d[0]); w.rows = static_cast<int>(d[1]); w.col0 = static_cast<int>(d[2]);
+            w.ncols = static_cast<int>(d[3]); w.ncommit = static_cast<int>(d[4]);
+            w.urow0 = static_cast<int>(d[8]); w.urows = static_cast<int>(d[9]);
+            const int64_t nnz = d[5], nnzl = d[6], nnzu = d[7];
+            if (w.rows <= 0 || w.ncols <= 0) throw qb::value_error("a decoding window has no detector rows or no fault columns");
+            if (w.row0 < 0 || w.row0 + w.rows > D) throw arg_error("window rows outside the detector range");
+            if (w.ncommit < 0 || w.ncommit > w.ncols) throw arg_error("ncommit outside [0, ncols]");
+            if (k + 1 < n_windows ? w.urows != m : w.urows != 0) throw arg_error("every window but the last must carry m rows, the last none");
+            w.cptr.assign(h_ptr + hp, h_ptr + hp + w.ncols + 1); hp += static_cast<size_t>(w.ncols) + 1;
+            if (w.cptr[0] != 0 || w.cptr[w.ncols] != nnz) throw arg_error("window column pointers do not match nnz");
+            w.crow.assign(h_idx + hi, h_idx + hi + nnz); hi += static_cast<size_t>(nnz);
+            for (int j = 0; j < w.ncols; ++j) {
+                if (w.cptr[j + 1] < w.cptr[j]) throw arg_error("column pointers must be non-decreasing");
+                for (int64_t e = w.cptr[j]; e < w.cptr[j + 1]; ++e) {
+                    if (w.crow[e] < 0 || w.crow[e] >= w.rows) throw arg_error("row index out of range");
+                    if (e > w.cptr[j] && w.crow[e] <= w.crow[e - 1]) throw arg_error("rows of a column must be strictly ascending");
+                }
+            }
+            w.priors.assign(priors + pp, priors + pp + w.ncols); pp += static_cast<size_t>(w.ncols);
+            w.lptr.assign(l_ptr + lp, l_ptr + lp + w.ncommit + 1); lp += static_cast<size_t>(w.ncommit) + 1;
+            if (w.lptr[0] != 0 || w.lptr[w.ncommit] != nnzl) throw arg_error("observable pointers do not match nnz_L");
+            if (nnzl) { if (!l_idx) throw arg_error("NULL argument"); w.lidx.assign(l_idx + li, l_idx + li + nnzl); li += static_cast<size_t>(nnzl); }
+            for (int32_t v : w.lidx) if (v < 0 || v >= K) throw arg_error("observable index out of range");
+            w.uptr.assign(u_ptr + up, u_ptr + up + w.ncommit + 1); up += static_cast<size_t>(w.ncommit) + 1;
+            if (w.uptr[0] != 0 || w.uptr[w.ncommit] != nnzu) throw arg_error("carry pointers do not match nnz_U");
+            if (nnzu) { if (!u_idx) throw arg_error("NULL argument"); w.uidx.assign(u_idx + ui, u_idx + ui + nnzu); ui += static_cast<size_t>(nnzu); }
+            for (int32_t v : w.uidx) if (v < 0 || v >= w.urows) throw arg_error("carry row out of range");
+            plan.windows.push_back(std::move(w));
+        }
+        *out = p.release();
+    });
+}
+
 void qb_plan_free(qb_plan* p) { delete p; }
 
 int qb_sw_create(qb_ctx* ctx, const qb_plan* plan, const qb_bp_opts* opts, qb_sw** out) {

@@ -82,6 +82,40 @@ class WindowPlan:
         (self.n_windows, self.m, self.K, self.D, self.W, self.F, self.num_rounds, wh) = (int(x) for x in info)
         self.whole_history = bool(wh)
 
+    @classmethod
+    def explicit(cls, m: int, K: int, D: int, windows) -> "WindowPlan":
+        """Plan from explicit windows (``qb_plan_create_explicit``).  Each window is a dict with ``row0``, ``H`` (scipy
+        sparse, rows x ncols), ``priors`` (ncols), ``L`` (K x ncommit) and ``U`` (m x ncommit, or None for the last window);
+        ``ncommit`` is the column count of ``L``."""
+        dims, hp, hi, pr, lp, li, up, ui = [], [], [], [], [], [], [], []
+        for k, w in enumerate(windows):
+            H = csc_matrix(w["H"]); H.sort_indices()
+            L = csc_matrix(w["L"]); L.sort_indices()
+            ncommit = L.shape[1]
+            U = w.get("U")
+            if U is None:
+                U = csc_matrix((0, ncommit), dtype=np.uint8)
+            U = csc_matrix(U); U.sort_indices()
+            dims.append([int(w["row0"]), H.shape[0], 0, H.shape[1], ncommit, H.nnz, L.nnz, U.nnz, int(w.get("urow0", 0)), U.shape[0]])
+            hp.append(H.indptr.astype(np.int64)); hi.append(H.indices.astype(np.int32))
+            pr.append(np.ascontiguousarray(w["priors"], dtype=np.float64))
+            lp.append(L.indptr.astype(np.int64)); li.append(L.indices.astype(np.int32))
+            up.append(U.indptr.astype(np.int64)); ui.append(U.indices.astype(np.int32))
+        cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs) if sum(len(x) for x in xs) else np.zeros(1, dtype=dt), dtype=dt)
+        dims = np.ascontiguousarray(dims, dtype=np.int64)
+        self = cls.__new__(cls)
+        self.dem = None
+        h = C.c_void_p()
+        N.check(N.lib().qb_plan_create_explicit(int(m), int(K), int(D), len(windows), N.ptr(dims), N.ptr(cat(hp, np.int64)),
+                                                N.ptr(cat(hi, np.int32)), N.ptr(cat(pr, np.float64)), N.ptr(cat(lp, np.int64)),
+                                                N.ptr(cat(li, np.int32)), N.ptr(cat(up, np.int64)), N.ptr(cat(ui, np.int32)), C.byref(h)))
+        self._h = h
+        info = np.zeros(8, dtype=np.int64)
+        N.check(N.lib().qb_plan_info(self._h, N.ptr(info)))
+        (self.n_windows, self.m, self.K, self.D, self.W, self.F, self.num_rounds, wh) = (int(x) for x in info)
+        self.whole_history = bool(wh)
+        return self
+
     def __del__(self):
         try:
             if getattr(self, "_h", None):

@@ -11,9 +11,11 @@ import hashlib
 import warnings
 
 import numpy as np
+from scipy.sparse import csc_matrix, hstack as sp_hstack, identity, kron as sp_kron
 
 from ..circuit import Circuit
 from ..engine import SlidingWindowDecoder
+from .base import WindowPlan
 from .inner import BpLsdDecoder, BpOsdDecoder, _GpuInnerDecoder
 
 
@@ -88,10 +90,96 @@ def sliding_window_circuit_mem(zcheck_samples, circuit, hz, lz, W, F, decoder1, 
     return dec.decode(zcheck_samples)
 
 
+def _phenom_plan(hz, lz, W, F, num_cor_rounds, W_last, D, priors1, priors2) -> WindowPlan:
+    """Windows of the phenomenological model (reference sliding_window.py:56-69): H = [I_W (x) hz | B (x) I_m] with B the
+    lower bidiagonal W x W matrix; the last window drops the final measurement-error block (its last round is ideal).
+    Commit and carry follow :86-88 -- correction = sum of the first F data-error blocks, carry = the F-th measurement-error
+    block -- written as the (L, U) pair the kernels apply: L[:, t n + q] = lz[:, q] for t < F, U[r, W n + (F-1) m + r] = 1."""
+    hz = csc_matrix(np.asarray(hz) % 2, dtype=np.uint8)
+    lz = csc_matrix(np.asarray(lz) % 2, dtype=np.uint8)
+    m, n = hz.shape
+    K = lz.shape[0]
+
+    def window(k, Wk, last, priors):
+        nm = Wk - 1 if last else Wk
+        B = np.eye(Wk, dtype=np.uint8)
+        for i in range(1, Wk):
+            B[i, i - 1] = 1
+        H = sp_hstack([sp_kron(identity(Wk, dtype=np.uint8, format="csc"), hz, format="csc"),
+                       sp_kron(csc_matrix(B[:, :nm]), identity(m, dtype=np.uint8, format="csc"), format="csc")], format="csc")
+        ncols = Wk * n + nm * m
+        ncommit_blocks = Wk if last else F
+        L = sp_hstack([lz] * ncommit_blocks + [csc_matrix((K, ncols - ncommit_blocks * n), dtype=np.uint8)], format="csc")
+        U = None
+        if not last:
+            U = csc_matrix((np.ones(m, dtype=np.uint8), (np.arange(m), Wk * n + (F - 1) * m + np.arange(m))), shape=(m, ncols))
+        pr = np.asarray(priors, dtype=np.float64)
+        pr = np.full(ncols, float(pr)) if pr.ndim == 0 else pr
+        if pr.shape != (ncols,):
+            raise ValueError("need one prior per column of the window matrix (%d), got %r" % (ncols, pr.shape))
+        return {"row0": F * k * m, "H": H, "priors": pr, "L": L, "U": U}
+
+    windows = [window(k, W, False, priors1) for k in range(num_cor_rounds)]
+    windows.append(window(num_cor_rounds, W_last, True, priors2))
+    return WindowPlan.explicit(m, K, D, windows)
+
+
+def _phenom_priors(params: dict):
+    for name in ("error_channel", "channel_probs", "error_rate"):
+        if params.get(name) is not None:
+            return params[name]
+    raise ValueError("the inner decoder needs error_rate, error_channel or channel_probs")
+
+
+_PHENOM_CACHE: "collections.OrderedDict" = collections.OrderedDict()
+
+
 def sliding_window_phenom_mem(zcheck_samples, hz, lz, W, F, decoder1, decoder2, dict1: dict, dict2: dict,
                               function_name1: str, function_name2: str, tqdm_on=False):
-    """Phenomenological sliding window (reference sliding_window.py:14-101): not on the GPU path yet."""
-    raise NotImplementedError("sliding_window_phenom_mem is not implemented on the GPU path yet (circuit-level windows only)")
+    """Phenomenological sliding window (reference ``sliding_window.py:14-101``) on the batched GPU kernels: same window
+    matrices, commit rule and carry rule; all shots of the batch are decoded together."""
+    if F == 0:
+        raise ValueError("Input parameter F cannot be zero.")
+    zcheck_samples = np.asarray(zcheck_samples)
+    hz = np.asarray(hz)
+    lz = np.asarray(lz)
+    m = hz.shape[0]
+    num_rounds = zcheck_samples.shape[1] // m - 2
+    if 2 + num_rounds - W >= 0:
+        num_cor_rounds = (2 + num_rounds - W) // F
+        if (2 + num_rounds - W) % F != 0:
+            num_cor_rounds += 1
+    else:
+        num_cor_rounds = 0
+        warnings.warn("Window size larger than the syndrome extraction rounds: Doing whole history correction")
+    W_last = num_rounds + 2 - F * num_cor_rounds
+    if num_cor_rounds and F > W:
+        raise ValueError("cannot reshape the first F data-error blocks out of a window of W < F rounds")
+    for cls in (decoder1, decoder2):
+        if not (isinstance(cls, type) and issubclass(cls, _GpuInnerDecoder)):
+            raise NotImplementedError(
+                "the GPU sliding-window path runs the engine's own inner decoders only (quits_b200.decoder.BpOsdDecoder / "
+                "BpLsdDecoder); got %r. There is no per-shot CPU fallback." % (cls,))
+    rate_names = ("error_rate", "error_channel", "channel_probs")
+    kw1 = _engine_kwargs(decoder1, {k: v for k, v in dict1.items() if k not in rate_names}, "")
+    kw2 = _engine_kwargs(decoder2, {k: v for k, v in dict2.items() if k not in rate_names}, "")
+    if kw1 != kw2 or function_name1 != "decode" or function_name2 != "decode":
+        raise NotImplementedError("different inner decoders for the sliding windows and the last window are not supported on the GPU path")
+    p1, p2 = _phenom_priors(dict1), _phenom_priors(dict2)
+    key = (hashlib.sha1(np.ascontiguousarray(hz % 2, dtype=np.uint8).tobytes()).hexdigest(), hz.shape,
+           hashlib.sha1(np.ascontiguousarray(lz % 2, dtype=np.uint8).tobytes()).hexdigest(), int(W), int(F), int(num_rounds),
+           hashlib.sha1(np.asarray(p1, dtype=np.float64).tobytes()).hexdigest(), hashlib.sha1(np.asarray(p2, dtype=np.float64).tobytes()).hexdigest(),
+           tuple(sorted((k, repr(v)) for k, v in kw1.items())))
+    dec = _PHENOM_CACHE.get(key)
+    if dec is None:
+        plan = _phenom_plan(hz, lz, W, F, num_cor_rounds, W_last, m * (num_rounds + 2), p1, p2)
+        dec = SlidingWindowDecoder.from_plan(plan, **kw1)
+        _PHENOM_CACHE[key] = dec
+        while len(_PHENOM_CACHE) > _DECODER_CACHE_SIZE:
+            _PHENOM_CACHE.popitem(last=False)
+    else:
+        _PHENOM_CACHE.move_to_end(key)
+    return dec.decode(zcheck_samples[:, :m * (num_rounds + 2)])
 
 
 __all__ = ["sliding_window_phenom_mem", "sliding_window_circuit_mem"]

@@ -62,6 +62,21 @@ class SlidingWindowDecoder:
         self.K, self.D = self.plan.K, self.plan.D
         self.stats = N.QbStats()
 
+    @classmethod
+    def from_plan(cls, plan: WindowPlan, ctx: Context = None, **bp_kwargs) -> "SlidingWindowDecoder":
+        """Decoder over an explicit window plan (``WindowPlan.explicit``), e.g. the phenomenological windows."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or Context.default()
+        self.circuit = None
+        self.plan = plan
+        self.opts = bp_options(**bp_kwargs)
+        h = C.c_void_p()
+        N.check(N.lib().qb_sw_create(self.ctx._h, plan._h, C.byref(self.opts), C.byref(h)))
+        self._h = h
+        self.K, self.D = plan.K, plan.D
+        self.stats = N.QbStats()
+        return self
+
     def __del__(self):
         try:
             if getattr(self, "_h", None):

@@ -211,3 +211,38 @@ def test_bp_layout_is_a_valid_conflict_free_arrangement(precision):
             assert sorted(s.tolist()) == list(range(len(s)))
         assert ratios[0] > 2.0 and ratios[1] > 1.5
         assert ratios[2] < 1.1 and ratios[3] < 1.25, ratios
+
+
+def test_phenomenological_windows_equal_the_reference_matrices():
+    """_phenom_plan builds exactly the matrices of reference sliding_window.py:56-69 and the commit / carry rule of :86-88."""
+    from quits_b200.decoder.sliding_window import _phenom_plan
+    rng = np.random.RandomState(7)
+    hz = (rng.rand(5, 9) < 0.4).astype(int)
+    hz[:, 0] = 1
+    lz = (rng.rand(2, 9) < 0.5).astype(int)
+    m, n = hz.shape
+    W, F, rounds = 4, 2, 6
+    ncor = (2 + rounds - W + F - 1) // F
+    W_last = rounds + 2 - F * ncor
+    plan = _phenom_plan(hz, lz, W, F, ncor, W_last, m * (rounds + 2), 0.03, 0.04)
+    assert plan.n_windows == ncor + 1
+    for k in range(plan.n_windows):
+        last = k == ncor
+        Wk = W_last if last else W
+        B = np.eye(Wk, dtype=int)
+        for i in range(1, Wk):
+            B[i, i - 1] = 1
+        if last:
+            B = B[:, :Wk - 1]
+        ref = np.column_stack((np.kron(np.eye(Wk, dtype=int), hz), np.kron(B, np.eye(m, dtype=int))))
+        w = plan.window(k)
+        assert w["row0"] == F * k * m and np.array_equal(w["H"].toarray(), ref)
+        assert np.allclose(w["priors"], 0.04 if last else 0.03)
+        e = rng.randint(0, 2, size=ref.shape[1])
+        blocks = Wk if last else F
+        corr = e[:blocks * n].reshape(blocks, n).sum(axis=0) % 2
+        assert np.array_equal(w["L"].toarray() @ e[:w["ncommit"]] % 2, lz @ corr % 2)
+        if not last:
+            assert np.array_equal(w["U"].toarray() @ e % 2, e[W * n + (F - 1) * m:W * n + F * m])
+    with pytest.raises(ValueError):
+        qb.sliding_window_bposd_phenom_mem(np.zeros((1, m * 8), dtype=bool), hz, lz, 4, 0)
