@@ -379,7 +379,7 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
 void finish_decoder(qb_sw* sw) {
     qb_ctx* ctx = sw->ctx;
     const qb_bp_opts& o = sw->opts;
-    if (o.bp_method != 0) throw qb::unsupported_error("bp_method 'product_sum' is not implemented on the GPU path yet; use bp_method='minimum_sum'");
+    if (o.bp_method != 0 && o.bp_method != 1) throw qb::value_error("bp_method must be 0 (minimum_sum) or 1 (product_sum)");
     if (o.schedule != 0) throw qb::unsupported_error("schedule 'serial' is not implemented on the GPU path yet; use schedule='parallel'");
     if (o.osd_method >= 0 && o.osd_order != 0) throw qb::unsupported_error("osd_order > 0 is not implemented on the GPU path yet; use osd_order=0");
     if (o.ms_scaling_factor < 0) throw qb::value_error("ms_scaling_factor must be >= 0");
@@ -395,7 +395,9 @@ void finish_decoder(qb_sw* sw) {
         w->bp_smem = qb::bp_smem_bytes(w->dev, prec, w->vglobal);
         if (w->bp_smem > 227 * 1024)
             throw qb::unsupported_error("window of " + std::to_string(w->dev.rows) + " rows is too tall for the BP kernel's per-row shared-memory state");
-        CK(qb::bp_configure(w->dev, prec, w->vglobal));
+        if (!qb::bp_supports(w->dev, o.bp_method, w->vglobal))
+            throw qb::unsupported_error("bp_method 'product_sum' needs a window that fits the compact shared-memory kernel (column weight <= 6)");
+        CK(qb::bp_configure(w->dev, prec, w->vglobal, o.bp_method));
         if (w->vglobal) {
             w->bp_grid = 148 * 2;
             max_slab = std::max(max_slab, static_cast<size_t>(w->dev.rows) * w->dev.RS * (prec / 8));
@@ -478,6 +480,7 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
     }
     qb::BpParams bp{};
     bp.max_iter = sw->max_iter;
+    bp.method = sw->opts.bp_method;
     bp.alpha = sw->alpha.as<double>();
     const size_t esz = static_cast<size_t>(sw->precision / 8);
     for (size_t k = 0; k < nw; ++k) {

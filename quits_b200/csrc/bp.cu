@@ -404,6 +404,72 @@ __device__ __forceinline__ R column_update(const uint4 rec, const R l0, const R 
     return llr;
 }
 
+// ---- product-sum (ldpc bp_method 'product_sum'): check->bit message = 2 atanh( prod_{others} tanh(v/2) ), sign from the syndrome.
+// The row summary is (s * prod of the non-zero tanh(v/2), number of zero factors); "the others" is obtained by dividing the
+// row product by the edge's own factor, which differs from ldpc's prefix/suffix products by rounding only (no bit parity with
+// the CPU here anyway: libm and CUDA tanh/log differ in the last ulps).
+template <typename R> struct Trans;
+template <> struct Trans<float> {
+    static __device__ __forceinline__ float th(float x) { return tanhf(x); }
+    static __device__ __forceinline__ float lg(float x) { return logf(x); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <> struct Trans<double> {
+    static __device__ __forceinline__ double th(double x) { return tanh(x); }
+    static __device__ __forceinline__ double lg(double x) { return log(x); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+
+template <typename R, int W>
+__device__ __forceinline__ R column_update_ps(const uint4 rec, const R l0, R* V, const typename Real<R>::pair* rsum,
+                                              uint32_t* cand, const uint32_t magic, const uint32_t rows) {
+    using RT = Real<R>;
+    using TT = Trans<R>;
+    const uint32_t e[6] = {rec.x & 0xFFFFu, rec.x >> 16, rec.y & 0xFFFFu, rec.y >> 16, rec.z & 0xFFFFu, rec.z >> 16};
+    R c[W], vn[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        const R v = V[e[q]];
+        const typename RT::pair s = rsum[__umulhi(e[q], magic)];
+        const R t = TT::th(RT::mul(v, R(0.5)));
+        R x = R(0);
+        if (s.y == R(0)) x = TT::div(s.x, t);
+        else if (s.y == R(1) && t == R(0)) x = s.x;
+        c[q] = TT::lg(TT::div(RT::add(R(1), x), RT::add(R(1), -x)));
+    }
+    R t = l0;
+#pragma unroll
+    for (int q = 0; q < W; ++q) { vn[q] = t; t = RT::add(t, c[q]); }
+    const R llr = t;
+    t = R(0);
+#pragma unroll
+    for (int q = W - 1; q >= 0; --q) { vn[q] = RT::add(vn[q], t); t = RT::add(t, c[q]); }
+#pragma unroll
+    for (int q = 0; q < W; ++q) V[e[q]] = vn[q];
+    if (llr <= R(0)) {
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            const uint32_t row = __umulhi(e[q], magic);
+            if (row < rows) atomicXor(&cand[row >> 5], 1u << (row & 31u));
+        }
+    }
+    return llr;
+}
+
+template <typename R>
+__device__ __forceinline__ R column_dispatch_ps(const uint4 rec, const R l0, R* V, const typename Real<R>::pair* rsum, uint32_t* cand,
+                                                const uint32_t magic, const uint32_t rows) {
+    switch (rec.w >> 28) {
+    case 0: return l0;
+    case 1: return column_update_ps<R, 1>(rec, l0, V, rsum, cand, magic, rows);
+    case 2: return column_update_ps<R, 2>(rec, l0, V, rsum, cand, magic, rows);
+    case 3: return column_update_ps<R, 3>(rec, l0, V, rsum, cand, magic, rows);
+    case 4: return column_update_ps<R, 4>(rec, l0, V, rsum, cand, magic, rows);
+    case 5: return column_update_ps<R, 5>(rec, l0, V, rsum, cand, magic, rows);
+    default: return column_update_ps<R, 6>(rec, l0, V, rsum, cand, magic, rows);
+    }
+}
+
 template <typename R, bool FIRST>
 __device__ __forceinline__ R column_dispatch(const uint4 rec, const R l0, const R alpha, R* V, const typename Real<R>::pair* rsum,
                                              uint32_t* cand, const uint32_t magic, const uint32_t rows) {
@@ -418,7 +484,7 @@ __device__ __forceinline__ R column_dispatch(const uint4 rec, const R l0, const 
     }
 }
 
-template <typename R, int NT, int MINB>
+template <typename R, int NT, int MINB, bool PS>
 __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, const BatchDev b, const BpParams p) {
     using RT = Real<R>;
     using CT = Compact<R>;
@@ -440,8 +506,8 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
     const uint32_t magic = w.rs_magic;
     R* const llr_all = reinterpret_cast<R*>(b.llr_buf);
     for (int i = tid; i < w.n_ptab; i += NT) ptab[i] = CT::ptab(w)[i];
-    if (tid == 0) {                          // the dummy row: summary (0, 0), one message slot
-        rsum[rows] = RT::mk(R(0), R(0));
+    if (tid == 0) {                          // the dummy row: its messages are +-0 (min-sum: minima 0; product-sum: two zero factors)
+        rsum[rows] = RT::mk(R(0), PS ? R(2) : R(0));
         V[rows * RS] = R(0);
     }
 
@@ -452,14 +518,37 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
         uint32_t hmask = 0;          // bit k <-> record tid + k*NT (records are the columns sorted by weight)
         bool conv = false;
         int it = 1;
+        if (PS) {                    // product-sum has no closed form for iteration 1: start from the priors in the message array
+            for (int r = tid; r < npad; r += NT) {
+                const uint4 rec = __ldg(w.colrec + r);
+                const R l0 = ptab[(rec.w >> 16) & 0xFFFu];
+                const uint32_t e[6] = {rec.x & 0xFFFFu, rec.x >> 16, rec.y & 0xFFFFu, rec.y >> 16, rec.z & 0xFFFFu, rec.z >> 16};
+#pragma unroll
+                for (int q = 0; q < 6; ++q) V[e[q]] = l0;
+            }
+            __syncthreads();
+        }
         for (; it <= p.max_iter; ++it) {
             const R alpha = static_cast<R>(__ldg(p.alpha + it));
-            const bool first = it == 1;
+            const bool first = !PS && it == 1;
             uint4 rec = __ldg(w.colrec + tid);               // NT <= npad is not guaranteed: colrec is padded to a multiple of NT
             // ---- check sweep: one thread per row -> (min1 | parity sign, min2)
             for (int i = tid; i < rows; i += NT) {
                 uint32_t neg = (syn[i >> 5] >> (i & 31)) & 1u;
                 Pair s;
+                if (PS) {
+                    const R* vr = V + i * RS;
+                    const int len = __ldg(w.rlen + i);
+                    R prod = (neg & 1u) ? R(-1) : R(1);
+                    int zc = 0;
+                    for (int q = 0; q < len; ++q) {
+                        const R t = Trans<R>::th(RT::mul(vr[q], R(0.5)));
+                        if (t == R(0)) ++zc;
+                        else prod = RT::mul(prod, t);
+                    }
+                    rsum[i] = RT::mk(prod, static_cast<R>(zc));
+                    continue;
+                }
                 if (first) {
                     s = CT::sum0(w, i);
                     neg += __ldg(w.neg0 + i);
@@ -493,8 +582,10 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
                 const uint4 cur = rec;
                 if (r + NT < npad) rec = __ldg(w.colrec + r + NT);
                 const R l0 = ptab[(cur.w >> 16) & 0xFFFu];
-                const R llr = first ? column_dispatch<R, true>(cur, l0, alpha, V, rsum, cand, magic, static_cast<uint32_t>(rows))
-                                    : column_dispatch<R, false>(cur, l0, alpha, V, rsum, cand, magic, static_cast<uint32_t>(rows));
+                R llr;
+                if (PS) llr = column_dispatch_ps<R>(cur, l0, V, rsum, cand, magic, static_cast<uint32_t>(rows));
+                else llr = first ? column_dispatch<R, true>(cur, l0, alpha, V, rsum, cand, magic, static_cast<uint32_t>(rows))
+                                 : column_dispatch<R, false>(cur, l0, alpha, V, rsum, cand, magic, static_cast<uint32_t>(rows));
                 const uint32_t j = cur.w & 0xFFFFu;                    // original column; 0xFFFF marks a padding record
                 if (j != 0xFFFFu) {
                     if (llr <= R(0)) hmask |= 1u << k;
@@ -544,12 +635,12 @@ Variant& variant(int prec, int cw, bool vg) {
     return v;
 }
 
-Variant& compact_variant(int prec) {
-    static Variant table[2] = {};
-    Variant& v = table[prec == 32 ? 0 : 1];
+Variant& compact_variant(int prec, int method) {
+    static Variant table[2][2] = {};
+    Variant& v = table[prec == 32 ? 0 : 1][method ? 1 : 0];
     if (!v.fn) {
-        if (prec == 32) { v.fn = bp_kernel_compact<float, 256, 4>; v.threads = 256; }
-        else { v.fn = bp_kernel_compact<double, 512, 2>; v.threads = 512; }
+        if (prec == 32) { v.fn = method ? bp_kernel_compact<float, 256, 4, true> : bp_kernel_compact<float, 256, 4, false>; v.threads = 256; }
+        else { v.fn = method ? bp_kernel_compact<double, 512, 2, true> : bp_kernel_compact<double, 512, 2, false>; v.threads = 512; }
     }
     return v;
 }
@@ -566,11 +657,14 @@ size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal) {
 
 int bp_threads(int precision) { return precision == 32 ? 256 : 512; }
 
-cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal) {
+bool bp_supports(const WinDev& w, int method, bool vglobal) { return method == 0 || use_compact(w, vglobal); }
+
+cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal, int method) {
     if (w.cw > 16) return cudaErrorInvalidValue;
+    if (!bp_supports(w, method, vglobal)) return cudaErrorInvalidValue;
     const size_t smem = bp_smem_bytes(w, precision, vglobal);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    Variant& v = use_compact(w, vglobal) ? compact_variant(precision) : variant(precision, w.cw, vglobal);
+    Variant& v = use_compact(w, vglobal) ? compact_variant(precision, method) : variant(precision, w.cw, vglobal);
     if (smem <= v.configured) return cudaSuccess;          // the attribute only ever grows (decoders of different sizes coexist)
     cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e == cudaSuccess) v.configured = smem;
@@ -579,7 +673,7 @@ cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal) {
 
 cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, bool vglobal, int grid, cudaStream_t st) {
     if (b.n_shots == 0) return cudaSuccess;
-    Variant& v = use_compact(w, vglobal) ? compact_variant(precision) : variant(precision, w.cw, vglobal);
+    Variant& v = use_compact(w, vglobal) ? compact_variant(precision, p.method) : variant(precision, w.cw, vglobal);
     const size_t smem = bp_smem_bytes(w, precision, vglobal);
     v.fn<<<grid, v.threads, smem, st>>>(w, b, p);
     return cudaGetLastError();

@@ -113,6 +113,7 @@ struct BatchDev {
 
 struct BpParams {
     int max_iter;
+    int method;               // 0 minimum_sum | 1 product_sum
     const double* alpha;      // [max_iter+1]  scaling factor of iteration it (index it), rounded to the precision in the kernel
 };
 
@@ -120,7 +121,8 @@ struct BpParams {
 constexpr uint32_t kNoAddr = 0xFFFFu;
 size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal);
 int bp_threads(int precision);
-cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal);
+bool bp_supports(const WinDev& w, int method, bool vglobal);
+cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal, int method);
 cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, bool vglobal, int grid, cudaStream_t st);
 
 size_t osd_sort_smem_bytes(const WinDev& w, int precision);
