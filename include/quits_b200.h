@@ -43,6 +43,12 @@ int qb_ctx_create(int device, qb_ctx** out);
 void qb_ctx_destroy(qb_ctx* ctx);
 int qb_ctx_synchronize(qb_ctx* ctx);
 
+/* Page-locked host buffers for the arrays that cross the boundary (detection events, predictions): a device<->host copy
+ * from pinned memory runs at PCIe speed instead of being staged through the driver's bounce buffer.  The Python layer
+ * hands these out as numpy arrays and recycles them.  No reference counterpart (stim / ldpc return ordinary numpy memory). */
+int qb_host_alloc(size_t bytes, void** out);
+void qb_host_free(void* p);
+
 /* ------------------------------------------------------------------------------------------------ circuit
  * Replaces stim.Circuit(text) as the reference's builders call it (src/quits/qldpc_code/bb.py:301,
  * circuit_construction/cardinal.py:267, zxcoloration.py:270).  Host only; accepts the Stim-text dialect emitted

@@ -4,6 +4,8 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
+import weakref
 
 import numpy as np
 
@@ -35,7 +37,7 @@ class QbCircuitInfo(C.Structure):
 
 
 # every symbol include/quits_b200.h declares (tests check the library exports all of them)
-SYMBOLS = ["qb_last_error", "qb_version", "qb_device_count", "qb_ctx_create", "qb_ctx_destroy", "qb_ctx_synchronize",
+SYMBOLS = ["qb_last_error", "qb_version", "qb_device_count", "qb_host_alloc", "qb_host_free", "qb_ctx_create", "qb_ctx_destroy", "qb_ctx_synchronize",
            "qb_circuit_parse", "qb_circuit_free", "qb_circuit_get_info", "qb_circuit_flat", "qb_sample", "qb_sample_packed",
            "qb_sample_faults", "qb_dem_from_circuit", "qb_dem_free", "qb_dem_sizes", "qb_dem_errors", "qb_dem_matrix",
            "qb_dem_from_errors", "qb_plan_create", "qb_plan_create_explicit", "qb_plan_free", "qb_plan_info", "qb_plan_window", "qb_plan_layout",
@@ -58,6 +60,9 @@ def lib():
     L.qb_last_error.restype = C.c_char_p
     L.qb_version.restype = C.c_int
     L.qb_device_count.restype = C.c_int
+    L.qb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.qb_host_free.argtypes = [vp]
+    L.qb_host_free.restype = None
     L.qb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.qb_ctx_destroy.argtypes = [vp]
     L.qb_ctx_destroy.restype = None
@@ -126,5 +131,48 @@ def device_count() -> int:
     return int(lib().qb_device_count())
 
 
+class _PinnedPool:
+    """Recycles page-locked host buffers behind numpy arrays.  cudaHostAlloc costs milliseconds per 100 MB, so buffers are
+    kept (rounded up to a power of two, at most ``limit`` bytes idle) and handed out again once the last numpy view of
+    them is gone."""
+
+    def __init__(self, limit=4 << 30):
+        self.free = {}
+        self.idle = 0
+        self.limit = limit
+        self.lock = threading.Lock()
+
+    def _release(self, ptr, cap):
+        with self.lock:
+            if self.idle + cap <= self.limit:
+                self.free.setdefault(cap, []).append(ptr)
+                self.idle += cap
+                return
+        lib().qb_host_free(C.c_void_p(ptr))
+
+    def empty(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        if nbytes < (1 << 20):                       # small arrays: ordinary memory
+            return np.empty(shape, dtype=dtype)
+        cap = 1 << (nbytes - 1).bit_length()
+        with self.lock:
+            lst = self.free.get(cap)
+            ptr = lst.pop() if lst else None
+            if ptr is not None:
+                self.idle -= cap
+        if ptr is None:
+            p = C.c_void_p()
+            check(lib().qb_host_alloc(cap, C.byref(p)))
+            ptr = p.value
+        raw = (C.c_uint8 * nbytes).from_address(ptr)
+        weakref.finalize(raw, self._release, ptr, cap)
+        return np.frombuffer(raw, dtype=dtype).reshape(shape)
+
+
+_pool = _PinnedPool()
+
+
 def empty(shape, dtype):
-    return np.empty(shape, dtype=dtype)
+    """Uninitialised numpy array for results that come back from the device (page-locked when large)."""
+    return _pool.empty(shape, dtype)

@@ -130,12 +130,12 @@ class Circuit:
         shots = int(shots)
         D, K = self.num_detectors, self.num_observables
         if packed:
-            det = np.zeros((shots, max(1, (D + 63) // 64)), dtype=np.uint64)
-            obs = np.zeros((shots, max(1, (K + 63) // 64)), dtype=np.uint64)
+            det = N.empty((shots, max(1, (D + 63) // 64)), np.uint64)
+            obs = N.empty((shots, max(1, (K + 63) // 64)), np.uint64)
             N.check(N.lib().qb_sample_packed(ctx._h, self._h, int(seed), int(shot0), shots, N.ptr(det), N.ptr(obs)))
             return det, obs
-        det = np.zeros((shots, D), dtype=np.bool_)
-        obs = np.zeros((shots, K), dtype=np.bool_)
+        det = N.empty((shots, D), np.bool_)
+        obs = N.empty((shots, K), np.bool_)
         N.check(N.lib().qb_sample(ctx._h, self._h, int(seed), int(shot0), shots, N.ptr(det), N.ptr(obs)))
         return det, obs
 

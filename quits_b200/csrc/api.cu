@@ -650,6 +650,20 @@ int qb_ctx_synchronize(qb_ctx* ctx) {
     return guard([&] { use_device(ctx); CK(cudaStreamSynchronize(ctx->stream)); });
 }
 
+int qb_host_alloc(size_t bytes, void** out) {
+    return guard([&] {
+        if (!out) throw arg_error("out is NULL");
+        *out = nullptr;
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); throw cuda_error("no CUDA device is available"); }
+        CK(cudaHostAlloc(out, std::max<size_t>(bytes, 16), cudaHostAllocPortable));
+    });
+}
+
+void qb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 // ------------------------------------------------------------------------------------------------ circuit
 int qb_circuit_parse(const char* text, size_t len, qb_circuit** out) {
     return guard([&] {

@@ -93,7 +93,9 @@ class SlidingWindowDecoder:
         if det.dtype != np.bool_ and det.dtype != np.uint8:
             det = (det % 2).astype(np.uint8)
         det = np.ascontiguousarray(det).view(np.uint8)
-        pred = np.zeros((det.shape[0], self.K), dtype=np.int64)
+        pred = N.empty((det.shape[0], self.K), np.int64)
+        if self.K == 0 or det.shape[0] == 0:
+            pred[...] = 0
         N.check(N.lib().qb_sw_decode(self._h, N.ptr(det), det.shape[0], N.ptr(pred), C.byref(self.stats)))
         return pred
 
