@@ -15,6 +15,6 @@ from .decoder import (BpLsdDecoder, BpOsdDecoder, detector_error_model_to_matrix
                       sliding_window_bplsd_phenom_mem, sliding_window_bposd_circuit_mem, sliding_window_bposd_phenom_mem,
                       sliding_window_circuit_mem, sliding_window_phenom_mem, spacetime)
 from .engine import MonteCarlo, SlidingWindowDecoder, run_sharded, shard_range  # noqa: E402
-from .simulation import get_stim_mem_result  # noqa: E402
+from .simulation import get_codecap_pL, get_stim_mem_result  # noqa: E402
 
 __version__ = "0.1.0"

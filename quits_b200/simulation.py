@@ -21,4 +21,36 @@ def get_stim_mem_result(circuit, num_trials, seed=-1):
     return c.sample(int(num_trials), int(seed))
 
 
-__all__ = ["get_stim_mem_result"]
+def get_codecap_pL(code, p, num_trials, decoder, dict, basis='Z', seed=-1, tqdm_on=False):
+    """Code-capacity logical error rate (reference ``src/quits/simulation.py:31-61``), all trials decoded in one GPU batch.
+
+    Same signature and the same use of numpy's global RNG as the reference: trial i draws ``np.random.binomial(1, p, n)``
+    (one vectorised call here; numpy fills it element by element from the same stream, so the noise is identical for a given
+    ``seed``).  ``decoder`` must be the engine's ``BpOsdDecoder`` / ``BpLsdDecoder`` class; ``dict`` holds its keyword arguments.
+    """
+    from .decoder.inner import _GpuInnerDecoder
+    if seed >= 0:
+        np.random.seed(seed)
+    basis = basis.upper()
+    if basis == 'Z':
+        parity_check_matrix, logical_codewords = code.hz, code.lz
+    elif basis == 'X':
+        parity_check_matrix, logical_codewords = code.hx, code.lx
+    else:
+        raise ValueError("basis must be 'Z' or 'X'")
+    if not (isinstance(decoder, type) and issubclass(decoder, _GpuInnerDecoder)):
+        raise NotImplementedError("get_codecap_pL on the GPU path needs quits_b200.decoder.BpOsdDecoder / BpLsdDecoder, got %r; "
+                                  "there is no per-shot CPU fallback" % (decoder,))
+    H = np.asarray(parity_check_matrix) % 2
+    Lg = np.asarray(logical_codewords) % 2
+    bpd = decoder(H, **dict)
+    num_trials = int(num_trials)
+    noise = np.random.binomial(1, p, (num_trials, H.shape[1]))
+    syndromes = (noise @ H.T % 2).astype(np.uint8)
+    decoded, _, _, _ = bpd.decode_batch(syndromes)
+    residual = (decoded.astype(np.int64) + noise) % 2
+    num_errors = int(np.any(residual @ Lg.T % 2, axis=1).sum())
+    return num_errors / num_trials
+
+
+__all__ = ["get_stim_mem_result", "get_codecap_pL"]

@@ -185,3 +185,25 @@ def test_seedless_sampling_is_random(qb):
     b, _ = qb.get_stim_mem_result(c, 256)
     assert not np.array_equal(a, b)
     assert 0.01 < a.mean() < 0.3
+
+
+def test_code_capacity_loop_matches_per_shot_oracle(qb):
+    """get_codecap_pL (reference simulation.py:31-61): same numpy noise stream as the reference's per-trial loop, every trial
+    decoded on the GPU; the count equals the reference loop run with the oracle's BP+OSD-0 as the inner decoder."""
+    import types
+    from oracle import cref
+    _, hz, lz = circuit_meta("bb72_r6_p1e-3")
+    code = types.SimpleNamespace(hz=hz, lz=lz, hx=hz, lx=lz)
+    p, trials, seed = 0.02, 300, 123
+    kw = dict(bp_method="minimum_sum", schedule="parallel", max_iter=20, osd_method="osd_0", osd_order=0, error_rate=p)
+    got = qb.get_codecap_pL(code, p, trials, qb.BpOsdDecoder, dict(kw), basis="Z", seed=seed)
+    np.random.seed(seed)
+    orc = cref.BpOsd(hz, np.full(hz.shape[1], p), max_iter=20, bp_method="minimum_sum", schedule="parallel", precision="f64")
+    errs = 0
+    for _ in range(trials):
+        noise = np.random.binomial(1, p, hz.shape[1])
+        e, _, _, _ = orc.decode(hz @ noise % 2)
+        errs += int((lz @ ((e + noise) % 2) % 2).any())
+    assert got == errs / trials
+    with pytest.raises(ValueError):
+        qb.get_codecap_pL(code, p, 1, qb.BpOsdDecoder, dict(kw), basis="Q")
