@@ -207,3 +207,87 @@ def test_code_capacity_loop_matches_per_shot_oracle(qb):
     assert got == errs / trials
     with pytest.raises(ValueError):
         qb.get_codecap_pL(code, p, 1, qb.BpOsdDecoder, dict(kw), basis="Q")
+
+
+def _random_ldpc(rng, rows, cols, col_w):
+    """Random sparse parity-check matrix with the given column weight (full column set, every row used)."""
+    from scipy.sparse import csc_matrix
+    indptr, indices = [0], []
+    for j in range(cols):
+        r = rng.choice(rows, size=col_w, replace=False)
+        r[0] = j % rows                                     # every row appears
+        r = np.unique(r)
+        indices.extend(sorted(int(x) for x in r))
+        indptr.append(len(indices))
+    return csc_matrix((np.ones(len(indices), dtype=np.uint8), np.array(indices), np.array(indptr)), shape=(rows, cols))
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("rows,cols,col_w,label", [(60, 150, 8, "generic kernel, column weight 8"),
+                                                   (48, 120, 12, "generic kernel, column weight 12"),
+                                                   (700, 2600, 6, "messages in a global slab (tall window)"),
+                                                   (150, 300, 3, "compact kernel, rank-deficient random matrix")])
+def test_inner_decoder_on_other_kernel_paths(qb, rows, cols, col_w, label, precision):
+    """The windows of the BB / HGP fixtures all take the compact shared-memory BP kernel; these random matrices force the
+    generic kernel (column weight > 6), the global-slab variant (rows x row stride too large for shared memory) and the
+    exact-row-order OSD, each against the oracle per shot."""
+    from oracle import cref
+    rng = np.random.RandomState(rows * 7 + col_w)
+    H = _random_ldpc(rng, rows, cols, col_w)
+    pri = rng.choice([0.01, 0.02, 0.03], size=cols)
+    n = 48
+    err = (rng.rand(n, cols) < pri[None, :] * 1.5).astype(np.uint8)
+    syn = (err @ H.T.toarray() % 2).astype(np.uint8)
+    dec = qb.BpOsdDecoder(H, channel_probs=pri, max_iter=12, bp_method="minimum_sum", schedule="parallel", osd_method="osd_0",
+                          osd_order=0, precision=precision, ms_scaling_factor=0.75)
+    ehat, llr, iters, conv = dec.decode_batch(syn)
+    orc = cref.BpOsd(H, pri, max_iter=12, bp_method="minimum_sum", schedule="parallel", precision=precision, ms_scaling_factor=0.75)
+    for i in range(n):
+        e, l, it, c = orc.decode(syn[i])
+        assert bool(conv[i]) == c and int(iters[i]) == it, (label, i)
+        assert np.array_equal(llr[i], l), (label, i, np.max(np.abs(llr[i] - l)))
+        assert np.array_equal(ehat[i], e), (label, i, c)
+
+
+def test_more_than_64_observables(qb):
+    """K = 70 logical operators: the observable prediction spans two 64-bit words per shot (the QLP codes of the reference
+    have K = 136).  Phenomenological window against a direct restatement of the reference loop (sliding_window.py:74-99)
+    over the oracle's per-shot decoder."""
+    from oracle import cref
+    rng = np.random.RandomState(5)
+    m, n, K, W, F, rounds = 12, 24, 70, 3, 2, 4
+    hz = np.zeros((m, n), dtype=int)
+    for j in range(n):
+        hz[rng.choice(m, size=3, replace=False), j] = 1
+    lz = (rng.rand(K, n) < 0.3).astype(int)
+    shots, rate = 200, 0.04
+    det = (rng.rand(shots, m * (rounds + 2)) < 0.08)
+    pred = qb.sliding_window_bposd_phenom_mem(det, hz, lz, W, F, error_rate=rate, **BP_KW)
+    assert pred.shape == (shots, K)
+    ncor = -(-(2 + rounds - W) // F)
+    W_last = rounds + 2 - F * ncor
+
+    def mat(Wk, last):
+        B = np.eye(Wk, dtype=int)
+        for i in range(1, Wk):
+            B[i, i - 1] = 1
+        if last:
+            B = B[:, :Wk - 1]
+        return np.column_stack((np.kron(np.eye(Wk, dtype=int), hz), np.kron(B, np.eye(m, dtype=int))))
+    H1, H2 = mat(W, False), mat(W_last, True)
+    d1 = cref.BpOsd(H1, np.full(H1.shape[1], rate), max_iter=10, bp_method="minimum_sum", schedule="parallel", precision="f64")
+    d2 = cref.BpOsd(H2, np.full(H2.shape[1], rate), max_iter=10, bp_method="minimum_sum", schedule="parallel", precision="f64")
+    for i in range(shots):
+        acc = np.zeros(n, dtype=int)
+        upd = np.zeros(m, dtype=int)
+        for k in range(ncor):
+            s = det[i, F * k * m:(F * k + W) * m].astype(int)
+            s[:m] = (s[:m] + upd) % 2
+            e = d1.decode(s)[0].astype(int)
+            acc = (acc + e[:F * n].reshape(F, n).sum(axis=0)) % 2
+            upd = e[W * n + (F - 1) * m:W * n + F * m]
+        s = det[i, F * ncor * m:].astype(int)
+        s[:m] = (s[:m] + upd) % 2
+        e = d2.decode(s)[0].astype(int)
+        acc = (acc + e[:W_last * n].reshape(W_last, n).sum(axis=0)) % 2
+        assert np.array_equal(pred[i], lz @ acc % 2), i
