@@ -124,10 +124,12 @@ def main():
     ap.add_argument("--shots", type=int, default=262144, help="shots per step per GPU")
     ap.add_argument("--e2e-shots", type=int, default=262144)
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--workload", default=WORKLOAD, help="circuit fixture under tests/golden/circuits (default: the headline workload)")
     ap.add_argument("--lanes", type=int, default=0, help="concurrent sub-batches per device batch (0 = engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    globals()["WORKLOAD"] = args.workload
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

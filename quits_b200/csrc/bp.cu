@@ -51,9 +51,10 @@ template <> struct Real<double> {
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- hand-off to OSD: the posteriors' 32-bin histogram (built while the last iteration stores them) selects the least
-// reliable columns -- the smallest bin prefix with >= kSelTarget columns, at most kSelCap -- and the CTA writes their
+// reliable columns -- tier 1: the smallest bin prefix with >= kOsdSelTarget columns; tier 2: the further bins that still fit
+// kOsdSelCap columns in total -- and the CTA writes their
 // (order key, column) pairs to HBM, so the OSD warp never scans the full posterior vector (osd.cu, fast path).
-constexpr int kSelWords = 36;        // 32 bins, selected count, boundary bin, 2 spare
+constexpr int kSelWords = 36;        // 32 bins, tier-1 count, tier-2 count, the two boundary bins
 
 template <typename R>
 __device__ __forceinline__ int llr_bin(const R v, const R scale) {
@@ -78,29 +79,31 @@ __device__ __forceinline__ void select_for_osd(const WinDev& w, const BatchDev& 
             const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, cum, o);
             if (tid >= o) cum += t;
         }
+        // tier 1: the smallest bin prefix with >= kOsdSelTarget columns; tier 2: everything else that still fits the buffer
+        const uint32_t fits = __ballot_sync(0xFFFFFFFFu, cum <= static_cast<uint32_t>(kOsdSelCap));
+        const int b2 = fits ? 31 - __clz(fits) : -1;
         const uint32_t enough = __ballot_sync(0xFFFFFFFFu, cum >= static_cast<uint32_t>(kOsdSelTarget));
-        int bsel = enough ? __ffs(enough) - 1 : 31;
-        if (__shfl_sync(0xFFFFFFFFu, cum, bsel) > static_cast<uint32_t>(kOsdSelCap)) {
-            const uint32_t fits = __ballot_sync(0xFFFFFFFFu, cum <= static_cast<uint32_t>(kOsdSelCap));
-            bsel = fits ? 31 - __clz(fits) : -1;
-        }
-        if (tid == 0) { hist[32] = 0; hist[33] = static_cast<uint32_t>(bsel); }
+        int b1 = enough ? __ffs(enough) - 1 : 31;
+        if (b1 > b2) b1 = b2;
+        if (tid == 0) { hist[32] = 0; hist[33] = 0; hist[34] = static_cast<uint32_t>(b1 + 1); hist[35] = static_cast<uint32_t>(b2 + 1); }
     }
     __syncthreads();
-    const int bsel = static_cast<int>(hist[33]);
+    const int b1 = static_cast<int>(hist[34]) - 1, b2 = static_cast<int>(hist[35]) - 1;
     const R scale = static_cast<R>(w.bin_scale);
     const R* llr = reinterpret_cast<const R*>(b.llr_buf) + static_cast<size_t>(shot) * b.llr_stride;
     KeyT* gkey = reinterpret_cast<KeyT*>(b.sel_key) + static_cast<size_t>(shot) * kOsdSelCap;
     uint16_t* gidx = b.sel_idx + static_cast<size_t>(shot) * kOsdSelCap;
     for (int j = tid; j < w.ncols; j += NT) {
         const R v = llr[j];
-        if (llr_bin<R>(v, scale) <= bsel) {
-            const uint32_t pos = atomicAdd(&hist[32], 1u);
-            if (pos < static_cast<uint32_t>(kOsdSelCap)) { gkey[pos] = order_key_of(v); gidx[pos] = static_cast<uint16_t>(j); }
+        const int bin = llr_bin<R>(v, scale);
+        if (bin <= b2) {                               // tier 1 fills the buffer from the front, tier 2 from the back
+            const uint32_t pos = bin <= b1 ? atomicAdd(&hist[32], 1u) : static_cast<uint32_t>(kOsdSelCap - 1) - atomicAdd(&hist[33], 1u);
+            gkey[pos] = order_key_of(v);
+            gidx[pos] = static_cast<uint16_t>(j);
         }
     }
     __syncthreads();
-    if (tid == 0) b.sel_cnt[shot] = static_cast<int>(hist[32]);
+    if (tid == 0) b.sel_cnt[shot] = static_cast<int>(hist[32] | (hist[33] << 16));
 }
 
 // shared-memory layout; returns the total.  off: V, rsum, rmeta, syn, cand, accs, car

@@ -447,12 +447,19 @@ __global__ void __launch_bounds__(32) osd_fast_kernel(const WinDev w, const Batc
         job = __shfl_sync(kFull, job, 0);
         if (job >= count) break;
         const int shot = b.fail_list[job];
-        const int S = b.sel_cnt[shot];                       // selection made by the BP kernel (bp.cu, select_for_osd)
+        // selection made by the BP kernel (bp.cu, select_for_osd): tier 1 at the front of the buffer, tier 2 at its back
+        const int packed = b.sel_cnt[shot];
+        const int S1 = packed & 0xFFFF, S2 = (packed >> 16) & 0xFFFF;
+        const KeyT* gkey = reinterpret_cast<const KeyT*>(b.sel_key) + static_cast<size_t>(shot) * kOsdSelCap;
+        const uint16_t* gidx = b.sel_idx + static_cast<size_t>(shot) * kOsdSelCap;
         bool finished = false;
-        if (S > 0 && S <= kOsdSelCap) {
-            const KeyT* gkey = reinterpret_cast<const KeyT*>(b.sel_key) + static_cast<size_t>(shot) * kOsdSelCap;
-            const uint16_t* gidx = b.sel_idx + static_cast<size_t>(shot) * kOsdSelCap;
-            for (int i = lane; i < S; i += 32) { selkey[i] = gkey[i]; selidx[i] = gidx[i]; }
+        for (int attempt = 0; attempt < 2 && !finished; ++attempt) {
+            // attempt 0 orders and eliminates over tier 1 alone; if that runs out, attempt 1 starts over on both tiers
+            const int S = attempt == 0 ? S1 : S1 + S2;
+            if (S == 0 || S > kOsdSelCap || (attempt == 1 && S2 == 0)) continue;
+            for (int i = lane; i < S1; i += 32) { selkey[i] = gkey[i]; selidx[i] = gidx[i]; }
+            if (attempt == 1)
+                for (int i = lane; i < S2; i += 32) { selkey[S1 + i] = gkey[kOsdSelCap - 1 - i]; selidx[S1 + i] = gidx[kOsdSelCap - 1 - i]; }
             // ---- bitonic sort on (key, column index) in shared memory, padded to a power of two with +inf entries
             int P = 32;
             while (P < S) P <<= 1;

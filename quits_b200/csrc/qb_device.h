@@ -97,7 +97,7 @@ struct BatchDev {
     int* fail_count;          // [1]
     void* sel_key;            // [n][kOsdSelCap] order keys (u32 / u64 by precision) of the least reliable columns of a failed shot
     uint16_t* sel_idx;        // [n][kOsdSelCap] their column indices (unordered; the OSD warp sorts them)
-    int* sel_cnt;             // [n] how many (0 .. kOsdSelCap); NULL when OSD is off
+    int* sel_cnt;             // [n] tier-1 count | tier-2 count << 16 (tier 1 from the front of the row, tier 2 from its back); NULL when OSD is off
     int* fast_next;           // [1] work counter of the persistent OSD fast-path grid
     int* ovf_list;            // [n] shots the fast path hands to the full sort + elimination
     int* ovf_count;           // [1]
