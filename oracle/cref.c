@@ -238,6 +238,12 @@ int qo_run(int n_ops, const int32_t* kind, const double* arg, const int64_t* tst
  *   - bit update: forward prefix sums over the column in ascending row order give v[e] and the
  *     posterior; hard decision e_j = [LLR_j <= 0]; stop as soon as H e == s; otherwise the
  *     backward suffix pass completes v[e]
+ *   - higher-order OSD (osd.hpp, restated from the published description; ldpc is not vendored): complete the row
+ *     reduction, then try flipping sets of NON-pivot columns (in the LLR order): osd_cs(w) = every single non-pivot
+ *     column, then every pair among the first w; osd_e(w) = every non-empty subset of the first w (pattern p = 1..2^w-1,
+ *     bit b <-> b-th non-pivot column).  A candidate's pivot bits are the reduced syndrome XOR the reduced flipped
+ *     columns; its weight is sum_{j: x_j = 1} log(1/p_j) over the column index (priors, not posteriors); the first
+ *     candidate strictly lighter than everything before it wins, starting from the OSD-0 solution.
  *   - OSD-0: columns by ascending posterior LLR (stable: ties by column index -- ldpc's own tie order
  *     comes from std::sort and is unspecified), row-reduce choosing as pivot row the first row at or
  *     below the current rank that has a 1 (rows swapped into place), solve on the pivots, rest 0.
@@ -253,7 +259,9 @@ typedef struct {
     int schedule;                     /* 0 = parallel (flooding), 1 = serial */
     double alpha;                     /* ms_scaling_factor; 0 => 1 - 2^-it */
     int precision;                    /* 64 or 32 */
-    int osd;                          /* 1: OSD-0 when BP fails; 0: return BP output */
+    int osd;                          /* 1: OSD when BP fails; 0: return BP output */
+    int osd_method;                   /* 0 osd_0 | 1 osd_e (exhaustive) | 2 osd_cs (combination sweep) */
+    int osd_order;
 } qo_bp;
 
 qo_bp* qo_bp_create(int m, int n, const int64_t* indptr /*csc n+1*/, const int32_t* indices /*rows, ascending*/,
@@ -282,7 +290,15 @@ qo_bp* qo_bp_create(int m, int n, const int64_t* indptr /*csc n+1*/, const int32
     free(fill);
     d->max_iter = max_iter; d->method = method; d->schedule = schedule; d->alpha = alpha;
     d->precision = precision; d->osd = osd;
+    d->osd_method = 0; d->osd_order = 0;
     return d;
+}
+
+/* osd_method: 0 osd_0 | 1 osd_e | 2 osd_cs; order 0 is OSD-0 whatever the method */
+void qo_bp_set_osd(qo_bp* d, int osd_method, int osd_order)
+{
+    d->osd_method = osd_method;
+    d->osd_order = osd_order < 0 ? 0 : (osd_method == 1 && osd_order > 20 ? 20 : (osd_order > 64 ? 64 : osd_order));
 }
 
 void qo_bp_free(qo_bp* d)
@@ -312,10 +328,18 @@ void qo_bp_free(qo_bp* d)
 #define BPFN(x) x##_f32
 #include "bp_impl.inc"
 
-/* OSD-0 on posterior LLRs (as doubles; f32 posteriors are widened exactly, so the order is unchanged). */
-static void osd0(const qo_bp* d, const uint8_t* syn, const double* llr, uint8_t* ehat)
+/* OSD on posterior LLRs (as doubles; f32 posteriors are widened exactly, so the order is unchanged). */
+static double sol_weight(const qo_bp* d, const uint8_t* x)
+{
+    double w = 0.0;
+    for (int j = 0; j < d->n; ++j) if (x[j]) w += log(1.0 / d->prior[j]);
+    return w;
+}
+
+static void osd_decode(const qo_bp* d, const uint8_t* syn, const double* llr, uint8_t* ehat)
 {
     int m = d->m, n = d->n;
+    const int higher = d->osd_method != 0 && d->osd_order > 0;
     int* order = (int*)malloc((size_t)n * sizeof(int));
     /* stable merge sort on (llr, index) */
     int* tmp = (int*)malloc((size_t)n * sizeof(int));
@@ -339,6 +363,7 @@ static void osd0(const qo_bp* d, const uint8_t* syn, const double* llr, uint8_t*
     }
     for (int i = 0; i < m; ++i) if (syn[i] & 1) A[(size_t)i * nw + (n >> 6)] |= 1ull << (n & 63);
     int* pivcol = (int*)malloc((size_t)m * sizeof(int));
+    uint8_t* ispiv = (uint8_t*)calloc((size_t)n + 1, 1);
     int rank = 0;
     uint64_t* swp = (uint64_t*)malloc((size_t)nw * 8);
     for (int k = 0; k < n && rank < m; ++k) {
@@ -357,12 +382,49 @@ static void osd0(const qo_bp* d, const uint8_t* syn, const double* llr, uint8_t*
             uint64_t* ri = &A[(size_t)i * nw];
             for (int q = w; q < nw; ++q) ri[q] ^= pr[q];
         }
+        ispiv[k] = 1;
         pivcol[rank++] = k;
     }
     memset(ehat, 0, (size_t)n);
     for (int r = 0; r < rank; ++r)
         if (A[(size_t)r * nw + (n >> 6)] & (1ull << (n & 63))) ehat[order[pivcol[r]]] = 1;
-    free(order); free(tmp); free(A); free(pivcol); free(swp);
+    if (higher) {
+        /* non-pivot columns in LLR order */
+        int nnp = 0;
+        int* np = (int*)malloc((size_t)n * sizeof(int) + 4);
+        for (int k = 0; k < n; ++k) if (!ispiv[k]) np[nnp++] = k;
+        int w = d->osd_order < nnp ? d->osd_order : nnp;
+        uint8_t* x = (uint8_t*)malloc((size_t)n + 8);
+        double best = sol_weight(d, ehat);
+        /* candidate = set of at most `w` non-pivot positions (CS singles range over all of them) */
+        int flip[64];
+        #define QO_TRY(NF)                                                                                   \
+            do {                                                                                             \
+                memset(x, 0, (size_t)n);                                                                     \
+                for (int r = 0; r < rank; ++r) {                                                             \
+                    uint64_t bitv = (A[(size_t)r * nw + (n >> 6)] >> (n & 63)) & 1ull;                       \
+                    for (int f = 0; f < (NF); ++f) bitv ^= (A[(size_t)r * nw + (flip[f] >> 6)] >> (flip[f] & 63)) & 1ull; \
+                    if (bitv) x[order[pivcol[r]]] = 1;                                                       \
+                }                                                                                            \
+                for (int f = 0; f < (NF); ++f) x[order[flip[f]]] = 1;                                        \
+                double cw = sol_weight(d, x);                                                                \
+                if (cw < best) { best = cw; memcpy(ehat, x, (size_t)n); }                                    \
+            } while (0)
+        if (d->osd_method == 2) {                     /* combination sweep */
+            for (int i = 0; i < nnp; ++i) { flip[0] = np[i]; QO_TRY(1); }
+            for (int i = 0; i < w; ++i)
+                for (int j = i + 1; j < w; ++j) { flip[0] = np[i]; flip[1] = np[j]; QO_TRY(2); }
+        } else {                                      /* exhaustive over the first w (w <= 20 enforced by the caller) */
+            for (uint32_t pat = 1; pat < (1u << w); ++pat) {
+                int nf = 0;
+                for (int b = 0; b < w; ++b) if ((pat >> b) & 1u) flip[nf++] = np[b];
+                QO_TRY(nf);
+            }
+        }
+        #undef QO_TRY
+        free(np); free(x);
+    }
+    free(order); free(tmp); free(A); free(pivcol); free(swp); free(ispiv);
 }
 
 /* decode one syndrome.  Returns 1 if BP converged.  llr_out (n doubles) = BP posteriors; iters_out = iterations run;
@@ -374,7 +436,7 @@ int qo_bp_decode(const qo_bp* d, const uint8_t* syn, uint8_t* ehat, double* llr_
     if (d->precision == 32) conv = bp_run_f32(d, syn, ehat, llr, iters_out);
     else conv = bp_run_f64(d, syn, ehat, llr, iters_out);
     int used = 0;
-    if (!conv && d->osd) { osd0(d, syn, llr, ehat); used = 1; }
+    if (!conv && d->osd) { osd_decode(d, syn, llr, ehat); used = 1; }
     if (used_osd_out) *used_osd_out = used;
     if (!llr_out) free(llr);
     return conv;

@@ -122,8 +122,11 @@ class BpOsd:
     METHODS = {"minimum_sum": 0, "min_sum": 0, "ms": 0, "msl": 0, "product_sum": 1, "ps": 1, "psl": 1, 0: 0, 1: 1}
     SCHEDULES = {"parallel": 0, "serial": 1, 0: 0, 1: 1}
 
+    OSD_METHODS = {"osd_0": 0, "osd0": 0, "osd_e": 1, "osde": 1, "exhaustive": 1, "osd_cs": 2, "osdcs": 2, "combination_sweep": 2,
+                   0: 0, 1: 1, 2: 2}
+
     def __init__(self, pcm, priors, max_iter, bp_method="minimum_sum", ms_scaling_factor=1.0, schedule="parallel",
-                 precision="f64", osd=True):
+                 precision="f64", osd=True, osd_method="osd_0", osd_order=0):
         import scipy.sparse as sp
         pcm = sp.csc_matrix(pcm)
         pcm.sort_indices()
@@ -136,6 +139,8 @@ class BpOsd:
                                     _p(self._priors, C.c_double), C.c_int(int(max_iter)), C.c_int(self.METHODS[bp_method]),
                                     C.c_int(self.SCHEDULES[schedule]), C.c_double(float(ms_scaling_factor)),
                                     C.c_int(32 if precision in ("f32", 32) else 64), C.c_int(1 if osd else 0))
+        lib().qo_bp_set_osd(C.c_void_p(self.h), C.c_int(self.OSD_METHODS[str(osd_method).lower() if isinstance(osd_method, str) else osd_method]),
+                            C.c_int(int(osd_order)))
         self.used_osd = 0
 
     def __del__(self):

@@ -204,11 +204,12 @@ class _OracleBpDecoderBase:
             raise ValueError("error_rate / error_channel / channel_probs required")
         order = int(kw.get(self._order_key, 0))
         method = str(kw.get(self._method_key, "osd_0")).lower().replace("_", "")
-        if order != 0 and method not in ("osd0", "lsd0"):
-            raise NotImplementedError("oracle implements order-0 post-processing only (got %s order %d)" % (method, order))
+        if order != 0 and method.startswith("lsd") and method != "lsd0":
+            raise NotImplementedError("oracle implements order-0 LSD post-processing only (got %s order %d)" % (method, order))
+        osd_method = {"osd0": "osd_0", "osde": "osd_e", "exhaustive": "osd_e", "osdcs": "osd_cs", "combinationsweep": "osd_cs"}.get(method, "osd_0")
         self._dec = cref.BpOsd(pcm, priors, max_iter=max_iter if max_iter > 0 else n, bp_method=bp_method,
                                ms_scaling_factor=ms_scaling_factor, schedule=schedule,
-                               precision=kw.get("precision", DEFAULT_PRECISION))
+                               precision=kw.get("precision", DEFAULT_PRECISION), osd_method=osd_method, osd_order=order)
         self.log_prob_ratios = None
         self.converge = None
         self.iter = None

@@ -135,7 +135,7 @@ namespace {
 
 struct WinOwned {
     qb::WinDev dev{};
-    DevBuf colE, llr0f, llr0d, lmask, uptr, uidx, cptr, crow, colrec, ptabf, ptabd, rlen, rsum0f, rsum0d, neg0;
+    DevBuf colE, llr0f, llr0d, osd_wt, lmask, uptr, uidx, cptr, crow, colrec, ptabf, ptabd, rlen, rsum0f, rsum0d, neg0;
     size_t bp_smem = 0;
     bool vglobal = false;
     int bp_grid = 0;            // persistent grid of the VGLOBAL variant (0: one CTA per shot)
@@ -150,6 +150,7 @@ struct qb_sw {
     qb_bp_opts opts{};
     bool single = false;
     bool use_osd = true;
+    bool osd_hi = false;          // osd_e / osd_cs with order > 0: full elimination + candidate sweeps
     int max_iter = 0;
     int precision = 64;
     std::vector<std::unique_ptr<WinOwned>> wins;
@@ -357,6 +358,11 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
     upload(wo.colE, colE, ctx->stream);
     upload(wo.llr0f, llr0f, ctx->stream);
     upload(wo.llr0d, llr0d, ctx->stream);
+    {
+        std::vector<double> owt(static_cast<size_t>(npad), 0.0);
+        for (int j = 0; j < ncols; ++j) owt[j] = std::log(1.0 / hw.priors[j]);
+        upload(wo.osd_wt, owt, ctx->stream);
+    }
     upload(wo.lmask, lmask, ctx->stream);
     upload(wo.uptr, uptr, ctx->stream, 2);
     upload(wo.uidx, uidx, ctx->stream, 2);
@@ -372,6 +378,7 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
         for (int j = 0; j < ncols; ++j) lmin = std::min(lmin, llr0d[j]);
         d.bin_scale = lmin > 1e-3 ? 10.0 / lmin : 10.0;
     }
+    d.osd_wt = wo.osd_wt.as<double>();
     d.colE = wo.colE.as<uint32_t>(); d.llr0f = wo.llr0f.as<float>(); d.llr0d = wo.llr0d.as<double>(); d.lmask = wo.lmask.as<uint64_t>();
     d.uptr = wo.uptr.as<int32_t>(); d.uidx = wo.uidx.as<uint16_t>(); d.cptr = wo.cptr.as<int32_t>(); d.crow = wo.crow.as<uint16_t>();
 }
@@ -381,7 +388,10 @@ void finish_decoder(qb_sw* sw) {
     const qb_bp_opts& o = sw->opts;
     if (o.bp_method != 0 && o.bp_method != 1) throw qb::value_error("bp_method must be 0 (minimum_sum) or 1 (product_sum)");
     if (o.schedule != 0) throw qb::unsupported_error("schedule 'serial' is not implemented on the GPU path yet; use schedule='parallel'");
-    if (o.osd_method >= 0 && o.osd_order != 0) throw qb::unsupported_error("osd_order > 0 is not implemented on the GPU path yet; use osd_order=0");
+    if (o.osd_order < 0) throw qb::value_error("osd_order must be >= 0");
+    if (o.osd_method == 1 && o.osd_order > 12) throw qb::unsupported_error("osd_e beyond order 12 (4095 patterns per shot) is not supported on the GPU path");
+    if (o.osd_method == 2 && o.osd_order > 32) throw qb::unsupported_error("osd_cs beyond order 32 is not supported on the GPU path");
+    sw->osd_hi = o.osd_method > 0 && o.osd_order > 0;
     if (o.ms_scaling_factor < 0) throw qb::value_error("ms_scaling_factor must be >= 0");
     if (o.precision != 0 && o.precision != 32 && o.precision != 64) throw qb::value_error("precision must be 32 or 64");
     sw->precision = o.precision == 32 ? 32 : 64;
@@ -411,7 +421,7 @@ void finish_decoder(qb_sw* sw) {
                                             " exceeds what the OSD kernels handle (rows <= 768)");
             CK(qb::osd_configure(w->dev, prec));
             const int sort_per_sm = static_cast<int>((227 * 1024) / (qb::osd_sort_smem_bytes(w->dev, prec) + 1024));
-            const int elim_per_sm = static_cast<int>((227 * 1024) / (qb::osd_elim_smem_bytes(w->dev) + 1024));
+            const int elim_per_sm = static_cast<int>((227 * 1024) / (qb::osd_elim_smem_bytes(w->dev, sw->osd_hi) + 1024));
             w->sort_grid = 148 * std::max(1, std::min(sort_per_sm, 6));
             w->elim_grid = 148 * std::max(1, std::min(elim_per_sm, 16));
             const int fast_per_sm = static_cast<int>((227 * 1024) / (qb::osd_fast_smem_bytes(w->dev) + 1024));
@@ -514,7 +524,9 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.sort_next = ctr + 3;
             b.osd_next = ctr + 4;
             b.ovf_list = sw->use_osd ? sw->ovf_list.as<int>() + s0 : nullptr;
-            if (sw->use_osd) {
+            b.osd_method = sw->opts.osd_method;
+            b.osd_order = sw->opts.osd_order;
+            if (sw->use_osd && !sw->osd_hi) {
                 b.sel_key = static_cast<unsigned char*>(sw->sel_key.p) + s0 * qb::kOsdSelCap * esz;
                 b.sel_idx = sw->sel_idx.as<uint16_t>() + s0 * qb::kOsdSelCap;
                 b.sel_cnt = sw->sel_cnt.as<int>() + s0;
@@ -531,6 +543,14 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             if (stats) stats->bp_launches++;
             if (sw->use_osd) {
                 if (sw->opts.profile) sw->t_osd.begin(ls);
+                if (sw->osd_hi) {
+                    // higher-order OSD needs the complete elimination over the complete column order
+                    CK(qb::launch_osd_sort(w.dev, b, sw->precision, std::min(w.sort_grid, nl), ls));
+                    CK(qb::launch_osd_elim(w.dev, b, true, std::min(w.elim_grid, nl), ls));
+                    if (sw->opts.profile) sw->t_osd.end(ls);
+                    if (stats) stats->osd_launches += 2;
+                    continue;
+                }
                 // fast path: per-warp selection of the least reliable columns + elimination; the (rare) shots it cannot finish
                 // go through the full sort + elimination, which read the overflow list instead of the fail list
                 CK(qb::launch_osd_fast(w.dev, b, sw->precision, std::min(w.fast_grid, nl), ls));
@@ -538,7 +558,7 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
                 bo.fail_list = b.ovf_list;
                 bo.fail_count = b.ovf_count;
                 CK(qb::launch_osd_sort(w.dev, bo, sw->precision, std::min(w.sort_grid, std::max(1, nl / 64)), ls));
-                CK(qb::launch_osd_elim(w.dev, bo, std::min(w.elim_grid, std::max(1, nl / 64)), ls));
+                CK(qb::launch_osd_elim(w.dev, bo, false, std::min(w.elim_grid, std::max(1, nl / 64)), ls));
                 if (sw->opts.profile) sw->t_osd.end(ls);
                 if (stats) stats->osd_launches += 3;
             }

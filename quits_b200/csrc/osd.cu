@@ -33,6 +33,7 @@ namespace qb {
 
 namespace {
 
+constexpr int kOsdMaxOrder = 32;       // osd_cs: pairs among the first <= 32 non-pivot columns; osd_e: order <= 12 (4095 patterns)
 constexpr int kSortThreads = 128;
 constexpr int kSortWarps = 4;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
@@ -166,11 +167,11 @@ __global__ void __launch_bounds__(kSortThreads) osd_sort_kernel(const WinDev w, 
 
 // ====================================================================================================== elimination
 struct ElimLayout {
-    size_t T, rvec, freem, svec, seq, pivcol, pivrow, slot, accs, car, selkey, selidx, bins, total;
+    size_t T, rvec, freem, svec, seq, pivcol, pivrow, slot, accs, car, selkey, selidx, bins, pivpos, ispiv, skeys, pinfo, pwt, ybuf, rw, scol, swt, flips, total;
     int TS;
 };
 
-__host__ __device__ inline ElimLayout elim_layout(const WinDev& w, int NQ, bool exact, int selcap) {
+__host__ __device__ inline ElimLayout elim_layout(const WinDev& w, int NQ, bool exact, int selcap, bool hi = false) {
     ElimLayout L;
     L.TS = (w.rows + 31) / 32 * 32;
     size_t o = 0;
@@ -187,6 +188,19 @@ __host__ __device__ inline ElimLayout elim_layout(const WinDev& w, int NQ, bool 
     L.selkey = o; o += au(static_cast<size_t>(selcap) * 8);
     L.selidx = o; o += au(static_cast<size_t>(selcap) * 2);
     L.bins = o; o += selcap ? 128 : 0;
+    // higher-order OSD (osd_e / osd_cs with order > 0)
+    int P = 32;
+    while (P < w.rows) P <<= 1;
+    L.pivpos = o; o += hi ? au(static_cast<size_t>(w.rows) * 2) : 0;
+    L.ispiv = o; o += hi ? au(static_cast<size_t>((w.ncols + 31) / 32) * 4) : 0;
+    L.skeys = o; o += hi ? au(static_cast<size_t>(P) * 4) : 0;
+    L.pinfo = o; o += hi ? au(static_cast<size_t>(w.rows) * 4) : 0;
+    L.pwt = o; o += hi ? au(static_cast<size_t>(w.rows) * 8) : 0;
+    L.ybuf = o; o += hi ? au(static_cast<size_t>(32) * (4 * NQ + 1) * 4) : 0;
+    L.rw = o; o += hi ? static_cast<size_t>(kOsdMaxOrder) * NQ * 16 : 0;
+    L.scol = o; o += hi ? au(static_cast<size_t>(kOsdMaxOrder) * 4 * 2) : 0;
+    L.swt = o; o += hi ? au(static_cast<size_t>(kOsdMaxOrder) * 8) : 0;
+    L.flips = o; o += hi ? au(static_cast<size_t>(kOsdMaxOrder + 2) * 4) : 0;
     L.total = o;
     return L;
 }
@@ -195,9 +209,246 @@ __device__ __forceinline__ uint32_t comp(const uint4& v, int c) { return c == 0 
 __device__ __forceinline__ void xor4(uint4& a, const uint4& b) { a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w; }
 __device__ __forceinline__ uint32_t and_any(const uint4& a, const uint4& b) { return (a.x & b.x) | (a.y & b.y) | (a.z & b.z) | (a.w & b.w); }
 
+// ====================================================================================================== higher-order OSD
+// osd_cs / osd_e with order > 0 (ldpc osd.hpp, restated in oracle/cref.c osd_decode): after the COMPLETE elimination, flip sets
+// of non-pivot columns (in LLR order) and keep the lightest solution, weight = sum over set bits, in column-index order, of
+// log(1/p_j).  One candidate per lane: the lane forms the candidate's pivot bits y = T s xor T c (the same sparse gather the
+// elimination uses), parks y in shared memory and walks the pivots in column order adding weights with __dadd_rn, the flipped
+// columns merged in at their place -- the same additions in the same order as the CPU oracle, so ties between candidates
+// (ubiquitous with 9 distinct priors) resolve identically: first candidate that is strictly lighter wins.
+template <int NQ>
+__device__ __forceinline__ void gather_reduced(const WinDev& w, const uint4* T4, const int TS, const uint16_t* slot_of_row, const int col,
+                                               uint4 (&v)[NQ]) {
+    const int qb = __ldg(w.cptr + col), qe = __ldg(w.cptr + col + 1);
+    for (int q = qb; q < qe; ++q) {
+        const int row = __ldg(w.crow + q);
+        const uint32_t s = slot_of_row[row];
+        if (s != 0xFFFFu) {
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) xor4(v[i], T4[i * TS + s]);
+        }                                   // rows without a pivot carry no solution bit: ignored
+    }
+}
+
+template <int NQ>
+__device__ void osd_higher(const WinDev& w, const BatchDev& b, unsigned char* sm, const ElimLayout& L, const int rank,
+                           const uint16_t* order, const int n, const int lane) {
+    constexpr int YS = 4 * NQ + 1;
+    const uint4* T4 = reinterpret_cast<const uint4*>(sm + L.T);
+    const int TS = L.TS;
+    uint4* svec = reinterpret_cast<uint4*>(sm + L.svec);
+    uint32_t* svec32 = reinterpret_cast<uint32_t*>(svec);
+    const uint16_t* pivcol = reinterpret_cast<const uint16_t*>(sm + L.pivcol);
+    const uint16_t* pivrow = reinterpret_cast<const uint16_t*>(sm + L.pivrow);
+    const uint16_t* slot_of_row = reinterpret_cast<const uint16_t*>(sm + L.slot);
+    const uint16_t* pivpos = reinterpret_cast<const uint16_t*>(sm + L.pivpos);
+    uint32_t* ispiv = reinterpret_cast<uint32_t*>(sm + L.ispiv);
+    uint32_t* skeys = reinterpret_cast<uint32_t*>(sm + L.skeys);
+    uint32_t* pinfo = reinterpret_cast<uint32_t*>(sm + L.pinfo);
+    double* pwt = reinterpret_cast<double*>(sm + L.pwt);
+    uint32_t* ybuf = reinterpret_cast<uint32_t*>(sm + L.ybuf) + lane * YS;
+    uint4* rw = reinterpret_cast<uint4*>(sm + L.rw);
+    uint32_t* scol = reinterpret_cast<uint32_t*>(sm + L.scol);            // [kOsdMaxOrder] column, then [kOsdMaxOrder] pattern bit
+    uint32_t* sbit = scol + kOsdMaxOrder;
+    double* swt = reinterpret_cast<double*>(sm + L.swt);
+    uint32_t* flips = reinterpret_cast<uint32_t*>(sm + L.flips);
+    const double* wt = w.osd_wt;
+
+    // ---- pivot positions as a bitmap over the sorted order; pivots sorted by column index
+    const int npw = (n + 31) / 32;
+    for (int i = lane; i < npw; i += 32) ispiv[i] = 0;
+    int P = 32;
+    while (P < rank) P <<= 1;
+    for (int i = lane; i < P; i += 32) skeys[i] = i < rank ? (static_cast<uint32_t>(pivcol[i]) << 16) | static_cast<uint32_t>(i) : 0xFFFFFFFFu;
+    __syncwarp();
+    for (int s = lane; s < rank; s += 32) atomicOr(&ispiv[pivpos[s] >> 5], 1u << (pivpos[s] & 31));
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (P >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const uint32_t a = skeys[i], c = skeys[l];
+                if ((a > c) == ((i & k) == 0)) { skeys[i] = c; skeys[l] = a; }
+            }
+            __syncwarp();
+        }
+    }
+    for (int t = lane; t < rank; t += 32) {
+        const uint32_t s = skeys[t] & 0xFFFFu, pc = skeys[t] >> 16;
+        pinfo[t] = (static_cast<uint32_t>(pivrow[s]) << 16) | pc;
+        pwt[t] = __ldg(wt + pc);
+    }
+    // ---- the first `ord` non-pivot columns: reduced vectors, and their columns sorted by index for the weight merge
+    const int ord_req = min(b.osd_order, b.osd_method == 1 ? 12 : kOsdMaxOrder);
+    int ord = 0;
+    int mycol = -1;
+    for (int c0 = 0; c0 < n && ord < ord_req; c0 += 32) {
+        const int p = c0 + lane;
+        const bool np = p < n && !((ispiv[p >> 5] >> (p & 31)) & 1u);
+        const uint32_t bal = __ballot_sync(kFull, np);
+        const int idx = ord + __popc(bal & ((1u << lane) - 1u));
+        const int colp = np ? static_cast<int>(order[p]) : -1;
+        // hand the column of the idx-th non-pivot position to lane idx
+#pragma unroll 1
+        for (uint32_t mm = bal; mm; mm &= mm - 1) {
+            const int src = __ffs(mm) - 1;
+            const int di = __shfl_sync(kFull, idx, src), dc = __shfl_sync(kFull, colp, src);
+            if (di < ord_req && lane == di) mycol = dc;
+        }
+        ord = min(ord_req, ord + __popc(bal));
+    }
+    __syncwarp();
+    {
+        uint4 v[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) v[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (lane < ord) gather_reduced<NQ>(w, T4, TS, slot_of_row, mycol, v);
+        if (lane < ord) {
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) rw[lane * NQ + i] = v[i];
+        }
+        // rank of my column among the `ord` (distinct) columns
+        int rk = 0;
+        for (int o = 0; o < ord; ++o) rk += __shfl_sync(kFull, mycol, o) < mycol ? 1 : 0;
+        if (lane < ord) { scol[rk] = static_cast<uint32_t>(mycol); sbit[rk] = static_cast<uint32_t>(lane); swt[rk] = __ldg(wt + mycol); }
+    }
+    __syncwarp();
+
+    // weight of the candidate whose pivot bits sit in this lane's ybuf row; single: one flipped column xc (or none: xc < 0);
+    // pattern: the flipped columns are the members of `pat` among the first `ord` non-pivot columns
+    auto weigh = [&](const bool active, const int xc, const uint32_t pat) -> double {
+        double ws = 0.0;
+        bool pending = xc >= 0;
+        const double wx = pending ? __ldg(wt + xc) : 0.0;
+        int ip = 0;
+        for (int t = 0; t < rank; ++t) {
+            const uint32_t info = pinfo[t];
+            const int pc = static_cast<int>(info & 0xFFFFu), row = static_cast<int>(info >> 16);
+            if (pending && xc < pc) { ws = __dadd_rn(ws, wx); pending = false; }
+            while (ip < ord && static_cast<int>(scol[ip]) < pc) {
+                if ((pat >> sbit[ip]) & 1u) ws = __dadd_rn(ws, swt[ip]);
+                ++ip;
+            }
+            if (active && ((ybuf[row >> 5] >> (row & 31)) & 1u)) ws = __dadd_rn(ws, pwt[t]);
+        }
+        if (pending) ws = __dadd_rn(ws, wx);
+        while (ip < ord) {
+            if ((pat >> sbit[ip]) & 1u) ws = __dadd_rn(ws, swt[ip]);
+            ++ip;
+        }
+        return ws;
+    };
+    auto park = [&](const uint4 (&v)[NQ]) {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) { ybuf[4 * i] = v[i].x; ybuf[4 * i + 1] = v[i].y; ybuf[4 * i + 2] = v[i].z; ybuf[4 * i + 3] = v[i].w; }
+    };
+
+    // ---- OSD-0 solution
+    uint4 y0[NQ];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) y0[i] = svec[i];
+    park(y0);
+    __syncwarp();
+    const double w0 = weigh(true, -1, 0u);
+    double bestw = w0;
+    int bestid = 0x7FFFFFFF, bestkind = 0;
+    uint32_t bestarg = 0;
+    int nextid = 0;
+    // ---- combination sweep: every single non-pivot column, in LLR order
+    if (b.osd_method == 2) {
+        for (int c0 = 0; c0 < n; c0 += 32) {
+            const int p = c0 + lane;
+            const bool np = p < n && !((ispiv[p >> 5] >> (p & 31)) & 1u);
+            const uint32_t bal = __ballot_sync(kFull, np);
+            if (!bal) continue;
+            const int id = nextid + __popc(bal & ((1u << lane) - 1u));
+            nextid += __popc(bal);
+            int col = -1;
+            uint4 v[NQ];
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) v[i] = y0[i];
+            if (np) {
+                col = order[p];
+                gather_reduced<NQ>(w, T4, TS, slot_of_row, col, v);
+            }
+            park(v);
+            __syncwarp();
+            const double cw = weigh(np, col, 0u);
+            if (np && cw < bestw) { bestw = cw; bestid = id; bestkind = 1; bestarg = static_cast<uint32_t>(col); }
+            __syncwarp();
+        }
+    }
+    // ---- patterns over the first `ord` non-pivot columns: pairs i < j (combination sweep) or every non-empty subset (exhaustive)
+    {
+        const int npat = b.osd_method == 2 ? ord * (ord - 1) / 2 : (1 << ord) - 1;
+        for (int c0 = 0; c0 < npat; c0 += 32) {
+            const int c = c0 + lane;
+            const bool act = c < npat;
+            uint32_t pat = 0;
+            if (act) {
+                if (b.osd_method == 2) {                 // c-th pair in the order i = 0.., j = i+1..
+                    int i = 0, rem = c;
+                    while (rem >= ord - 1 - i) { rem -= ord - 1 - i; ++i; }
+                    pat = (1u << i) | (1u << (i + 1 + rem));
+                } else {
+                    pat = static_cast<uint32_t>(c) + 1u;
+                }
+            }
+            uint4 v[NQ];
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) v[i] = y0[i];
+            for (int bb = 0; bb < ord; ++bb) {
+                if ((pat >> bb) & 1u) {
+#pragma unroll
+                    for (int i = 0; i < NQ; ++i) xor4(v[i], rw[bb * NQ + i]);
+                }
+            }
+            park(v);
+            __syncwarp();
+            const double cw = weigh(act, -1, pat);
+            if (act && cw < bestw) { bestw = cw; bestid = nextid + c; bestkind = 2; bestarg = pat; }
+            __syncwarp();
+        }
+    }
+    // ---- the earliest candidate of minimal weight, if strictly lighter than OSD-0
+    double mw = bestw;
+    int mid = bestid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ow = __shfl_xor_sync(kFull, mw, o);
+        const int oid = __shfl_xor_sync(kFull, mid, o);
+        if (ow < mw || (ow == mw && oid < mid)) { mw = ow; mid = oid; }
+    }
+    if (lane == 0) flips[0] = 0;
+    __syncwarp();
+    if (mw < w0 && bestid == mid && bestid != 0x7FFFFFFF) {        // exactly one lane owns the winning id
+        uint4 v[NQ];
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) v[i] = y0[i];
+        int nf = 0;
+        if (bestkind == 1) {
+            gather_reduced<NQ>(w, T4, TS, slot_of_row, static_cast<int>(bestarg), v);
+            flips[1 + nf++] = bestarg;
+        } else {
+            for (int bb = 0; bb < ord; ++bb) {
+                if ((bestarg >> bb) & 1u) {
+#pragma unroll
+                    for (int i = 0; i < NQ; ++i) xor4(v[i], rw[bb * NQ + i]);
+                }
+            }
+            for (int q = 0; q < ord; ++q)
+                if ((bestarg >> sbit[q]) & 1u) flips[1 + nf++] = scol[q];
+        }
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) svec[i] = v[i];
+        flips[0] = static_cast<uint32_t>(nf);
+    }
+    __syncwarp();
+}
+
 // One shot, one warp: eliminate over `order[0 .. n_avail)` (the first n_avail columns of the OSD order out of n).  Returns
 // false -- and commits nothing -- when those columns ran out before the answer was final although more columns exist.
-template <int NQ, bool EXACT>
+template <int NQ, bool EXACT, bool HI = false>
 __device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, unsigned char* sm, const ElimLayout& L, const int shot,
                                          const uint16_t* order, const int n, const int n_total) {
     uint4* T4 = reinterpret_cast<uint4*>(sm + L.T);
@@ -320,6 +571,7 @@ __device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, uns
                     freem32[wsel] &= ~bsel;
                     pivcol[rank] = static_cast<uint16_t>(pcol);
                     pivrow[rank] = static_cast<uint16_t>(prow);
+                    if (HI) reinterpret_cast<uint16_t*>(sm + L.pivpos)[rank] = static_cast<uint16_t>(base - 32 + pl);
                     slot_of_row[prow] = static_cast<uint16_t>(rank);
                 }
                 __syncwarp();
@@ -361,19 +613,22 @@ __device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, uns
                 // Early exit (exact): once the reduced syndrome is zero on every free row, no later pivot can change it
                 // (an operation only acts on a vector that has the pivot row's bit, and pivot rows are taken from the
                 // free rows), and every later pivot gets solution bit 0.
-                {
+                if (!HI) {
                     const uint32_t y = lane < 4 * NQ ? (svec32[lane] & freem32[lane]) : 0u;
                     if (!__any_sync(kFull, y != 0u)) { done = true; break; }
                 }
             }
         }
         if (!done && rank < m && n < n_total) return false;      // ran out of sorted columns: the caller retries with the full order
-        // ---- solution on the pivots (reduced syndrome), commit
+        // ---- solution on the pivots (reduced syndrome; higher-order OSD may replace it and flip non-pivot columns), commit
         __syncwarp();
-        for (int rr = lane; rr < rank; rr += 32) {
-            const int row = pivrow[rr];
-            if (!((svec32[row >> 5] >> (row & 31)) & 1u)) continue;
-            const int j = pivcol[rr];
+        int nflip = 0;
+        const uint32_t* flips = reinterpret_cast<const uint32_t*>(sm + L.flips);
+        if (HI) {
+            osd_higher<NQ>(w, b, sm, L, rank, order, n, lane);
+            nflip = static_cast<int>(flips[0]);
+        }
+        auto commit_column = [&](const int j) {
             if (b.ehat_out) atomicOr(&b.ehat_out[static_cast<size_t>(shot) * b.ehat_stride32 + (j >> 5)], 1u << (j & 31));
             if (j < w.ncommit) {
                 for (int wd = 0; wd < w.KW; ++wd) {
@@ -388,7 +643,12 @@ __device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, uns
                     }
                 }
             }
+        };
+        for (int rr = lane; rr < rank; rr += 32) {
+            const int row = pivrow[rr];
+            if ((svec32[row >> 5] >> (row & 31)) & 1u) commit_column(pivcol[rr]);
         }
+        for (int f = lane; f < nflip; f += 32) commit_column(static_cast<int>(flips[1 + f]));
         __syncwarp();
         for (int i = lane; i < w.KW; i += 32) {
             const uint64_t v = (static_cast<uint64_t>(accs[2 * i + 1]) << 32) | accs[2 * i];
@@ -405,10 +665,10 @@ __device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, uns
     return true;
 }
 
-template <int NQ, bool EXACT>
+template <int NQ, bool EXACT, bool HI>
 __global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const BatchDev b) {
     extern __shared__ __align__(16) unsigned char sm[];
-    const ElimLayout L = elim_layout(w, NQ, EXACT, 0);
+    const ElimLayout L = elim_layout(w, NQ, EXACT, 0, HI);
     const int lane = threadIdx.x;
     const int count = *b.fail_count;
     for (;;) {
@@ -420,7 +680,7 @@ __global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const Batc
         const uint16_t* order = b.order_alt ? b.order_alt + static_cast<size_t>(shot) * b.llr_stride
                                             : reinterpret_cast<const uint16_t*>(static_cast<const unsigned char*>(b.llr_buf) +
                                                                                 static_cast<size_t>(shot) * b.llr_stride * b.llr_esize);
-        elim_job<NQ, EXACT>(w, b, sm, L, shot, order, w.ncols, w.ncols);
+        elim_job<NQ, EXACT, HI>(w, b, sm, L, shot, order, w.ncols, w.ncols);
     }
 }
 
@@ -489,20 +749,24 @@ __global__ void __launch_bounds__(32) osd_fast_kernel(const WinDev w, const Batc
 
 inline int elim_nq(const WinDev& w) { return (w.rows + 127) / 128; }
 
-template <typename F>
-inline cudaError_t elim_dispatch(const WinDev& w, F&& f) {
+template <bool HI, typename F>
+inline cudaError_t elim_dispatch_h(const WinDev& w, F&& f) {
     const bool exact = !w.full_row_rank;
     switch (elim_nq(w)) {
-    case 1: return exact ? f(osd_elim_kernel<1, true>) : f(osd_elim_kernel<1, false>);
-    case 2: return exact ? f(osd_elim_kernel<2, true>) : f(osd_elim_kernel<2, false>);
-    case 3: return exact ? f(osd_elim_kernel<3, true>) : f(osd_elim_kernel<3, false>);
-    case 4: return exact ? f(osd_elim_kernel<4, true>) : f(osd_elim_kernel<4, false>);
-    case 5: return exact ? f(osd_elim_kernel<5, true>) : f(osd_elim_kernel<5, false>);
-    case 6: return exact ? f(osd_elim_kernel<6, true>) : f(osd_elim_kernel<6, false>);
+    case 1: return exact ? f(osd_elim_kernel<1, true, HI>) : f(osd_elim_kernel<1, false, HI>);
+    case 2: return exact ? f(osd_elim_kernel<2, true, HI>) : f(osd_elim_kernel<2, false, HI>);
+    case 3: return exact ? f(osd_elim_kernel<3, true, HI>) : f(osd_elim_kernel<3, false, HI>);
+    case 4: return exact ? f(osd_elim_kernel<4, true, HI>) : f(osd_elim_kernel<4, false, HI>);
+    case 5: return exact ? f(osd_elim_kernel<5, true, HI>) : f(osd_elim_kernel<5, false, HI>);
+    case 6: return exact ? f(osd_elim_kernel<6, true, HI>) : f(osd_elim_kernel<6, false, HI>);
     }
     return cudaErrorInvalidValue;
 }
 
+template <typename F>
+inline cudaError_t elim_dispatch(const WinDev& w, bool hi, F&& f) {
+    return hi ? elim_dispatch_h<true>(w, f) : elim_dispatch_h<false>(w, f);
+}
 
 template <typename R, typename F>
 inline cudaError_t fast_dispatch_r(const WinDev& w, F&& f) {
@@ -526,17 +790,18 @@ inline cudaError_t fast_dispatch(const WinDev& w, int precision, F&& f) {
 }  // namespace
 
 size_t osd_sort_smem_bytes(const WinDev& w, int precision) { return sort_layout(w, precision == 32 ? 4 : 8).total; }
-size_t osd_elim_smem_bytes(const WinDev& w) { return elim_layout(w, elim_nq(w), !w.full_row_rank, 0).total; }
+size_t osd_elim_smem_bytes(const WinDev& w, bool hi) { return elim_layout(w, elim_nq(w), !w.full_row_rank, 0, hi).total; }
 size_t osd_fast_smem_bytes(const WinDev& w) { return elim_layout(w, elim_nq(w), !w.full_row_rank, kSelCap).total; }
 
 bool osd_supported(const WinDev& w, int precision) {
-    return w.rows <= 768 && w.ncols <= 65535 && osd_sort_smem_bytes(w, precision) <= 220 * 1024 && osd_fast_smem_bytes(w) <= 220 * 1024;
+    return w.rows <= 768 && w.ncols <= 65535 && osd_sort_smem_bytes(w, precision) <= 220 * 1024 && osd_fast_smem_bytes(w) <= 220 * 1024 &&
+           osd_elim_smem_bytes(w, true) <= 220 * 1024;
 }
 
 cudaError_t osd_configure(const WinDev& w, int precision) {
     // several windows may share one instantiation: the attributes only ever grow
-    static size_t sort_have[2] = {}, elim_have[2][8] = {}, fast_have[2][2][8] = {};
-    const size_t ss = osd_sort_smem_bytes(w, precision), es = osd_elim_smem_bytes(w), fs = osd_fast_smem_bytes(w);
+    static size_t sort_have[2] = {}, elim_have[2][2][8] = {}, fast_have[2][2][8] = {};
+    const size_t ss = osd_sort_smem_bytes(w, precision), fs = osd_fast_smem_bytes(w);
     size_t& sh = sort_have[precision == 32 ? 0 : 1];
     if (ss > sh) {
         cudaError_t e = precision == 32
@@ -545,13 +810,16 @@ cudaError_t osd_configure(const WinDev& w, int precision) {
         if (e != cudaSuccess) return e;
         sh = ss;
     }
-    size_t& eh = elim_have[w.full_row_rank ? 0 : 1][elim_nq(w) & 7];
-    if (es > eh) {
-        cudaError_t e = elim_dispatch(w, [&](auto kern) {
-            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(es));
-        });
-        if (e != cudaSuccess) return e;
-        eh = es;
+    for (int hi = 0; hi < 2; ++hi) {
+        const size_t es = osd_elim_smem_bytes(w, hi != 0);
+        size_t& eh = elim_have[hi][w.full_row_rank ? 0 : 1][elim_nq(w) & 7];
+        if (es > eh) {
+            cudaError_t e = elim_dispatch(w, hi != 0, [&](auto kern) {
+                return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(es));
+            });
+            if (e != cudaSuccess) return e;
+            eh = es;
+        }
     }
     size_t& fh = fast_have[precision == 32 ? 0 : 1][w.full_row_rank ? 0 : 1][elim_nq(w) & 7];
     if (fs > fh) {
@@ -581,10 +849,10 @@ cudaError_t launch_osd_sort(const WinDev& w, const BatchDev& b, int precision, i
     return cudaGetLastError();
 }
 
-cudaError_t launch_osd_elim(const WinDev& w, const BatchDev& b, int grid, cudaStream_t st) {
+cudaError_t launch_osd_elim(const WinDev& w, const BatchDev& b, bool hi, int grid, cudaStream_t st) {
     if (b.n_shots == 0) return cudaSuccess;
-    const size_t smem = osd_elim_smem_bytes(w);
-    return elim_dispatch(w, [&](auto kern) {
+    const size_t smem = osd_elim_smem_bytes(w, hi);
+    return elim_dispatch(w, hi, [&](auto kern) {
         kern<<<grid, 32, smem, st>>>(w, b);
         return cudaGetLastError();
     });

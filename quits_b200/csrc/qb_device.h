@@ -54,6 +54,7 @@ struct WinDev {
     int carry_rows;           // rows of the carry this window emits (0 for the last window)
     int KW;                   // u64 words per observable mask
     int rowsW32, nW32;
+    const double* osd_wt;     // [ncols] log(1/p_j): weights of the higher-order OSD sweeps
     double bin_scale;         // OSD fast path: LLR -> selection bin scale, 10 / (smallest prior LLR of the window)
     int full_row_rank;        // GF(2) rank of the window matrix == rows (then OSD's answer does not depend on pivot-row order)
     const uint32_t* colE;     // [cw][ncols_pad]  (row << 8 | slot), kNoEdge when the column is shorter
@@ -109,6 +110,7 @@ struct BatchDev {
     int32_t* iters_out;       // optional [n]
     uint8_t* conv_out;        // optional [n]
     int write_llr_always;
+    int osd_method, osd_order; // 0 osd_0 | 1 osd_e | 2 osd_cs; order 0 = OSD-0
 };
 
 struct BpParams {
@@ -126,13 +128,13 @@ cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal, int metho
 cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, bool vglobal, int grid, cudaStream_t st);
 
 size_t osd_sort_smem_bytes(const WinDev& w, int precision);
-size_t osd_elim_smem_bytes(const WinDev& w);
+size_t osd_elim_smem_bytes(const WinDev& w, bool hi);
 size_t osd_fast_smem_bytes(const WinDev& w);
 bool osd_supported(const WinDev& w, int precision);
 cudaError_t osd_configure(const WinDev& w, int precision);
 cudaError_t launch_osd_fast(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
 cudaError_t launch_osd_sort(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
-cudaError_t launch_osd_elim(const WinDev& w, const BatchDev& b, int grid, cudaStream_t st);
+cudaError_t launch_osd_elim(const WinDev& w, const BatchDev& b, bool hi, int grid, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------- results
 // pred[n][K] int64 from acc bits; counts[0] += shots whose prediction differs from obs_rows in any observable,

@@ -173,7 +173,7 @@ def test_decoder_edge_cases(qb):
     with pytest.raises(NotImplementedError):
         qb.sliding_window_bposd_circuit_mem(det, c, hz, lz, 3, 2)               # reference defaults: product_sum / serial
     with pytest.raises(NotImplementedError):
-        qb.sliding_window_bposd_circuit_mem(det, c, hz, lz, 3, 2, max_iter=10, osd_order=1, bp_method="minimum_sum",
+        qb.sliding_window_bposd_circuit_mem(det, c, hz, lz, 3, 2, max_iter=10, osd_order=40, bp_method="minimum_sum",
                                             schedule="parallel", osd_method="osd_cs")
     with pytest.raises(ValueError):
         qb.sliding_window_bposd_circuit_mem(np.zeros((2, 7), dtype=bool), c, hz, lz, 3, 2, **BP_KW)
@@ -291,3 +291,44 @@ def test_more_than_64_observables(qb):
         e = d2.decode(s)[0].astype(int)
         acc = (acc + e[:W_last * n].reshape(W_last, n).sum(axis=0)) % 2
         assert np.array_equal(pred[i], lz @ acc % 2), i
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("osd_method,osd_order", [("osd_cs", 1), ("osd_cs", 6), ("osd_e", 5)])
+@pytest.mark.parametrize("case,window", [("bb72_r6_p3e-3_W5F3", 0), ("bb144_r10_p3e-3_W5F3", 1), ("bb144_r10_p1e-3_W5F3", 3)])
+def test_higher_order_osd_matches_oracle_per_shot(qb, case, window, osd_method, osd_order, precision):
+    """osd_cs / osd_e with order > 0 (every notebook of the reference uses osd_cs order 1, doc/06B cell 3): the GPU's
+    complete elimination + candidate sweep returns exactly the oracle's error estimate -- same candidate order, same
+    log(1/p) additions in column order, so ties between equally light candidates resolve identically."""
+    from oracle import cref
+    g = decode_case(case)
+    w = _oracle_windows(case_circuit(case), g["m"], g["W"], g["F"])[window]
+    H, pri = w["H"], w["priors"]
+    n = min(g["shots"], 64)
+    syn = g["det"][:n, w["row0"]:w["row0"] + H.shape[0]].astype(np.uint8)
+    kw = dict(max_iter=4, bp_method="minimum_sum", schedule="parallel", osd_method=osd_method, osd_order=osd_order)
+    dec = qb.BpOsdDecoder(H, channel_probs=pri, precision=precision, **kw)
+    ehat, llr, iters, conv = dec.decode_batch(syn)
+    orc = cref.BpOsd(H, pri, precision=precision, **kw)
+    n_osd = 0
+    for i in range(n):
+        e, l, it, c = orc.decode(syn[i])
+        assert bool(conv[i]) == c and int(iters[i]) == it
+        assert np.array_equal(ehat[i], e), (i, c, int(ehat[i].sum()), int(e.sum()))
+        n_osd += orc.used_osd
+    assert n_osd >= 3          # the sweep was actually exercised
+
+
+def test_higher_order_osd_sliding_window(qb):
+    """Sliding-window decode with the notebooks' post-processing (osd_cs, order 1) equals the oracle loop bit for bit."""
+    from oracle import cref
+    case = "bb72_r6_p3e-3_W5F3"
+    g = decode_case(case)
+    name = case_circuit(case)
+    _, hz, lz = circuit_meta(name)
+    kw = dict(max_iter=10, osd_order=1, bp_method="minimum_sum", schedule="parallel", osd_method="osd_cs")
+    pred = qb.sliding_window_bposd_circuit_mem(g["det"], qb.Circuit(circuit_text(name)), hz, lz, g["W"], g["F"], **kw)
+    wins = _oracle_windows(name, g["m"], g["W"], g["F"])
+    opred, _ = cref.sw_decode(wins, g["m"], g["K"], g["det"].astype(np.uint8), max_iter=10, bp_method="minimum_sum", schedule="parallel",
+                              precision="f64", osd_method="osd_cs", osd_order=1)
+    assert np.array_equal(pred, opred.astype(np.int64))
