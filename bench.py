@@ -55,7 +55,8 @@ def load_workload():
 
 
 def config(shots, precision):
-    return {"workload": "%s custom circuit, W=%d F=%d, min-sum flooding BP max_iter=10 + OSD-0" % (WORKLOAD, W, F),
+    return {"workload": "%s custom circuit, W=%d F=%d, %s flooding BP max_iter=%d + %s order %d" % (
+                WORKLOAD, W, F, BP_KW["bp_method"], BP_KW["max_iter"], BP_KW["osd_method"], BP_KW["osd_order"]),
             "shots_per_step_per_gpu": int(shots), "precision": precision, "seed": SEED,
             "l2": "flushed between timed steps (256 MiB write); per-step message/LLR working set also exceeds L2"}
 
@@ -72,7 +73,8 @@ def cpu_arm(shots, nthreads=0):
     t0 = time.perf_counter()
     det, obs = cref.sample(fc, SEED, 0, shots, nthreads=threads)
     pred, stats = cref.sw_decode(wins, hz.shape[0], lz.shape[0], det, nthreads=threads, max_iter=BP_KW["max_iter"],
-                                 bp_method=BP_KW["bp_method"], schedule=BP_KW["schedule"], precision="f64")
+                                 bp_method=BP_KW["bp_method"], schedule=BP_KW["schedule"], precision="f64",
+                                 osd_method=BP_KW["osd_method"], osd_order=BP_KW["osd_order"])
     fails = int(np.any(pred != obs, axis=1).sum())
     dt = time.perf_counter() - t0
     return shots / dt, dt, threads, fails
@@ -125,11 +127,20 @@ def main():
     ap.add_argument("--e2e-shots", type=int, default=262144)
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--workload", default=WORKLOAD, help="circuit fixture under tests/golden/circuits (default: the headline workload)")
+    ap.add_argument("--bp-method", default=None, help="secondary points: minimum_sum (headline) | product_sum")
+    ap.add_argument("--osd-method", default=None, help="secondary points: osd_0 (headline) | osd_cs | osd_e")
+    ap.add_argument("--osd-order", type=int, default=None)
     ap.add_argument("--lanes", type=int, default=0, help="concurrent sub-batches per device batch (0 = engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     globals()["WORKLOAD"] = args.workload
+    if args.bp_method:
+        BP_KW["bp_method"] = args.bp_method
+    if args.osd_method:
+        BP_KW["osd_method"] = args.osd_method
+    if args.osd_order is not None:
+        BP_KW["osd_order"] = args.osd_order
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

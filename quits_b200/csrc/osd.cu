@@ -278,6 +278,42 @@ __device__ void osd_higher(const WinDev& w, const BatchDev& b, unsigned char* sm
         pinfo[t] = (static_cast<uint32_t>(pivrow[s]) << 16) | pc;
         pwt[t] = __ldg(wt + pc);
     }
+    // ---- re-index the pivot rows by the rank of their pivot's column: bit t of a (permuted) vector <-> t-th pivot in column
+    //      order, so that a candidate's weight is a walk over its SET bits in ascending order instead of over all pivots.
+    //      Rows without a pivot carry no solution bit and are dropped.
+    {
+        uint16_t* rowperm = reinterpret_cast<uint16_t*>(sm + L.pivpos);           // pivpos is dead once ispiv is built
+        __syncwarp();
+        for (int t = lane; t < rank; t += 32) rowperm[t] = static_cast<uint16_t>(pinfo[t] >> 16);      // t -> row
+        __syncwarp();
+        uint16_t* t_of_row = reinterpret_cast<uint16_t*>(skeys);                  // scratch: row -> t (skeys is dead)
+        for (int r = lane; r < w.rows; r += 32) t_of_row[r] = 0xFFFFu;
+        __syncwarp();
+        for (int t = lane; t < rank; t += 32) t_of_row[rowperm[t]] = static_cast<uint16_t>(t);
+        __syncwarp();
+        uint4* T4w = reinterpret_cast<uint4*>(sm + L.T);
+        auto permute = [&](uint4* vec, const int stride) {                        // in place, through this lane's ybuf row
+            for (int i = 0; i < 4 * NQ; ++i) ybuf[i] = 0;
+            for (int i = 0; i < NQ; ++i) {
+                const uint4 q = vec[i * stride];
+                const uint32_t wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t bits = wd[c];
+                    while (bits) {
+                        const int r = 32 * (4 * i + c) + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        const uint32_t t = t_of_row[r];
+                        if (t != 0xFFFFu) ybuf[t >> 5] |= 1u << (t & 31);
+                    }
+                }
+            }
+            for (int i = 0; i < NQ; ++i) vec[i * stride] = make_uint4(ybuf[4 * i], ybuf[4 * i + 1], ybuf[4 * i + 2], ybuf[4 * i + 3]);
+        };
+        for (int sl = lane; sl < rank; sl += 32) permute(T4w + sl, TS);
+        if (lane == 0) permute(svec, 1);
+        __syncwarp();
+    }
     // ---- the first `ord` non-pivot columns: reduced vectors, and their columns sorted by index for the weight merge
     const int ord_req = min(b.osd_order, b.osd_method == 1 ? 12 : kOsdMaxOrder);
     int ord = 0;
@@ -314,42 +350,53 @@ __device__ void osd_higher(const WinDev& w, const BatchDev& b, unsigned char* sm
     }
     __syncwarp();
 
-    // weight of the candidate whose pivot bits sit in this lane's ybuf row; single: one flipped column xc (or none: xc < 0);
-    // pattern: the flipped columns are the members of `pat` among the first `ord` non-pivot columns
-    auto weigh = [&](const bool active, const int xc, const uint32_t pat) -> double {
-        double ws = 0.0;
-        bool pending = xc >= 0;
-        const double wx = pending ? __ldg(wt + xc) : 0.0;
-        int ip = 0;
-        for (int t = 0; t < rank; ++t) {
-            const uint32_t info = pinfo[t];
-            const int pc = static_cast<int>(info & 0xFFFFu), row = static_cast<int>(info >> 16);
-            if (pending && xc < pc) { ws = __dadd_rn(ws, wx); pending = false; }
-            while (ip < ord && static_cast<int>(scol[ip]) < pc) {
-                if ((pat >> sbit[ip]) & 1u) ws = __dadd_rn(ws, swt[ip]);
-                ++ip;
-            }
-            if (active && ((ybuf[row >> 5] >> (row & 31)) & 1u)) ws = __dadd_rn(ws, pwt[t]);
+    // weight of a candidate: its pivot bits v (permuted: bit t <-> t-th pivot in column order) plus its flipped columns -- one
+    // column xc (xc < 0: none) or the members of `pat` among the first `ord` non-pivot columns -- added in ascending column
+    // order.  tpos(c) = number of pivots whose column is < c (binary search over the sorted pivot columns).
+    auto tpos = [&](const int c) {
+        int lo = 0, hi = rank;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (static_cast<int>(pinfo[mid] & 0xFFFFu) < c) lo = mid + 1; else hi = mid;
         }
-        if (pending) ws = __dadd_rn(ws, wx);
-        while (ip < ord) {
-            if ((pat >> sbit[ip]) & 1u) ws = __dadd_rn(ws, swt[ip]);
-            ++ip;
-        }
-        return ws;
+        return lo;
     };
-    auto park = [&](const uint4 (&v)[NQ]) {
+    auto weigh = [&](const uint4 (&v)[NQ], const int xc, const uint32_t pat) -> double {
+        double ws = 0.0;
+        int ip = 0;                                       // next flipped column (pattern members in ascending column order)
+        int nextcol = 0x7FFFFFFF, nextt = 0x7FFFFFFF;
+        double nextw = 0.0;
+        bool single = xc >= 0;
+        auto advance = [&]() {
+            nextt = 0x7FFFFFFF;
+            if (single) { single = false; nextcol = xc; nextw = __ldg(wt + xc); nextt = tpos(xc); return; }
+            while (ip < ord && !((pat >> sbit[ip]) & 1u)) ++ip;
+            if (ip < ord) { nextcol = static_cast<int>(scol[ip]); nextw = swt[ip]; nextt = tpos(nextcol); ++ip; }
+        };
+        advance();
 #pragma unroll
-        for (int i = 0; i < NQ; ++i) { ybuf[4 * i] = v[i].x; ybuf[4 * i + 1] = v[i].y; ybuf[4 * i + 2] = v[i].z; ybuf[4 * i + 3] = v[i].w; }
+        for (int i = 0; i < NQ; ++i) {
+            const uint32_t wd[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t bits = wd[c];
+                while (bits) {
+                    const int t = 32 * (4 * i + c) + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    while (nextt <= t) { ws = __dadd_rn(ws, nextw); advance(); }
+                    ws = __dadd_rn(ws, pwt[t]);
+                }
+            }
+        }
+        while (nextt != 0x7FFFFFFF) { ws = __dadd_rn(ws, nextw); advance(); }
+        return ws;
     };
 
     // ---- OSD-0 solution
     uint4 y0[NQ];
 #pragma unroll
     for (int i = 0; i < NQ; ++i) y0[i] = svec[i];
-    park(y0);
-    __syncwarp();
-    const double w0 = weigh(true, -1, 0u);
+    const double w0 = weigh(y0, -1, 0u);
     double bestw = w0;
     int bestid = 0x7FFFFFFF, bestkind = 0;
     uint32_t bestarg = 0;
@@ -371,11 +418,8 @@ __device__ void osd_higher(const WinDev& w, const BatchDev& b, unsigned char* sm
                 col = order[p];
                 gather_reduced<NQ>(w, T4, TS, slot_of_row, col, v);
             }
-            park(v);
-            __syncwarp();
-            const double cw = weigh(np, col, 0u);
+            const double cw = np ? weigh(v, col, 0u) : 0.0;
             if (np && cw < bestw) { bestw = cw; bestid = id; bestkind = 1; bestarg = static_cast<uint32_t>(col); }
-            __syncwarp();
         }
     }
     // ---- patterns over the first `ord` non-pivot columns: pairs i < j (combination sweep) or every non-empty subset (exhaustive)
@@ -403,11 +447,8 @@ __device__ void osd_higher(const WinDev& w, const BatchDev& b, unsigned char* sm
                     for (int i = 0; i < NQ; ++i) xor4(v[i], rw[bb * NQ + i]);
                 }
             }
-            park(v);
-            __syncwarp();
-            const double cw = weigh(act, -1, pat);
+            const double cw = act ? weigh(v, -1, pat) : 0.0;
             if (act && cw < bestw) { bestw = cw; bestid = nextid + c; bestkind = 2; bestarg = pat; }
-            __syncwarp();
         }
     }
     // ---- the earliest candidate of minimal weight, if strictly lighter than OSD-0
@@ -644,9 +685,15 @@ __device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, uns
                 }
             }
         };
-        for (int rr = lane; rr < rank; rr += 32) {
-            const int row = pivrow[rr];
-            if ((svec32[row >> 5] >> (row & 31)) & 1u) commit_column(pivcol[rr]);
+        if (HI) {                            // osd_higher left the solution indexed by pivot rank in column order
+            const uint32_t* pinfo = reinterpret_cast<const uint32_t*>(sm + L.pinfo);
+            for (int t = lane; t < rank; t += 32)
+                if ((svec32[t >> 5] >> (t & 31)) & 1u) commit_column(static_cast<int>(pinfo[t] & 0xFFFFu));
+        } else {
+            for (int rr = lane; rr < rank; rr += 32) {
+                const int row = pivrow[rr];
+                if ((svec32[row >> 5] >> (row & 31)) & 1u) commit_column(pivcol[rr]);
+            }
         }
         for (int f = lane; f < nflip; f += 32) commit_column(static_cast<int>(flips[1 + f]));
         __syncwarp();
