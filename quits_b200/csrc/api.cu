@@ -135,6 +135,7 @@ namespace {
 
 struct WinOwned {
     qb::WinDev dev{};
+    DevBuf ser_steps, ser_pairs, ser_cols;
     DevBuf colE, llr0f, llr0d, osd_wt, lmask, uptr, uidx, cptr, crow, colrec, ptabf, ptabd, rlen, rsum0f, rsum0d, neg0;
     size_t bp_smem = 0;
     bool vglobal = false;
@@ -150,6 +151,7 @@ struct qb_sw {
     qb_bp_opts opts{};
     bool single = false;
     bool use_osd = true;
+    bool serial = false;          // ldpc schedule='serial'
     bool osd_hi = false;          // osd_e / osd_cs with order > 0: full elimination + candidate sweeps
     int max_iter = 0;
     int precision = 64;
@@ -346,6 +348,50 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
             upload(wo.neg0, neg0, ctx->stream);
             upload(wo.rsum0d, s0d, ctx->stream);
             upload(wo.rsum0f, s0f, ctx->stream);
+            // ---- serial schedule: dependency levels of the column sequence, cut into steps of <= 16 (column, row) pairs
+            {
+                constexpr int kPairs = 16, kCols = 128;
+                std::vector<int> lastlvl(static_cast<size_t>(rows), 0), lvl(static_cast<size_t>(ncols), 1);
+                int nlev = 1;
+                for (int j = 0; j < ncols; ++j) {
+                    int l = 1;
+                    for (int64_t e2 = hw.cptr[j]; e2 < hw.cptr[j + 1]; ++e2) l = std::max(l, lastlvl[hw.crow[e2]] + 1);
+                    lvl[j] = l;
+                    for (int64_t e2 = hw.cptr[j]; e2 < hw.cptr[j + 1]; ++e2) lastlvl[hw.crow[e2]] = l;
+                    nlev = std::max(nlev, l);
+                }
+                std::vector<std::vector<int>> bylevel(static_cast<size_t>(nlev) + 1);
+                for (int j = 0; j < ncols; ++j) bylevel[lvl[j]].push_back(j);
+                std::vector<uint32_t> steps, pairs, cols;          // steps: 4 words each; cols: 2 words each
+                for (int l = 1; l <= nlev; ++l) {
+                    size_t i = 0;
+                    const std::vector<int>& cl = bylevel[l];
+                    while (i < cl.size()) {
+                        const uint32_t pair_begin = static_cast<uint32_t>(pairs.size()), col_begin = static_cast<uint32_t>(cols.size() / 2);
+                        int np = 0, nc = 0;
+                        while (i < cl.size() && nc < kCols) {
+                            const int j = cl[i];
+                            const int wt = static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]);
+                            if (np + wt > kPairs) break;
+                            cols.push_back(static_cast<uint32_t>(j) | (static_cast<uint32_t>(pidx[j]) << 16));
+                            cols.push_back(static_cast<uint32_t>(np) | (static_cast<uint32_t>(wt) << 8));
+                            for (int64_t e2 = hw.cptr[j]; e2 < hw.cptr[j + 1]; ++e2)
+                                pairs.push_back((static_cast<uint32_t>(hw.crow[e2]) * static_cast<uint32_t>(rs) + static_cast<uint32_t>(layout.slot[e2])) |
+                                                (static_cast<uint32_t>(hw.crow[e2]) << 16));
+                            np += wt; ++nc; ++i;
+                        }
+                        steps.push_back(pair_begin); steps.push_back(static_cast<uint32_t>(np));
+                        steps.push_back(col_begin); steps.push_back(static_cast<uint32_t>(nc));
+                    }
+                }
+                upload(wo.ser_steps, steps, ctx->stream, 4);
+                upload(wo.ser_pairs, pairs, ctx->stream, 2);
+                upload(wo.ser_cols, cols, ctx->stream, 2);
+                d.ser_nsteps = static_cast<int>(steps.size() / 4);
+                d.ser_steps = wo.ser_steps.as<uint4>();
+                d.ser_pairs = wo.ser_pairs.as<uint32_t>();
+                d.ser_cols = wo.ser_cols.as<uint2>();
+            }
             d.compact = 1;
             d.n_ptab = static_cast<int>(ptab.size());
             d.rs_magic = magic;
@@ -383,11 +429,14 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
     d.uptr = wo.uptr.as<int32_t>(); d.uidx = wo.uidx.as<uint16_t>(); d.cptr = wo.cptr.as<int32_t>(); d.crow = wo.crow.as<uint16_t>();
 }
 
+static bool rows_fit_serial(const qb::WinDev& d, int prec) { return qb::bp_serial_smem_bytes(d, prec) <= 227 * 1024; }
+
 void finish_decoder(qb_sw* sw) {
     qb_ctx* ctx = sw->ctx;
     const qb_bp_opts& o = sw->opts;
     if (o.bp_method != 0 && o.bp_method != 1) throw qb::value_error("bp_method must be 0 (minimum_sum) or 1 (product_sum)");
-    if (o.schedule != 0) throw qb::unsupported_error("schedule 'serial' is not implemented on the GPU path yet; use schedule='parallel'");
+    if (o.schedule != 0 && o.schedule != 1) throw qb::value_error("schedule must be 0 (parallel) or 1 (serial)");
+    sw->serial = o.schedule == 1;
     if (o.osd_order < 0) throw qb::value_error("osd_order must be >= 0");
     if (o.osd_method == 1 && o.osd_order > 12) throw qb::unsupported_error("osd_e beyond order 12 (4095 patterns per shot) is not supported on the GPU path");
     if (o.osd_method == 2 && o.osd_order > 32) throw qb::unsupported_error("osd_cs beyond order 32 is not supported on the GPU path");
@@ -401,6 +450,11 @@ void finish_decoder(qb_sw* sw) {
     size_t max_slab = 0;
     for (auto& w : sw->wins) {
         // messages in shared memory when they fit, else in an L2-resident global slab per CTA
+        if (sw->serial) {
+            if (!w->dev.compact || rows_fit_serial(w->dev, prec) == false)
+                throw qb::unsupported_error("schedule 'serial' needs a window that fits the compact shared-memory layout (column weight <= 6, messages <= 227 KB)");
+            CK(qb::bp_serial_configure(w->dev, prec, o.bp_method));
+        }
         w->vglobal = qb::bp_smem_bytes(w->dev, prec, false) > 227 * 1024;
         w->bp_smem = qb::bp_smem_bytes(w->dev, prec, w->vglobal);
         if (w->bp_smem > 227 * 1024)
@@ -538,7 +592,8 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.conv_out = want_ehat ? sw->conv.as<uint8_t>() : nullptr;
             b.write_llr_always = want_llr ? 1 : 0;
             if (sw->opts.profile) sw->t_bp.begin(ls);
-            CK(qb::launch_bp(w.dev, b, bp, sw->precision, w.vglobal, w.vglobal ? std::min(w.bp_grid, nl) : nl, ls));
+            if (sw->serial) CK(qb::launch_bp_serial(w.dev, b, bp, sw->precision, nl, ls));
+            else CK(qb::launch_bp(w.dev, b, bp, sw->precision, w.vglobal, w.vglobal ? std::min(w.bp_grid, nl) : nl, ls));
             if (sw->opts.profile) sw->t_bp.end(ls);
             if (stats) stats->bp_launches++;
             if (sw->use_osd) {

@@ -140,16 +140,27 @@ __device__ __forceinline__ void load_syndrome(const WinDev& w, const BatchDev& b
 }
 
 // ---- after BP: commit acc ^= L e[:ncommit], carry = U e[:ncommit] (sliding_window.py:172-175), or hand the shot to OSD
+// hard decisions come either as a per-thread mask (bit k <-> column / record tid + k*NT) or, when `ebits` is given, as a bit
+// array over the columns in shared memory (serial kernel)
 template <typename R, int NT, bool RECORDS = false>
 __device__ __forceinline__ void finish_shot(const WinDev& w, const BatchDev& b, int shot, int tid, bool conv, int it, uint32_t hmask,
-                                            const uint32_t* syn, uint32_t* accs, uint32_t* car, uint32_t* hist) {
+                                            const uint32_t* syn, uint32_t* accs, uint32_t* car, uint32_t* hist,
+                                            const uint32_t* ebits = nullptr) {
     const int carryW = (w.carry_rows + 31) / 32;
     if (conv) {
-        uint32_t hm = hmask;
-        while (hm) {
+        int wd0 = ebits ? tid : 0;
+        uint32_t hm = ebits ? (wd0 < w.nW32 ? ebits[wd0] : 0u) : hmask;
+        for (;;) {
+            if (!hm) {
+                if (!ebits) break;
+                wd0 += NT;
+                if (wd0 >= w.nW32) break;
+                hm = ebits[wd0];
+                continue;
+            }
             const int kk = __ffs(hm) - 1;
             hm &= hm - 1;
-            int j = tid + kk * NT;
+            int j = ebits ? 32 * wd0 + kk : tid + kk * NT;
             if (RECORDS) j = static_cast<int>(__ldg(&w.colrec[j].w) & 0xFFFFu);      // record -> original column
             if (b.ehat_out) atomicOr(&b.ehat_out[static_cast<size_t>(shot) * b.ehat_stride32 + (j >> 5)], 1u << (j & 31));
             if (j < w.ncommit) {
@@ -607,6 +618,157 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
     }
 }
 
+// =====================================================================================================================
+// Serial schedule (ldpc schedule='serial', the reference wrappers' default, decoder/bposd.py:54): the columns are updated one
+// after the other in index order, each from the CURRENT messages of its rows (oracle/bp_impl.inc, serial branch).  Columns
+// that share no row commute, so the host cuts the column sequence into dependency levels (api.cu, serial tables) and the
+// kernel walks "steps" of up to NT/8 independent (column, row) pairs: eight lanes scan one row for the minimum / parity /
+// tanh product over the OTHER edges, the pair leader forms the check->bit message, then one thread per column does the
+// prefix / suffix sums in the oracle's order and writes the column's new messages.  Two block barriers per step, ~1100 steps
+// per iteration on the gross-code windows: latency bound, an order of magnitude slower than flooding -- as it is on the CPU.
+// =====================================================================================================================
+constexpr int kSerialThreads = 128;
+constexpr int kSerialPairs = kSerialThreads / 8;
+
+// off: V, syn, cand, accs, car, ptab, hist, ebits, cbuf
+__host__ __device__ inline size_t bps_layout(const WinDev& w, int rsize, size_t* off /*[9]*/) {
+    size_t o = 0;
+    off[0] = o; o += align_up((static_cast<size_t>(w.rows) * w.RS + 1) * rsize, 16);
+    off[1] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
+    off[2] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
+    off[3] = o; o += align_up(static_cast<size_t>(w.KW) * 8, 16);
+    off[4] = o; o += align_up(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4, 16);
+    off[5] = o; o += align_up(static_cast<size_t>(w.n_ptab) * rsize, 16);
+    off[6] = o; o += kSelWords * 4;
+    off[7] = o; o += align_up(static_cast<size_t>(w.nW32) * 4, 16);
+    off[8] = o; o += align_up(static_cast<size_t>(kSerialPairs) * rsize, 16);
+    return o;
+}
+
+template <typename R, bool PS>
+__global__ void __launch_bounds__(kSerialThreads) bp_kernel_serial(const WinDev w, const BatchDev b, const BpParams p) {
+    using RT = Real<R>;
+    using CT = Compact<R>;
+    constexpr int NT = kSerialThreads;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    size_t off[9];
+    bps_layout(w, sizeof(R), off);
+    R* V = reinterpret_cast<R*>(smem_raw + off[0]);
+    uint32_t* syn = reinterpret_cast<uint32_t*>(smem_raw + off[1]);
+    uint32_t* cand = reinterpret_cast<uint32_t*>(smem_raw + off[2]);
+    uint32_t* accs = reinterpret_cast<uint32_t*>(smem_raw + off[3]);
+    uint32_t* car = reinterpret_cast<uint32_t*>(smem_raw + off[4]);
+    R* ptab = reinterpret_cast<R*>(smem_raw + off[5]);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + off[6]);
+    uint32_t* ebits = reinterpret_cast<uint32_t*>(smem_raw + off[7]);
+    R* cbuf = reinterpret_cast<R*>(smem_raw + off[8]);
+
+    const int tid = threadIdx.x, grp = tid >> 3, l8 = tid & 7;
+    const int rows = w.rows, RS = w.RS, npad = w.ncols_pad;
+    R* const llr_all = reinterpret_cast<R*>(b.llr_buf);
+    for (int i = tid; i < w.n_ptab; i += NT) ptab[i] = CT::ptab(w)[i];
+
+    for (int shot = blockIdx.x; shot < b.n_shots; shot += gridDim.x) {
+        __syncthreads();
+        load_syndrome(w, b, shot, tid, syn, accs, car);
+        for (int r = tid; r < npad; r += NT) {                  // every message starts at its column's prior
+            const uint4 rec = __ldg(w.colrec + r);
+            const R l0 = ptab[(rec.w >> 16) & 0xFFFu];
+            const uint32_t e[6] = {rec.x & 0xFFFFu, rec.x >> 16, rec.y & 0xFFFFu, rec.y >> 16, rec.z & 0xFFFFu, rec.z >> 16};
+#pragma unroll
+            for (int q = 0; q < 6; ++q) V[e[q]] = l0;
+        }
+        __syncthreads();
+        bool conv = false;
+        int it = 1;
+        for (; it <= p.max_iter; ++it) {
+            const R alpha = static_cast<R>(__ldg(p.alpha + it));
+            const bool last = it == p.max_iter;
+            for (int i = tid; i < w.rowsW32; i += NT) cand[i] = 0;
+            for (int i = tid; i < w.nW32; i += NT) ebits[i] = 0;
+            if (last && tid < 32) hist[tid] = 0;
+            __syncthreads();
+            for (int s = 0; s < w.ser_nsteps; ++s) {
+                const uint4 hdr = __ldg(w.ser_steps + s);        // pair_begin, n_pairs, col_begin, n_cols
+                // ---- eight lanes per (column, row) pair: message of the row to the column from the row's other edges
+                {
+                    const bool act = grp < static_cast<int>(hdr.y);       // idle groups run the shuffles too (full-warp mask)
+                    const uint32_t pr = act ? __ldg(w.ser_pairs + hdr.x + grp) : 0u;
+                    const int addr = static_cast<int>(pr & 0xFFFFu), row = static_cast<int>(pr >> 16);
+                    const int base = row * RS, own = addr - base, len = act ? __ldg(w.rlen + row) : 0;
+                    R acc = PS ? R(1) : RT::big();
+                    uint32_t neg = 0;
+                    for (int k = l8; k < len; k += 8) {
+                        if (k == own) continue;
+                        const R v = V[base + k];
+                        if (PS) {
+                            acc = RT::mul(acc, Trans<R>::th(RT::mul(v, R(0.5))));
+                        } else {
+                            const R a = CT::mag(v);
+                            acc = a < acc ? a : acc;
+                            neg += v <= R(0) ? 1u : 0u;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 4; o > 0; o >>= 1) {
+                        const R other = __shfl_xor_sync(0xFFFFFFFFu, acc, o, 8);
+                        acc = PS ? RT::mul(acc, other) : (other < acc ? other : acc);
+                        neg += __shfl_xor_sync(0xFFFFFFFFu, neg, o, 8);
+                    }
+                    if (act && l8 == 0) {
+                        const uint32_t sbit = (syn[row >> 5] >> (row & 31)) & 1u;
+                        R c;
+                        if (PS) {
+                            const R x = Trans<R>::lg(Trans<R>::div(RT::add(R(1), acc), RT::add(R(1), -acc)));
+                            c = sbit ? -x : x;
+                        } else {
+                            c = RT::mul(acc, ((sbit + neg) & 1u) ? -alpha : alpha);
+                        }
+                        cbuf[grp] = c;
+                    }
+                }
+                __syncthreads();
+                // ---- one thread per column of the step: prefix / suffix sums in the oracle's order, new messages, hard decision
+                if (tid < static_cast<int>(hdr.w)) {
+                    const uint2 cr = __ldg(w.ser_cols + hdr.z + tid);   // x = column | prior index << 16, y = first pair | weight << 8
+                    const int j = static_cast<int>(cr.x & 0xFFFFu), first = static_cast<int>(cr.y & 0xFFu), wt = static_cast<int>((cr.y >> 8) & 0xFFu);
+                    const R l0 = ptab[(cr.x >> 16) & 0xFFFu];
+                    R c[6], vn[6];
+                    uint32_t pa[6];
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) {
+                        c[q] = q < wt ? cbuf[first + q] : R(0);
+                        pa[q] = q < wt ? __ldg(w.ser_pairs + hdr.x + first + q) : 0u;
+                    }
+                    R t = l0;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) if (q < wt) { vn[q] = t; t = RT::add(t, c[q]); }
+                    const R llr = t;
+                    t = R(0);
+#pragma unroll
+                    for (int q = 5; q >= 0; --q) if (q < wt) { vn[q] = RT::add(vn[q], t); t = RT::add(t, c[q]); }
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) if (q < wt) V[pa[q] & 0xFFFFu] = vn[q];
+                    if (llr <= R(0)) {
+                        atomicOr(&ebits[j >> 5], 1u << (j & 31));
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) if (q < wt) atomicXor(&cand[(pa[q] >> 16) >> 5], 1u << ((pa[q] >> 16) & 31u));
+                    }
+                    if (last || b.write_llr_always) llr_all[static_cast<size_t>(shot) * b.llr_stride + j] = llr;
+                    if (last) atomicAdd(&hist[llr_bin<R>(llr, static_cast<R>(w.bin_scale))], 1u);
+                }
+                __syncthreads();
+            }
+            // ---- stop test H e == s (after the full sweep, as the oracle does)
+            int mismatch = 0;
+            for (int i = tid; i < w.rowsW32; i += NT) mismatch |= cand[i] != syn[i];
+            if (!__syncthreads_or(mismatch)) { conv = true; break; }
+        }
+        if (it > p.max_iter) it = p.max_iter;
+        finish_shot<R, NT, false>(w, b, shot, tid, conv, it, 0u, syn, accs, car, hist, ebits);
+    }
+}
+
 // kernel variants: (precision, column-weight template, V in shared or global)
 using KernelPtr = void (*)(const WinDev, const BatchDev, const BpParams);
 
@@ -651,6 +813,34 @@ Variant& compact_variant(int prec, int method) {
 inline bool use_compact(const WinDev& w, bool vglobal) { return w.compact && !vglobal; }
 
 }  // namespace
+
+size_t bp_serial_smem_bytes(const WinDev& w, int precision) {
+    size_t off[9];
+    return bps_layout(w, precision == 32 ? 4 : 8, off);
+}
+
+static KernelPtr serial_kernel(int precision, int method) {
+    if (precision == 32) return method ? bp_kernel_serial<float, true> : bp_kernel_serial<float, false>;
+    return method ? bp_kernel_serial<double, true> : bp_kernel_serial<double, false>;
+}
+
+cudaError_t bp_serial_configure(const WinDev& w, int precision, int method) {
+    if (!w.compact || !w.ser_steps) return cudaErrorInvalidValue;
+    const size_t smem = bp_serial_smem_bytes(w, precision);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    static size_t have[2][2] = {};
+    size_t& h = have[precision == 32 ? 0 : 1][method ? 1 : 0];
+    if (smem <= h) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(serial_kernel(precision, method), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) h = smem;
+    return e;
+}
+
+cudaError_t launch_bp_serial(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, int grid, cudaStream_t st) {
+    if (b.n_shots == 0) return cudaSuccess;
+    serial_kernel(precision, p.method)<<<grid, kSerialThreads, bp_serial_smem_bytes(w, precision), st>>>(w, b, p);
+    return cudaGetLastError();
+}
 
 size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal) {
     size_t off[8];

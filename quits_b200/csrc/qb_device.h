@@ -77,6 +77,11 @@ struct WinDev {
     const float2* rsum0f;     // [rows] iteration-1 row summaries (min1, min2 of the prior LLRs along the row)
     const double2* rsum0d;
     const uint8_t* neg0;      // [rows] parity of #{prior LLR <= 0} along the row
+    // serial schedule (bp_kernel_serial): steps of independent (column, row) pairs in column order
+    int ser_nsteps;
+    const uint4* ser_steps;   // [ser_nsteps] pair_begin, n_pairs, col_begin, n_cols
+    const uint32_t* ser_pairs;// message address | row << 16, the pairs of a column contiguous and in ascending row order
+    const uint2* ser_cols;    // column | prior index << 16, first pair (within the step) | weight << 8
 };
 
 struct BatchDev {
@@ -125,6 +130,9 @@ size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal);
 int bp_threads(int precision);
 bool bp_supports(const WinDev& w, int method, bool vglobal);
 cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal, int method);
+size_t bp_serial_smem_bytes(const WinDev& w, int precision);
+cudaError_t bp_serial_configure(const WinDev& w, int precision, int method);
+cudaError_t launch_bp_serial(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, int grid, cudaStream_t st);
 cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, bool vglobal, int grid, cudaStream_t st);
 
 size_t osd_sort_smem_bytes(const WinDev& w, int precision);

@@ -170,8 +170,7 @@ def test_decoder_edge_cases(qb):
     assert det.shape == (0, c.num_detectors) and obs.shape == (0, c.num_observables)
     det, obs = qb.get_stim_mem_result(c, 1, seed=1)                              # ragged: a single shot of a 64-shot word
     assert det.shape == (1, c.num_detectors)
-    with pytest.raises(NotImplementedError):
-        qb.sliding_window_bposd_circuit_mem(det, c, hz, lz, 3, 2)               # reference defaults: product_sum / serial
+    assert qb.sliding_window_bposd_circuit_mem(det, c, hz, lz, 3, 2).shape == (1, c.num_observables)   # reference defaults
     with pytest.raises(NotImplementedError):
         qb.sliding_window_bposd_circuit_mem(det, c, hz, lz, 3, 2, max_iter=10, osd_order=40, bp_method="minimum_sum",
                                             schedule="parallel", osd_method="osd_cs")
@@ -332,3 +331,50 @@ def test_higher_order_osd_sliding_window(qb):
     opred, _ = cref.sw_decode(wins, g["m"], g["K"], g["det"].astype(np.uint8), max_iter=10, bp_method="minimum_sum", schedule="parallel",
                               precision="f64", osd_method="osd_cs", osd_order=1)
     assert np.array_equal(pred, opred.astype(np.int64))
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("case,window", [("bb72_r6_p3e-3_W5F3", 0), ("bb144_r10_p1e-3_W5F3", 1), ("bb144_r10_p3e-3_W5F3", 3),
+                                         ("toric3_zxcol_r3_p1e-3_W3F2", 0)])
+def test_serial_schedule_matches_oracle_per_shot(qb, case, window, precision):
+    """schedule='serial' (the reference wrappers' default, decoder/bposd.py:54), min-sum: the level-scheduled GPU sweep gives the
+    oracle's error estimate, iteration count and posteriors bit for bit (columns that share no row commute)."""
+    from oracle import cref
+    g = decode_case(case)
+    w = _oracle_windows(case_circuit(case), g["m"], g["W"], g["F"])[window]
+    H, pri = w["H"], w["priors"]
+    n = min(g["shots"], 48)
+    syn = g["det"][:n, w["row0"]:w["row0"] + H.shape[0]].astype(np.uint8)
+    kw = dict(max_iter=6, bp_method="minimum_sum", schedule="serial", osd_method="osd_0", osd_order=0, ms_scaling_factor=0.9)
+    dec = qb.BpOsdDecoder(H, channel_probs=pri, precision=precision, **kw)
+    ehat, llr, iters, conv = dec.decode_batch(syn)
+    orc = cref.BpOsd(H, pri, precision=precision, **kw)
+    for i in range(n):
+        e, l, it, c = orc.decode(syn[i])
+        assert bool(conv[i]) == c and int(iters[i]) == it, i
+        assert np.array_equal(llr[i], l), (i, np.max(np.abs(llr[i] - l)))
+        assert np.array_equal(ehat[i], e), i
+
+
+def test_reference_default_decoder_settings_run(qb):
+    """The reference's own defaults -- product_sum, serial, osd_cs (decoder/bposd.py:54) -- and the notebooks' setting
+    (max_iter=10, osd_order=1, doc/06B cell 3) through the drop-in call: serial min-sum + osd_cs 1 is bit-exact with the
+    oracle loop; with product-sum the predictions agree except where a posterior sits on a rounding boundary."""
+    from oracle import cref
+    case = "bb72_r6_p1e-3_W5F3"
+    g = decode_case(case)
+    name = case_circuit(case)
+    _, hz, lz = circuit_meta(name)
+    det = g["det"][:192]
+    c = qb.Circuit(circuit_text(name))
+    wins = _oracle_windows(name, g["m"], g["W"], g["F"])
+    kw = dict(max_iter=10, osd_order=1, bp_method="minimum_sum", schedule="serial", osd_method="osd_cs")
+    pred = qb.sliding_window_bposd_circuit_mem(det, c, hz, lz, g["W"], g["F"], **kw)
+    opred, _ = cref.sw_decode(wins, g["m"], g["K"], det.astype(np.uint8), precision="f64", **kw)
+    assert np.array_equal(pred, opred.astype(np.int64))
+    kw["bp_method"] = "product_sum"
+    pred = qb.sliding_window_bposd_circuit_mem(det, c, hz, lz, g["W"], g["F"], **kw)
+    opred, _ = cref.sw_decode(wins, g["m"], g["K"], det.astype(np.uint8), precision="f64", **kw)
+    assert int(np.any(pred != opred.astype(np.int64), axis=1).sum()) <= 2
+    dflt = qb.sliding_window_bposd_circuit_mem(det, c, hz, lz, g["W"], g["F"])          # max_iter=2, osd_order=0, product_sum, serial, osd_cs
+    assert dflt.shape == pred.shape and dflt.dtype == np.int64
