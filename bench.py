@@ -55,8 +55,9 @@ def load_workload():
 
 
 def config(shots, precision):
-    return {"workload": "%s custom circuit, W=%d F=%d, %s flooding BP max_iter=%d + %s order %d" % (
-                WORKLOAD, W, F, BP_KW["bp_method"], BP_KW["max_iter"], BP_KW["osd_method"], BP_KW["osd_order"]),
+    return {"workload": "%s custom circuit, W=%d F=%d, %s %s BP max_iter=%d + %s order %d" % (
+                WORKLOAD, W, F, BP_KW["bp_method"], "flooding" if BP_KW["schedule"] == "parallel" else "serial", BP_KW["max_iter"],
+                BP_KW["osd_method"], BP_KW["osd_order"]),
             "shots_per_step_per_gpu": int(shots), "precision": precision, "seed": SEED,
             "l2": "flushed between timed steps (256 MiB write); per-step message/LLR working set also exceeds L2"}
 
@@ -128,6 +129,7 @@ def main():
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--workload", default=WORKLOAD, help="circuit fixture under tests/golden/circuits (default: the headline workload)")
     ap.add_argument("--bp-method", default=None, help="secondary points: minimum_sum (headline) | product_sum")
+    ap.add_argument("--schedule", default=None, help="secondary points: parallel (headline) | serial")
     ap.add_argument("--osd-method", default=None, help="secondary points: osd_0 (headline) | osd_cs | osd_e")
     ap.add_argument("--osd-order", type=int, default=None)
     ap.add_argument("--lanes", type=int, default=0, help="concurrent sub-batches per device batch (0 = engine default)")
@@ -137,6 +139,8 @@ def main():
     globals()["WORKLOAD"] = args.workload
     if args.bp_method:
         BP_KW["bp_method"] = args.bp_method
+    if args.schedule:
+        BP_KW["schedule"] = args.schedule
     if args.osd_method:
         BP_KW["osd_method"] = args.osd_method
     if args.osd_order is not None:

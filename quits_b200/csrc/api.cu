@@ -362,34 +362,44 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
                 }
                 std::vector<std::vector<int>> bylevel(static_cast<size_t>(nlev) + 1);
                 for (int j = 0; j < ncols; ++j) bylevel[lvl[j]].push_back(j);
-                std::vector<uint32_t> steps, pairs, cols;          // steps: 4 words each; cols: 2 words each
+                // fixed-stride tables so that the kernel can prefetch step s+1 without a dependent load:
+                // steps[s] = n_pairs | n_cols << 8; pairs[s][16] = (address | row << 16, row length); cols[s][16] = (column | prior
+                // index << 16, first pair | weight << 8)
+                std::vector<uint32_t> steps, pairs, cols;
                 for (int l = 1; l <= nlev; ++l) {
                     size_t i = 0;
                     const std::vector<int>& cl = bylevel[l];
                     while (i < cl.size()) {
-                        const uint32_t pair_begin = static_cast<uint32_t>(pairs.size()), col_begin = static_cast<uint32_t>(cols.size() / 2);
+                        const size_t pbase = pairs.size(), cbase = cols.size();
+                        pairs.resize(pbase + 2 * kPairs, 0u);
+                        cols.resize(cbase + 2 * kPairs, 0u);
                         int np = 0, nc = 0;
-                        while (i < cl.size() && nc < kCols) {
+                        while (i < cl.size() && nc < kPairs) {
                             const int j = cl[i];
                             const int wt = static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]);
                             if (np + wt > kPairs) break;
-                            cols.push_back(static_cast<uint32_t>(j) | (static_cast<uint32_t>(pidx[j]) << 16));
-                            cols.push_back(static_cast<uint32_t>(np) | (static_cast<uint32_t>(wt) << 8));
-                            for (int64_t e2 = hw.cptr[j]; e2 < hw.cptr[j + 1]; ++e2)
-                                pairs.push_back((static_cast<uint32_t>(hw.crow[e2]) * static_cast<uint32_t>(rs) + static_cast<uint32_t>(layout.slot[e2])) |
-                                                (static_cast<uint32_t>(hw.crow[e2]) << 16));
-                            np += wt; ++nc; ++i;
+                            cols[cbase + 2 * nc] = static_cast<uint32_t>(j) | (static_cast<uint32_t>(pidx[j]) << 16);
+                            cols[cbase + 2 * nc + 1] = static_cast<uint32_t>(np) | (static_cast<uint32_t>(wt) << 8);
+                            for (int64_t e2 = hw.cptr[j]; e2 < hw.cptr[j + 1]; ++e2, ++np) {
+                                const uint32_t r = static_cast<uint32_t>(hw.crow[e2]);
+                                pairs[pbase + 2 * np] = (r * static_cast<uint32_t>(rs) + static_cast<uint32_t>(layout.slot[e2])) | (r << 16);
+                                pairs[pbase + 2 * np + 1] = static_cast<uint32_t>(fillr[r]);
+                            }
+                            ++nc; ++i;
                         }
-                        steps.push_back(pair_begin); steps.push_back(static_cast<uint32_t>(np));
-                        steps.push_back(col_begin); steps.push_back(static_cast<uint32_t>(nc));
+                        steps.push_back(static_cast<uint32_t>(np) | (static_cast<uint32_t>(nc) << 8));
                     }
                 }
+                (void)kCols;
+                steps.push_back(0u);                                 // the prefetch of the step after the last one lands here
+                pairs.resize(pairs.size() + 2 * kPairs, 0u);
+                cols.resize(cols.size() + 2 * kPairs, 0u);
                 upload(wo.ser_steps, steps, ctx->stream, 4);
                 upload(wo.ser_pairs, pairs, ctx->stream, 2);
                 upload(wo.ser_cols, cols, ctx->stream, 2);
-                d.ser_nsteps = static_cast<int>(steps.size() / 4);
-                d.ser_steps = wo.ser_steps.as<uint4>();
-                d.ser_pairs = wo.ser_pairs.as<uint32_t>();
+                d.ser_nsteps = static_cast<int>(steps.size()) - 1;
+                d.ser_steps = wo.ser_steps.as<uint32_t>();
+                d.ser_pairs = wo.ser_pairs.as<uint2>();
                 d.ser_cols = wo.ser_cols.as<uint2>();
             }
             d.compact = 1;

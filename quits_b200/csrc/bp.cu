@@ -630,8 +630,8 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
 constexpr int kSerialThreads = 128;
 constexpr int kSerialPairs = kSerialThreads / 8;
 
-// off: V, syn, cand, accs, car, ptab, hist, ebits, cbuf
-__host__ __device__ inline size_t bps_layout(const WinDev& w, int rsize, size_t* off /*[9]*/) {
+// off: V, syn, cand, accs, car, ptab, hist, ebits, cbuf, pbuf
+__host__ __device__ inline size_t bps_layout(const WinDev& w, int rsize, size_t* off /*[10]*/) {
     size_t o = 0;
     off[0] = o; o += align_up((static_cast<size_t>(w.rows) * w.RS + 1) * rsize, 16);
     off[1] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
@@ -642,6 +642,7 @@ __host__ __device__ inline size_t bps_layout(const WinDev& w, int rsize, size_t*
     off[6] = o; o += kSelWords * 4;
     off[7] = o; o += align_up(static_cast<size_t>(w.nW32) * 4, 16);
     off[8] = o; o += align_up(static_cast<size_t>(kSerialPairs) * rsize, 16);
+    off[9] = o; o += align_up(static_cast<size_t>(kSerialPairs) * 4, 16);
     return o;
 }
 
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(kSerialThreads) bp_kernel_serial(const WinDev 
     using CT = Compact<R>;
     constexpr int NT = kSerialThreads;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    size_t off[9];
+    size_t off[10];
     bps_layout(w, sizeof(R), off);
     R* V = reinterpret_cast<R*>(smem_raw + off[0]);
     uint32_t* syn = reinterpret_cast<uint32_t*>(smem_raw + off[1]);
@@ -662,6 +663,7 @@ __global__ void __launch_bounds__(kSerialThreads) bp_kernel_serial(const WinDev 
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + off[6]);
     uint32_t* ebits = reinterpret_cast<uint32_t*>(smem_raw + off[7]);
     R* cbuf = reinterpret_cast<R*>(smem_raw + off[8]);
+    uint32_t* pbuf = reinterpret_cast<uint32_t*>(smem_raw + off[9]);
 
     const int tid = threadIdx.x, grp = tid >> 3, l8 = tid & 7;
     const int rows = w.rows, RS = w.RS, npad = w.ncols_pad;
@@ -688,14 +690,21 @@ __global__ void __launch_bounds__(kSerialThreads) bp_kernel_serial(const WinDev 
             for (int i = tid; i < w.nW32; i += NT) ebits[i] = 0;
             if (last && tid < 32) hist[tid] = 0;
             __syncthreads();
+            // records of step 0; inside the loop the records of step s+1 are fetched before the barriers of step s
+            uint32_t hdr = __ldg(w.ser_steps);
+            uint2 pr = __ldg(w.ser_pairs + grp);
+            uint2 cr = tid < kSerialPairs ? __ldg(w.ser_cols + tid) : make_uint2(0u, 0u);
             for (int s = 0; s < w.ser_nsteps; ++s) {
-                const uint4 hdr = __ldg(w.ser_steps + s);        // pair_begin, n_pairs, col_begin, n_cols
+                const int n_pairs = static_cast<int>(hdr & 0xFFu), n_cols = static_cast<int>(hdr >> 8);
+                const uint2 mypair = pr, mycol = cr;
+                hdr = __ldg(w.ser_steps + s + 1);
+                pr = __ldg(w.ser_pairs + static_cast<size_t>(s + 1) * kSerialPairs + grp);
+                if (tid < kSerialPairs) cr = __ldg(w.ser_cols + static_cast<size_t>(s + 1) * kSerialPairs + tid);
                 // ---- eight lanes per (column, row) pair: message of the row to the column from the row's other edges
                 {
-                    const bool act = grp < static_cast<int>(hdr.y);       // idle groups run the shuffles too (full-warp mask)
-                    const uint32_t pr = act ? __ldg(w.ser_pairs + hdr.x + grp) : 0u;
-                    const int addr = static_cast<int>(pr & 0xFFFFu), row = static_cast<int>(pr >> 16);
-                    const int base = row * RS, own = addr - base, len = act ? __ldg(w.rlen + row) : 0;
+                    const bool act = grp < n_pairs;                        // idle groups run the shuffles too (full-warp mask)
+                    const int addr = static_cast<int>(mypair.x & 0xFFFFu), row = static_cast<int>(mypair.x >> 16);
+                    const int base = row * RS, own = addr - base, len = act ? static_cast<int>(mypair.y) : 0;
                     R acc = PS ? R(1) : RT::big();
                     uint32_t neg = 0;
                     for (int k = l8; k < len; k += 8) {
@@ -725,20 +734,20 @@ __global__ void __launch_bounds__(kSerialThreads) bp_kernel_serial(const WinDev 
                             c = RT::mul(acc, ((sbit + neg) & 1u) ? -alpha : alpha);
                         }
                         cbuf[grp] = c;
+                        pbuf[grp] = mypair.x;
                     }
                 }
                 __syncthreads();
                 // ---- one thread per column of the step: prefix / suffix sums in the oracle's order, new messages, hard decision
-                if (tid < static_cast<int>(hdr.w)) {
-                    const uint2 cr = __ldg(w.ser_cols + hdr.z + tid);   // x = column | prior index << 16, y = first pair | weight << 8
-                    const int j = static_cast<int>(cr.x & 0xFFFFu), first = static_cast<int>(cr.y & 0xFFu), wt = static_cast<int>((cr.y >> 8) & 0xFFu);
-                    const R l0 = ptab[(cr.x >> 16) & 0xFFFu];
+                if (tid < n_cols) {
+                    const int j = static_cast<int>(mycol.x & 0xFFFFu), first = static_cast<int>(mycol.y & 0xFFu), wt = static_cast<int>((mycol.y >> 8) & 0xFFu);
+                    const R l0 = ptab[(mycol.x >> 16) & 0xFFFu];
                     R c[6], vn[6];
                     uint32_t pa[6];
 #pragma unroll
                     for (int q = 0; q < 6; ++q) {
                         c[q] = q < wt ? cbuf[first + q] : R(0);
-                        pa[q] = q < wt ? __ldg(w.ser_pairs + hdr.x + first + q) : 0u;
+                        pa[q] = q < wt ? pbuf[first + q] : 0u;
                     }
                     R t = l0;
 #pragma unroll
@@ -815,7 +824,7 @@ inline bool use_compact(const WinDev& w, bool vglobal) { return w.compact && !vg
 }  // namespace
 
 size_t bp_serial_smem_bytes(const WinDev& w, int precision) {
-    size_t off[9];
+    size_t off[10];
     return bps_layout(w, precision == 32 ? 4 : 8, off);
 }
 

@@ -79,9 +79,9 @@ struct WinDev {
     const uint8_t* neg0;      // [rows] parity of #{prior LLR <= 0} along the row
     // serial schedule (bp_kernel_serial): steps of independent (column, row) pairs in column order
     int ser_nsteps;
-    const uint4* ser_steps;   // [ser_nsteps] pair_begin, n_pairs, col_begin, n_cols
-    const uint32_t* ser_pairs;// message address | row << 16, the pairs of a column contiguous and in ascending row order
-    const uint2* ser_cols;    // column | prior index << 16, first pair (within the step) | weight << 8
+    const uint32_t* ser_steps;// [ser_nsteps + 1] n_pairs | n_cols << 8
+    const uint2* ser_pairs;   // [ser_nsteps + 1][16] (message address | row << 16, row length); a column's pairs contiguous, ascending rows
+    const uint2* ser_cols;    // [ser_nsteps + 1][16] (column | prior index << 16, first pair of the step | weight << 8)
 };
 
 struct BatchDev {
