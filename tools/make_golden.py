@@ -49,6 +49,8 @@ CASES = [
     ("hgp225_r3_p1e-2", 3, 2, 128, 18),
     ("hgp225_r3_p1e-2", 5, 3, 96, 19),          # W > rounds: whole-history window (the reference warns)
     ("toric3_zxcol_r3_p1e-3", 3, 2, 1024, 21),
+    ("qt633_zxcol_r12_p1e-3", 5, 3, 128, 22),    # BASELINE config 4 (circuit from tools/make_circuits_more.py), BP-OSD inner decoder
+    ("hgp225_r15_p1e-3", 5, 3, 48, 23),          # the notebooks' HGP run: 540 x 6480 windows
 ]
 
 
@@ -84,7 +86,10 @@ def main():
     for sub in ("windows", "decode", "dem"):
         os.makedirs(os.path.join(G, sub), exist_ok=True)
     done_dem = set()
+    only = sys.argv[1:]                         # optional: substrings of the case names to (re)generate
     for name, W, F, shots, seed in CASES:
+        if only and not any(o in name for o in only):
+            continue
         text, hz, lz = load(name)
         circ = stim.Circuit(text)
         m = hz.shape[0]
