@@ -308,8 +308,17 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "shots/s", "cores": threads, "kind": "port",
                                     "sample": "%d shots of the same workload in %.1f s (oracle C port: frame sampler + window loop, fp64, OpenMP)" % (shots, dt)}
         print(json.dumps(line))
+    # orderly teardown: drop the engine objects while the CUDA context is alive, leave NCCL, then exit without running the
+    # interpreter's arbitrary-order finalisation (a rank that outlives its peers' NCCL teardown must not touch the device again)
+    sys.stdout.flush()
+    del mc
+    ctx.synchronize()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

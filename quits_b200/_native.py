@@ -2,6 +2,7 @@
 missing the import fails loudly, and every compute entry point fails loudly without a CUDA device."""
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
 import threading
@@ -45,6 +46,22 @@ SYMBOLS = ["qb_last_error", "qb_version", "qb_device_count", "qb_host_alloc", "q
            "qb_sw_decode_packed", "qb_bp_decode_batch", "qb_mc_run"]
 
 _lib = None
+
+# Set at interpreter exit: from then on no destructor calls into the CUDA runtime (the driver may already be unloading, and the
+# order in which Python drops the remaining objects is arbitrary); the OS reclaims everything.
+_alive = True
+
+
+def _shutdown():
+    global _alive
+    _alive = False
+
+
+atexit.register(_shutdown)
+
+
+def alive() -> bool:
+    return _alive
 
 
 def lib():
@@ -143,6 +160,8 @@ class _PinnedPool:
         self.lock = threading.Lock()
 
     def _release(self, ptr, cap):
+        if not _alive:
+            return
         with self.lock:
             if self.idle + cap <= self.limit:
                 self.free.setdefault(cap, []).append(ptr)
@@ -166,7 +185,7 @@ class _PinnedPool:
             check(lib().qb_host_alloc(cap, C.byref(p)))
             ptr = p.value
         raw = (C.c_uint8 * nbytes).from_address(ptr)
-        weakref.finalize(raw, self._release, ptr, cap)
+        weakref.finalize(raw, self._release, ptr, cap).atexit = False
         return np.frombuffer(raw, dtype=dtype).reshape(shape)
 
 

@@ -48,7 +48,7 @@ class Context:
 
     def __del__(self):
         try:
-            if getattr(self, "_h", None):
+            if getattr(self, "_h", None) and N.alive():
                 N.lib().qb_ctx_destroy(self._h)
                 self._h = None
         except Exception:
@@ -96,7 +96,7 @@ class Circuit:
 
     def __del__(self):
         try:
-            if getattr(self, "_h", None):
+            if getattr(self, "_h", None) and N.alive():
                 N.lib().qb_circuit_free(self._h)
                 self._h = None
         except Exception:
@@ -170,7 +170,7 @@ class DetectorErrorModel:
 
     def __del__(self):
         try:
-            if getattr(self, "_h", None):
+            if getattr(self, "_h", None) and N.alive():
                 N.lib().qb_dem_free(self._h)
                 self._h = None
         except Exception:

@@ -118,7 +118,7 @@ class WindowPlan:
 
     def __del__(self):
         try:
-            if getattr(self, "_h", None):
+            if getattr(self, "_h", None) and N.alive():
                 N.lib().qb_plan_free(self._h)
                 self._h = None
         except Exception:

@@ -50,7 +50,7 @@ class _GpuInnerDecoder:
 
     def __del__(self):
         try:
-            if getattr(self, "_h", None):
+            if getattr(self, "_h", None) and N.alive():
                 N.lib().qb_sw_free(self._h)
                 self._h = None
         except Exception:

@@ -79,7 +79,7 @@ class SlidingWindowDecoder:
 
     def __del__(self):
         try:
-            if getattr(self, "_h", None):
+            if getattr(self, "_h", None) and N.alive():
                 N.lib().qb_sw_free(self._h)
                 self._h = None
         except Exception:
