@@ -172,7 +172,7 @@ class _PinnedPool:
     def empty(self, shape, dtype):
         dtype = np.dtype(dtype)
         nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
-        if nbytes < (1 << 20):                       # small arrays: ordinary memory
+        if nbytes < (1 << 20) or nbytes > (2 << 30):  # small arrays, and arrays too large to page-lock sensibly: ordinary memory
             return np.empty(shape, dtype=dtype)
         cap = 1 << (nbytes - 1).bit_length()
         with self.lock:
@@ -182,7 +182,8 @@ class _PinnedPool:
                 self.idle -= cap
         if ptr is None:
             p = C.c_void_p()
-            check(lib().qb_host_alloc(cap, C.byref(p)))
+            if lib().qb_host_alloc(cap, C.byref(p)) != 0 or not p.value:
+                return np.empty(shape, dtype=dtype)    # page-locking failed (limits, fragmentation): pageable memory still works
             ptr = p.value
         raw = (C.c_uint8 * nbytes).from_address(ptr)
         weakref.finalize(raw, self._release, ptr, cap).atexit = False

@@ -502,7 +502,8 @@ void finish_decoder(qb_sw* sw) {
     std::vector<double> alpha(static_cast<size_t>(max_iter) + 1, 1.0);
     for (int it = 1; it <= max_iter; ++it) alpha[it] = o.ms_scaling_factor == 0.0 ? 1.0 - std::pow(2.0, -1.0 * it) : o.ms_scaling_factor;
     upload(sw->alpha, alpha, ctx->stream);
-    sw->cap = o.capacity > 0 ? o.capacity : 65536;
+    // batches start on 64-shot word boundaries (the sampler numbers shots by word): capacity is rounded down to a multiple of 64
+    sw->cap = o.capacity > 0 ? std::max(64, o.capacity / 64 * 64) : 65536;
     sw->lanes = o.lanes > 0 ? std::min(o.lanes, static_cast<int32_t>(qb_ctx::kMaxLanes)) : 1;
     if (max_slab) sw->lanes = 1;                      // the global message slabs are indexed by CTA, not by sub-batch
     sw->DW = std::max(1, (sw->plan.D + 63) / 64);

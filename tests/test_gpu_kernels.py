@@ -130,11 +130,13 @@ def test_frame_propagation_is_linear(qb):
     assert np.array_equal(det[2 * n:], det[:n] ^ det[n:2 * n]) and np.array_equal(obs[2 * n:], obs[:n] ^ obs[n:2 * n])
 
 
-def test_full_size_against_live_oracle_and_batching(qb):
-    """Headline workload, 4096 shots: GPU pipeline == oracle pipeline run live (C restatement, fp64), and the result does
-    not depend on the device batch size or on how the shot range is split."""
+@pytest.mark.parametrize("name", ["bb144_r10_p1e-3", "bb144_r10_p3e-3"])
+def test_full_size_against_live_oracle_and_batching(qb, name):
+    """Headline workload (and its p = 3e-3 sibling, where three of four windows go to OSD and the fast path's second tier and
+    overflow route are exercised), 4096 shots: GPU pipeline == oracle pipeline run live (C restatement, fp64), and the result
+    does not depend on the device batch size or on how the shot range is split."""
     from oracle import cref, stimtext
-    name, W, F, shots, seed = "bb144_r10_p1e-3", 5, 3, 4096, 31337
+    W, F, shots, seed = 5, 3, 4096, 31337
     _, hz, lz = circuit_meta(name)
     c = qb.Circuit(circuit_text(name))
     det, obs = qb.get_stim_mem_result(c, shots, seed=seed)
