@@ -294,19 +294,21 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
             if (k == ptab.size()) { if (ptab.size() > 4096) break; ptab.push_back(llr0d[j]); }
             pidx[j] = static_cast<int>(k);
         }
-        const bool fits = cw <= 6 && static_cast<long long>(rows) * rs + 1 < 65535 && ncols < 65535 && ptab.size() <= 4096 && rs <= 255;
+        const bool fits = cw <= 6 && static_cast<long long>(rows) * rs + 512 + 2 * rs < 65535 && ncols < 65535 && ptab.size() <= 4096 && rs <= 255;
         if (fits) {
             const uint32_t magic = static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(rs)) + 1u;
-            for (uint32_t a = 0; a <= static_cast<uint32_t>(rows) * rs; ++a)
+            for (uint32_t a = 0; a <= static_cast<uint32_t>(rows) * rs + 512 + static_cast<uint32_t>(rs); ++a)
                 if (static_cast<uint32_t>((static_cast<uint64_t>(a) * magic) >> 32) != a / rs) throw std::runtime_error("internal: row magic is not exact");
             const std::vector<int>& order = layout.order;
-            // records: 6 x u16 message address (dummy edges point at the dummy row's slot rows*rs), then
-            // w = original column | prior index << 16 | weight of the heaviest column of the record's warp << 28
-            const uint32_t dummy = static_cast<uint32_t>(rows) * static_cast<uint32_t>(rs);
+            // records: 6 x u16 message address (dummy edges point at the private dummy slot rows*rs + r % NT of the thread that
+            // handles record r), then w = original column | prior index << 16 | weight of the heaviest column of the record's warp << 28
+            const uint32_t dummy0 = static_cast<uint32_t>(rows) * static_cast<uint32_t>(rs);
+            const uint32_t nthreads = precision == 32 ? 256u : 512u;          // threads of bp_kernel_compact (bp.cu)
             const int nrec = std::max(npad, 1024);           // the kernel prefetches record `tid` before it tests tid < npad
             std::vector<uint32_t> rec(static_cast<size_t>(nrec) * 4, 0);
             for (int r = 0; r < nrec; ++r) {
                 uint32_t* o = &rec[static_cast<size_t>(r) * 4];
+                const uint32_t dummy = dummy0 + static_cast<uint32_t>(r) % nthreads;
                 uint32_t e[6] = {dummy, dummy, dummy, dummy, dummy, dummy};
                 uint32_t word3 = 0xFFFFu;                     // padding record: no column
                 if (r < ncols) {

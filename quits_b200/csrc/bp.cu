@@ -324,9 +324,9 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
 //   * one 16-byte record per column (6 u16 message addresses + prior index) -> a single LDG.128 per column and sweep,
 //     prefetched one record ahead;
 //   * records are sorted by column weight and every warp runs the code path of its heaviest column (the weight field of
-//     a record holds the warp's maximum).  Lighter columns are padded with DUMMY edges that point at a dummy row
-//     (index `rows`) whose summary is (0, 0): their check->bit message is +-0, and x + (+-0) == x exactly, so the padding
-//     needs no predication at all;
+//     a record holds the warp's maximum).  Lighter columns are padded with DUMMY edges that point at a private dummy slot
+//     of the handling thread in a dummy row (index >= `rows`) whose summary is (0, 0): their check->bit message is +-0, and
+//     x + (+-0) == x exactly, so the padding needs no predication at all (and, the slots being private, races with nobody);
 //   * the row summary is (min1 with the row's sign parity in its sign bit, min2): the edge that holds the minimum is
 //     recognised by |v| == min1 (if two edges tie, min2 == min1 and either choice gives the same value), so no argmin;
 //     the sign of a message is applied by XOR on the sign bit (mul(m, -a) == -mul(m, a) exactly in round-to-nearest);
@@ -359,11 +359,15 @@ template <> struct Compact<double> {
     }
 };
 
-// off: V, rsum, syn, cand, accs, car, ptab.  V and rsum carry one extra entry for the dummy row.
+// off: V, rsum, syn, cand, accs, car, ptab.  Behind the rows*RS real message slots V carries one private dummy slot per thread
+// (dummy edges of a record handled by thread t point at slot rows*RS + t: nothing is shared, so nothing races), and rsum carries
+// the dummy rows those addresses divide down to.
+__host__ __device__ inline int bp_dummy_slots(int rsize) { return rsize == 4 ? 256 : 512; }      // = threads of the compact kernel
+__host__ __device__ inline int bp_dummy_rows(const WinDev& w, int rsize) { return bp_dummy_slots(rsize) / w.RS + 2; }
 __host__ __device__ inline size_t bpc_layout(const WinDev& w, int rsize, size_t* off /*[8]*/) {
     size_t o = 0;
-    off[0] = o; o += align_up((static_cast<size_t>(w.rows) * w.RS + 1) * rsize, 16);
-    off[1] = o; o += align_up(static_cast<size_t>(w.rows + 1) * 2 * rsize, 16);
+    off[0] = o; o += align_up((static_cast<size_t>(w.rows) * w.RS + bp_dummy_slots(rsize)) * rsize, 16);
+    off[1] = o; o += align_up(static_cast<size_t>(w.rows + bp_dummy_rows(w, rsize)) * 2 * rsize, 16);
     off[2] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
     off[3] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
     off[4] = o; o += align_up(static_cast<size_t>(w.KW) * 8, 16);
@@ -520,10 +524,9 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
     const uint32_t magic = w.rs_magic;
     R* const llr_all = reinterpret_cast<R*>(b.llr_buf);
     for (int i = tid; i < w.n_ptab; i += NT) ptab[i] = CT::ptab(w)[i];
-    if (tid == 0) {                          // the dummy row: its messages are +-0 (min-sum: minima 0; product-sum: two zero factors)
-        rsum[rows] = RT::mk(R(0), PS ? R(2) : R(0));
-        V[rows * RS] = R(0);
-    }
+    // the dummy rows: their messages are +-0 (min-sum: minima 0; product-sum: two zero factors); one dummy slot per thread
+    if (tid < bp_dummy_rows(w, sizeof(R))) rsum[rows + tid] = RT::mk(R(0), PS ? R(2) : R(0));
+    V[rows * RS + tid] = R(0);
 
     for (int shot = blockIdx.x; shot < b.n_shots; shot += gridDim.x) {
         __syncthreads();
@@ -538,7 +541,8 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
                 const R l0 = ptab[(rec.w >> 16) & 0xFFFu];
                 const uint32_t e[6] = {rec.x & 0xFFFFu, rec.x >> 16, rec.y & 0xFFFFu, rec.y >> 16, rec.z & 0xFFFFu, rec.z >> 16};
 #pragma unroll
-                for (int q = 0; q < 6; ++q) V[e[q]] = l0;
+                for (int q = 0; q < 6; ++q)
+                    if (e[q] < static_cast<uint32_t>(rows * RS)) V[e[q]] = l0;
             }
             __syncthreads();
         }
@@ -597,9 +601,10 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
                 if (r + NT < npad) rec = __ldg(w.colrec + r + NT);
                 const R l0 = ptab[(cur.w >> 16) & 0xFFFu];
                 R llr;
-                if (PS) llr = column_dispatch_ps<R>(cur, l0, V, rsum, cand, magic, static_cast<uint32_t>(rows));
-                else llr = first ? column_dispatch<R, true>(cur, l0, alpha, V, rsum, cand, magic, static_cast<uint32_t>(rows))
-                                 : column_dispatch<R, false>(cur, l0, alpha, V, rsum, cand, magic, static_cast<uint32_t>(rows));
+                const uint32_t urows = static_cast<uint32_t>(rows);
+                if (PS) llr = column_dispatch_ps<R>(cur, l0, V, rsum, cand, magic, urows);
+                else llr = first ? column_dispatch<R, true>(cur, l0, alpha, V, rsum, cand, magic, urows)
+                                 : column_dispatch<R, false>(cur, l0, alpha, V, rsum, cand, magic, urows);
                 const uint32_t j = cur.w & 0xFFFFu;                    // original column; 0xFFFF marks a padding record
                 if (j != 0xFFFFu) {
                     if (llr <= R(0)) hmask |= 1u << k;
@@ -678,7 +683,8 @@ __global__ void __launch_bounds__(kSerialThreads) bp_kernel_serial(const WinDev 
             const R l0 = ptab[(rec.w >> 16) & 0xFFFu];
             const uint32_t e[6] = {rec.x & 0xFFFFu, rec.x >> 16, rec.y & 0xFFFFu, rec.y >> 16, rec.z & 0xFFFFu, rec.z >> 16};
 #pragma unroll
-            for (int q = 0; q < 6; ++q) V[e[q]] = l0;
+            for (int q = 0; q < 6; ++q)
+                if (e[q] < static_cast<uint32_t>(rows * RS)) V[e[q]] = l0;
         }
         __syncthreads();
         bool conv = false;
@@ -784,7 +790,7 @@ using KernelPtr = void (*)(const WinDev, const BatchDev, const BpParams);
 struct Variant {
     KernelPtr fn;
     int threads;
-    size_t configured;
+    size_t configured[kMaxDevices];
 };
 
 template <typename R, int CW, bool VG>
@@ -837,8 +843,8 @@ cudaError_t bp_serial_configure(const WinDev& w, int precision, int method) {
     if (!w.compact || !w.ser_steps) return cudaErrorInvalidValue;
     const size_t smem = bp_serial_smem_bytes(w, precision);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static size_t have[2][2] = {};
-    size_t& h = have[precision == 32 ? 0 : 1][method ? 1 : 0];
+    static size_t have[kMaxDevices][2][2] = {};
+    size_t& h = have[device_slot()][precision == 32 ? 0 : 1][method ? 1 : 0];
     if (smem <= h) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(serial_kernel(precision, method), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e == cudaSuccess) h = smem;
@@ -867,9 +873,10 @@ cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal, int metho
     const size_t smem = bp_smem_bytes(w, precision, vglobal);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     Variant& v = use_compact(w, vglobal) ? compact_variant(precision, method) : variant(precision, w.cw, vglobal);
-    if (smem <= v.configured) return cudaSuccess;          // the attribute only ever grows (decoders of different sizes coexist)
+    size_t& have = v.configured[device_slot()];
+    if (smem <= have) return cudaSuccess;                   // the attribute only ever grows (decoders of different sizes coexist)
     cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e == cudaSuccess) v.configured = smem;
+    if (e == cudaSuccess) have = smem;
     return e;
 }
 

@@ -274,7 +274,8 @@ cudaError_t launch_frame(const FrameArgs& a, cudaStream_t st) {
     int wpb = 4;
     while (wpb > 1 && per_warp * wpb > budget / 3) --wpb;          // keep >= 3 CTAs per SM when possible
     const size_t smem = per_warp * wpb;
-    static size_t configured = 0;
+    static size_t configured_dev[kMaxDevices] = {};
+    size_t& configured = configured_dev[device_slot()];
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;

@@ -847,7 +847,11 @@ bool osd_supported(const WinDev& w, int precision) {
 
 cudaError_t osd_configure(const WinDev& w, int precision) {
     // several windows may share one instantiation: the attributes only ever grow
-    static size_t sort_have[2] = {}, elim_have[2][2][8] = {}, fast_have[2][2][8] = {};
+    static size_t sort_have_d[kMaxDevices][2] = {}, elim_have_d[kMaxDevices][2][2][8] = {}, fast_have_d[kMaxDevices][2][2][8] = {};
+    const int dev = device_slot();
+    auto& sort_have = sort_have_d[dev];
+    auto& elim_have = elim_have_d[dev];
+    auto& fast_have = fast_have_d[dev];
     const size_t ss = osd_sort_smem_bytes(w, precision), fs = osd_fast_smem_bytes(w);
     size_t& sh = sort_have[precision == 32 ? 0 : 1];
     if (ss > sh) {

@@ -13,6 +13,15 @@
 
 namespace qb {
 
+// cudaFuncSetAttribute is per device: the "largest shared-memory size configured so far" caches are kept per device so that
+// one process may drive several GPUs (the usual deployment is one process per GPU)
+constexpr int kMaxDevices = 32;
+inline int device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & (kMaxDevices - 1);
+}
+
 // ---------------------------------------------------------------------------------------------- K1
 struct FrameArgs {
     const TapeOp* ops;

@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Small pass over every kernel family, meant to be run under compute-sanitizer on the GPU box:
+
+    compute-sanitizer --tool memcheck python tools/sanitize_run.py
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import quits_b200 as qb  # noqa: E402
+from bench import load_workload  # noqa: E402
+
+
+def circuit(name):
+    with open(os.path.join(ROOT, "tests", "golden", "circuits", name + ".stim")) as f:
+        return qb.Circuit(f.read())
+
+
+def main():
+    warnings.simplefilter("ignore")
+    text, hz, lz = load_workload()
+    c = qb.Circuit(text)
+    scale = float(os.environ.get("QB_SANITIZE_SCALE", "1"))           # racecheck is slow: QB_SANITIZE_SCALE=0.2
+    n = lambda x: max(8, int(x * scale))
+    det, obs = qb.get_stim_mem_result(c, n(300), seed=3)
+    base = dict(max_iter=10, osd_order=0, bp_method="minimum_sum", schedule="parallel", osd_method="osd_0")
+    for kw in (base, dict(base, bp_method="product_sum"), dict(base, osd_method="osd_cs", osd_order=2),
+               dict(base, osd_method="osd_e", osd_order=3), dict(base, schedule="serial", max_iter=3),
+               dict(base, schedule="serial", bp_method="product_sum", max_iter=2)):
+        for prec in ("f64", "f32"):
+            dec = qb.SlidingWindowDecoder(c, hz.shape[0], 5, 3, precision=prec, **kw)
+            pred = dec.decode(det)
+            print(kw["bp_method"], kw["schedule"], kw["osd_method"], kw["osd_order"], prec, "logical errors",
+                  int(np.any((obs - pred) % 2, axis=1).sum()), flush=True)
+    mc = qb.MonteCarlo(c, hz.shape[0], 5, 3, capacity=192, **base)
+    print("fused", mc.run(n(500), 9)[0][0], flush=True)
+    c3 = circuit("bb144_r10_p3e-3")                      # OSD-heavy: second tier and overflow route
+    d3, o3 = qb.get_stim_mem_result(c3, n(400), seed=4)
+    print("p=3e-3", int(np.any((o3 - qb.sliding_window_bposd_circuit_mem(d3, c3, hz, lz, 5, 3, **base)) % 2, axis=1).sum()), flush=True)
+    hg = circuit("hgp225_r3_p1e-2")                      # whole-history window, generic paths
+    dh, oh = qb.get_stim_mem_result(hg, n(100), seed=5)
+    hzh, lzh = np.zeros((108, 225), dtype=np.uint8), np.zeros((9, 225), dtype=np.uint8)
+    print("hgp", qb.sliding_window_bposd_circuit_mem(dh, hg, hzh, lzh, 3, 2, **base).sum(), flush=True)
+    rng = np.random.RandomState(1)
+    print("phenom", qb.sliding_window_bposd_phenom_mem(rng.rand(n(64), 72 * 12) < 0.05, (rng.rand(72, 144) < 0.04).astype(int),
+                                                       (rng.rand(12, 144) < 0.3).astype(int), 5, 3, error_rate=0.02, **base).sum(), flush=True)
+
+
+if __name__ == "__main__":
+    main()
