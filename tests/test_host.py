@@ -246,3 +246,38 @@ def test_phenomenological_windows_equal_the_reference_matrices():
             assert np.array_equal(w["U"].toarray() @ e % 2, e[W * n + (F - 1) * m:W * n + F * m])
     with pytest.raises(ValueError):
         qb.sliding_window_bposd_phenom_mem(np.zeros((1, m * 8), dtype=bool), hz, lz, 4, 0)
+
+
+def test_explicit_plan_validation():
+    """qb_plan_create_explicit rejects malformed windows with the boundary's exception types."""
+    from scipy.sparse import csc_matrix
+    m, K, D = 2, 1, 6
+    H = csc_matrix(np.array([[1, 0, 1], [0, 1, 1], [1, 1, 0], [0, 0, 1]], dtype=np.uint8))
+    L = csc_matrix(np.array([[1, 0, 1]], dtype=np.uint8))
+    U = csc_matrix(np.array([[0, 1, 0], [0, 0, 1]], dtype=np.uint8))
+    good = [{"row0": 0, "H": H, "priors": [0.1, 0.2, 0.3], "L": L, "U": U},
+            {"row0": 2, "H": H, "priors": [0.1, 0.2, 0.3], "L": L, "U": None}]
+    plan = WindowPlan.explicit(m, K, D, good)
+    assert plan.n_windows == 2 and plan.K == 1 and plan.D == 6
+    w0 = plan.window(0)
+    assert np.array_equal(w0["H"].toarray(), H.toarray()) and np.array_equal(w0["U"].toarray(), U.toarray())
+    with pytest.raises(TypeError):                      # rows outside the detector range
+        WindowPlan.explicit(m, K, D, [dict(good[0], row0=4), good[1]])
+    with pytest.raises(TypeError):                      # the last window must not carry, the others must carry m rows
+        WindowPlan.explicit(m, K, D, [good[0], dict(good[1], U=U)])
+    with pytest.raises(TypeError):
+        WindowPlan.explicit(m, K, D, [dict(good[0], U=None), good[1]])
+    with pytest.raises(TypeError):                      # observable index out of range
+        WindowPlan.explicit(m, K, D, [dict(good[0], L=csc_matrix(np.array([[1, 0, 0], [0, 1, 0]], dtype=np.uint8))), good[1]])
+
+
+def test_phenom_argument_errors():
+    hz = np.eye(3, 4, dtype=int)
+    lz = np.ones((1, 4), dtype=int)
+    det = np.zeros((2, 3 * 6), dtype=bool)
+    with pytest.raises(ValueError):
+        qb.sliding_window_bposd_phenom_mem(det, hz, lz, 3, 0)
+    with pytest.raises(ValueError):                     # F > W: the reference fails reshaping F blocks out of W
+        qb.sliding_window_bposd_phenom_mem(det, hz, lz, 2, 3, bp_method="minimum_sum", schedule="parallel", osd_method="osd_0")
+    with pytest.raises(NotImplementedError):            # foreign inner decoder classes are not run per shot
+        qb.sliding_window_phenom_mem(det, hz, lz, 3, 2, dict, dict, {"error_rate": 0.1}, {"error_rate": 0.1}, "decode", "decode")
