@@ -15,9 +15,9 @@ def sliding_window_bposd_phenom_mem(zcheck_samples, hz, lz, W, F, error_rate=0.0
 
 def sliding_window_bposd_circuit_mem(zcheck_samples, circuit, hz, lz, W, F, max_iter=2, osd_order=0, bp_method='product_sum',
                                      schedule='serial', osd_method='osd_cs', tqdm_on=False):
-    """Drop-in for the reference function of the same name.  The GPU kernels implement ``bp_method`` 'minimum_sum' and
-    'product_sum' with ``schedule='parallel'`` and order-0 post-processing (OSD-0; 'osd_cs' / 'osd_e' with ``osd_order=0`` are
-    the same thing); ``schedule='serial'`` and ``osd_order > 0`` raise NotImplementedError -- there is no CPU fallback."""
+    """Drop-in for the reference function of the same name, same defaults.  The GPU kernels cover ``bp_method`` 'minimum_sum'
+    and 'product_sum', ``schedule`` 'parallel' and 'serial', and ``osd_method`` 'osd_0' / 'osd_cs' (order <= 32) / 'osd_e'
+    (order <= 12); anything else raises NotImplementedError -- there is no CPU fallback."""
     params = lambda: {'bp_method': bp_method, 'max_iter': max_iter, 'schedule': schedule, 'osd_method': osd_method,
                       'osd_order': osd_order}
     return sliding_window_circuit_mem(zcheck_samples, circuit, hz, lz, W, F, BpOsdDecoder, BpOsdDecoder, params(), params(),
