@@ -423,6 +423,7 @@ __device__ __forceinline__ R column_update(const uint4 rec, const R l0, const R 
 }
 
 // ---- product-sum (ldpc bp_method 'product_sum'): check->bit message = 2 atanh( prod_{others} tanh(v/2) ), sign from the syndrome.
+// The message array holds tanh(v/2) instead of v (one tanh per edge and iteration, taken when the message is written).
 // The row summary is (s * prod of the non-zero tanh(v/2), number of zero factors); "the others" is obtained by dividing the
 // row product by the edge's own factor, which differs from ldpc's prefix/suffix products by rounding only (no bit parity with
 // the CPU here anyway: libm and CUDA tanh/log differ in the last ulps).
@@ -447,9 +448,8 @@ __device__ __forceinline__ R column_update_ps(const uint4 rec, const R l0, R* V,
     R c[W], vn[W];
 #pragma unroll
     for (int q = 0; q < W; ++q) {
-        const R v = V[e[q]];
+        const R t = V[e[q]];                                   // tanh(v/2) of the message, stored by the previous sweep
         const typename RT::pair s = rsum[__umulhi(e[q], magic)];
-        const R t = TT::th(RT::mul(v, R(0.5)));
         R x = R(0);
         if (s.y == R(0)) x = TT::div(s.x, t);
         else if (s.y == R(1) && t == R(0)) x = s.x;
@@ -463,7 +463,7 @@ __device__ __forceinline__ R column_update_ps(const uint4 rec, const R l0, R* V,
 #pragma unroll
     for (int q = W - 1; q >= 0; --q) { vn[q] = RT::add(vn[q], t); t = RT::add(t, c[q]); }
 #pragma unroll
-    for (int q = 0; q < W; ++q) V[e[q]] = vn[q];
+    for (int q = 0; q < W; ++q) V[e[q]] = TT::th(RT::mul(vn[q], R(0.5)));
     if (llr <= R(0)) {
 #pragma unroll
         for (int q = 0; q < W; ++q) {
@@ -538,11 +538,11 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
         if (PS) {                    // product-sum has no closed form for iteration 1: start from the priors in the message array
             for (int r = tid; r < npad; r += NT) {
                 const uint4 rec = __ldg(w.colrec + r);
-                const R l0 = ptab[(rec.w >> 16) & 0xFFFu];
+                const R t0 = Trans<R>::th(RT::mul(ptab[(rec.w >> 16) & 0xFFFu], R(0.5)));
                 const uint32_t e[6] = {rec.x & 0xFFFFu, rec.x >> 16, rec.y & 0xFFFFu, rec.y >> 16, rec.z & 0xFFFFu, rec.z >> 16};
 #pragma unroll
                 for (int q = 0; q < 6; ++q)
-                    if (e[q] < static_cast<uint32_t>(rows * RS)) V[e[q]] = l0;
+                    if (e[q] < static_cast<uint32_t>(rows * RS)) V[e[q]] = t0;
             }
             __syncthreads();
         }
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
                     R prod = (neg & 1u) ? R(-1) : R(1);
                     int zc = 0;
                     for (int q = 0; q < len; ++q) {
-                        const R t = Trans<R>::th(RT::mul(vr[q], R(0.5)));
+                        const R t = vr[q];
                         if (t == R(0)) ++zc;
                         else prod = RT::mul(prod, t);
                     }
@@ -681,10 +681,11 @@ __global__ void __launch_bounds__(kSerialThreads) bp_kernel_serial(const WinDev 
         for (int r = tid; r < npad; r += NT) {                  // every message starts at its column's prior
             const uint4 rec = __ldg(w.colrec + r);
             const R l0 = ptab[(rec.w >> 16) & 0xFFFu];
+            const R m0 = PS ? Trans<R>::th(RT::mul(l0, R(0.5))) : l0;        // product-sum keeps tanh(v/2) in the message array
             const uint32_t e[6] = {rec.x & 0xFFFFu, rec.x >> 16, rec.y & 0xFFFFu, rec.y >> 16, rec.z & 0xFFFFu, rec.z >> 16};
 #pragma unroll
             for (int q = 0; q < 6; ++q)
-                if (e[q] < static_cast<uint32_t>(rows * RS)) V[e[q]] = l0;
+                if (e[q] < static_cast<uint32_t>(rows * RS)) V[e[q]] = m0;
         }
         __syncthreads();
         bool conv = false;
@@ -717,7 +718,7 @@ __global__ void __launch_bounds__(kSerialThreads) bp_kernel_serial(const WinDev 
                         if (k == own) continue;
                         const R v = V[base + k];
                         if (PS) {
-                            acc = RT::mul(acc, Trans<R>::th(RT::mul(v, R(0.5))));
+                            acc = RT::mul(acc, v);
                         } else {
                             const R a = CT::mag(v);
                             acc = a < acc ? a : acc;
@@ -763,7 +764,7 @@ __global__ void __launch_bounds__(kSerialThreads) bp_kernel_serial(const WinDev 
 #pragma unroll
                     for (int q = 5; q >= 0; --q) if (q < wt) { vn[q] = RT::add(vn[q], t); t = RT::add(t, c[q]); }
 #pragma unroll
-                    for (int q = 0; q < 6; ++q) if (q < wt) V[pa[q] & 0xFFFFu] = vn[q];
+                    for (int q = 0; q < 6; ++q) if (q < wt) V[pa[q] & 0xFFFFu] = PS ? Trans<R>::th(RT::mul(vn[q], R(0.5))) : vn[q];
                     if (llr <= R(0)) {
                         atomicOr(&ebits[j >> 5], 1u << (j & 31));
 #pragma unroll
