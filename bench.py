@@ -296,8 +296,30 @@ def main():
         te = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        # same loop through the packed entry points of the C ABI (qb_sample_packed -> qb_sw_decode_packed): host buffers again, but
+        # one bit per detector instead of one byte, and the comparison on packed words
+        dec_p = dec32 if dec32 is not None else qb.SlidingWindowDecoder(circuit, hz.shape[0], W, F, ctx=ctx, **BP_KW)
+
+        def e2e_packed_step(i):
+            detp, obsp = circuit.sample(Se, SEED + 2000 + i * world + rank, packed=True)
+            predp = dec_p.decode_packed(detp)
+            return int(np.count_nonzero((predp ^ obsp).any(axis=1)))
+        e2e_packed_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            e2e_packed_step(1 + i)
+        barrier()
+        tp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
         if rank == 0:
             D, K = circuit.num_detectors, circuit.num_observables
+            DW, KW = (D + 63) // 64, (K + 63) // 64
+            line["e2e_packed"] = {"value": Se * n_e2e * world / float(tp.item()), "unit": "shots/s", "h2d_bytes_per_step": Se * DW * 8,
+                                  "d2h_bytes_per_step": Se * (DW + KW) * 8 + Se * KW * 8,
+                                  "path": "Circuit.sample(packed=True) -> SlidingWindowDecoder.decode_packed (qb_sample_packed / qb_sw_decode_packed, "
+                                          "u64 bit rows in host memory)"}
             line["e2e"] = {"value": Se * n_e2e * world / float(te.item()), "unit": "shots/s", "h2d_bytes_per_step": Se * D,
                            "d2h_bytes_per_step": Se * (D + K) + Se * K * 8, "shots_per_step_per_gpu": Se, "steps": n_e2e,
                            "path": "get_stim_mem_result -> sliding_window_bposd_circuit_mem (numpy host buffers, host wall clock)"}

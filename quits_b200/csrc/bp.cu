@@ -425,7 +425,8 @@ __device__ __forceinline__ R column_update(const uint4 rec, const R l0, const R 
 // ---- product-sum (ldpc bp_method 'product_sum'): check->bit message = 2 atanh( prod_{others} tanh(v/2) ), sign from the syndrome.
 // The message array holds tanh(v/2) instead of v (one tanh per edge and iteration, taken when the message is written).
 // The row summary is (s * prod of the non-zero tanh(v/2), number of zero factors); "the others" is obtained by dividing the
-// row product by the edge's own factor, which differs from ldpc's prefix/suffix products by rounding only (no bit parity with
+// row product by the edge's own factor, which differs from ldpc's prefix/suffix products by rounding only (x is formed
+// explicitly, as ldpc does, so that saturation -- x rounding to exactly 1, message +inf -- happens at the same places) (no bit parity with
 // the CPU here anyway: libm and CUDA tanh/log differ in the last ulps).
 template <typename R> struct Trans;
 template <> struct Trans<float> {
