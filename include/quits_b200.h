@@ -108,7 +108,7 @@ typedef struct {
     int32_t schedule;           /* 0 'parallel' (flooding) | 1 'serial' (columns in index order, no random reshuffle) */
     int32_t max_iter;           /* 0 => number of columns (ldpc convention) */
     double ms_scaling_factor;   /* 0.0 => 1 - 2^-iteration */
-    int32_t osd_method;         /* 0 'osd_0' | 1 'osd_e' | 2 'osd_cs' | -1 no post-processing */
+    int32_t osd_method;         /* 0 'osd_0' | 1 'osd_e' | 2 'osd_cs' | 3 'lsd_0' (BpLsdDecoder, order 0) | -1 no post-processing */
     int32_t osd_order;          /* 0 = OSD-0 whatever the method; osd_e: <= 12, osd_cs: <= 32 */
     int32_t precision;          /* 64 (default when 0): messages in fp64 as ldpc computes; 32: fp32 messages */
     int32_t capacity;           /* shots per device batch; 0 => default */

@@ -260,7 +260,7 @@ typedef struct {
     double alpha;                     /* ms_scaling_factor; 0 => 1 - 2^-it */
     int precision;                    /* 64 or 32 */
     int osd;                          /* 1: OSD when BP fails; 0: return BP output */
-    int osd_method;                   /* 0 osd_0 | 1 osd_e (exhaustive) | 2 osd_cs (combination sweep) */
+    int osd_method;                   /* 0 osd_0 | 1 osd_e (exhaustive) | 2 osd_cs (combination sweep) | 3 lsd_0 */
     int osd_order;
 } qo_bp;
 
@@ -294,7 +294,7 @@ qo_bp* qo_bp_create(int m, int n, const int64_t* indptr /*csc n+1*/, const int32
     return d;
 }
 
-/* osd_method: 0 osd_0 | 1 osd_e | 2 osd_cs; order 0 is OSD-0 whatever the method */
+/* osd_method: 0 osd_0 | 1 osd_e | 2 osd_cs (order 0 is OSD-0 whatever the method) | 3 lsd_0 (LSD post-processing, order 0) */
 void qo_bp_set_osd(qo_bp* d, int osd_method, int osd_order)
 {
     d->osd_method = osd_method;
@@ -427,6 +427,180 @@ static void osd_decode(const qo_bp* d, const uint8_t* syn, const double* llr, ui
     free(order); free(tmp); free(A); free(pivcol); free(swp); free(ispiv);
 }
 
+/* ============================================================================================
+ * LSD-0 (ldpc v2 BpLsdDecoder, lsd_order = 0, bits_per_step = 1, on-the-fly elimination).  Restated from the published
+ * algorithm (Hillmann, Berent, Quintavalle, Eisert, Wille, Roffe: "Localized statistics decoding", 2024, and ldpc's
+ * lsd.hpp as far as remembered; ldpc is not vendored -- parity unpinned, like the rest of this section):
+ *   - one cluster per unsatisfied check (ascending check index = cluster id): checks {i}, boundary {i}, no bits
+ *   - while some active cluster is invalid: every cluster that was active and invalid at the start of the round, in
+ *     ascending (number of bits, id) order, grows by ONE bit if it is still active: among the bits adjacent to its boundary checks
+ *     and not in the cluster, the one with the smallest BP posterior LLR (ties: smallest index; ldpc's tie order comes from
+ *     std::sort over a hash-set walk and is unspecified).  Boundary checks without such a bit leave the boundary.
+ *     The bit's column joins the cluster with its checks; a check that belongs to another cluster makes the two collide:
+ *     they merge (in the order the collisions were met), the one with fewer bits into the other (ties: into the growing side),
+ *     its bits appended to the survivor's column list in their own order, its elimination discarded.
+ *   - the survivor's new columns are row-reduced "on the fly" after the columns it had already reduced; the cluster is valid
+ *     when its syndrome lies in the span of its columns
+ *   - solution of a cluster: the unique one supported on its pivot columns = the first linearly independent columns of its
+ *     column list (so the pivot-row rule is immaterial); bits outside every cluster are 0
+ * A cluster that is invalid and has no bit left to add (syndrome outside the image of H) stops growing and contributes the
+ * pivot part of its reduced syndrome.
+ * ============================================================================================ */
+typedef struct {
+    int active, valid, stuck;
+    int nbits, capbits; int* cols;
+    int nelim;
+    int nchecks, capchecks; int* checks;
+    int nops, capops; int* oprow; int* opcol; uint64_t* opvec;
+} lsd_cl;
+
+static void lsd_push(int** a, int* n, int* cap, int v)
+{
+    if (*n == *cap) { *cap = *cap ? 2 * *cap : 8; *a = (int*)realloc(*a, (size_t)*cap * sizeof(int)); }
+    (*a)[(*n)++] = v;
+}
+
+static void lsd_decode(const qo_bp* d, const uint8_t* syn, const double* llr, uint8_t* ehat)
+{
+    const int m = d->m, n = d->n, nw = (m + 63) / 64;
+    memset(ehat, 0, (size_t)n);
+    int nc = 0;
+    for (int i = 0; i < m; ++i) nc += syn[i] & 1;
+    if (nc == 0) return;
+    lsd_cl* cl = (lsd_cl*)calloc((size_t)nc, sizeof(lsd_cl));
+    int* bit_owner = (int*)malloc((size_t)n * sizeof(int));
+    int* check_owner = (int*)malloc((size_t)m * sizeof(int));
+    uint8_t* isb = (uint8_t*)calloc((size_t)m, 1);
+    uint8_t* ispiv = (uint8_t*)calloc((size_t)m, 1);
+    uint64_t* v = (uint64_t*)malloc((size_t)nw * 8);
+    uint64_t* z = (uint64_t*)malloc((size_t)nw * 8);
+    int* inv = (int*)malloc((size_t)nc * sizeof(int));
+    int* mlist = (int*)malloc((size_t)nc * sizeof(int));
+    for (int j = 0; j < n; ++j) bit_owner[j] = -1;
+    for (int i = 0; i < m; ++i) check_owner[i] = -1;
+    for (int i = 0, c = 0; i < m; ++i)
+        if (syn[i] & 1) {
+            cl[c].active = 1;
+            lsd_push(&cl[c].checks, &cl[c].nchecks, &cl[c].capchecks, i);
+            check_owner[i] = c; isb[i] = 1;
+            ++c;
+        }
+    int ninv = nc;
+    for (int c = 0; c < nc; ++c) inv[c] = c;
+    #define LSD_REDUCED_SYNDROME(C)                                                                   \
+        do {                                                                                          \
+            memset(z, 0, (size_t)nw * 8);                                                             \
+            for (int q_ = 0; q_ < (C)->nchecks; ++q_) {                                               \
+                int r_ = (C)->checks[q_];                                                             \
+                if (syn[r_] & 1) z[r_ >> 6] |= 1ull << (r_ & 63);                                     \
+            }                                                                                         \
+            for (int o_ = 0; o_ < (C)->nops; ++o_) {                                                  \
+                int p_ = (C)->oprow[o_];                                                              \
+                if ((z[p_ >> 6] >> (p_ & 63)) & 1ull)                                                 \
+                    for (int q_ = 0; q_ < nw; ++q_) z[q_] ^= (C)->opvec[(size_t)o_ * nw + q_];        \
+            }                                                                                         \
+        } while (0)
+    while (ninv > 0) {
+        for (int t = 0; t < ninv; ++t) {
+            lsd_cl* c = &cl[inv[t]];
+            const int cid = inv[t];
+            if (!c->active) continue;
+            /* growth candidates */
+            int best = -1;
+            for (int q = 0; q < c->nchecks; ++q) {
+                int r = c->checks[q];
+                if (!isb[r]) continue;
+                int any = 0;
+                for (int e = d->rowptr[r]; e < d->rowptr[r + 1]; ++e) {
+                    int j = d->colidx[e];
+                    if (bit_owner[j] == cid) continue;
+                    any = 1;
+                    if (best < 0 || llr[j] < llr[best] || (llr[j] == llr[best] && j < best)) best = j;
+                }
+                if (!any) isb[r] = 0;
+            }
+            if (best < 0) { if (!c->valid) { c->valid = 1; c->stuck = 1; } continue; }
+            /* the bit joins the cluster; collisions are noted */
+            int nm = 0;
+            bit_owner[best] = cid;
+            lsd_push(&c->cols, &c->nbits, &c->capbits, best);
+            for (int q = d->colptr[best]; q < d->colptr[best + 1]; ++q) {
+                int r = d->colrow[q], o = check_owner[r];
+                if (o == cid) continue;
+                if (o < 0) { check_owner[r] = cid; isb[r] = 1; lsd_push(&c->checks, &c->nchecks, &c->capchecks, r); continue; }
+                int seen = 0;
+                for (int k = 0; k < nm; ++k) seen |= mlist[k] == o;
+                if (!seen) mlist[nm++] = o;
+            }
+            int big = cid;
+            for (int k = 0; k < nm; ++k) {
+                int a = big, b2 = mlist[k];
+                int small;
+                if (cl[a].nbits < cl[b2].nbits) { small = a; big = b2; } else { small = b2; big = a; }
+                lsd_cl* S = &cl[small]; lsd_cl* B = &cl[big];
+                for (int q = 0; q < S->nbits; ++q) { bit_owner[S->cols[q]] = big; lsd_push(&B->cols, &B->nbits, &B->capbits, S->cols[q]); }
+                for (int q = 0; q < S->nchecks; ++q) { check_owner[S->checks[q]] = big; lsd_push(&B->checks, &B->nchecks, &B->capchecks, S->checks[q]); }
+                for (int o = 0; o < S->nops; ++o) ispiv[S->oprow[o]] = 0;
+                S->nops = 0; S->active = 0;
+            }
+            /* on-the-fly elimination of the survivor's new columns */
+            lsd_cl* B = &cl[big];
+            for (int k = B->nelim; k < B->nbits; ++k) {
+                int j = B->cols[k];
+                memset(v, 0, (size_t)nw * 8);
+                for (int q = d->colptr[j]; q < d->colptr[j + 1]; ++q) v[d->colrow[q] >> 6] |= 1ull << (d->colrow[q] & 63);
+                for (int o = 0; o < B->nops; ++o) {
+                    int p = B->oprow[o];
+                    if ((v[p >> 6] >> (p & 63)) & 1ull)
+                        for (int q = 0; q < nw; ++q) v[q] ^= B->opvec[(size_t)o * nw + q];
+                }
+                int p = -1;
+                for (int r = 0; r < m && p < 0; ++r) if (((v[r >> 6] >> (r & 63)) & 1ull) && !ispiv[r]) p = r;
+                if (p < 0) continue;
+                if (B->nops == B->capops) {
+                    B->capops = B->capops ? 2 * B->capops : 8;
+                    B->oprow = (int*)realloc(B->oprow, (size_t)B->capops * sizeof(int));
+                    B->opcol = (int*)realloc(B->opcol, (size_t)B->capops * sizeof(int));
+                    B->opvec = (uint64_t*)realloc(B->opvec, (size_t)B->capops * nw * 8);
+                }
+                v[p >> 6] &= ~(1ull << (p & 63));                 /* the row operation leaves the pivot row itself alone */
+                memcpy(&B->opvec[(size_t)B->nops * nw], v, (size_t)nw * 8);
+                B->oprow[B->nops] = p; B->opcol[B->nops] = j; B->nops++;
+                ispiv[p] = 1;
+            }
+            B->nelim = B->nbits;
+            LSD_REDUCED_SYNDROME(B);
+            int ok = 1;
+            for (int q = 0; q < B->nchecks && ok; ++q) {
+                int r = B->checks[q];
+                if (((z[r >> 6] >> (r & 63)) & 1ull) && !ispiv[r]) ok = 0;
+            }
+            B->valid = ok; B->stuck = 0;
+        }
+        /* next round: active and invalid clusters, smallest first (stable) */
+        ninv = 0;
+        for (int c = 0; c < nc; ++c) if (cl[c].active && !cl[c].valid) inv[ninv++] = c;
+        for (int a = 1; a < ninv; ++a) {
+            int x = inv[a], b2 = a - 1;
+            while (b2 >= 0 && cl[inv[b2]].nbits > cl[x].nbits) { inv[b2 + 1] = inv[b2]; --b2; }
+            inv[b2 + 1] = x;
+        }
+    }
+    for (int c = 0; c < nc; ++c) {
+        lsd_cl* B = &cl[c];
+        if (B->active) {
+            LSD_REDUCED_SYNDROME(B);
+            for (int o = 0; o < B->nops; ++o) {
+                int p = B->oprow[o];
+                if ((z[p >> 6] >> (p & 63)) & 1ull) ehat[B->opcol[o]] = 1;
+            }
+        }
+        free(B->cols); free(B->checks); free(B->oprow); free(B->opcol); free(B->opvec);
+    }
+    #undef LSD_REDUCED_SYNDROME
+    free(cl); free(bit_owner); free(check_owner); free(isb); free(ispiv); free(v); free(z); free(inv); free(mlist);
+}
+
 /* decode one syndrome.  Returns 1 if BP converged.  llr_out (n doubles) = BP posteriors; iters_out = iterations run;
  * used_osd_out = 1 if the returned ehat came from OSD. */
 int qo_bp_decode(const qo_bp* d, const uint8_t* syn, uint8_t* ehat, double* llr_out, int* iters_out, int* used_osd_out)
@@ -436,7 +610,7 @@ int qo_bp_decode(const qo_bp* d, const uint8_t* syn, uint8_t* ehat, double* llr_
     if (d->precision == 32) conv = bp_run_f32(d, syn, ehat, llr, iters_out);
     else conv = bp_run_f64(d, syn, ehat, llr, iters_out);
     int used = 0;
-    if (!conv && d->osd) { osd_decode(d, syn, llr, ehat); used = 1; }
+    if (!conv && d->osd) { if (d->osd_method == 3) lsd_decode(d, syn, llr, ehat); else osd_decode(d, syn, llr, ehat); used = 1; }
     if (used_osd_out) *used_osd_out = used;
     if (!llr_out) free(llr);
     return conv;

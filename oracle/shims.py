@@ -203,10 +203,14 @@ class _OracleBpDecoderBase:
         else:
             raise ValueError("error_rate / error_channel / channel_probs required")
         order = int(kw.get(self._order_key, 0))
-        method = str(kw.get(self._method_key, "osd_0")).lower().replace("_", "")
-        if order != 0 and method.startswith("lsd") and method != "lsd0":
-            raise NotImplementedError("oracle implements order-0 LSD post-processing only (got %s order %d)" % (method, order))
-        osd_method = {"osd0": "osd_0", "osde": "osd_e", "exhaustive": "osd_e", "osdcs": "osd_cs", "combinationsweep": "osd_cs"}.get(method, "osd_0")
+        method = str(kw.get(self._method_key, getattr(self, "_default_method", "osd_0"))).lower().replace("_", "")
+        if method.startswith("lsd"):
+            # ldpc's lsd_method only matters for lsd_order > 0 (the order-0 solve is the same for lsd_0 / lsd_cs / lsd_e)
+            if order != 0 and method != "lsd0":
+                raise NotImplementedError("oracle implements order-0 LSD post-processing only (got %s order %d)" % (method, order))
+            osd_method, order = "lsd_0", 0
+        else:
+            osd_method = {"osd0": "osd_0", "osde": "osd_e", "exhaustive": "osd_e", "osdcs": "osd_cs", "combinationsweep": "osd_cs"}.get(method, "osd_0")
         self._dec = cref.BpOsd(pcm, priors, max_iter=max_iter if max_iter > 0 else n, bp_method=bp_method,
                                ms_scaling_factor=ms_scaling_factor, schedule=schedule,
                                precision=kw.get("precision", DEFAULT_PRECISION), osd_method=osd_method, osd_order=order)
@@ -227,6 +231,7 @@ class BpOsdDecoder(_OracleBpDecoderBase):
 class BpLsdDecoder(_OracleBpDecoderBase):
     _order_key = "lsd_order"
     _method_key = "lsd_method"
+    _default_method = "lsd_0"
 
 
 def install(force=False):

@@ -136,11 +136,11 @@ namespace {
 struct WinOwned {
     qb::WinDev dev{};
     DevBuf ser_steps, ser_pairs, ser_cols;
-    DevBuf colE, llr0f, llr0d, osd_wt, lmask, uptr, uidx, cptr, crow, colrec, ptabf, ptabd, rlen, rsum0f, rsum0d, neg0;
+    DevBuf colE, llr0f, llr0d, osd_wt, lmask, uptr, uidx, cptr, crow, rptr, rcol, colrec, ptabf, ptabd, rlen, rsum0f, rsum0d, neg0;
     size_t bp_smem = 0;
     bool vglobal = false;
     int bp_grid = 0;            // persistent grid of the VGLOBAL variant (0: one CTA per shot)
-    int sort_grid = 0, elim_grid = 0, fast_grid = 0;
+    int sort_grid = 0, elim_grid = 0, fast_grid = 0, lsd_grid = 0;
 };
 
 }  // namespace
@@ -151,6 +151,7 @@ struct qb_sw {
     qb_bp_opts opts{};
     bool single = false;
     bool use_osd = true;
+    bool use_lsd = false;         // BpLsdDecoder post-processing (lsd_0) instead of OSD
     bool serial = false;          // ldpc schedule='serial'
     bool osd_hi = false;          // osd_e / osd_cs with order > 0: full elimination + candidate sweeps
     int max_iter = 0;
@@ -162,7 +163,10 @@ struct qb_sw {
     int lanes = 1, lanes_used = 1;    // concurrent sub-batches per batch (decode_batch)
     int DW = 0, KW = 0, carryW = 0, synW = 0;
     size_t llr_stride = 0;
-    DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, ovf_list, order, sel_key, sel_idx, sel_cnt, counters, stats, pred, ehat, iters, conv, vscratch;
+    DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, ovf_list, order, sel_key, sel_idx, sel_cnt, counters, stats, pred, ehat, iters, conv, vscratch, lsd_scratch;
+    size_t lsd_slab = 0;
+    int lsd_cols = 0;
+    int lsd_grid = 0, lsd_slabs_per_lane = 0;
     EventTimer t_bp, t_osd;
 };
 
@@ -426,6 +430,18 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
     upload(wo.uidx, uidx, ctx->stream, 2);
     upload(wo.cptr, cptr, ctx->stream, 2);
     upload(wo.crow, crow, ctx->stream, 2);
+    {
+        // CSR view of the window (ascending columns inside a row): the growth-candidate scan of the LSD kernel
+        std::vector<int32_t> rptr(static_cast<size_t>(rows) + 1, 0);
+        for (int32_t r : hw.crow) rptr[static_cast<size_t>(r) + 1]++;
+        for (int r = 0; r < rows; ++r) rptr[r + 1] += rptr[r];
+        std::vector<uint16_t> rcol(hw.crow.size());
+        std::vector<int32_t> fill(rptr.begin(), rptr.end() - 1);
+        for (int j = 0; j < ncols; ++j)
+            for (int64_t e = hw.cptr[j]; e < hw.cptr[j + 1]; ++e) rcol[static_cast<size_t>(fill[hw.crow[e]]++)] = static_cast<uint16_t>(j);
+        upload(wo.rptr, rptr, ctx->stream, 2);
+        upload(wo.rcol, rcol, ctx->stream, 2);
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     d.rows = rows; d.ncols = ncols; d.ncols_pad = npad; d.RS = rs; d.cw = cw_alloc; d.ncommit = hw.ncommit;
     d.row0 = hw.row0; d.carry_rows = hw.urows; d.KW = KW;
@@ -439,6 +455,7 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
     d.osd_wt = wo.osd_wt.as<double>();
     d.colE = wo.colE.as<uint32_t>(); d.llr0f = wo.llr0f.as<float>(); d.llr0d = wo.llr0d.as<double>(); d.lmask = wo.lmask.as<uint64_t>();
     d.uptr = wo.uptr.as<int32_t>(); d.uidx = wo.uidx.as<uint16_t>(); d.cptr = wo.cptr.as<int32_t>(); d.crow = wo.crow.as<uint16_t>();
+    d.rptr = wo.rptr.as<int32_t>(); d.rcol = wo.rcol.as<uint16_t>();
 }
 
 static bool rows_fit_serial(const qb::WinDev& d, int prec) { return qb::bp_serial_smem_bytes(d, prec) <= 227 * 1024; }
@@ -457,7 +474,11 @@ void finish_decoder(qb_sw* sw) {
     if (o.precision != 0 && o.precision != 32 && o.precision != 64) throw qb::value_error("precision must be 32 or 64");
     sw->precision = o.precision == 32 ? 32 : 64;
     const int prec = sw->precision;
-    sw->use_osd = o.osd_method >= 0;
+    if (o.osd_method > 3) throw qb::value_error("osd_method must be -1 (off), 0 (osd_0), 1 (osd_e), 2 (osd_cs) or 3 (lsd_0)");
+    sw->use_osd = o.osd_method >= 0 && o.osd_method <= 2;
+    sw->use_lsd = o.osd_method == 3;
+    if (sw->use_lsd && o.osd_order != 0)
+        throw qb::unsupported_error("LSD post-processing beyond order 0 (lsd_order > 0) is not supported on the GPU path");
     int max_npad = 0, max_rowsW = 0, max_iter = 0;
     size_t max_slab = 0;
     for (auto& w : sw->wins) {
@@ -493,8 +514,24 @@ void finish_decoder(qb_sw* sw) {
             const int fast_per_sm = static_cast<int>((227 * 1024) / (qb::osd_fast_smem_bytes(w->dev) + 1024));
             w->fast_grid = 148 * std::max(1, std::min(fast_per_sm, 16));
         }
+        if (sw->use_lsd) {
+            if (!qb::lsd_supported(w->dev))
+                throw qb::unsupported_error("window of " + std::to_string(w->dev.rows) + " x " + std::to_string(w->dev.ncols) +
+                                            " exceeds what the LSD kernel handles (rows <= 1024, columns < 65535)");
+            CK(qb::lsd_configure(w->dev, prec));
+            const int per_sm = static_cast<int>((227 * 1024) / (qb::lsd_smem_bytes(w->dev) + 1024));
+            w->lsd_grid = 148 * std::max(1, std::min(per_sm, 16));
+        }
     }
     if (max_slab) sw->vscratch.ensure(max_slab * 148 * 2 + 16);
+    if (sw->use_lsd) {
+        // one slab per persistent warp: bit owners (0xFFFF = none between shots), column-order links, operation vectors
+        int max_rows = 0;
+        for (auto& w : sw->wins) max_rows = std::max(max_rows, w->dev.rows);
+        sw->lsd_cols = max_npad;
+        sw->lsd_slab = qb::lsd_slab_bytes(max_npad, max_rows);
+        for (auto& w : sw->wins) sw->lsd_grid = std::max(sw->lsd_grid, w->lsd_grid);
+    }
     if (o.max_iter == 0 && sw->wins.size() > 1) {
         // ldpc's "0 => number of columns" differs per window; the kernel takes one value
         for (auto& w : sw->wins)
@@ -506,7 +543,9 @@ void finish_decoder(qb_sw* sw) {
     upload(sw->alpha, alpha, ctx->stream);
     // batches start on 64-shot word boundaries (the sampler numbers shots by word): capacity is rounded down to a multiple of 64
     sw->cap = o.capacity > 0 ? std::max(64, o.capacity / 64 * 64) : 65536;
-    sw->lanes = o.lanes > 0 ? std::min(o.lanes, static_cast<int32_t>(qb_ctx::kMaxLanes)) : 1;
+    // LSD: a few shots grow clusters of hundreds of bits and keep one warp busy for milliseconds after the rest of the launch has
+    // drained; with sub-batches on side streams the BP kernel of another sub-batch fills the machine meanwhile
+    sw->lanes = o.lanes > 0 ? std::min(o.lanes, static_cast<int32_t>(qb_ctx::kMaxLanes)) : (sw->use_lsd ? static_cast<int>(qb_ctx::kMaxLanes) : 1);
     if (max_slab) sw->lanes = 1;                      // the global message slabs are indexed by CTA, not by sub-batch
     sw->DW = std::max(1, (sw->plan.D + 63) / 64);
     sw->KW = std::max(1, (sw->plan.K + 63) / 64);
@@ -528,6 +567,16 @@ void ensure_batch(qb_sw* sw, int n) {
         sw->sel_key.ensure(N * qb::kOsdSelCap * (sw->precision / 8) + 16);
         sw->sel_idx.ensure(N * qb::kOsdSelCap * 2 + 16);
         sw->sel_cnt.ensure(N * 4 + 16);
+    }
+    if (sw->use_lsd) {
+        // one slab per persistent warp and sub-batch lane: bit owners (0xFFFF = none between shots), column-order links, operation vectors
+        const int per_lane = std::min(sw->lsd_grid, n);
+        if (per_lane > sw->lsd_slabs_per_lane) {
+            const size_t bytes = sw->lsd_slab * static_cast<size_t>(per_lane) * qb_ctx::kMaxLanes + 16;
+            sw->lsd_scratch.ensure(bytes);
+            CK(cudaMemsetAsync(sw->lsd_scratch.p, 0xFF, bytes, sw->ctx->stream));
+            sw->lsd_slabs_per_lane = per_lane;
+        }
     }
     const size_t nw = sw->wins.size() * qb_ctx::kMaxLanes;
     sw->counters.ensure(nw * kCounterSlots * sizeof(int) + 16);
@@ -593,6 +642,9 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.ovf_list = sw->use_osd ? sw->ovf_list.as<int>() + s0 : nullptr;
             b.osd_method = sw->opts.osd_method;
             b.osd_order = sw->opts.osd_order;
+            b.lsd_scratch = sw->lsd_scratch.p ? static_cast<unsigned char*>(sw->lsd_scratch.p) + static_cast<size_t>(l) * sw->lsd_slab * sw->lsd_slabs_per_lane : nullptr;
+            b.lsd_slab = sw->lsd_slab;
+            b.lsd_cols = sw->lsd_cols;
             if (sw->use_osd && !sw->osd_hi) {
                 b.sel_key = static_cast<unsigned char*>(sw->sel_key.p) + s0 * qb::kOsdSelCap * esz;
                 b.sel_idx = sw->sel_idx.as<uint16_t>() + s0 * qb::kOsdSelCap;
@@ -609,6 +661,12 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             else CK(qb::launch_bp(w.dev, b, bp, sw->precision, w.vglobal, w.vglobal ? std::min(w.bp_grid, nl) : nl, ls));
             if (sw->opts.profile) sw->t_bp.end(ls);
             if (stats) stats->bp_launches++;
+            if (sw->use_lsd) {
+                if (sw->opts.profile) sw->t_osd.begin(ls);
+                CK(qb::launch_lsd(w.dev, b, sw->precision, std::min(w.lsd_grid, nl), ls));
+                if (sw->opts.profile) sw->t_osd.end(ls);
+                if (stats) stats->osd_launches += 1;
+            }
             if (sw->use_osd) {
                 if (sw->opts.profile) sw->t_osd.begin(ls);
                 if (sw->osd_hi) {

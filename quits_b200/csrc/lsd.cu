@@ -1,0 +1,490 @@
+// quits_b200/csrc/lsd.cu -- K4L: localized statistics decoding, order 0: the post-processing stage of ldpc's BpLsdDecoder
+// (reference src/quits/decoder/bplsd.py:38-50,74-86 constructs it; sliding_window.py:171,182 calls decode()).  sm_100a.
+//
+// The algorithm is the one oracle/cref.c lsd_decode restates (Hillmann et al., "Localized statistics decoding"):
+// one cluster per unsatisfied check; every invalid cluster, smallest first, grows by the least reliable bit (smallest BP
+// posterior, ties by index) next to its boundary checks; clusters that meet on a check merge, the one with fewer bits into the
+// other; a cluster is valid once its syndrome lies in the span of its columns (on-the-fly elimination: the survivor of a merge
+// keeps its reduction, the columns of the absorbed cluster are reduced again behind it); the answer of a cluster is the
+// solution supported on the first independent columns of its column list.
+//
+// Mapping: ONE WARP per failed shot (persistent grid pulling shot indices from the list the BP kernel wrote), because the
+// algorithm is a serial walk over small data-dependent structures; the lanes share the work inside a step:
+//   * GF(2) vectors over the window's checks (<= 1024) are one 32-bit word per lane: the reduced syndrome z, the pivot-row
+//     mask P, the boundary mask B live in registers; clusters are disjoint in their checks, so ONE z / P / B serves all of them
+//   * the row operations of all clusters sit in one array in creation order (pivot row in shared memory, 128-byte vector in
+//     an L2-resident scratch slab); reducing a new column tests 32 operations per step (one per lane) and applies the hits in
+//     order -- an operation of another cluster can never hit, its pivot row is not a check of this cluster.  The operations of
+//     an absorbed cluster are marked dead; the array is compacted when it fills up
+//   * cluster membership: u16 owner per check (shared memory) and per bit (scratch slab), singly linked lists for the checks
+//     and the bits (= column order) of a cluster, so that a merge is a relabelling walk over the smaller side plus a splice
+//   * the growth candidates of a cluster are found by the lanes striding over the CSR rows of its boundary checks
+// Integer/bit work plus comparisons of posteriors the BP kernel left in HBM: results are bit-exact with the oracle.
+#include <cstdint>
+
+#include "qb_device.h"
+
+namespace qb {
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr uint32_t kNone = 0xFFFFu;
+constexpr uint32_t kDead = 0xFFFFu;
+constexpr uint32_t kDirty = 0xFFFEu;      // row cache: best candidate not computed / no longer free
+constexpr uint32_t kActive = 1u, kValid = 2u;
+
+__host__ __device__ inline size_t al16(size_t x) { return (x + 15) / 16 * 16; }
+
+struct LsdLayout {
+    size_t v, rbkey, rbcol, dlist, cown, cnext, chead, ctail, bhead, btail, bue, nbits, flag, inv, inv2, oppiv, opcol, ml, accs, car, total;
+    int opcap;
+};
+
+__host__ __device__ inline int lsd_opcap(const int rows) { return (rows + 31) / 32 * 32 + 32; }
+
+__host__ __device__ inline LsdLayout lsd_layout(const WinDev& w) {
+    LsdLayout L;
+    const size_t m = static_cast<size_t>(w.rows);
+    L.opcap = lsd_opcap(w.rows);
+    size_t o = 0;
+    L.v = o; o += 128;
+    L.rbkey = o; o += al16(m * 8);
+    L.rbcol = o; o += al16(m * 2);
+    L.dlist = o; o += al16(m * 2);
+    L.cown = o; o += al16(m * 2);
+    L.cnext = o; o += al16(m * 2);
+    L.chead = o; o += al16(m * 2);
+    L.ctail = o; o += al16(m * 2);
+    L.bhead = o; o += al16(m * 2);
+    L.btail = o; o += al16(m * 2);
+    L.bue = o; o += al16(m * 2);
+    L.nbits = o; o += al16(m * 2);
+    L.flag = o; o += al16(m);
+    L.inv = o; o += al16(m * 2);
+    L.inv2 = o; o += al16(m * 2);
+    L.oppiv = o; o += al16(static_cast<size_t>(L.opcap) * 2);
+    L.opcol = o; o += al16(static_cast<size_t>(L.opcap) * 2);
+    L.ml = o; o += 64;
+    L.accs = o; o += al16(static_cast<size_t>(2 * w.KW) * 4);
+    L.car = o; o += al16(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4);
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ uint64_t lsd_key(float f) {
+    const uint32_t u = __float_as_uint(f + 0.0f);
+    return (u & 0x80000000u) ? static_cast<uint32_t>(~u) : (u | 0x80000000u);
+}
+__device__ __forceinline__ uint64_t lsd_key(double f) {
+    const uint64_t u = static_cast<uint64_t>(__double_as_longlong(f + 0.0));
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+template <typename R>
+__global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev b) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const LsdLayout L = lsd_layout(w);
+    uint32_t* vsm = reinterpret_cast<uint32_t*>(sm + L.v);
+    uint64_t* rbkey = reinterpret_cast<uint64_t*>(sm + L.rbkey);
+    uint16_t* rbcol = reinterpret_cast<uint16_t*>(sm + L.rbcol);
+    uint16_t* dlist = reinterpret_cast<uint16_t*>(sm + L.dlist);
+    uint16_t* cown = reinterpret_cast<uint16_t*>(sm + L.cown);
+    uint16_t* cnext = reinterpret_cast<uint16_t*>(sm + L.cnext);
+    uint16_t* chead = reinterpret_cast<uint16_t*>(sm + L.chead);
+    uint16_t* ctail = reinterpret_cast<uint16_t*>(sm + L.ctail);
+    uint16_t* bhead = reinterpret_cast<uint16_t*>(sm + L.bhead);
+    uint16_t* btail = reinterpret_cast<uint16_t*>(sm + L.btail);
+    uint16_t* bue = reinterpret_cast<uint16_t*>(sm + L.bue);
+    uint16_t* nbits = reinterpret_cast<uint16_t*>(sm + L.nbits);
+    uint8_t* flag = reinterpret_cast<uint8_t*>(sm + L.flag);
+    uint16_t* inv = reinterpret_cast<uint16_t*>(sm + L.inv);
+    uint16_t* inv2 = reinterpret_cast<uint16_t*>(sm + L.inv2);
+    uint16_t* oppiv = reinterpret_cast<uint16_t*>(sm + L.oppiv);
+    uint16_t* opcol = reinterpret_cast<uint16_t*>(sm + L.opcol);
+    uint16_t* ml = reinterpret_cast<uint16_t*>(sm + L.ml);
+    uint32_t* accs = reinterpret_cast<uint32_t*>(sm + L.accs);
+    uint32_t* car = reinterpret_cast<uint32_t*>(sm + L.car);
+    const int lane = threadIdx.x;
+    const int m = w.rows;
+    const int carryW = (w.carry_rows + 31) / 32;
+    const int opcap = L.opcap;
+    // per-CTA scratch slab: bit owner, bit successor (column order of a cluster), operation vectors
+    unsigned char* slab = static_cast<unsigned char*>(b.lsd_scratch) + static_cast<size_t>(blockIdx.x) * b.lsd_slab;
+    // (the owner array sits at the same place for every window of the decoder: b.lsd_cols = widest window)
+    uint16_t* bown = reinterpret_cast<uint16_t*>(slab);                                   // 0xFFFF between shots
+    uint16_t* bnext = bown + b.lsd_cols;
+    uint32_t* opvec = reinterpret_cast<uint32_t*>(slab + al16(static_cast<size_t>(b.lsd_cols) * 4));
+    const int count = *b.fail_count;
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = atomicAdd(b.osd_next, 1);
+        job = __shfl_sync(kFull, job, 0);
+        if (job >= count) break;
+        const int shot = b.fail_list[job];
+        const uint32_t* syn = b.syn_buf + static_cast<size_t>(shot) * b.syn_stride32;
+        const R* llr = reinterpret_cast<const R*>(b.llr_buf) + static_cast<size_t>(shot) * b.llr_stride;
+        __syncwarp();
+        // ---- initial clusters: one per unsatisfied check, ascending
+        const int left = m - 32 * lane;
+        const uint32_t Sw = (lane < w.rowsW32 ? syn[lane] : 0u) & (left >= 32 ? kFull : (left > 0 ? (1u << left) - 1u : 0u));   // raw syndrome word of this lane
+        uint32_t zw = Sw, Pw = 0u, Bw = Sw;
+        for (int i = lane; i < m; i += 32) { cown[i] = static_cast<uint16_t>(kNone); rbcol[i] = static_cast<uint16_t>(kDirty); }
+        for (int i = lane; i < 2 * w.KW; i += 32) accs[i] = 0;
+        for (int i = lane; i <= carryW; i += 32) car[i] = 0;
+        int nc;
+        {
+            const int mine = __popc(Sw);
+            int incl = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(kFull, incl, d);
+                if (lane >= d) incl += t;
+            }
+            nc = __shfl_sync(kFull, incl, 31);
+            __syncwarp();
+            int id = incl - mine;
+            for (uint32_t x = Sw; x; x &= x - 1, ++id) {
+                const int r = lane * 32 + __ffs(x) - 1;
+                cown[r] = static_cast<uint16_t>(id);
+                cnext[r] = static_cast<uint16_t>(kNone);
+                chead[id] = ctail[id] = static_cast<uint16_t>(r);
+                bhead[id] = btail[id] = bue[id] = static_cast<uint16_t>(kNone);
+                nbits[id] = 0;
+                flag[id] = static_cast<uint8_t>(kActive);
+                inv[id] = static_cast<uint16_t>(id);
+            }
+        }
+        __syncwarp();
+        int ninv = nc, nops = 0;
+        unsigned long long grown = 0;
+        auto bit_of = [&](const uint32_t word, const int r) -> uint32_t { return (__shfl_sync(kFull, word, r >> 5) >> (r & 31)) & 1u; };
+        while (ninv > 0) {
+            for (int t = 0; t < ninv; ++t) {
+                const int cid = inv[t];
+                if (!(flag[cid] & kActive)) continue;
+                // ---- growth candidates: the free bits next to the cluster's boundary checks.  (Every bit of a cluster has all its
+                // checks in the cluster, so a bit next to one of this cluster's checks is either in this cluster or in none.)  The best
+                // free bit of a row is cached; it stays the best until that very bit joins a cluster.
+                uint64_t bkey = ~0ull;
+                uint32_t bcol = kNone;
+                int nd = 0;
+                for (int i = 0; i < w.rowsW32; ++i) {
+                    const uint32_t bw = __shfl_sync(kFull, Bw, i);
+                    const int r = 32 * i + lane;
+                    const bool mine = ((bw >> lane) & 1u) && cown[r] == cid;
+                    const uint32_t c = mine ? rbcol[r] : kNone;
+                    const bool dirty = mine && c == kDirty;
+                    if (mine && !dirty) {
+                        const uint64_t k = rbkey[r];
+                        if (k < bkey || (k == bkey && c < bcol)) { bkey = k; bcol = c; }
+                    }
+                    const uint32_t dm = __ballot_sync(kFull, dirty);
+                    if (dirty) dlist[nd + __popc(dm & ((1u << lane) - 1u))] = static_cast<uint16_t>(r);
+                    nd += __popc(dm);
+                }
+                __syncwarp();
+                for (int d0 = 0; d0 < nd; d0 += 4) {                // rescan the rows without a cached candidate, four at a time
+                    uint32_t rr[4], cc[4][2];
+                    int e0[4], e1[4];
+                    uint64_t kk[4];
+                    uint32_t kc[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        rr[k] = d0 + k < nd ? dlist[d0 + k] : kNone;
+                        e0[k] = rr[k] != kNone ? __ldg(w.rptr + rr[k]) : 0;
+                        e1[k] = rr[k] != kNone ? __ldg(w.rptr + rr[k] + 1) : 0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) cc[k][q] = e0[k] + lane + 32 * q < e1[k] ? __ldg(w.rcol + e0[k] + lane + 32 * q) : kNone;
+                    uint32_t ow[4][2];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) ow[k][q] = cc[k][q] != kNone ? bown[cc[k][q]] : 0u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        kk[k] = ~0ull; kc[k] = kNone;
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            if (cc[k][q] != kNone && ow[k][q] == kNone) {
+                                const uint64_t key = lsd_key(llr[cc[k][q]]);
+                                if (key < kk[k] || (key == kk[k] && cc[k][q] < kc[k])) { kk[k] = key; kc[k] = cc[k][q]; }
+                            }
+                        }
+                        for (int e = e0[k] + lane + 64; e < e1[k]; e += 32) {          // rows longer than 64 entries
+                            const uint32_t c = __ldg(w.rcol + e);
+                            if (bown[c] != kNone) continue;
+                            const uint64_t key = lsd_key(llr[c]);
+                            if (key < kk[k] || (key == kk[k] && c < kc[k])) { kk[k] = key; kc[k] = c; }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) {
+                            const uint64_t ok = __shfl_xor_sync(kFull, kk[k], d);
+                            const uint32_t oc = __shfl_xor_sync(kFull, kc[k], d);
+                            if (ok < kk[k] || (ok == kk[k] && oc < kc[k])) { kk[k] = ok; kc[k] = oc; }
+                        }
+                        if (rr[k] == kNone) continue;
+                        if (lane == 0) { rbkey[rr[k]] = kk[k]; rbcol[rr[k]] = static_cast<uint16_t>(kc[k]); }
+                        if (kc[k] == kNone) {                        // no free bit left next to this check: it leaves the boundary
+                            if (lane == static_cast<int>(rr[k] >> 5)) Bw &= ~(1u << (rr[k] & 31));
+                        } else if (kk[k] < bkey || (kk[k] == bkey && kc[k] < bcol)) { bkey = kk[k]; bcol = kc[k]; }
+                    }
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const uint64_t ok = __shfl_xor_sync(kFull, bkey, d);
+                    const uint32_t oc = __shfl_xor_sync(kFull, bcol, d);
+                    if (ok < bkey || (ok == bkey && oc < bcol)) { bkey = ok; bcol = oc; }
+                }
+                if (bcol == kNone) {                               // nothing left to add: stop growing (syndrome outside the image)
+                    if (lane == 0) flag[cid] |= static_cast<uint8_t>(kValid);
+                    __syncwarp();
+                    continue;
+                }
+                ++grown;
+                // ---- the bit joins the cluster; its checks join too, checks of other clusters are collisions
+                const int best = static_cast<int>(bcol);
+                const int q0 = __ldg(w.cptr + best), wt = __ldg(w.cptr + best + 1) - q0;
+                int nm = 0;
+                if (lane == 0) {
+                    bown[best] = static_cast<uint16_t>(cid);
+                    bnext[best] = static_cast<uint16_t>(kNone);
+                    if (btail[cid] == kNone) bhead[cid] = static_cast<uint16_t>(best);
+                    else bnext[btail[cid]] = static_cast<uint16_t>(best);
+                    btail[cid] = static_cast<uint16_t>(best);
+                    if (bue[cid] == kNone) bue[cid] = static_cast<uint16_t>(best);
+                    nbits[cid] = static_cast<uint16_t>(nbits[cid] + 1);
+                }
+                __syncwarp();
+                for (int q = 0; q < wt; ++q) {
+                    const uint32_t r = __ldg(w.crow + q0 + q);
+                    const uint32_t o = cown[r];
+                    if (lane == 0 && rbcol[r] == static_cast<uint32_t>(best)) rbcol[r] = static_cast<uint16_t>(kDirty);
+                    if (o == static_cast<uint32_t>(cid)) continue;
+                    if (o == kNone) {
+                        if (lane == 0) {
+                            cown[r] = static_cast<uint16_t>(cid);
+                            cnext[r] = static_cast<uint16_t>(kNone);
+                            cnext[ctail[cid]] = static_cast<uint16_t>(r);
+                            ctail[cid] = static_cast<uint16_t>(r);
+                        }
+                        if (lane == static_cast<int>(r >> 5)) Bw |= 1u << (r & 31);
+                        __syncwarp();
+                        continue;
+                    }
+                    bool seen = false;
+                    for (int k = 0; k < nm; ++k) seen |= ml[k] == o;
+                    if (!seen) {
+                        if (lane == 0) ml[nm] = static_cast<uint16_t>(o);
+                        ++nm;
+                        __syncwarp();
+                    }
+                }
+                // ---- merges, in the order the collisions were met: fewer bits into more bits, ties into the growing side
+                int big = cid;
+                for (int k = 0; k < nm; ++k) {
+                    const int o = ml[k];
+                    int small;
+                    if (nbits[big] < nbits[o]) { small = big; big = o; } else { small = o; }
+                    // the absorbed cluster's reduction is discarded: its operations die, its checks go back to the raw syndrome
+                    if (nbits[small]) {
+                        for (int i = lane; i < nops; i += 32) {
+                            const uint32_t p = oppiv[i];
+                            if (p != kDead && cown[p] == small) oppiv[i] = static_cast<uint16_t>(kDead);
+                        }
+                    }
+                    __syncwarp();
+                    for (uint32_t r = chead[small]; r != kNone; r = cnext[r]) {
+                        if (lane == 0) cown[r] = static_cast<uint16_t>(big);
+                        if (lane == static_cast<int>(r >> 5)) {
+                            const uint32_t bit = 1u << (r & 31);
+                            zw = (zw & ~bit) | (Sw & bit);
+                            Pw &= ~bit;
+                        }
+                    }
+                    for (uint32_t j = bhead[small]; j != kNone; j = bnext[j])
+                        if (lane == 0) bown[j] = static_cast<uint16_t>(big);
+                    if (lane == 0) {
+                        cnext[ctail[big]] = chead[small];
+                        ctail[big] = ctail[small];
+                        if (bhead[small] != kNone) {
+                            if (btail[big] == kNone) bhead[big] = bhead[small];
+                            else bnext[btail[big]] = bhead[small];
+                            btail[big] = btail[small];
+                            if (bue[big] == kNone) bue[big] = bhead[small];
+                        }
+                        nbits[big] = static_cast<uint16_t>(nbits[big] + nbits[small]);
+                        flag[small] = 0;
+                    }
+                    __syncwarp();
+                }
+                // ---- on-the-fly elimination of the survivor's new columns, in column-list order
+                for (uint32_t j = bue[big]; j != kNone; j = bnext[j]) {
+                    uint32_t vw = 0u;
+                    {
+                        const int c0 = __ldg(w.cptr + j), c1 = __ldg(w.cptr + j + 1);
+                        for (int q = c0; q < c1; ++q) {
+                            const uint32_t r = __ldg(w.crow + q);
+                            if (lane == static_cast<int>(r >> 5)) vw |= 1u << (r & 31);
+                        }
+                    }
+                    for (int base = 0; base < nops; base += 32) {
+                        const uint32_t p = base + lane < nops ? oppiv[base + lane] : kDead;
+                        uint32_t todo = kFull;
+                        for (;;) {
+                            __syncwarp();
+                            vsm[lane] = vw;
+                            __syncwarp();
+                            const bool hit = p != kDead && ((vsm[p >> 5] >> (p & 31)) & 1u);
+                            const uint32_t mask = __ballot_sync(kFull, hit) & todo;
+                            if (!mask) break;
+                            const int i = __ffs(mask) - 1;
+                            vw ^= opvec[static_cast<size_t>(base + i) * 32 + lane];
+                            todo = i == 31 ? 0u : (kFull << (i + 1));
+                            if (!todo) break;
+                        }
+                    }
+                    // pivot row: first check of the reduced column that is not a pivot row yet
+                    const uint32_t freew = vw & ~Pw;
+                    const uint32_t fm = __ballot_sync(kFull, freew != 0u);
+                    if (!fm) continue;                               // dependent on the columns before it
+                    const int pl = __ffs(fm) - 1;
+                    const int p = pl * 32 + __ffs(__shfl_sync(kFull, freew, pl)) - 1;
+                    if (nops == opcap) {                             // drop the dead operations, keeping the order
+                        int wr = 0;
+                        for (int i = 0; i < nops; ++i) {
+                            const uint32_t pi = oppiv[i];
+                            if (pi == kDead) continue;
+                            if (wr != i) {
+                                const uint32_t x = opvec[static_cast<size_t>(i) * 32 + lane];
+                                const uint32_t ci = opcol[i];
+                                __syncwarp();
+                                opvec[static_cast<size_t>(wr) * 32 + lane] = x;
+                                if (lane == 0) { oppiv[wr] = static_cast<uint16_t>(pi); opcol[wr] = static_cast<uint16_t>(ci); }
+                                __syncwarp();
+                            }
+                            ++wr;
+                        }
+                        nops = wr;
+                    }
+                    if (lane == pl) { vw &= ~(1u << (p & 31)); Pw |= 1u << (p & 31); }     // the row operation leaves the pivot row alone
+                    opvec[static_cast<size_t>(nops) * 32 + lane] = vw;
+                    if (lane == 0) { oppiv[nops] = static_cast<uint16_t>(p); opcol[nops] = static_cast<uint16_t>(j); }
+                    ++nops;
+                    if (bit_of(zw, p)) zw ^= vw;
+                    __syncwarp();
+                }
+                // ---- valid when the reduced syndrome vanishes on the cluster's non-pivot checks
+                bool bad = false;
+                for (uint32_t x = zw & ~Pw; x; x &= x - 1) bad |= cown[lane * 32 + __ffs(x) - 1] == big;
+                const bool invalid = __any_sync(kFull, bad);
+                if (lane == 0) {
+                    bue[big] = static_cast<uint16_t>(kNone);
+                    flag[big] = static_cast<uint8_t>(kActive | (invalid ? 0u : kValid));
+                }
+                __syncwarp();
+            }
+            // ---- next round: the active invalid clusters, fewest bits first (stable in the cluster id)
+            int k = 0;
+            for (int base = 0; base < nc; base += 32) {
+                const int id = base + lane;
+                const bool in = id < nc && (flag[id] & (kActive | kValid)) == kActive;
+                const uint32_t mask = __ballot_sync(kFull, in);
+                if (in) inv2[k + __popc(mask & ((1u << lane) - 1u))] = static_cast<uint16_t>(id);
+                k += __popc(mask);
+            }
+            __syncwarp();
+            for (int a = lane; a < k; a += 32) {
+                const uint32_t ida = inv2[a], na = nbits[ida];
+                int rank = 0;
+                for (int c = 0; c < k; ++c) {
+                    const uint32_t idc = inv2[c], ncb = nbits[idc];
+                    rank += (ncb < na || (ncb == na && idc < ida)) ? 1 : 0;
+                }
+                inv[rank] = static_cast<uint16_t>(ida);
+            }
+            ninv = k;
+            __syncwarp();
+        }
+        // ---- solution: pivot column i is set iff the reduced syndrome has its pivot row; commit (acc ^= L e, carry = U e)
+        __syncwarp();
+        vsm[lane] = zw;
+        __syncwarp();
+        int alive = 0;
+        for (int i = lane; i < nops; i += 32) {
+            const uint32_t p = oppiv[i];
+            if (p == kDead) continue;
+            ++alive;
+            if (!((vsm[p >> 5] >> (p & 31)) & 1u)) continue;
+            const int j = opcol[i];
+            if (b.ehat_out) atomicOr(&b.ehat_out[static_cast<size_t>(shot) * b.ehat_stride32 + (j >> 5)], 1u << (j & 31));
+            if (j < w.ncommit) {
+                for (int wd = 0; wd < w.KW; ++wd) {
+                    const uint64_t lm = __ldg(w.lmask + static_cast<size_t>(j) * w.KW + wd);
+                    if (static_cast<uint32_t>(lm)) atomicXor(&accs[2 * wd], static_cast<uint32_t>(lm));
+                    if (static_cast<uint32_t>(lm >> 32)) atomicXor(&accs[2 * wd + 1], static_cast<uint32_t>(lm >> 32));
+                }
+                if (w.carry_rows) {
+                    for (int q = __ldg(w.uptr + j); q < __ldg(w.uptr + j + 1); ++q) {
+                        const uint32_t ur = __ldg(w.uidx + q);
+                        atomicXor(&car[ur >> 5], 1u << (ur & 31));
+                    }
+                }
+            }
+        }
+        // the bit owners go back to "none" for the next shot of this slab
+        for (int id = 0; id < nc; ++id) {
+            if (!(flag[id] & kActive)) continue;
+            for (uint32_t j = bhead[id]; j != kNone; j = bnext[j])
+                if (lane == 0) bown[j] = static_cast<uint16_t>(kNone);
+        }
+        __syncwarp();
+        for (int i = lane; i < w.KW; i += 32) {
+            const uint64_t v = (static_cast<uint64_t>(accs[2 * i + 1]) << 32) | accs[2 * i];
+            b.acc[static_cast<size_t>(shot) * w.KW + i] ^= v;
+        }
+        for (int i = lane; i < carryW; i += 32) b.carry[static_cast<size_t>(shot) * b.carry_stride32 + i] = car[i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) alive += __shfl_xor_sync(kFull, alive, d);
+        if (lane == 0) {
+            atomicAdd(&b.stats[2], 1ull);
+            atomicAdd(&b.stats[3], grown);
+            atomicAdd(&b.stats[4], static_cast<unsigned long long>(alive));
+            atomicMax(&b.stats[5], grown);
+        }
+    }
+}
+
+}  // namespace
+
+size_t lsd_smem_bytes(const WinDev& w) { return lsd_layout(w).total; }
+size_t lsd_slab_bytes(int cols_cap, int max_rows) { return al16(static_cast<size_t>(cols_cap) * 4) + static_cast<size_t>(lsd_opcap(max_rows)) * 128; }
+bool lsd_supported(const WinDev& w) { return w.rows <= 1024 && w.ncols < 65535 && lsd_smem_bytes(w) <= 200 * 1024; }
+
+cudaError_t lsd_configure(const WinDev& w, int precision) {
+    static size_t have_d[kMaxDevices][2] = {};
+    size_t& have = have_d[device_slot()][precision == 32 ? 0 : 1];
+    const size_t s = lsd_smem_bytes(w);
+    if (s > have) {
+        cudaError_t e = precision == 32 ? cudaFuncSetAttribute(lsd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s))
+                                        : cudaFuncSetAttribute(lsd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s));
+        if (e != cudaSuccess) return e;
+        have = s;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_lsd(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st) {
+    if (b.n_shots == 0) return cudaSuccess;
+    const size_t smem = lsd_smem_bytes(w);
+    if (precision == 32) lsd_kernel<float><<<grid, 32, smem, st>>>(w, b);
+    else lsd_kernel<double><<<grid, 32, smem, st>>>(w, b);
+    return cudaGetLastError();
+}
+
+}  // namespace qb

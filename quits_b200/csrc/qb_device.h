@@ -74,6 +74,8 @@ struct WinDev {
     const uint16_t* uidx;
     const int32_t* cptr;      // [ncols+1] plain CSC of the window (OSD gather)
     const uint16_t* crow;
+    const int32_t* rptr;      // [rows+1] CSR of the window, ascending columns (LSD growth candidates)
+    const uint16_t* rcol;
     // compact form (cw <= 6, rows*RS < 65535, <= 1024 distinct priors): one 16-byte record per column
     //   rec = 6 x u16 message address (row*RS + slot, 0xFFFF = none), u16 prior index, u16 unused
     int compact;
@@ -124,7 +126,10 @@ struct BatchDev {
     int32_t* iters_out;       // optional [n]
     uint8_t* conv_out;        // optional [n]
     int write_llr_always;
-    int osd_method, osd_order; // 0 osd_0 | 1 osd_e | 2 osd_cs; order 0 = OSD-0
+    int osd_method, osd_order; // 0 osd_0 | 1 osd_e | 2 osd_cs; order 0 = OSD-0 | 3 lsd_0
+    void* lsd_scratch;        // LSD only: [grid] slabs of lsd_slab bytes (bit owners, column-order links, operation vectors)
+    size_t lsd_slab;
+    int lsd_cols;             // columns of the widest window (fixes the slab layout)
 };
 
 struct BpParams {
@@ -152,6 +157,13 @@ cudaError_t osd_configure(const WinDev& w, int precision);
 cudaError_t launch_osd_fast(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
 cudaError_t launch_osd_sort(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
 cudaError_t launch_osd_elim(const WinDev& w, const BatchDev& b, bool hi, int grid, cudaStream_t st);
+
+// K4L (lsd.cu): localized statistics decoding, order 0, one warp per failed shot (persistent grid)
+size_t lsd_smem_bytes(const WinDev& w);
+size_t lsd_slab_bytes(int cols_cap, int max_rows);
+bool lsd_supported(const WinDev& w);
+cudaError_t lsd_configure(const WinDev& w, int precision);
+cudaError_t launch_lsd(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------- results
 // pred[n][K] int64 from acc bits; counts[0] += shots whose prediction differs from obs_rows in any observable,

@@ -79,15 +79,33 @@ class BpOsdDecoder(_GpuInnerDecoder):
     """ldpc.bposd_decoder.BpOsdDecoder-shaped (kwargs as in reference decoder/bposd.py:74-84)."""
 
 
+def lsd_engine_options(kw: dict) -> dict:
+    """ldpc BpLsdDecoder keywords -> engine keywords.  ``lsd_method`` only matters beyond order 0 (the order-0 solve of a
+    cluster is the same for lsd_0 / lsd_cs / lsd_e), and only order 0 runs on the GPU."""
+    kw = dict(kw)
+    method = str(kw.pop("lsd_method", "lsd_0")).lower()
+    order = int(kw.pop("lsd_order", 0))
+    kw.pop("bits_per_step", None)
+    if method in ("off", "none"):
+        kw["osd_method"] = "off"
+        return kw
+    if method.replace("_", "") not in ("lsd0", "lsdcs", "lsde"):
+        raise ValueError("unknown lsd_method %r" % method)
+    if order != 0 and method.replace("_", "") != "lsd0":
+        raise NotImplementedError("BP-LSD post-processing beyond order 0 (lsd_method=%r, lsd_order=%d) is not implemented on the "
+                                  "GPU path" % (method, order))
+    kw["osd_method"] = "lsd_0"
+    kw["osd_order"] = 0
+    return kw
+
+
 class BpLsdDecoder(_GpuInnerDecoder):
-    """ldpc.bplsd_decoder.BpLsdDecoder-shaped (kwargs as in reference decoder/bplsd.py:74-84).  LSD post-processing is
-    not implemented on the GPU yet: constructing one raises NotImplementedError unless post-processing is off."""
-    _order_key = "lsd_order"
-    _method_key = "lsd_method"
+    """ldpc.bplsd_decoder.BpLsdDecoder-shaped (kwargs as in reference decoder/bplsd.py:74-84): BP, then localized statistics
+    decoding of order 0 on the shots BP leaves unconverged (``csrc/lsd.cu``)."""
+    _order_key = "osd_order"
+    _method_key = "osd_method"
     _default_method = "lsd_0"
 
     def __init__(self, pcm, **kw):
-        method = str(kw.get("lsd_method", "lsd_0")).lower()
-        if method not in ("off", "none"):
-            raise NotImplementedError("BP-LSD post-processing (lsd_method=%r) is not implemented on the GPU path yet" % method)
-        super().__init__(pcm, **kw)
+        ctx = kw.pop("ctx", None)
+        super().__init__(pcm, ctx=ctx, **lsd_engine_options(kw))

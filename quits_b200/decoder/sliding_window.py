@@ -16,7 +16,7 @@ from scipy.sparse import csc_matrix, hstack as sp_hstack, identity, kron as sp_k
 from ..circuit import Circuit
 from ..engine import SlidingWindowDecoder
 from .base import WindowPlan
-from .inner import BpLsdDecoder, BpOsdDecoder, _GpuInnerDecoder
+from .inner import BpLsdDecoder, BpOsdDecoder, _GpuInnerDecoder, lsd_engine_options
 
 
 # Decoders are set up once per (circuit text, window geometry, options) and reused by later calls of the drop-in functions:
@@ -44,11 +44,7 @@ def _cached_decoder(circuit, m, W, F, num_cor_rounds, kw) -> SlidingWindowDecode
 def _engine_kwargs(decoder_cls, params: dict, rate_name: str) -> dict:
     kw = {k: v for k, v in params.items() if k != rate_name}
     if issubclass(decoder_cls, BpLsdDecoder):
-        method = str(kw.pop("lsd_method", "lsd_0")).lower()
-        kw.pop("lsd_order", None)
-        if method not in ("off", "none"):
-            raise NotImplementedError("BP-LSD post-processing (lsd_method=%r) is not implemented on the GPU path yet" % method)
-        kw["osd_method"] = "off"
+        kw = lsd_engine_options(kw)
     return kw
 
 

@@ -380,3 +380,81 @@ def test_reference_default_decoder_settings_run(qb):
     assert int(np.any(pred != opred.astype(np.int64), axis=1).sum()) <= 2
     dflt = qb.sliding_window_bposd_circuit_mem(det, c, hz, lz, g["W"], g["F"])          # max_iter=2, osd_order=0, product_sum, serial, osd_cs
     assert dflt.shape == pred.shape and dflt.dtype == np.int64
+
+
+# ---------------------------------------------------------------------------------------------- BP-LSD (order 0)
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+@pytest.mark.parametrize("case,window,max_iter", [("bb72_r6_p3e-3_W5F3", 0, 3), ("bb144_r10_p3e-3_W5F3", 1, 2), ("bb144_r10_p1e-3_W5F3", 3, 4),
+                                                  ("hgp225_r3_p1e-2_W3F2", 0, 2), ("toric3_zxcol_r3_p1e-3_W3F2", 1, 1)])
+def test_lsd_matches_oracle_per_shot(qb, case, window, max_iter, precision):
+    """BpLsdDecoder (reference decoder/bplsd.py:38-50): BP posteriors, then LSD-0 on the shots BP leaves unconverged.  The GPU's
+    cluster growth / merge / on-the-fly elimination returns the oracle's error estimate bit for bit, and it satisfies the syndrome."""
+    from oracle import cref
+    g = decode_case(case)
+    w = _oracle_windows(case_circuit(case), g["m"], g["W"], g["F"])[window]
+    H, pri = w["H"], w["priors"]
+    n = min(g["shots"], 96)
+    syn = g["det"][:n, w["row0"]:w["row0"] + H.shape[0]].astype(np.uint8)
+    kw = dict(max_iter=max_iter, bp_method="minimum_sum", schedule="parallel")
+    dec = qb.BpLsdDecoder(H, channel_probs=pri, precision=precision, lsd_method="lsd_cs", lsd_order=0, **kw)
+    ehat, llr, iters, conv = dec.decode_batch(syn)
+    orc = cref.BpOsd(H, pri, precision=precision, osd_method="lsd_0", **kw)
+    n_lsd = 0
+    Hd = H.toarray()
+    for i in range(n):
+        e, l, it, c = orc.decode(syn[i])
+        assert bool(conv[i]) == c and int(iters[i]) == it
+        assert np.array_equal(llr[i], l)
+        assert np.array_equal(ehat[i], e), (i, c, int(ehat[i].sum()), int(e.sum()))
+        if w.get("U") is not None:                # (the last window is rank deficient and may face an inconsistent raw syndrome:
+            assert np.array_equal(Hd @ ehat[i] % 2, syn[i])      # its clusters then stop growing when they run out of bits)
+        n_lsd += orc.used_osd
+    assert n_lsd >= 3
+
+
+@pytest.mark.parametrize("rows,cols,col_w,rate", [(24, 60, 3, 0.08), (60, 150, 8, 0.03), (150, 300, 3, 0.05), (700, 2600, 6, 0.02),
+                                                  (1000, 3000, 4, 0.03)])
+def test_lsd_on_random_matrices(qb, rows, cols, col_w, rate):
+    """Dense merging (high fault rates on small random matrices: many collisions, re-reductions behind a surviving cluster, the
+    operation array filling up and being compacted), rank-deficient matrices, rows up to the kernel's 1024-check limit."""
+    from oracle import cref
+    rng = np.random.RandomState(rows + 13 * col_w)
+    H = _random_ldpc(rng, rows, cols, col_w)
+    pri = rng.choice([0.01, 0.02, 0.03], size=cols)
+    n = 64
+    err = (rng.rand(n, cols) < rate).astype(np.uint8)
+    syn = (err @ H.T.toarray() % 2).astype(np.uint8)
+    kw = dict(max_iter=2, bp_method="minimum_sum", schedule="parallel", ms_scaling_factor=0.75)
+    dec = qb.BpLsdDecoder(H, channel_probs=pri, lsd_order=0, **kw)
+    ehat, llr, iters, conv = dec.decode_batch(syn)
+    orc = cref.BpOsd(H, pri, osd_method="lsd_0", **kw)
+    Hd = H.toarray()
+    n_lsd = 0
+    for i in range(n):
+        e, l, it, c = orc.decode(syn[i])
+        assert bool(conv[i]) == c
+        assert np.array_equal(ehat[i], e), (i, c, int(ehat[i].sum()), int(e.sum()))
+        assert np.array_equal(Hd @ ehat[i] % 2, syn[i])
+        n_lsd += orc.used_osd
+    assert n_lsd >= 8
+
+
+def test_lsd_sliding_window(qb):
+    """sliding_window_bplsd_circuit_mem (reference decoder/bplsd.py:54-86) equals the oracle's window loop with LSD-0 bit for bit;
+    orders beyond 0 are refused loudly."""
+    from oracle import cref
+    case = "bb72_r6_p3e-3_W5F3"
+    g = decode_case(case)
+    name = case_circuit(case)
+    _, hz, lz = circuit_meta(name)
+    circ = qb.Circuit(circuit_text(name))
+    pred = qb.sliding_window_bplsd_circuit_mem(g["det"], circ, hz, lz, g["W"], g["F"], max_iter=3, lsd_order=0, bp_method="minimum_sum",
+                                               schedule="parallel", lsd_method="lsd_cs")
+    wins = _oracle_windows(name, g["m"], g["W"], g["F"])
+    opred, st = cref.sw_decode(wins, g["m"], g["K"], g["det"].astype(np.uint8), max_iter=3, bp_method="minimum_sum", schedule="parallel",
+                               precision="f64", osd_method="lsd_0")
+    assert pred.dtype == np.int64 and np.array_equal(pred, opred.astype(np.int64))
+    assert st[:, 2].sum() > 0
+    with pytest.raises(NotImplementedError):
+        qb.sliding_window_bplsd_circuit_mem(g["det"][:4], circ, hz, lz, g["W"], g["F"], max_iter=3, lsd_order=2, bp_method="minimum_sum",
+                                            schedule="parallel", lsd_method="lsd_cs")

@@ -281,3 +281,19 @@ def test_phenom_argument_errors():
         qb.sliding_window_bposd_phenom_mem(det, hz, lz, 2, 3, bp_method="minimum_sum", schedule="parallel", osd_method="osd_0")
     with pytest.raises(NotImplementedError):            # foreign inner decoder classes are not run per shot
         qb.sliding_window_phenom_mem(det, hz, lz, 3, 2, dict, dict, {"error_rate": 0.1}, {"error_rate": 0.1}, "decode", "decode")
+
+
+def test_lsd_option_mapping():
+    """BpLsdDecoder keywords (reference decoder/bplsd.py:38-49,74-83): order 0 maps onto the engine's lsd_0 whatever lsd_method says;
+    higher orders are refused loudly (no CPU fallback)."""
+    from quits_b200.decoder.inner import lsd_engine_options
+    from quits_b200.engine import bp_options
+    kw = lsd_engine_options({"bp_method": "product_sum", "max_iter": 2, "schedule": "serial", "lsd_method": "lsd_cs", "lsd_order": 0})
+    assert kw == {"bp_method": "product_sum", "max_iter": 2, "schedule": "serial", "osd_method": "lsd_0", "osd_order": 0}
+    o = bp_options(**kw)
+    assert (o.osd_method, o.osd_order, o.bp_method, o.schedule) == (3, 0, 1, 1)
+    assert lsd_engine_options({"lsd_method": "off"})["osd_method"] == "off"
+    with pytest.raises(NotImplementedError):
+        lsd_engine_options({"lsd_method": "lsd_cs", "lsd_order": 1})
+    with pytest.raises(ValueError):
+        lsd_engine_options({"lsd_method": "osd_cs"})

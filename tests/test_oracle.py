@@ -156,3 +156,121 @@ def test_restated_window_loop_equals_reference_loop(case):
         pred, stats = cref.sw_decode(wins, g["m"], g["K"], g["det"].astype(np.uint8), max_iter=BP_KW["max_iter"],
                                      bp_method=BP_KW["bp_method"], schedule=BP_KW["schedule"], precision=prec)
         assert np.array_equal(pred.astype(np.int64), g["pred_" + prec]), prec
+
+
+# ---------------------------------------------------------------------------------------------- LSD-0
+# A literal, per-cluster restatement of the same published algorithm (python sets and lists, each cluster's local matrix
+# solved from scratch after every growth step): pins the C version's incremental machinery (one operation list per cluster,
+# survivors keeping their reduction across merges).
+def _gf2_greedy_solve(A, s):
+    """A [r][c] uint8, s [r]: returns (in_image, x supported on the greedy-first independent columns)."""
+    r, c = A.shape
+    basis = []   # (reduced vector, pivot row, combination over columns as set)
+    piv_cols = []
+    for j in range(c):
+        v = A[:, j].copy(); comb = {j}
+        for (bv, pr, bc) in basis:
+            if v[pr]:
+                v ^= bv; comb ^= bc
+        nz = np.flatnonzero(v)
+        if nz.size:
+            basis.append((v, int(nz[0]), comb)); piv_cols.append(j)
+    z = s.copy(); x = set()
+    for (bv, pr, bc) in basis:
+        if z[pr]:
+            z ^= bv; x ^= bc
+    return (not z.any()), sorted(x)
+
+def _lsd0_literal(H, syn, llr):
+    m, n = H.shape
+    rows = [np.flatnonzero(H[i]) for i in range(m)]
+    cols = [np.flatnonzero(H[:, j]) for j in range(n)]
+    bit_owner = [-1]*n; check_owner=[-1]*m
+    cl = {}
+    for i in np.flatnonzero(syn):
+        cid = len(cl)
+        cl[cid] = dict(bits=[], checks=[int(i)], boundary={int(i)}, active=True, valid=False)
+        check_owner[i] = cid
+    def validate(c):
+        A = H[np.ix_(c['checks'], c['bits'])] if c['bits'] else np.zeros((len(c['checks']),0),np.uint8)
+        ok, x = _gf2_greedy_solve(A.astype(np.uint8), syn[c['checks']].astype(np.uint8))
+        return ok, [c['bits'][k] for k in x]
+    inv = sorted(cl)
+    while inv:
+        for cid in inv:
+            c = cl[cid]
+            if not c['active']: continue
+            cand = []
+            for r in sorted(c['boundary']):
+                ext = [int(j) for j in rows[r] if bit_owner[j] != cid]
+                if not ext: c['boundary'].discard(r)
+                cand += ext
+            if not cand:
+                c['valid'] = True
+                continue
+            best = min(cand, key=lambda j: (llr[j], j))
+            bit_owner[best] = cid; c['bits'].append(best)
+            ml = []
+            for r in cols[best]:
+                o = check_owner[r]
+                if o == cid: continue
+                if o < 0:
+                    check_owner[r] = cid; c['checks'].append(int(r)); c['boundary'].add(int(r))
+                elif o not in ml: ml.append(o)
+            big = cid
+            for o in ml:
+                a, b = big, o
+                if len(cl[a]['bits']) < len(cl[b]['bits']): small, big = a, b
+                else: small, big = b, a
+                S, B = cl[small], cl[big]
+                for j in S['bits']: bit_owner[j] = big; B['bits'].append(j)
+                for r in S['checks']: check_owner[r] = big; B['checks'].append(r)
+                B['boundary'] |= S['boundary']
+                S['active'] = False
+            cl[big]['valid'] = validate(cl[big])[0]
+        inv = sorted([k for k in cl if cl[k]['active'] and not cl[k]['valid']], key=lambda k: (len(cl[k]['bits']), k))
+    e = np.zeros(n, np.uint8)
+    for k in cl:
+        if cl[k]['active']:
+            for j in validate(cl[k])[1]: e[j] = 1
+    return e
+
+
+def test_lsd0_equals_the_literal_restatement():
+    rng = np.random.default_rng(5)
+    n_lsd = 0
+    for trial in range(120):
+        m = int(rng.integers(4, 30)); n = int(rng.integers(m, 3 * m + 5))
+        H = (rng.random((m, n)) < min(0.5, 3.0 / m)).astype(np.uint8)
+        for j in range(n):
+            if not H[:, j].any():
+                H[rng.integers(m), j] = 1
+        p = rng.uniform(0.01, 0.2, n)
+        dec = cref.BpOsd(sp.csc_matrix(H), p, max_iter=int(rng.integers(1, 4)), bp_method="minimum_sum", osd_method="lsd_0")
+        for t in range(4):
+            err = (rng.random(n) < 0.15).astype(np.uint8)
+            syn = (H @ err % 2).astype(np.uint8)
+            e, llr, it, conv = dec.decode(syn)
+            assert np.array_equal(H @ e % 2, syn)
+            if not conv:
+                n_lsd += 1
+                assert np.array_equal(_lsd0_literal(H, syn, llr), e)
+    assert n_lsd > 200
+
+
+def test_lsd0_on_a_decoding_window():
+    """On a real window (gross code, p = 3e-3) LSD-0 satisfies the syndrome and stays local: far fewer columns than OSD-0's
+    rank-many pivots."""
+    from oracle import windows as owin
+    case = "bb144_r10_p3e-3_W5F3"
+    g = decode_case(case)
+    w = owin.plan(odem.analyze(stimtext.parse_flat(circuit_text(case_circuit(case)))), g["m"], g["W"], g["F"])[1]
+    H, pri = w["H"], w["priors"]
+    dec = cref.BpOsd(H, pri, max_iter=3, bp_method="minimum_sum", osd_method="lsd_0")
+    syn = g["det"][:24, w["row0"]:w["row0"] + H.shape[0]].astype(np.uint8)
+    used = 0
+    for s in syn:
+        e, llr, it, conv = dec.decode(s)
+        assert np.array_equal(H @ e % 2, s)
+        used += dec.used_osd
+    assert used >= 3
