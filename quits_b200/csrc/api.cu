@@ -135,7 +135,7 @@ namespace {
 
 struct WinOwned {
     qb::WinDev dev{};
-    DevBuf ser_steps, ser_pairs, ser_cols;
+    DevBuf ser_steps, ser_pairs, ser_cols, ser32_rec;
     DevBuf colE, llr0f, llr0d, osd_wt, lmask, uptr, uidx, cptr, crow, rptr, rcol, colrec, ptabf, ptabd, rlen, rsum0f, rsum0d, neg0;
     size_t bp_smem = 0;
     bool vglobal = false;
@@ -395,6 +395,40 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
                         }
                         steps.push_back(static_cast<uint32_t>(np) | (static_cast<uint32_t>(nc) << 8));
                     }
+                }
+                // warp-per-shot form: steps of <= 5 columns of one level, lane 6g + q = edge q of column g; lighter columns and
+                // the empty places of a step point at the private dummy slot of the lane (rows*rs + lane)
+                {
+                    std::vector<uint32_t> rec32;
+                    int nsteps32 = 0;
+                    const uint32_t realN = static_cast<uint32_t>(rows) * static_cast<uint32_t>(rs);
+                    auto push_step = [&](const int* cj, int n) {
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const int g = lane / 6, q = lane % 6;
+                            uint32_t addr = realN + static_cast<uint32_t>(lane), hi = q == 0 ? 0xFFFFu : 0u;
+                            if (g < n) {
+                                const int j = cj[g];
+                                const int wt = static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]);
+                                if (q < wt) {
+                                    const int64_t e2 = hw.cptr[j] + q;
+                                    addr = static_cast<uint32_t>(hw.crow[e2]) * static_cast<uint32_t>(rs) + static_cast<uint32_t>(layout.slot[e2]);
+                                }
+                                if (q == 0) hi = static_cast<uint32_t>(j);
+                                if (q == 1) hi = static_cast<uint32_t>(pidx[j]);
+                            }
+                            rec32.push_back(addr | (hi << 16));
+                        }
+                        ++nsteps32;
+                    };
+                    for (int l = 1; l <= nlev; ++l) {
+                        const std::vector<int>& cl = bylevel[l];
+                        for (size_t i = 0; i < cl.size(); i += 5) push_step(cl.data() + i, static_cast<int>(std::min<size_t>(5, cl.size() - i)));
+                    }
+                    const int real_steps = nsteps32;
+                    for (int k = 0; k < 4; ++k) push_step(nullptr, 0);       // the rows in flight past the last step land here
+                    upload(wo.ser32_rec, rec32, ctx->stream, 4);
+                    d.ser32_nsteps = real_steps;
+                    d.ser32_rec = wo.ser32_rec.as<uint32_t>();
                 }
                 (void)kCols;
                 steps.push_back(0u);                                 // the prefetch of the step after the last one lands here

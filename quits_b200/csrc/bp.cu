@@ -786,6 +786,243 @@ __global__ void __launch_bounds__(kSerialThreads) bp_kernel_serial(const WinDev 
     }
 }
 
+// =====================================================================================================================
+// Serial schedule, second form: ONE WARP per shot, one LANE per edge, incrementally maintained row summaries
+// (bp_kernel_serial_warp).  The oracle's serial sweep forms the message of row i to column j from the row's OTHER current
+// messages -- a scan of ~35 entries per edge in the kernel above.  Here every row keeps its summary up to date as the sweep goes:
+//   min-sum      (min1 with the parity of the syndrome bit and of #{v <= 0} in its sign bit, min2): "the others" is min2 when the
+//                edge's own |v| equals min1, else min1 (exact: a minimum does not depend on the order it is taken in), and after the
+//                column's new messages are written the summary is patched in O(1) -- except when an edge that held min1 or
+//                min2 grows past min2: then the third smallest is needed and the warp re-scans that row together (32 lanes,
+//                redux.sync minima on the order-preserving bit patterns)
+//   product-sum  no summary: dividing the own factor out of a running row product drifts and, near saturation (tanh(v/2) == 1,
+//                x -> 1), turns a last-ulp excess into log(negative) = NaN that an incremental product never forgets; each lane
+//                multiplies the other factors of its row itself, in two chains (the tolerance path of the kernel above)
+// so a min-sum edge costs O(1) instead of O(row length), and there is no block barrier in either variant.  A step is up to five independent columns
+// of one dependency level; lanes 6g .. 6g+5 hold the (at most six) edges of column g, exchange their check->bit messages by
+// shuffle, and each forms the column's prefix / suffix sums in the oracle's order; one 128-byte record row per step, the rows
+// of the next four steps already in registers.  ~1140 steps x a few hundred cycles per iteration and shot-window; the number
+// of concurrent shots is still set by the message array (two per SM in fp64), so the kernel stays latency bound -- on a
+// several times shorter chain.
+// =====================================================================================================================
+constexpr int kSerCols = 5;          // columns per step
+constexpr int kSerEdges = 6;         // lanes per column (the compact layout holds columns of weight <= 6)
+
+// off: V, rsum, syn, cand, accs, car, ptab, hist, ebits
+__host__ __device__ inline size_t bpsw_layout(const WinDev& w, int rsize, size_t* off /*[9]*/) {
+    size_t o = 0;
+    off[0] = o; o += align_up((static_cast<size_t>(w.rows) * w.RS + 32) * rsize, 16);          // + one private dummy slot per lane
+    off[1] = o; o += align_up((static_cast<size_t>(w.rows) + 34) * 2 * rsize, 16);              // + the rows the dummy slots divide down to
+    off[2] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
+    off[3] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
+    off[4] = o; o += align_up(static_cast<size_t>(w.KW) * 8, 16);
+    off[5] = o; o += align_up(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4, 16);
+    off[6] = o; o += align_up(static_cast<size_t>(w.n_ptab) * rsize, 16);
+    off[7] = o; o += kSelWords * 4;
+    off[8] = o; o += align_up(static_cast<size_t>(w.nW32) * 4, 16);
+    return o;
+}
+
+// warp minimum of non-negative reals through their bit patterns (monotone for x >= 0)
+__device__ __forceinline__ float warp_min_mag(float x) {
+    return __uint_as_float(__reduce_min_sync(0xFFFFFFFFu, __float_as_uint(x)));
+}
+__device__ __forceinline__ double warp_min_mag(double x) {
+    const uint32_t hi = static_cast<uint32_t>(__double2hiint(x)), lo = static_cast<uint32_t>(__double2loint(x));
+    const uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, hi);
+    const uint32_t ml = __reduce_min_sync(0xFFFFFFFFu, hi == mh ? lo : 0xFFFFFFFFu);
+    return __hiloint2double(static_cast<int>(mh), static_cast<int>(ml));
+}
+
+template <typename R> __device__ __forceinline__ uint32_t sign_bit(R x);
+template <> __device__ __forceinline__ uint32_t sign_bit<float>(float x) { return __float_as_uint(x) >> 31; }
+template <> __device__ __forceinline__ uint32_t sign_bit<double>(double x) { return static_cast<uint32_t>(__double2hiint(x)) >> 31; }
+
+// the two smallest |v| of a row, by the whole warp; the parity already in the summary's sign bit is kept
+template <typename R>
+__device__ __noinline__ void serial_rescan_row(const R* vr, const int len, typename Real<R>::pair* srow, const int lane) {
+    using RT = Real<R>;
+    using CT = Compact<R>;
+    R l1 = RT::big(), l2 = RT::big();
+    for (int k = lane; k < len; k += 32) {
+        const R a = CT::mag(vr[k]);
+        const bool p = a < l1, q = a < l2;
+        l2 = p ? l1 : (q ? a : l2);
+        l1 = p ? a : l1;
+    }
+    const R m1 = warp_min_mag(l1);
+    const R m2 = warp_min_mag(l1 == m1 ? l2 : l1);
+    const uint32_t holders = __ballot_sync(0xFFFFFFFFu, l1 == m1);
+    if (lane == 0) *srow = RT::mk(CT::signed_by(m1, sign_bit<R>(srow->x)), __popc(holders) >= 2 ? m1 : m2);
+    __syncwarp();
+}
+
+template <typename R> __device__ __forceinline__ R shfl_real(R x, int src);
+template <> __device__ __forceinline__ float shfl_real<float>(float x, int src) { return __shfl_sync(0xFFFFFFFFu, x, src); }
+template <> __device__ __forceinline__ double shfl_real<double>(double x, int src) { return __shfl_sync(0xFFFFFFFFu, x, src); }
+
+template <typename R, bool PS>
+__global__ void __launch_bounds__(32) bp_kernel_serial_warp(const WinDev w, const BatchDev b, const BpParams p) {
+    using RT = Real<R>;
+    using CT = Compact<R>;
+    using TT = Trans<R>;
+    using Pair = typename RT::pair;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    size_t off[9];
+    bpsw_layout(w, sizeof(R), off);
+    R* V = reinterpret_cast<R*>(smem_raw + off[0]);
+    Pair* rsum = reinterpret_cast<Pair*>(smem_raw + off[1]);
+    uint32_t* syn = reinterpret_cast<uint32_t*>(smem_raw + off[2]);
+    uint32_t* cand = reinterpret_cast<uint32_t*>(smem_raw + off[3]);
+    uint32_t* accs = reinterpret_cast<uint32_t*>(smem_raw + off[4]);
+    uint32_t* car = reinterpret_cast<uint32_t*>(smem_raw + off[5]);
+    R* ptab = reinterpret_cast<R*>(smem_raw + off[6]);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + off[7]);
+    uint32_t* ebits = reinterpret_cast<uint32_t*>(smem_raw + off[8]);
+
+    const int lane = threadIdx.x;
+    const int grp = lane / kSerEdges, q = lane - grp * kSerEdges, gbase = grp * kSerEdges;      // lanes 30, 31: group 5, never active
+    const int rows = w.rows, RS = w.RS, npad = w.ncols_pad;
+    const uint32_t realN = static_cast<uint32_t>(rows) * static_cast<uint32_t>(RS);
+    const uint32_t magic = w.rs_magic;
+    R* const llr_all = reinterpret_cast<R*>(b.llr_buf);
+    for (int i = lane; i < w.n_ptab; i += 32) ptab[i] = CT::ptab(w)[i];
+    V[realN + lane] = R(0);
+    for (int i = rows + lane; i < rows + 34; i += 32) rsum[i] = RT::mk(R(0), PS ? R(2) : R(0));
+    const uint32_t* tab = w.ser32_rec;
+
+    for (int shot = blockIdx.x; shot < b.n_shots; shot += gridDim.x) {
+        __syncthreads();
+        load_syndrome(w, b, shot, lane, syn, accs, car);
+        // bit -> check messages start at the priors (product-sum keeps tanh(v/2))
+        for (int r = lane; r < npad; r += 32) {
+            const uint4 rec = __ldg(w.colrec + r);
+            const R l0 = ptab[(rec.w >> 16) & 0xFFFu];
+            const R v0 = PS ? TT::th(RT::mul(l0, R(0.5))) : l0;
+            const uint32_t e[6] = {rec.x & 0xFFFFu, rec.x >> 16, rec.y & 0xFFFFu, rec.y >> 16, rec.z & 0xFFFFu, rec.z >> 16};
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                if (e[k] < realN) V[e[k]] = v0;
+        }
+        __syncthreads();
+        for (int i = lane; i < rows; i += 32) {
+            const uint32_t sbit = (syn[i >> 5] >> (i & 31)) & 1u;
+            if (!PS) {
+                const Pair s0 = CT::sum0(w, i);
+                rsum[i] = RT::mk(CT::signed_by(s0.x, (sbit + __ldg(w.neg0 + i)) & 1u), s0.y);
+            }
+        }
+        __syncthreads();
+        bool conv = false;
+        int it = 1;
+        for (; it <= p.max_iter; ++it) {
+            const R alpha = static_cast<R>(__ldg(p.alpha + it));
+            const bool last = it == p.max_iter;
+            for (int i = lane; i < w.rowsW32; i += 32) cand[i] = 0;
+            for (int i = lane; i < w.nW32; i += 32) ebits[i] = 0;
+            if (last) hist[lane] = 0;
+            __syncthreads();
+            // record rows of the next four steps in registers (the table is padded by four rows)
+            uint32_t r0 = __ldg(tab + lane), r1 = __ldg(tab + 32 + lane), r2 = __ldg(tab + 64 + lane), r3 = __ldg(tab + 96 + lane);
+            const int ns = w.ser32_nsteps;
+#pragma unroll 1
+            for (int s = 0; s < ns; ++s) {
+                const uint32_t rec = r0;
+                r0 = r1; r1 = r2; r2 = r3;
+                r3 = __ldg(tab + static_cast<size_t>(s + 4) * 32 + lane);
+                // lane word: message address | (q == 0: column, q == 1: prior index) << 16
+                const uint32_t e = rec & 0xFFFFu;
+                const uint32_t j = __shfl_sync(0xFFFFFFFFu, rec, gbase) >> 16;
+                const uint32_t pi = (__shfl_sync(0xFFFFFFFFu, rec, gbase + 1) >> 16) & 0xFFFu;
+                const bool active = j != 0xFFFFu && grp < kSerCols;
+                const bool real = active && e < realN;
+                const uint32_t row = __umulhi(e, magic);
+                const R vold = V[e];
+                const Pair sm = rsum[row];
+                R c;
+                if (PS) {
+                    c = R(0);
+                    if (real) {
+                        const R* vr = V + row * RS;
+                        const int len = __ldg(w.rlen + row), own = static_cast<int>(e) - static_cast<int>(row) * RS;
+                        R pa = R(1), pb = R(1);
+                        int k = 0;
+                        for (; k + 1 < len; k += 2) {
+                            const R ta = vr[k], tb = vr[k + 1];
+                            pa = k == own ? pa : RT::mul(pa, ta);
+                            pb = k + 1 == own ? pb : RT::mul(pb, tb);
+                        }
+                        if (k < len && k != own) pa = RT::mul(pa, vr[k]);
+                        const R x = RT::mul(pa, pb);
+                        const R lx = TT::lg(TT::div(RT::add(R(1), x), RT::add(R(1), -x)));
+                        c = ((syn[row >> 5] >> (row & 31u)) & 1u) ? -lx : lx;
+                    }
+                } else {
+                    const R m1 = CT::mag(sm.x);
+                    const R m = CT::mag(vold) == m1 ? sm.y : m1;
+                    c = CT::flip(RT::mul(m, alpha), sm.x, vold <= R(0));
+                }
+                // the column's sums in the oracle's order: v_q = (l0 + c_0 + .. + c_{q-1}) + (c_5 + .. + c_{q+1}); dummy edges add +-0
+                R ck[kSerEdges];
+#pragma unroll
+                for (int k = 0; k < kSerEdges; ++k) ck[k] = shfl_real<R>(c, gbase + k);
+                R t = ptab[pi], pre = R(0), suf = R(0);
+#pragma unroll
+                for (int k = 0; k < kSerEdges; ++k) { pre = k == q ? t : pre; t = RT::add(t, ck[k]); }
+                const R llr = t;
+                t = R(0);
+#pragma unroll
+                for (int k = kSerEdges - 1; k >= 0; --k) { suf = k == q ? t : suf; t = RT::add(t, ck[k]); }
+                const R vn = RT::add(pre, suf);
+                bool rescan = false;
+                if (real) {
+                    if (PS) {
+                        V[e] = TT::th(RT::mul(vn, R(0.5)));
+                    } else {
+                        V[e] = vn;
+                        const R a = CT::mag(vold), an = CT::mag(vn);
+                        R m1 = CT::mag(sm.x), m2 = sm.y;
+                        const uint32_t par = sign_bit<R>(sm.x) ^ (vold <= R(0) ? 1u : 0u) ^ (vn <= R(0) ? 1u : 0u);
+                        if (a == m1) {                        // this edge held the row minimum (or tied with it)
+                            if (an <= m2) m1 = an;
+                            else rescan = true;
+                        } else if (a == m2) {                 // ... the second minimum
+                            if (an < m1) { m2 = m1; m1 = an; }
+                            else if (an <= m2) m2 = an;
+                            else rescan = true;
+                        } else if (an < m1) { m2 = m1; m1 = an; }
+                        else if (an < m2) m2 = an;
+                        rsum[row] = RT::mk(CT::signed_by(m1, par), m2);      // a row to re-scan keeps its new parity here
+                    }
+                    if (llr <= R(0)) atomicXor(&cand[row >> 5], 1u << (row & 31u));
+                }
+                if (active && q == 0) {
+                    if (llr <= R(0)) atomicOr(&ebits[j >> 5], 1u << (j & 31));
+                    if (last || b.write_llr_always) llr_all[static_cast<size_t>(shot) * b.llr_stride + j] = llr;
+                    if (last) atomicAdd(&hist[llr_bin<R>(llr, static_cast<R>(w.bin_scale))], 1u);
+                }
+                __syncwarp();
+                if (!PS) {
+                    uint32_t mask = __ballot_sync(0xFFFFFFFFu, rescan);
+                    while (mask) {
+                        const int src = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const uint32_t rr = __shfl_sync(0xFFFFFFFFu, row, src);
+                        serial_rescan_row<R>(V + rr * RS, __ldg(w.rlen + rr), rsum + rr, lane);
+                    }
+                }
+            }
+            // ---- stop test H e == s (after the full sweep, as the oracle does)
+            __syncthreads();
+            int mismatch = 0;
+            for (int i = lane; i < w.rowsW32; i += 32) mismatch |= cand[i] != syn[i];
+            if (!__syncthreads_or(mismatch)) { conv = true; break; }
+        }
+        if (it > p.max_iter) it = p.max_iter;
+        finish_shot<R, 32, false>(w, b, shot, lane, conv, it, 0u, syn, accs, car, hist, ebits);
+    }
+}
+
 // kernel variants: (precision, column-weight template, V in shared or global)
 using KernelPtr = void (*)(const WinDev, const BatchDev, const BpParams);
 
@@ -831,12 +1068,22 @@ inline bool use_compact(const WinDev& w, bool vglobal) { return w.compact && !vg
 
 }  // namespace
 
+// the warp-per-shot form needs everything its single warp indexes by lane to fit 32 lanes
+static bool serial_warp_ok(const WinDev& w) {
+    return w.ser32_rec != nullptr && w.rowsW32 <= 32 && 2 * w.KW <= 32 && (w.carry_rows + 31) / 32 + 1 <= 32;
+}
+
 size_t bp_serial_smem_bytes(const WinDev& w, int precision) {
     size_t off[10];
+    if (serial_warp_ok(w)) return bpsw_layout(w, precision == 32 ? 4 : 8, off);
     return bps_layout(w, precision == 32 ? 4 : 8, off);
 }
 
-static KernelPtr serial_kernel(int precision, int method) {
+static KernelPtr serial_kernel(int precision, int method, bool warp) {
+    if (warp) {
+        if (precision == 32) return method ? bp_kernel_serial_warp<float, true> : bp_kernel_serial_warp<float, false>;
+        return method ? bp_kernel_serial_warp<double, true> : bp_kernel_serial_warp<double, false>;
+    }
     if (precision == 32) return method ? bp_kernel_serial<float, true> : bp_kernel_serial<float, false>;
     return method ? bp_kernel_serial<double, true> : bp_kernel_serial<double, false>;
 }
@@ -845,17 +1092,19 @@ cudaError_t bp_serial_configure(const WinDev& w, int precision, int method) {
     if (!w.compact || !w.ser_steps) return cudaErrorInvalidValue;
     const size_t smem = bp_serial_smem_bytes(w, precision);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static size_t have[kMaxDevices][2][2] = {};
-    size_t& h = have[device_slot()][precision == 32 ? 0 : 1][method ? 1 : 0];
+    static size_t have[kMaxDevices][2][2][2] = {};
+    const bool warp = serial_warp_ok(w);
+    size_t& h = have[device_slot()][precision == 32 ? 0 : 1][method ? 1 : 0][warp ? 1 : 0];
     if (smem <= h) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(serial_kernel(precision, method), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(serial_kernel(precision, method, warp), cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e == cudaSuccess) h = smem;
     return e;
 }
 
 cudaError_t launch_bp_serial(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, int grid, cudaStream_t st) {
     if (b.n_shots == 0) return cudaSuccess;
-    serial_kernel(precision, p.method)<<<grid, kSerialThreads, bp_serial_smem_bytes(w, precision), st>>>(w, b, p);
+    const bool warp = serial_warp_ok(w);
+    serial_kernel(precision, p.method, warp)<<<grid, warp ? 32 : kSerialThreads, bp_serial_smem_bytes(w, precision), st>>>(w, b, p);
     return cudaGetLastError();
 }
 

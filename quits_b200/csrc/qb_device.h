@@ -93,6 +93,10 @@ struct WinDev {
     const uint32_t* ser_steps;// [ser_nsteps + 1] n_pairs | n_cols << 8
     const uint2* ser_pairs;   // [ser_nsteps + 1][16] (message address | row << 16, row length); a column's pairs contiguous, ascending rows
     const uint2* ser_cols;    // [ser_nsteps + 1][16] (column | prior index << 16, first pair of the step | weight << 8)
+    // serial schedule, warp-per-shot form (bp_kernel_serial_warp): steps of <= 5 independent columns, one lane per edge
+    int ser32_nsteps;
+    const uint32_t* ser32_rec;// [ser32_nsteps + 4][32] lane 6g+q: message address of edge q of the step's column g (the lane's private dummy
+                              // slot rows*RS + lane when there is none) | (q == 0: column, 0xFFFF = no column; q == 1: prior index) << 16
 };
 
 struct BatchDev {
