@@ -458,3 +458,32 @@ def test_lsd_sliding_window(qb):
     with pytest.raises(NotImplementedError):
         qb.sliding_window_bplsd_circuit_mem(g["det"][:4], circ, hz, lz, g["W"], g["F"], max_iter=3, lsd_order=2, bp_method="minimum_sum",
                                             schedule="parallel", lsd_method="lsd_cs")
+
+
+def test_lsd_edge_cases(qb):
+    """Empty batch, all-zero syndromes, a single unsatisfied check (one cluster that grows until a weight-one explanation exists or
+    merges), a syndrome with every check unsatisfied, and batches that are not a multiple of anything."""
+    from oracle import cref
+    name = "toric3_zxcol_r3_p1e-3"
+    _, hz, lz = circuit_meta(name)
+    c = qb.Circuit(circuit_text(name))
+    kw = dict(max_iter=2, lsd_order=0, bp_method="minimum_sum", schedule="parallel", lsd_method="lsd_0")
+    empty = qb.sliding_window_bplsd_circuit_mem(np.zeros((0, c.num_detectors), dtype=bool), c, hz, lz, 3, 2, **kw)
+    assert empty.shape == (0, c.num_observables) and empty.dtype == np.int64
+    assert qb.sliding_window_bplsd_circuit_mem(np.zeros((5, c.num_detectors), dtype=bool), c, hz, lz, 3, 2, **kw).sum() == 0
+    assert qb.sliding_window_bplsd_circuit_mem(np.zeros((1, c.num_detectors), dtype=bool), c, hz, lz, 3, 2).shape == (1, c.num_observables)
+    w = _oracle_windows(name, hz.shape[0], 3, 2)[0]
+    H, pri = w["H"], w["priors"]
+    m = H.shape[0]
+    syn = np.zeros((m + 3, m), dtype=np.uint8)
+    syn[np.arange(m), np.arange(m)] = 1          # one-hot syndromes
+    syn[m] = 1                                   # every check unsatisfied
+    syn[m + 1, ::2] = 1
+    dec = qb.BpLsdDecoder(H, channel_probs=pri, max_iter=1, bp_method="minimum_sum", schedule="parallel", lsd_order=0)
+    ehat, llr, iters, conv = dec.decode_batch(syn)
+    orc = cref.BpOsd(H, pri, max_iter=1, bp_method="minimum_sum", schedule="parallel", osd_method="lsd_0")
+    Hd = H.toarray()
+    for i in range(syn.shape[0]):
+        e, l, it, cv = orc.decode(syn[i])
+        assert bool(conv[i]) == cv and np.array_equal(ehat[i], e), i
+        assert np.array_equal(Hd @ ehat[i] % 2, syn[i]), i

@@ -245,7 +245,7 @@ def test_phenomenological_windows_equal_the_reference_matrices():
         if not last:
             assert np.array_equal(w["U"].toarray() @ e % 2, e[W * n + (F - 1) * m:W * n + F * m])
     with pytest.raises(ValueError):
-        qb.sliding_window_bposd_phenom_mem(np.zeros((1, m * 8), dtype=bool), hz, lz, 4, 0)
+        qb.sliding_window_bposd_phenom_mem(np.zeros((1, m * 8), dtype=bool), hz, lz, 4, 0, 0.05)
 
 
 def test_explicit_plan_validation():
@@ -276,9 +276,17 @@ def test_phenom_argument_errors():
     lz = np.ones((1, 4), dtype=int)
     det = np.zeros((2, 3 * 6), dtype=bool)
     with pytest.raises(ValueError):
-        qb.sliding_window_bposd_phenom_mem(det, hz, lz, 3, 0)
+        qb.sliding_window_bposd_phenom_mem(det, hz, lz, 3, 0, 0.05)
     with pytest.raises(ValueError):                     # F > W: the reference fails reshaping F blocks out of W
-        qb.sliding_window_bposd_phenom_mem(det, hz, lz, 2, 3, bp_method="minimum_sum", schedule="parallel", osd_method="osd_0")
+        qb.sliding_window_bposd_phenom_mem(det, hz, lz, 2, 3, 0.05, bp_method="minimum_sum", schedule="parallel", osd_method="osd_0")
+    # the rate is mandatory, as in the reference (decoder/bposd.py:33-36, bplsd.py:33-36); error_rate is the deprecated alias
+    for fn in (qb.sliding_window_bposd_phenom_mem, qb.sliding_window_bplsd_phenom_mem):
+        with pytest.raises(ValueError, match="eff_error_rate_per_fault"):
+            fn(det, hz, lz, 3, 2)
+        with pytest.raises(ValueError, match="cannot be zero"):
+            fn(det, hz, lz, 3, 0, error_rate=0.05)
+        with pytest.raises(ValueError, match="cannot be zero"):
+            fn(det, hz, lz, 3, 0, eff_error_rate_per_fault=0.05)
     with pytest.raises(NotImplementedError):            # foreign inner decoder classes are not run per shot
         qb.sliding_window_phenom_mem(det, hz, lz, 3, 2, dict, dict, {"error_rate": 0.1}, {"error_rate": 0.1}, "decode", "decode")
 
@@ -297,3 +305,17 @@ def test_lsd_option_mapping():
         lsd_engine_options({"lsd_method": "lsd_cs", "lsd_order": 1})
     with pytest.raises(ValueError):
         lsd_engine_options({"lsd_method": "osd_cs"})
+
+
+def test_drop_in_signatures_equal_the_reference():
+    """Parameter names, order and defaults of every drop-in function equal the reference's (tests/golden/ref_signatures.json was
+    written with inspect.signature over quits.decoder / quits.simulation of the reference tree, v1.1.0)."""
+    import inspect
+    import json
+    with open(os.path.join(GOLDEN, "ref_signatures.json")) as f:
+        want = json.load(f)
+    assert len(want) == 10
+    for name, params in want.items():
+        got = [[k, repr(v.default) if v.default is not inspect._empty else None]
+               for k, v in inspect.signature(getattr(qb, name)).parameters.items()]
+        assert got == params, name

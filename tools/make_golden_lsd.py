@@ -6,6 +6,8 @@ behind the ``ldpc.bplsd_decoder.BpLsdDecoder`` shim.  Build container only (need
     python tools/make_golden_lsd.py
 
 Writes tests/golden/decode_lsd/<case>.npz = {pred_f32, pred_f64, max_iter}; the inputs are tests/golden/decode/<case>.npz.
+The same for the phenomenological twin ``sliding_window_bplsd_phenom_mem`` (decoder/bplsd.py:10-51) on the inputs of
+tests/golden/phenom/<case>.npz -> tests/golden/phenom_lsd/<case>.npz.
 """
 import os
 import sys
@@ -21,7 +23,7 @@ from oracle import shims  # noqa: E402
 shims.install()
 sys.path.insert(0, "/root/reference/src")
 import stim  # noqa: E402  (the shim)
-from quits.decoder import sliding_window_bplsd_circuit_mem  # noqa: E402
+from quits.decoder import sliding_window_bplsd_circuit_mem, sliding_window_bplsd_phenom_mem  # noqa: E402
 
 from conftest import case_circuit, circuit_meta, circuit_text, decode_case  # noqa: E402
 
@@ -30,6 +32,8 @@ G = os.path.join(ROOT, "tests", "golden")
 CASES = [("qt633_zxcol_r12_p1e-3_W5F3", 10),        # BASELINE config 4: quantum-Tanner 633 code, 12 rounds, BP-LSD inner decoder
          ("bb144_r10_p1e-3_W5F3", 10), ("bb144_r10_p3e-3_W5F3", 4), ("bb72_r6_p3e-3_W5F3", 3), ("hgp225_r3_p1e-2_W3F2", 5),
          ("toric3_zxcol_r3_p1e-3_W3F2", 2)]
+PHENOM_CASES = [("bb72_r6_p3e-3_W4F2", 3), ("bb144_r10_p1e-3_W5F3", 4), ("hgp225_r3_p1e-2_W3F2", 3), ("hgp225_r3_p1e-2_W6F3", 3),
+                ("toric3_zxcol_r3_p1e-3_W3F1", 2)]
 
 
 def main():
@@ -52,6 +56,24 @@ def main():
                             pred_f32=preds["f32"].astype(np.uint8), pred_f64=preds["f64"].astype(np.uint8))
         print("%-30s shots %d  pL(f32) %.4f  pL(f64) %.4f  (BP-OSD-0 fixture: %.4f)" % (
             case, g["shots"], pl["f32"], pl["f64"], float(np.mean(np.any((g["obs"].astype(int) - g["pred_f64"]) % 2, axis=1)))))
+    os.makedirs(os.path.join(G, "phenom_lsd"), exist_ok=True)
+    for case, max_iter in PHENOM_CASES:
+        z = np.load(os.path.join(G, "phenom", case + ".npz"))
+        D = int(z["D"])
+        det = np.unpackbits(z["det"], axis=1, bitorder="little")[:, :D].astype(np.bool_)
+        _, hz, lz = circuit_meta(case.rsplit("_W", 1)[0])
+        preds = {}
+        for prec in ("f32", "f64"):
+            shims.DEFAULT_PRECISION = prec
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                preds[prec] = sliding_window_bplsd_phenom_mem(det, hz, lz, int(z["W"]), int(z["F"]), float(z["error_rate"]), max_iter=max_iter,
+                                                              lsd_order=0, bp_method="minimum_sum", schedule="parallel", lsd_method="lsd_cs")
+        shims.DEFAULT_PRECISION = "f64"
+        np.savez_compressed(os.path.join(G, "phenom_lsd", case + ".npz"), max_iter=np.int64(max_iter),
+                            pred_f32=preds["f32"].astype(np.uint8), pred_f64=preds["f64"].astype(np.uint8))
+        print("phenom %-30s shots %d  differs from the BP-OSD-0 fixture on %d shots" % (
+            case, det.shape[0], int(np.any(preds["f64"] != z["pred_f64"], axis=1).sum())))
 
 
 if __name__ == "__main__":
