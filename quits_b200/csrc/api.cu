@@ -102,6 +102,20 @@ struct qb_ctx {
     static constexpr int kMaxLanes = 4;
     cudaStream_t aux[kMaxLanes - 1] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes - 1] = {};
+    // copy stream of the host-buffer entry points: transfers of one chunk overlap the kernels of the next
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_ready[2] = {}, ev_done[2] = {};
+    DevBuf det_rows_alt, obs_rows_alt, det_bytes_alt, obs_bytes_alt;
+    cudaStream_t copy_stream() {
+        if (!copy) {
+            CK(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                CK(cudaEventCreateWithFlags(&ev_ready[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+            }
+        }
+        return copy;
+    }
     cudaStream_t lane_stream(int lane) {
         if (lane == 0) return stream;
         if (!aux[lane - 1]) {
@@ -163,7 +177,7 @@ struct qb_sw {
     int lanes = 1, lanes_used = 1;    // concurrent sub-batches per batch (decode_batch)
     int DW = 0, KW = 0, carryW = 0, synW = 0;
     size_t llr_stride = 0;
-    DevBuf det_rows, det_bytes, carry, acc, llr, syn, fail_list, ovf_list, order, sel_key, sel_idx, sel_cnt, counters, stats, pred, ehat, iters, conv, vscratch, lsd_scratch;
+    DevBuf det_rows, det_bytes, det_bytes_alt, carry, acc, llr, syn, fail_list, ovf_list, order, sel_key, sel_idx, sel_cnt, counters, stats, pred, ehat, iters, conv, vscratch, lsd_scratch;
     size_t lsd_slab = 0;
     int lsd_cols = 0;
     int lsd_grid = 0, lsd_slabs_per_lane = 0;
@@ -823,6 +837,11 @@ void qb_ctx_destroy(qb_ctx* ctx) {
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->copy) { cudaStreamSynchronize(ctx->copy); cudaStreamDestroy(ctx->copy); }
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
+        if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+    }
     delete ctx;
 }
 
@@ -903,28 +922,45 @@ static void sample_impl(qb_ctx* ctx, qb_circuit* c, uint64_t seed, uint64_t shot
     qb::FrameArgs a = frame_args(c, seed);
     if (qb::frame_smem_per_warp(a) > 200 * 1024) throw qb::unsupported_error("circuit too large for the shared-memory frame kernel");
     const int D = c->fc.n_det, K = c->fc.n_obs;
-    for (uint64_t done = 0; done < n_shots; done += kSampleChunk) {
-        const uint64_t n = std::min(kSampleChunk, n_shots - done);
+    const bool to_host = det || obs || det_rows || obs_rows;
+    // results that go back to the host are produced in chunks of 65536 shots into two buffer sets: the device-to-host copies of a
+    // chunk run on the copy stream while the frame kernel of the next chunk runs
+    const uint64_t chunk = to_host ? (1ull << 16) : kSampleChunk;
+    cudaStream_t cs = to_host ? ctx->copy_stream() : nullptr;
+    int k = 0;
+    for (uint64_t done = 0; done < n_shots; done += chunk, ++k) {
+        const uint64_t n = std::min(chunk, n_shots - done);
         const uint64_t nwords = (n + 63) / 64;
-        ctx->det_rows.ensure(nwords * 64 * a.DW * 8 + 16);
-        ctx->obs_rows.ensure(nwords * 64 * a.KW * 8 + 16);
+        const int bsel = to_host ? (k & 1) : 0;
+        DevBuf& rows_d = bsel ? ctx->det_rows_alt : ctx->det_rows;
+        DevBuf& rows_o = bsel ? ctx->obs_rows_alt : ctx->obs_rows;
+        DevBuf& bytes_d = bsel ? ctx->det_bytes_alt : ctx->det_bytes;
+        DevBuf& bytes_o = bsel ? ctx->obs_bytes_alt : ctx->obs_bytes;
+        if (to_host && k >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_done[bsel], 0));      // the copies of chunk k-2 have left this set
+        rows_d.ensure(std::min<uint64_t>(chunk, n_shots) / 64 * 64 * a.DW * 8 + 64 * a.DW * 8 + 16);
+        rows_o.ensure(std::min<uint64_t>(chunk, n_shots) / 64 * 64 * a.KW * 8 + 64 * a.KW * 8 + 16);
         a.word0 = (shot0 + done) / 64;
         a.n_words = nwords;
-        a.det_rows = ctx->det_rows.as<uint64_t>();
-        a.obs_rows = ctx->obs_rows.as<uint64_t>();
+        a.det_rows = rows_d.as<uint64_t>();
+        a.obs_rows = rows_o.as<uint64_t>();
         CK(qb::launch_frame(a, ctx->stream));
         if (det || obs) {
-            ctx->det_bytes.ensure(n * std::max(D, 1) + 16);
-            ctx->obs_bytes.ensure(n * std::max(K, 1) + 16);
-            CK(qb::launch_unpack_bits(a.det_rows, a.DW, D, n, ctx->det_bytes.as<uint8_t>(), ctx->stream));
-            CK(qb::launch_unpack_bits(a.obs_rows, a.KW, K, n, ctx->obs_bytes.as<uint8_t>(), ctx->stream));
-            if (det && D) CK(cudaMemcpyAsync(det + done * D, ctx->det_bytes.p, n * D, cudaMemcpyDeviceToHost, ctx->stream));
-            if (obs && K) CK(cudaMemcpyAsync(obs + done * K, ctx->obs_bytes.p, n * K, cudaMemcpyDeviceToHost, ctx->stream));
+            bytes_d.ensure(std::min<uint64_t>(chunk, n_shots) * std::max(D, 1) + 16);
+            bytes_o.ensure(std::min<uint64_t>(chunk, n_shots) * std::max(K, 1) + 16);
+            CK(qb::launch_unpack_bits(a.det_rows, a.DW, D, n, bytes_d.as<uint8_t>(), ctx->stream));
+            CK(qb::launch_unpack_bits(a.obs_rows, a.KW, K, n, bytes_o.as<uint8_t>(), ctx->stream));
         }
-        if (det_rows) CK(cudaMemcpyAsync(det_rows + done * a.DW, a.det_rows, n * a.DW * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (obs_rows) CK(cudaMemcpyAsync(obs_rows + done * a.KW, a.obs_rows, n * a.KW * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        if (!to_host) continue;
+        CK(cudaEventRecord(ctx->ev_ready[bsel], ctx->stream));
+        CK(cudaStreamWaitEvent(cs, ctx->ev_ready[bsel], 0));
+        if (det && D) CK(cudaMemcpyAsync(det + done * D, bytes_d.p, n * D, cudaMemcpyDeviceToHost, cs));
+        if (obs && K) CK(cudaMemcpyAsync(obs + done * K, bytes_o.p, n * K, cudaMemcpyDeviceToHost, cs));
+        if (det_rows) CK(cudaMemcpyAsync(det_rows + done * a.DW, a.det_rows, n * a.DW * 8, cudaMemcpyDeviceToHost, cs));
+        if (obs_rows) CK(cudaMemcpyAsync(obs_rows + done * a.KW, a.obs_rows, n * a.KW * 8, cudaMemcpyDeviceToHost, cs));
+        CK(cudaEventRecord(ctx->ev_done[bsel], cs));
     }
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (cs) CK(cudaStreamSynchronize(cs));
 }
 
 int qb_sample(qb_ctx* ctx, qb_circuit* c, uint64_t seed, uint64_t shot0, uint64_t n_shots, uint8_t* det, uint8_t* obs) {
@@ -1248,13 +1284,28 @@ int qb_sw_decode(qb_sw* sw, const uint8_t* det, uint64_t n, int64_t* pred, qb_st
         use_device(ctx);
         cudaStream_t st = ctx->stream;
         const int D = sw->plan.D, K = sw->plan.K;
-        for (uint64_t done = 0; done < n; done += static_cast<uint64_t>(sw->cap)) {
+        // the host-to-device copy of batch k+1 runs on the copy stream while batch k is decoded (two staging buffers; the stream
+        // is synchronised at the end of every batch, so a buffer is free again two batches later)
+        cudaStream_t cs = ctx->copy_stream();
+        const size_t cap = static_cast<size_t>(std::min<uint64_t>(sw->cap, n));
+        sw->det_bytes.ensure(cap * D + 16);
+        if (n > static_cast<uint64_t>(sw->cap)) sw->det_bytes_alt.ensure(cap * D + 16);
+        auto stage = [&](uint64_t first, int which) {
+            const size_t nb = static_cast<size_t>(std::min<uint64_t>(sw->cap, n - first));
+            DevBuf& buf = which ? sw->det_bytes_alt : sw->det_bytes;
+            CK(cudaMemcpyAsync(buf.p, det + first * D, nb * D, cudaMemcpyHostToDevice, cs));
+            CK(cudaEventRecord(ctx->ev_ready[which], cs));
+        };
+        if (n) stage(0, 0);
+        int kb = 0;
+        for (uint64_t done = 0; done < n; done += static_cast<uint64_t>(sw->cap), ++kb) {
             const int nb = static_cast<int>(std::min<uint64_t>(sw->cap, n - done));
-            sw->det_bytes.ensure(static_cast<size_t>(nb) * D + 16);
+            const int which = kb & 1;
             sw->det_rows.ensure(static_cast<size_t>(nb) * sw->DW * 8 + 16);
             sw->pred.ensure(static_cast<size_t>(nb) * std::max(K, 1) * 8 + 16);
-            CK(cudaMemcpyAsync(sw->det_bytes.p, det + done * D, static_cast<size_t>(nb) * D, cudaMemcpyHostToDevice, st));
-            CK(qb::launch_pack_bits(sw->det_bytes.as<uint8_t>(), D, nb, sw->det_rows.as<uint64_t>(), sw->DW, st));
+            CK(cudaStreamWaitEvent(st, ctx->ev_ready[which], 0));
+            CK(qb::launch_pack_bits((which ? sw->det_bytes_alt : sw->det_bytes).as<uint8_t>(), D, nb, sw->det_rows.as<uint64_t>(), sw->DW, st));
+            if (done + static_cast<uint64_t>(sw->cap) < n) stage(done + static_cast<uint64_t>(sw->cap), which ^ 1);
             decode_batch(sw, sw->det_rows.as<uint64_t>(), nb, false, false, stats);
             CK(qb::launch_expand_pred(sw->acc.as<uint64_t>(), sw->KW, K, nb, sw->pred.as<int64_t>(), st));
             if (K) CK(cudaMemcpyAsync(pred + done * K, sw->pred.p, static_cast<size_t>(nb) * K * 8, cudaMemcpyDeviceToHost, st));
