@@ -460,8 +460,15 @@ static void lsd_push(int** a, int* n, int* cap, int v)
     (*a)[(*n)++] = v;
 }
 
+/* diagnostics of the last lsd_decode of this thread: row operations created (survivors re-reduce absorbed columns, so this can
+ * exceed the number of checks), bits added, merges -- lets a test prove that a case drives the GPU kernel's operation array
+ * through its compaction */
+static _Thread_local int64_t lsd_diag[3];
+void qo_lsd_diag(int64_t* out) { out[0] = lsd_diag[0]; out[1] = lsd_diag[1]; out[2] = lsd_diag[2]; }
+
 static void lsd_decode(const qo_bp* d, const uint8_t* syn, const double* llr, uint8_t* ehat)
 {
+    lsd_diag[0] = lsd_diag[1] = lsd_diag[2] = 0;
     const int m = d->m, n = d->n, nw = (m + 63) / 64;
     memset(ehat, 0, (size_t)n);
     int nc = 0;
@@ -522,6 +529,7 @@ static void lsd_decode(const qo_bp* d, const uint8_t* syn, const double* llr, ui
             if (best < 0) { if (!c->valid) { c->valid = 1; c->stuck = 1; } continue; }
             /* the bit joins the cluster; collisions are noted */
             int nm = 0;
+            lsd_diag[1]++;
             bit_owner[best] = cid;
             lsd_push(&c->cols, &c->nbits, &c->capbits, best);
             for (int q = d->colptr[best]; q < d->colptr[best + 1]; ++q) {
@@ -542,6 +550,7 @@ static void lsd_decode(const qo_bp* d, const uint8_t* syn, const double* llr, ui
                 for (int q = 0; q < S->nchecks; ++q) { check_owner[S->checks[q]] = big; lsd_push(&B->checks, &B->nchecks, &B->capchecks, S->checks[q]); }
                 for (int o = 0; o < S->nops; ++o) ispiv[S->oprow[o]] = 0;
                 S->nops = 0; S->active = 0;
+                lsd_diag[2]++;
             }
             /* on-the-fly elimination of the survivor's new columns */
             lsd_cl* B = &cl[big];
@@ -566,6 +575,7 @@ static void lsd_decode(const qo_bp* d, const uint8_t* syn, const double* llr, ui
                 v[p >> 6] &= ~(1ull << (p & 63));                 /* the row operation leaves the pivot row itself alone */
                 memcpy(&B->opvec[(size_t)B->nops * nw], v, (size_t)nw * 8);
                 B->oprow[B->nops] = p; B->opcol[B->nops] = j; B->nops++;
+                lsd_diag[0]++;
                 ispiv[p] = 1;
             }
             B->nelim = B->nbits;

@@ -163,6 +163,13 @@ class BpOsd:
         self.used_osd = used.value
         return e, llr, it.value, bool(conv)
 
+    @staticmethod
+    def lsd_diag():
+        """(row operations created, bits added, merges) of this thread's last LSD call."""
+        out = np.zeros(3, dtype=np.int64)
+        lib().qo_lsd_diag(_p(out, C.c_int64))
+        return tuple(int(x) for x in out)
+
 
 def sw_decode(windows, m, K, det, nthreads=0, **bpkw):
     """Restated sliding-window loop over prepared windows.

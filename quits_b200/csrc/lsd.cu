@@ -40,7 +40,8 @@ struct LsdLayout {
     int opcap;
 };
 
-__host__ __device__ inline int lsd_opcap(const int rows) { return (rows + 31) / 32 * 32 + 32; }
+// capacity of the operation array: the live operations have distinct pivot rows (<= rows), the dead ones go at a compaction
+__host__ __device__ inline int lsd_opcap(const int rows) { return (rows + 31) / 32 * 32 + 8; }
 
 __host__ __device__ inline LsdLayout lsd_layout(const WinDev& w) {
     LsdLayout L;

@@ -413,7 +413,7 @@ def test_lsd_matches_oracle_per_shot(qb, case, window, max_iter, precision):
 
 
 @pytest.mark.parametrize("rows,cols,col_w,rate", [(24, 60, 3, 0.08), (60, 150, 8, 0.03), (150, 300, 3, 0.05), (700, 2600, 6, 0.02),
-                                                  (1000, 3000, 4, 0.03)])
+                                                  (1000, 3000, 4, 0.03), (30, 90, 3, 0.3), (64, 200, 3, 0.3)])
 def test_lsd_on_random_matrices(qb, rows, cols, col_w, rate):
     """Dense merging (high fault rates on small random matrices: many collisions, re-reductions behind a surviving cluster, the
     operation array filling up and being compacted), rank-deficient matrices, rows up to the kernel's 1024-check limit."""
@@ -429,14 +429,18 @@ def test_lsd_on_random_matrices(qb, rows, cols, col_w, rate):
     ehat, llr, iters, conv = dec.decode_batch(syn)
     orc = cref.BpOsd(H, pri, osd_method="lsd_0", **kw)
     Hd = H.toarray()
-    n_lsd = 0
+    n_lsd = n_over = 0
     for i in range(n):
         e, l, it, c = orc.decode(syn[i])
         assert bool(conv[i]) == c
         assert np.array_equal(ehat[i], e), (i, c, int(ehat[i].sum()), int(e.sum()))
         assert np.array_equal(Hd @ ehat[i] % 2, syn[i])
         n_lsd += orc.used_osd
+        if orc.used_osd:
+            n_over += orc.lsd_diag()[0] > (rows + 31) // 32 * 32 + 8       # more row operations than the kernel's array holds
     assert n_lsd >= 8
+    if rate >= 0.3:
+        assert n_over >= 3          # the dense cases drive the operation array through its compaction
 
 
 def test_lsd_sliding_window(qb):
@@ -487,3 +491,30 @@ def test_lsd_edge_cases(qb):
         e, l, it, cv = orc.decode(syn[i])
         assert bool(conv[i]) == cv and np.array_equal(ehat[i], e), i
         assert np.array_equal(Hd @ ehat[i] % 2, syn[i]), i
+
+
+@pytest.mark.parametrize("bp_method", ["minimum_sum", "product_sum"])
+def test_serial_schedule_on_a_tall_window_takes_the_cta_kernel(qb, bp_method):
+    """A window taller than 1024 checks does not fit the warp-per-shot serial kernel (one 32-bit word of syndrome per lane) and
+    takes the first form (128-thread CTA, eight lanes per (column, row) pair); same bar: min-sum bit-exact, product-sum within
+    tolerance.  OSD / LSD stop at 768 / 1024 rows, so post-processing is off here."""
+    from oracle import cref
+    rng = np.random.RandomState(77)
+    rows, cols = 1100, 2600
+    H = _random_ldpc(rng, rows, cols, 3)
+    pri = rng.choice([0.004, 0.006, 0.01], size=cols)
+    n = 24
+    err = (rng.rand(n, cols) < pri[None, :]).astype(np.uint8)
+    syn = (err @ H.T.toarray() % 2).astype(np.uint8)
+    kw = dict(max_iter=5, bp_method=bp_method, schedule="serial")
+    dec = qb.BpOsdDecoder(H, channel_probs=pri, osd_method="off", **kw)
+    ehat, llr, iters, conv = dec.decode_batch(syn)
+    orc = cref.BpOsd(H, pri, osd=False, **kw)
+    for i in range(n):
+        e, l, it, c = orc.decode(syn[i])
+        if bp_method == "minimum_sum":
+            assert bool(conv[i]) == c and int(iters[i]) == it, i
+            assert np.array_equal(llr[i], l) and np.array_equal(ehat[i], e), i
+        elif int(iters[i]) == it:
+            fin = np.isfinite(l) & np.isfinite(llr[i])
+            assert np.allclose(llr[i][fin], l[fin], rtol=1e-5, atol=1e-5), i
