@@ -252,9 +252,9 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
     const int rows = hw.rows, ncols = hw.ncols;
     if (rows <= 0) throw qb::value_error("a decoding window has no detector rows");
     if (ncols <= 0) throw qb::value_error("a decoding window has no fault columns");
-    if (rows >= (1 << 16) || ncols > 8192)
+    if (rows > 8192 || ncols >= 65535)
         throw qb::unsupported_error("window of " + std::to_string(rows) + " x " + std::to_string(ncols) +
-                                    " exceeds what the shared-memory BP kernel handles (rows < 65536, cols <= 8192)");
+                                    " exceeds what the BP kernels handle (rows <= 8192, columns < 65535)");
     std::vector<int> fillr(static_cast<size_t>(rows), 0);
     int cw = 0;
     for (int j = 0; j < ncols; ++j) cw = std::max(cw, static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]));
@@ -565,7 +565,7 @@ void finish_decoder(qb_sw* sw) {
         if (sw->use_lsd) {
             if (!qb::lsd_supported(w->dev))
                 throw qb::unsupported_error("window of " + std::to_string(w->dev.rows) + " x " + std::to_string(w->dev.ncols) +
-                                            " exceeds what the LSD kernel handles (rows <= 1024, columns < 65535)");
+                                            " exceeds what the LSD kernel handles (rows <= 3072, columns < 65535)");
             CK(qb::lsd_configure(w->dev, prec));
             const int per_sm = static_cast<int>((227 * 1024) / (qb::lsd_smem_bytes(w->dev) + 1024));
             w->lsd_grid = 148 * std::max(1, std::min(per_sm, 16));
@@ -591,6 +591,12 @@ void finish_decoder(qb_sw* sw) {
     upload(sw->alpha, alpha, ctx->stream);
     // batches start on 64-shot word boundaries (the sampler numbers shots by word): capacity is rounded down to a multiple of 64
     sw->cap = o.capacity > 0 ? std::max(64, o.capacity / 64 * 64) : 65536;
+    {
+        // the posterior scratch is capacity x widest window: keep it under 4 GiB for very wide windows
+        const size_t per_shot = static_cast<size_t>(max_npad) * (prec / 8);
+        const size_t fit = (size_t(4) << 30) / std::max<size_t>(per_shot, 1);
+        if (static_cast<size_t>(sw->cap) > fit) sw->cap = static_cast<int>(std::max<size_t>(64, fit / 64 * 64));
+    }
     // LSD: a few shots grow clusters of hundreds of bits and keep one warp busy for milliseconds after the rest of the launch has
     // drained; with sub-batches on side streams the BP kernel of another sub-batch fills the machine meanwhile
     sw->lanes = o.lanes > 0 ? std::min(o.lanes, static_cast<int32_t>(qb_ctx::kMaxLanes)) : (sw->use_lsd ? static_cast<int>(qb_ctx::kMaxLanes) : 1);

@@ -106,8 +106,9 @@ __device__ __forceinline__ void select_for_osd(const WinDev& w, const BatchDev& 
     if (tid == 0) b.sel_cnt[shot] = static_cast<int>(hist[32] | (hist[33] << 16));
 }
 
-// shared-memory layout; returns the total.  off: V, rsum, rmeta, syn, cand, accs, car
-__host__ __device__ inline size_t bp_layout(const WinDev& w, int rsize, bool vglobal, size_t* off /*[8]*/) {
+// shared-memory layout; returns the total.  off: V, rsum, rmeta, syn, cand, accs, car, hist, ebits (hard decisions as a bit array:
+// windows wider than 32 columns per thread, where the per-thread mask runs out)
+__host__ __device__ inline size_t bp_layout(const WinDev& w, int rsize, bool vglobal, size_t* off /*[9]*/) {
     size_t o = 0;
     off[0] = o; o += vglobal ? 0 : align_up(static_cast<size_t>(w.rows) * w.RS * rsize, 16);
     off[1] = o; o += align_up(static_cast<size_t>(w.rows) * 2 * rsize, 16);
@@ -117,6 +118,7 @@ __host__ __device__ inline size_t bp_layout(const WinDev& w, int rsize, bool vgl
     off[5] = o; o += align_up(static_cast<size_t>(w.KW) * 8, 16);
     off[6] = o; o += align_up(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4, 16);
     off[7] = o; o += kSelWords * 4;
+    off[8] = o; o += align_up(static_cast<size_t>(w.nW32) * 4, 16);
     return o;
 }
 
@@ -208,7 +210,7 @@ template <typename R, int CW, int NT, int MINB, bool VGLOBAL>
 __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const BatchDev b, const BpParams p) {
     using RT = Real<R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    size_t off[8];
+    size_t off[9];
     bp_layout(w, sizeof(R), VGLOBAL, off);
     R* V = VGLOBAL ? reinterpret_cast<R*>(b.vscratch) + static_cast<size_t>(blockIdx.x) * (static_cast<size_t>(w.rows) * w.RS)
                    : reinterpret_cast<R*>(smem_raw + off[0]);
@@ -219,9 +221,11 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
     uint32_t* accs = reinterpret_cast<uint32_t*>(smem_raw + off[5]);
     uint32_t* car = reinterpret_cast<uint32_t*>(smem_raw + off[6]);
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + off[7]);
+    uint32_t* ebits = reinterpret_cast<uint32_t*>(smem_raw + off[8]);
 
     const int tid = threadIdx.x;
     const int rows = w.rows, ncols = w.ncols, RS = w.RS, npad = w.ncols_pad;
+    const bool wide = ncols > 32 * NT;          // more than 32 columns per thread: hard decisions go to the bit array
     R* const llr_all = reinterpret_cast<R*>(b.llr_buf);
 
     for (int shot = blockIdx.x; shot < b.n_shots; shot += gridDim.x) {
@@ -263,6 +267,7 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
             if (tid < w.rowsW32) cand[tid] = 0;
             const bool last = it == p.max_iter;
             if (last && tid < 32) hist[tid] = 0;
+            if (wide) for (int i = tid; i < w.nW32; i += NT) ebits[i] = 0;
             __syncthreads();
             // ---- bit sweep: one thread per column
             hmask = 0;
@@ -300,7 +305,8 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
                 for (int q = 0; q < CW; ++q)
                     if (e[q] != kNoEdge) V[addr[q]] = vn[q];
                 if (llr <= R(0)) {
-                    hmask |= 1u << k;
+                    if (wide) atomicOr(&ebits[j >> 5], 1u << (j & 31));
+                    else hmask |= 1u << k;
 #pragma unroll
                     for (int q = 0; q < CW; ++q)
                         if (e[q] != kNoEdge) atomicXor(&cand[e[q] >> 13], 1u << ((e[q] >> 8) & 31u));
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
         }
         if (it > p.max_iter) it = p.max_iter;
 
-        finish_shot<R, NT, false>(w, b, shot, tid, conv, it, hmask, syn, accs, car, hist);
+        finish_shot<R, NT, false>(w, b, shot, tid, conv, it, hmask, syn, accs, car, hist, wide ? ebits : nullptr);
     }
 }
 
@@ -1109,7 +1115,7 @@ cudaError_t launch_bp_serial(const WinDev& w, const BatchDev& b, const BpParams&
 }
 
 size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal) {
-    size_t off[8];
+    size_t off[9];
     if (use_compact(w, vglobal)) return bpc_layout(w, precision == 32 ? 4 : 8, off);
     return bp_layout(w, precision == 32 ? 4 : 8, vglobal, off);
 }

@@ -10,7 +10,8 @@
 //
 // Mapping: ONE WARP per failed shot (persistent grid pulling shot indices from the list the BP kernel wrote), because the
 // algorithm is a serial walk over small data-dependent structures; the lanes share the work inside a step:
-//   * GF(2) vectors over the window's checks (<= 1024) are one 32-bit word per lane: the reduced syndrome z, the pivot-row
+//   * GF(2) vectors over the window's checks are NW 32-bit words per lane (NW = 1 up to 1024 checks -- every BB / HGP window --,
+//     2 or 3 up to 3072; word i of a vector sits in lane i % 32, slot i / 32): the reduced syndrome z, the pivot-row
 //     mask P, the boundary mask B live in registers; clusters are disjoint in their checks, so ONE z / P / B serves all of them
 //   * the row operations of all clusters sit in one array in creation order (pivot row in shared memory, 128-byte vector in
 //     an L2-resident scratch slab); reducing a new column tests 32 operations per step (one per lane) and applies the hits in
@@ -48,7 +49,7 @@ __host__ __device__ inline LsdLayout lsd_layout(const WinDev& w) {
     const size_t m = static_cast<size_t>(w.rows);
     L.opcap = lsd_opcap(w.rows);
     size_t o = 0;
-    L.v = o; o += 128;
+    L.v = o; o += 128 * 3;
     L.rbkey = o; o += al16(m * 8);
     L.rbcol = o; o += al16(m * 2);
     L.dlist = o; o += al16(m * 2);
@@ -81,7 +82,26 @@ __device__ __forceinline__ uint64_t lsd_key(double f) {
     return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
-template <typename R>
+// word i of a vector over the checks: lane i % 32, slot i / 32
+template <int NW>
+__device__ __forceinline__ uint32_t vec_bit(const uint32_t (&v)[NW], const int r) {
+    const int wi = r >> 5, slot = wi >> 5;
+    uint32_t word = v[0];
+#pragma unroll
+    for (int s = 1; s < NW; ++s) word = slot == s ? v[s] : word;
+    return (__shfl_sync(kFull, word, wi & 31) >> (r & 31)) & 1u;
+}
+template <int NW>
+__device__ __forceinline__ void vec_set(uint32_t (&v)[NW], const int r, const int lane, const bool on) {
+    const int wi = r >> 5, slot = wi >> 5;
+    if (lane != (wi & 31)) return;
+    const uint32_t bit = 1u << (r & 31);
+#pragma unroll
+    for (int s = 0; s < NW; ++s)
+        if (slot == s) v[s] = on ? (v[s] | bit) : (v[s] & ~bit);
+}
+
+template <typename R, int NW>
 __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev b) {
     extern __shared__ __align__(16) unsigned char sm[];
     const LsdLayout L = lsd_layout(w);
@@ -114,7 +134,7 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
     // (the owner array sits at the same place for every window of the decoder: b.lsd_cols = widest window)
     uint16_t* bown = reinterpret_cast<uint16_t*>(slab);                                   // 0xFFFF between shots
     uint16_t* bnext = bown + b.lsd_cols;
-    uint32_t* opvec = reinterpret_cast<uint32_t*>(slab + al16(static_cast<size_t>(b.lsd_cols) * 4));
+    uint32_t* opvec = reinterpret_cast<uint32_t*>(slab + al16(static_cast<size_t>(b.lsd_cols) * 4));          // [opcap][NW][32]
     const int count = *b.fail_count;
     for (;;) {
         int job = 0;
@@ -126,26 +146,31 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
         const R* llr = reinterpret_cast<const R*>(b.llr_buf) + static_cast<size_t>(shot) * b.llr_stride;
         __syncwarp();
         // ---- initial clusters: one per unsatisfied check, ascending
-        const int left = m - 32 * lane;
-        const uint32_t Sw = (lane < w.rowsW32 ? syn[lane] : 0u) & (left >= 32 ? kFull : (left > 0 ? (1u << left) - 1u : 0u));   // raw syndrome word of this lane
-        uint32_t zw = Sw, Pw = 0u, Bw = Sw;
+        uint32_t Sw[NW], zw[NW], Pw[NW], Bw[NW];          // raw syndrome, reduced syndrome, pivot rows, boundary checks
+#pragma unroll
+        for (int s = 0; s < NW; ++s) {
+            const int wi = 32 * s + lane, left = m - 32 * wi;
+            Sw[s] = (wi < w.rowsW32 ? syn[wi] : 0u) & (left >= 32 ? kFull : (left > 0 ? (1u << left) - 1u : 0u));
+            zw[s] = Sw[s]; Pw[s] = 0u; Bw[s] = Sw[s];
+        }
         for (int i = lane; i < m; i += 32) { cown[i] = static_cast<uint16_t>(kNone); rbcol[i] = static_cast<uint16_t>(kDirty); }
         for (int i = lane; i < 2 * w.KW; i += 32) accs[i] = 0;
         for (int i = lane; i <= carryW; i += 32) car[i] = 0;
-        int nc;
-        {
-            const int mine = __popc(Sw);
+        int nc = 0;
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < NW; ++s) {
+            const int mine = __popc(Sw[s]);
             int incl = mine;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const int t = __shfl_up_sync(kFull, incl, d);
                 if (lane >= d) incl += t;
             }
-            nc = __shfl_sync(kFull, incl, 31);
-            __syncwarp();
-            int id = incl - mine;
-            for (uint32_t x = Sw; x; x &= x - 1, ++id) {
-                const int r = lane * 32 + __ffs(x) - 1;
+            int id = nc + incl - mine;
+            nc += __shfl_sync(kFull, incl, 31);
+            for (uint32_t x = Sw[s]; x; x &= x - 1, ++id) {
+                const int r = (32 * s + lane) * 32 + __ffs(x) - 1;
                 cown[r] = static_cast<uint16_t>(id);
                 cnext[r] = static_cast<uint16_t>(kNone);
                 chead[id] = ctail[id] = static_cast<uint16_t>(r);
@@ -158,7 +183,6 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
         __syncwarp();
         int ninv = nc, nops = 0;
         unsigned long long grown = 0;
-        auto bit_of = [&](const uint32_t word, const int r) -> uint32_t { return (__shfl_sync(kFull, word, r >> 5) >> (r & 31)) & 1u; };
         while (ninv > 0) {
             for (int t = 0; t < ninv; ++t) {
                 const int cid = inv[t];
@@ -170,7 +194,10 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
                 uint32_t bcol = kNone;
                 int nd = 0;
                 for (int i = 0; i < w.rowsW32; ++i) {
-                    const uint32_t bw = __shfl_sync(kFull, Bw, i);
+                    uint32_t bsrc = Bw[0];
+#pragma unroll
+                    for (int s = 1; s < NW; ++s) bsrc = (i >> 5) == s ? Bw[s] : bsrc;
+                    const uint32_t bw = __shfl_sync(kFull, bsrc, i & 31);
                     const int r = 32 * i + lane;
                     const bool mine = ((bw >> lane) & 1u) && cown[r] == cid;
                     const uint32_t c = mine ? rbcol[r] : kNone;
@@ -232,7 +259,7 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
                         if (rr[k] == kNone) continue;
                         if (lane == 0) { rbkey[rr[k]] = kk[k]; rbcol[rr[k]] = static_cast<uint16_t>(kc[k]); }
                         if (kc[k] == kNone) {                        // no free bit left next to this check: it leaves the boundary
-                            if (lane == static_cast<int>(rr[k] >> 5)) Bw &= ~(1u << (rr[k] & 31));
+                            vec_set<NW>(Bw, static_cast<int>(rr[k]), lane, false);
                         } else if (kk[k] < bkey || (kk[k] == bkey && kc[k] < bcol)) { bkey = kk[k]; bcol = kc[k]; }
                     }
                 }
@@ -274,7 +301,7 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
                             cnext[ctail[cid]] = static_cast<uint16_t>(r);
                             ctail[cid] = static_cast<uint16_t>(r);
                         }
-                        if (lane == static_cast<int>(r >> 5)) Bw |= 1u << (r & 31);
+                        vec_set<NW>(Bw, static_cast<int>(r), lane, true);
                         __syncwarp();
                         continue;
                     }
@@ -302,10 +329,11 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
                     __syncwarp();
                     for (uint32_t r = chead[small]; r != kNone; r = cnext[r]) {
                         if (lane == 0) cown[r] = static_cast<uint16_t>(big);
-                        if (lane == static_cast<int>(r >> 5)) {
+                        if (lane == static_cast<int>((r >> 5) & 31u)) {
                             const uint32_t bit = 1u << (r & 31);
-                            zw = (zw & ~bit) | (Sw & bit);
-                            Pw &= ~bit;
+#pragma unroll
+                            for (int s = 0; s < NW; ++s)
+                                if (static_cast<int>(r >> 10) == s) { zw[s] = (zw[s] & ~bit) | (Sw[s] & bit); Pw[s] &= ~bit; }
                         }
                     }
                     for (uint32_t j = bhead[small]; j != kNone; j = bnext[j])
@@ -326,46 +354,56 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
                 }
                 // ---- on-the-fly elimination of the survivor's new columns, in column-list order
                 for (uint32_t j = bue[big]; j != kNone; j = bnext[j]) {
-                    uint32_t vw = 0u;
+                    uint32_t vw[NW];
+#pragma unroll
+                    for (int s = 0; s < NW; ++s) vw[s] = 0u;
                     {
                         const int c0 = __ldg(w.cptr + j), c1 = __ldg(w.cptr + j + 1);
-                        for (int q = c0; q < c1; ++q) {
-                            const uint32_t r = __ldg(w.crow + q);
-                            if (lane == static_cast<int>(r >> 5)) vw |= 1u << (r & 31);
-                        }
+                        for (int q = c0; q < c1; ++q) vec_set<NW>(vw, static_cast<int>(__ldg(w.crow + q)), lane, true);
                     }
                     for (int base = 0; base < nops; base += 32) {
                         const uint32_t p = base + lane < nops ? oppiv[base + lane] : kDead;
                         uint32_t todo = kFull;
                         for (;;) {
                             __syncwarp();
-                            vsm[lane] = vw;
+#pragma unroll
+                            for (int s = 0; s < NW; ++s) vsm[32 * s + lane] = vw[s];
                             __syncwarp();
                             const bool hit = p != kDead && ((vsm[p >> 5] >> (p & 31)) & 1u);
                             const uint32_t mask = __ballot_sync(kFull, hit) & todo;
                             if (!mask) break;
                             const int i = __ffs(mask) - 1;
-                            vw ^= opvec[static_cast<size_t>(base + i) * 32 + lane];
+#pragma unroll
+                            for (int s = 0; s < NW; ++s) vw[s] ^= opvec[(static_cast<size_t>(base + i) * NW + s) * 32 + lane];
                             todo = i == 31 ? 0u : (kFull << (i + 1));
                             if (!todo) break;
                         }
                     }
                     // pivot row: first check of the reduced column that is not a pivot row yet
-                    const uint32_t freew = vw & ~Pw;
-                    const uint32_t fm = __ballot_sync(kFull, freew != 0u);
-                    if (!fm) continue;                               // dependent on the columns before it
-                    const int pl = __ffs(fm) - 1;
-                    const int p = pl * 32 + __ffs(__shfl_sync(kFull, freew, pl)) - 1;
+                    int p = -1;
+#pragma unroll
+                    for (int s = 0; s < NW; ++s) {
+                        const uint32_t freew = vw[s] & ~Pw[s];
+                        const uint32_t fm = __ballot_sync(kFull, freew != 0u);
+                        if (p < 0 && fm) {
+                            const int pl = __ffs(fm) - 1;
+                            p = (32 * s + pl) * 32 + __ffs(__shfl_sync(kFull, freew, pl)) - 1;
+                        }
+                    }
+                    if (p < 0) continue;                             // dependent on the columns before it
                     if (nops == opcap) {                             // drop the dead operations, keeping the order
                         int wr = 0;
                         for (int i = 0; i < nops; ++i) {
                             const uint32_t pi = oppiv[i];
                             if (pi == kDead) continue;
                             if (wr != i) {
-                                const uint32_t x = opvec[static_cast<size_t>(i) * 32 + lane];
+                                uint32_t x[NW];
+#pragma unroll
+                                for (int s = 0; s < NW; ++s) x[s] = opvec[(static_cast<size_t>(i) * NW + s) * 32 + lane];
                                 const uint32_t ci = opcol[i];
                                 __syncwarp();
-                                opvec[static_cast<size_t>(wr) * 32 + lane] = x;
+#pragma unroll
+                                for (int s = 0; s < NW; ++s) opvec[(static_cast<size_t>(wr) * NW + s) * 32 + lane] = x[s];
                                 if (lane == 0) { oppiv[wr] = static_cast<uint16_t>(pi); opcol[wr] = static_cast<uint16_t>(ci); }
                                 __syncwarp();
                             }
@@ -373,16 +411,23 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
                         }
                         nops = wr;
                     }
-                    if (lane == pl) { vw &= ~(1u << (p & 31)); Pw |= 1u << (p & 31); }     // the row operation leaves the pivot row alone
-                    opvec[static_cast<size_t>(nops) * 32 + lane] = vw;
+                    vec_set<NW>(vw, p, lane, false);                 // the row operation leaves the pivot row alone
+                    vec_set<NW>(Pw, p, lane, true);
+#pragma unroll
+                    for (int s = 0; s < NW; ++s) opvec[(static_cast<size_t>(nops) * NW + s) * 32 + lane] = vw[s];
                     if (lane == 0) { oppiv[nops] = static_cast<uint16_t>(p); opcol[nops] = static_cast<uint16_t>(j); }
                     ++nops;
-                    if (bit_of(zw, p)) zw ^= vw;
+                    if (vec_bit<NW>(zw, p)) {
+#pragma unroll
+                        for (int s = 0; s < NW; ++s) zw[s] ^= vw[s];
+                    }
                     __syncwarp();
                 }
                 // ---- valid when the reduced syndrome vanishes on the cluster's non-pivot checks
                 bool bad = false;
-                for (uint32_t x = zw & ~Pw; x; x &= x - 1) bad |= cown[lane * 32 + __ffs(x) - 1] == big;
+#pragma unroll
+                for (int s = 0; s < NW; ++s)
+                    for (uint32_t x = zw[s] & ~Pw[s]; x; x &= x - 1) bad |= cown[(32 * s + lane) * 32 + __ffs(x) - 1] == big;
                 const bool invalid = __any_sync(kFull, bad);
                 if (lane == 0) {
                     bue[big] = static_cast<uint16_t>(kNone);
@@ -414,7 +459,8 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
         }
         // ---- solution: pivot column i is set iff the reduced syndrome has its pivot row; commit (acc ^= L e, carry = U e)
         __syncwarp();
-        vsm[lane] = zw;
+#pragma unroll
+        for (int s = 0; s < NW; ++s) vsm[32 * s + lane] = zw[s];
         __syncwarp();
         int alive = 0;
         for (int i = lane; i < nops; i += 32) {
@@ -461,19 +507,31 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
     }
 }
 
+inline int lsd_nw(const int rows) { return (rows + 1023) / 1024; }
+
+template <typename F>
+inline cudaError_t lsd_dispatch(const WinDev& w, int precision, F&& f) {
+    const int nw = lsd_nw(w.rows);
+    if (precision == 32) return nw <= 1 ? f(lsd_kernel<float, 1>) : (nw == 2 ? f(lsd_kernel<float, 2>) : f(lsd_kernel<float, 3>));
+    return nw <= 1 ? f(lsd_kernel<double, 1>) : (nw == 2 ? f(lsd_kernel<double, 2>) : f(lsd_kernel<double, 3>));
+}
+
 }  // namespace
 
 size_t lsd_smem_bytes(const WinDev& w) { return lsd_layout(w).total; }
-size_t lsd_slab_bytes(int cols_cap, int max_rows) { return al16(static_cast<size_t>(cols_cap) * 4) + static_cast<size_t>(lsd_opcap(max_rows)) * 128; }
-bool lsd_supported(const WinDev& w) { return w.rows <= 1024 && w.ncols < 65535 && lsd_smem_bytes(w) <= 200 * 1024; }
+size_t lsd_slab_bytes(int cols_cap, int max_rows) {
+    return al16(static_cast<size_t>(cols_cap) * 4) + static_cast<size_t>(lsd_opcap(max_rows)) * 128 * lsd_nw(max_rows);
+}
+bool lsd_supported(const WinDev& w) { return w.rows <= 3072 && w.ncols < 65535 && lsd_smem_bytes(w) <= 200 * 1024; }
 
 cudaError_t lsd_configure(const WinDev& w, int precision) {
-    static size_t have_d[kMaxDevices][2] = {};
-    size_t& have = have_d[device_slot()][precision == 32 ? 0 : 1];
+    static size_t have_d[kMaxDevices][2][4] = {};
+    size_t& have = have_d[device_slot()][precision == 32 ? 0 : 1][lsd_nw(w.rows) & 3];
     const size_t s = lsd_smem_bytes(w);
     if (s > have) {
-        cudaError_t e = precision == 32 ? cudaFuncSetAttribute(lsd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s))
-                                        : cudaFuncSetAttribute(lsd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s));
+        cudaError_t e = lsd_dispatch(w, precision, [&](auto kern) {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s));
+        });
         if (e != cudaSuccess) return e;
         have = s;
     }
@@ -483,9 +541,10 @@ cudaError_t lsd_configure(const WinDev& w, int precision) {
 cudaError_t launch_lsd(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st) {
     if (b.n_shots == 0) return cudaSuccess;
     const size_t smem = lsd_smem_bytes(w);
-    if (precision == 32) lsd_kernel<float><<<grid, 32, smem, st>>>(w, b);
-    else lsd_kernel<double><<<grid, 32, smem, st>>>(w, b);
-    return cudaGetLastError();
+    return lsd_dispatch(w, precision, [&](auto kern) {
+        kern<<<grid, 32, smem, st>>>(w, b);
+        return cudaGetLastError();
+    });
 }
 
 }  // namespace qb

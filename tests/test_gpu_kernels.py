@@ -518,3 +518,38 @@ def test_serial_schedule_on_a_tall_window_takes_the_cta_kernel(qb, bp_method):
         elif int(iters[i]) == it:
             fin = np.isfinite(l) & np.isfinite(llr[i])
             assert np.allclose(llr[i][fin], l[fin], rtol=1e-5, atol=1e-5), i
+
+
+def test_wide_tall_window_bp_and_lsd(qb):
+    """A window of the size BASELINE config 5 produces (the 1020-qubit QLP code: 2250 checks x ~30000 faults, column weight up to
+    15): BP takes the generic kernel with its messages in a global slab and its hard decisions in a bit array (more than 32
+    columns per thread), LSD runs with three words per lane.  Per shot against the oracle, bit for bit."""
+    from oracle import cref
+    rng = np.random.RandomState(5)
+    rows, cols = 2250, 30000
+    indptr, indices = [0], []
+    for j in range(cols):
+        wt = 2 + int(rng.randint(0, 6)) if j % 50 else 15
+        indices += list(np.sort(rng.choice(rows, size=wt, replace=False)))
+        indptr.append(len(indices))
+    from scipy.sparse import csc_matrix
+    H = csc_matrix((np.ones(len(indices), dtype=np.uint8), np.array(indices), np.array(indptr)), shape=(rows, cols))
+    pri = rng.choice([0.0005, 0.001, 0.002], size=cols)
+    n = 8
+    err = (rng.rand(n, cols) < pri[None, :] * 2).astype(np.uint8)
+    syn = np.asarray((H @ err.T).T % 2, dtype=np.uint8)
+    kw = dict(max_iter=3, bp_method="minimum_sum", schedule="parallel")
+    dec = qb.BpLsdDecoder(H, channel_probs=pri, lsd_order=0, **kw)
+    ehat, llr, iters, conv = dec.decode_batch(syn)
+    orc = cref.BpOsd(H, pri, osd_method="lsd_0", **kw)
+    n_lsd = 0
+    for i in range(n):
+        e, l, it, c = orc.decode(syn[i])
+        assert bool(conv[i]) == c and int(iters[i]) == it, i
+        assert np.array_equal(llr[i], l), i
+        assert np.array_equal(ehat[i], e), (i, c, int(ehat[i].sum()), int(e.sum()))
+        assert np.array_equal(np.asarray(H @ ehat[i]).ravel() % 2, syn[i])
+        n_lsd += orc.used_osd
+    assert n_lsd >= 3
+    with pytest.raises(NotImplementedError):          # OSD still stops at 768 checks
+        qb.BpOsdDecoder(H, channel_probs=pri, osd_method="osd_0", **kw)
