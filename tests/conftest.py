@@ -33,7 +33,12 @@ def pytest_configure(config):
 
 
 def circuit_text(name):
-    with open(os.path.join(GOLDEN, "circuits", name + ".stim")) as f:
+    path = os.path.join(GOLDEN, "circuits", name + ".stim")
+    if not os.path.exists(path) and os.path.exists(path + ".gz"):       # the large ones are committed compressed
+        import gzip
+        with gzip.open(path + ".gz", "rb") as f:
+            return f.read().decode()
+    with open(path) as f:
         return f.read()
 
 

@@ -319,3 +319,29 @@ def test_drop_in_signatures_equal_the_reference():
         got = [[k, repr(v.default) if v.default is not inspect._empty else None]
                for k, v in inspect.signature(getattr(qb, name)).parameters.items()]
         assert got == params, name
+
+
+def test_baseline_config5_host_pipeline():
+    """BASELINE config 5 -- QlpCode(b, b, 30) = [[1020,136]], zxcoloration, 20 rounds, p = 5e-4, frozen from the reference's own
+    builders (tools/make_circuit_qlp1020.py): the C++ front end, DEM analyser and window planner reproduce the sizes SURVEY
+    Appendix C probed with stim-shaped Python (9900 x 133320, nnz 659766, column weight <= 15, row weight <= 87, sum of priors
+    159.86; seven W5/F3 windows), in well under a second where the Python stand-in needed 9 s + minutes of scipy slicing."""
+    import time
+    text = circuit_text("qlp1020_zxcol_r20_p5e-4")
+    t0 = time.perf_counter()
+    c = qb.Circuit(text)
+    assert (c.num_qubits, c.num_detectors, c.num_observables) == (1920, 9900, 136)
+    dem = c.detector_error_model()
+    H, L, pri = qb.detector_error_model_to_matrix(dem)
+    plan = WindowPlan(dem, 450, 5, 3)
+    dt = time.perf_counter() - t0
+    assert H.shape == (9900, 133320) and H.nnz == 659766 and L.shape == (136, 133320)
+    assert int(np.diff(H.indptr).max()) == 15 and int(np.diff(H.tocsr().indptr).max()) == 87
+    assert abs(float(pri.sum()) - 159.86) < 0.01
+    assert plan.n_windows == 7
+    shapes = [(plan.window(k)["H"].shape, plan.window(k)["H"].nnz, plan.window(k)["ncommit"]) for k in range(7)]
+    assert shapes[0] == ((2250, 29250), 133984, 16650)
+    assert all(sh == ((2250, 31500), 150830, 18900) for sh in shapes[1:6])
+    assert shapes[6] == ((1800, 22170), 114184, 22170)
+    assert plan.window(3)["U"].shape == (450, 18900)
+    assert dt < 30.0
