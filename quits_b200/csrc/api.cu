@@ -155,6 +155,7 @@ struct WinOwned {
     bool vglobal = false;
     int bp_grid = 0;            // persistent grid of the VGLOBAL variant (0: one CTA per shot)
     int sort_grid = 0, elim_grid = 0, fast_grid = 0, lsd_grid = 0;
+    bool osd_big = false;       // OSD-0 through the slab kernel (more than 768 checks)
 };
 
 }  // namespace
@@ -166,6 +167,7 @@ struct qb_sw {
     bool single = false;
     bool use_osd = true;
     bool use_lsd = false;         // BpLsdDecoder post-processing (lsd_0) instead of OSD
+    bool use_slab = false;        // some window runs OSD-0 through the slab kernel (more than 768 checks)
     bool serial = false;          // ldpc schedule='serial'
     bool osd_hi = false;          // osd_e / osd_cs with order > 0: full elimination + candidate sweeps
     int max_iter = 0;
@@ -177,7 +179,7 @@ struct qb_sw {
     int lanes = 1, lanes_used = 1;    // concurrent sub-batches per batch (decode_batch)
     int DW = 0, KW = 0, carryW = 0, synW = 0;
     size_t llr_stride = 0;
-    DevBuf det_rows, det_bytes, det_bytes_alt, carry, acc, llr, syn, fail_list, ovf_list, order, sel_key, sel_idx, sel_cnt, counters, stats, pred, ehat, iters, conv, vscratch, lsd_scratch;
+    DevBuf det_rows, det_bytes, det_bytes_alt, carry, acc, llr, syn, fail_list, ovf_list, order, sel_key, sel_idx, sel_cnt, counters, stats, pred, ehat, iters, conv, vscratch, lsd_scratch, sort_scratch;
     size_t lsd_slab = 0;
     int lsd_cols = 0;
     int lsd_grid = 0, lsd_slabs_per_lane = 0;
@@ -494,7 +496,8 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
     d.rows = rows; d.ncols = ncols; d.ncols_pad = npad; d.RS = rs; d.cw = cw_alloc; d.ncommit = hw.ncommit;
     d.row0 = hw.row0; d.carry_rows = hw.urows; d.KW = KW;
     d.rowsW32 = (rows + 31) / 32; d.nW32 = (ncols + 31) / 32;
-    d.full_row_rank = gf2_rank(hw) == rows ? 1 : 0;
+    d.rank = gf2_rank(hw);
+    d.full_row_rank = d.rank == rows ? 1 : 0;
     {
         double lmin = DBL_MAX;
         for (int j = 0; j < ncols; ++j) lmin = std::min(lmin, llr0d[j]);
@@ -527,8 +530,9 @@ void finish_decoder(qb_sw* sw) {
     sw->use_lsd = o.osd_method == 3;
     if (sw->use_lsd && o.osd_order != 0)
         throw qb::unsupported_error("LSD post-processing beyond order 0 (lsd_order > 0) is not supported on the GPU path");
-    int max_npad = 0, max_rowsW = 0, max_iter = 0;
-    size_t max_slab = 0;
+    int max_npad = 0, max_rowsW = 0, max_iter = 0, big_rows = 0;
+    size_t max_slab = 0, sort_slab = 0;
+    bool any_big = false;
     for (auto& w : sw->wins) {
         // messages in shared memory when they fit, else in an L2-resident global slab per CTA
         if (sw->serial) {
@@ -550,10 +554,21 @@ void finish_decoder(qb_sw* sw) {
         max_npad = std::max(max_npad, w->dev.ncols_pad);
         max_rowsW = std::max(max_rowsW, w->dev.rowsW32);
         max_iter = std::max(max_iter, o.max_iter > 0 ? o.max_iter : w->dev.ncols);
-        if (sw->use_osd) {
-            if (!qb::osd_supported(w->dev, prec))
+        if (sw->use_osd && !qb::osd_supported(w->dev, prec)) {
+            // taller than the shared-memory elimination takes: OSD-0 through the slab kernel (lsd.cu, osd_big_kernel)
+            if (sw->osd_hi || !qb::osd_big_supported(w->dev))
                 throw qb::unsupported_error("window of " + std::to_string(w->dev.rows) + " x " + std::to_string(w->dev.ncols) +
-                                            " exceeds what the OSD kernels handle (rows <= 768)");
+                                            " exceeds what the OSD kernels handle (order 0: rows <= 3072; higher orders: rows <= 768)");
+            w->osd_big = true;
+            CK(qb::osd_sort_configure(w->dev, prec));
+            CK(qb::osd_big_configure(w->dev));
+            const int per_sm = static_cast<int>((227 * 1024) / (qb::osd_big_smem_bytes(w->dev) + 1024));
+            w->elim_grid = 148 * std::max(1, std::min(per_sm, 8));
+            w->sort_grid = 148 * 4;
+            any_big = true;
+            big_rows = std::max(big_rows, w->dev.rows);
+            sort_slab = std::max(sort_slab, qb::osd_sort_slab_bytes(w->dev, prec));
+        } else if (sw->use_osd) {
             CK(qb::osd_configure(w->dev, prec));
             const int sort_per_sm = static_cast<int>((227 * 1024) / (qb::osd_sort_smem_bytes(w->dev, prec) + 1024));
             const int elim_per_sm = static_cast<int>((227 * 1024) / (qb::osd_elim_smem_bytes(w->dev, sw->osd_hi) + 1024));
@@ -580,6 +595,13 @@ void finish_decoder(qb_sw* sw) {
         sw->lsd_slab = qb::lsd_slab_bytes(max_npad, max_rows);
         for (auto& w : sw->wins) sw->lsd_grid = std::max(sw->lsd_grid, w->lsd_grid);
     }
+    if (any_big) {
+        // the slab kernel's row operations (one slab per persistent warp) and the wide sort's key / index buffers (one per CTA)
+        sw->use_slab = true;
+        sw->lsd_slab = qb::osd_big_slab_bytes(big_rows);
+        for (auto& w : sw->wins) if (w->osd_big) sw->lsd_grid = std::max(sw->lsd_grid, w->elim_grid);
+        if (sort_slab) sw->sort_scratch.ensure(sort_slab * 148 * 4 + 16);
+    }
     if (o.max_iter == 0 && sw->wins.size() > 1) {
         // ldpc's "0 => number of columns" differs per window; the kernel takes one value
         for (auto& w : sw->wins)
@@ -600,7 +622,7 @@ void finish_decoder(qb_sw* sw) {
     // LSD: a few shots grow clusters of hundreds of bits and keep one warp busy for milliseconds after the rest of the launch has
     // drained; with sub-batches on side streams the BP kernel of another sub-batch fills the machine meanwhile
     sw->lanes = o.lanes > 0 ? std::min(o.lanes, static_cast<int32_t>(qb_ctx::kMaxLanes)) : (sw->use_lsd ? static_cast<int>(qb_ctx::kMaxLanes) : 1);
-    if (max_slab) sw->lanes = 1;                      // the global message slabs are indexed by CTA, not by sub-batch
+    if (max_slab || any_big) sw->lanes = 1;           // the global message / sort slabs are indexed by CTA, not by sub-batch
     sw->DW = std::max(1, (sw->plan.D + 63) / 64);
     sw->KW = std::max(1, (sw->plan.K + 63) / 64);
     sw->carryW = (sw->plan.m + 31) / 32 + 1;
@@ -622,11 +644,11 @@ void ensure_batch(qb_sw* sw, int n) {
         sw->sel_idx.ensure(N * qb::kOsdSelCap * 2 + 16);
         sw->sel_cnt.ensure(N * 4 + 16);
     }
-    if (sw->use_lsd) {
+    if (sw->use_lsd || sw->use_slab) {
         // one slab per persistent warp and sub-batch lane: bit owners (0xFFFF = none between shots), column-order links, operation vectors
         const int per_lane = std::min(sw->lsd_grid, n);
         if (per_lane > sw->lsd_slabs_per_lane) {
-            const size_t bytes = sw->lsd_slab * static_cast<size_t>(per_lane) * qb_ctx::kMaxLanes + 16;
+            const size_t bytes = sw->lsd_slab * static_cast<size_t>(per_lane) * static_cast<size_t>(std::max(sw->lanes, 1)) + 16;
             sw->lsd_scratch.ensure(bytes);
             CK(cudaMemsetAsync(sw->lsd_scratch.p, 0xFF, bytes, sw->ctx->stream));
             sw->lsd_slabs_per_lane = per_lane;
@@ -699,7 +721,8 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.lsd_scratch = sw->lsd_scratch.p ? static_cast<unsigned char*>(sw->lsd_scratch.p) + static_cast<size_t>(l) * sw->lsd_slab * sw->lsd_slabs_per_lane : nullptr;
             b.lsd_slab = sw->lsd_slab;
             b.lsd_cols = sw->lsd_cols;
-            if (sw->use_osd && !sw->osd_hi) {
+            b.sort_scratch = sw->sort_scratch.p;
+            if (sw->use_osd && !sw->osd_hi && !w.osd_big) {
                 b.sel_key = static_cast<unsigned char*>(sw->sel_key.p) + s0 * qb::kOsdSelCap * esz;
                 b.sel_idx = sw->sel_idx.as<uint16_t>() + s0 * qb::kOsdSelCap;
                 b.sel_cnt = sw->sel_cnt.as<int>() + s0;
@@ -720,6 +743,14 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
                 CK(qb::launch_lsd(w.dev, b, sw->precision, std::min(w.lsd_grid, nl), ls));
                 if (sw->opts.profile) sw->t_osd.end(ls);
                 if (stats) stats->osd_launches += 1;
+            }
+            if (sw->use_osd && w.osd_big) {
+                if (sw->opts.profile) sw->t_osd.begin(ls);
+                CK(qb::launch_osd_sort(w.dev, b, sw->precision, std::min(w.sort_grid, nl), ls));
+                CK(qb::launch_osd_big(w.dev, b, std::min(w.elim_grid, nl), ls));
+                if (sw->opts.profile) sw->t_osd.end(ls);
+                if (stats) stats->osd_launches += 2;
+                continue;
             }
             if (sw->use_osd) {
                 if (sw->opts.profile) sw->t_osd.begin(ls);

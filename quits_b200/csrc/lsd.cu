@@ -507,6 +507,181 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
     }
 }
 
+// =====================================================================================================================
+// OSD-0 for windows taller than the shared-memory elimination of osd.cu takes (768 < checks <= 3072; BASELINE config 5 has
+// 2250): the same lane-word vectors and row-operation array as the LSD kernel above, ONE warp per failed shot.  The columns come
+// in the order osd_sort_kernel wrote (ascending posterior, ties by index); each is reduced by the operations so far, and if it is
+// independent its pivot row is the first row IN THE ORACLE'S CURRENT ROW ORDER that carries it -- the oracle swaps the pivot row
+// up to position `rank`, which matters only for an inconsistent syndrome on a rank-deficient window, and is followed here
+// through the position list `seq`.  Exact early exit as in osd.cu: once the reduced syndrome vanishes on the free rows no later
+// pivot changes the answer.  An inconsistent syndrome runs until the rank of the window is reached.
+// =====================================================================================================================
+struct OsdBigLayout {
+    size_t v, seq, oppiv, opcol, accs, car, total;
+    int opcap;
+};
+
+__host__ __device__ inline OsdBigLayout osd_big_layout(const WinDev& w) {
+    OsdBigLayout L;
+    const size_t m = static_cast<size_t>(w.rows);
+    L.opcap = (w.rows + 31) / 32 * 32;
+    size_t o = 0;
+    L.v = o; o += 128 * 3;
+    L.seq = o; o += al16(m * 2 + 64);
+    L.oppiv = o; o += al16(static_cast<size_t>(L.opcap) * 2);
+    L.opcol = o; o += al16(static_cast<size_t>(L.opcap) * 2);
+    L.accs = o; o += al16(static_cast<size_t>(2 * w.KW) * 4);
+    L.car = o; o += al16(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4);
+    L.total = o;
+    return L;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(32) osd_big_kernel(const WinDev w, const BatchDev b) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    const OsdBigLayout L = osd_big_layout(w);
+    uint32_t* vsm = reinterpret_cast<uint32_t*>(sm + L.v);
+    uint16_t* seq = reinterpret_cast<uint16_t*>(sm + L.seq);
+    uint16_t* oppiv = reinterpret_cast<uint16_t*>(sm + L.oppiv);
+    uint16_t* opcol = reinterpret_cast<uint16_t*>(sm + L.opcol);
+    uint32_t* accs = reinterpret_cast<uint32_t*>(sm + L.accs);
+    uint32_t* car = reinterpret_cast<uint32_t*>(sm + L.car);
+    const int lane = threadIdx.x;
+    const int m = w.rows, n = w.ncols;
+    const int carryW = (w.carry_rows + 31) / 32;
+    uint32_t* opvec = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(b.lsd_scratch) + static_cast<size_t>(blockIdx.x) * b.lsd_slab);
+    const int count = *b.fail_count;
+    for (;;) {
+        int job = 0;
+        if (lane == 0) job = atomicAdd(b.osd_next, 1);
+        job = __shfl_sync(kFull, job, 0);
+        if (job >= count) break;
+        const int shot = b.fail_list[job];
+        const uint32_t* syn = b.syn_buf + static_cast<size_t>(shot) * b.syn_stride32;
+        const uint16_t* order = b.order_alt ? b.order_alt + static_cast<size_t>(shot) * b.llr_stride
+                                            : reinterpret_cast<const uint16_t*>(static_cast<const unsigned char*>(b.llr_buf) +
+                                                                                static_cast<size_t>(shot) * b.llr_stride * b.llr_esize);
+        __syncwarp();
+        uint32_t zw[NW], Pw[NW];
+#pragma unroll
+        for (int s = 0; s < NW; ++s) {
+            const int wi = 32 * s + lane, left = m - 32 * wi;
+            zw[s] = (wi < w.rowsW32 ? syn[wi] : 0u) & (left >= 32 ? kFull : (left > 0 ? (1u << left) - 1u : 0u));
+            Pw[s] = 0u;
+        }
+        for (int i = lane; i < m; i += 32) seq[i] = static_cast<uint16_t>(i);
+        for (int i = lane; i < 2 * w.KW; i += 32) accs[i] = 0;
+        for (int i = lane; i <= carryW; i += 32) car[i] = 0;
+        __syncwarp();
+        int rank = 0, examined = 0;
+        auto satisfied = [&]() {
+            bool open = false;
+#pragma unroll
+            for (int s = 0; s < NW; ++s) open |= (zw[s] & ~Pw[s]) != 0u;
+            return !__any_sync(kFull, open);
+        };
+        bool done = satisfied();
+        for (int k = 0; k < n && !done && rank < w.rank; ++k) {
+            const int j = order[k];
+            ++examined;
+            uint32_t vw[NW];
+#pragma unroll
+            for (int s = 0; s < NW; ++s) vw[s] = 0u;
+            {
+                const int c0 = __ldg(w.cptr + j), c1 = __ldg(w.cptr + j + 1);
+                for (int q = c0; q < c1; ++q) vec_set<NW>(vw, static_cast<int>(__ldg(w.crow + q)), lane, true);
+            }
+            for (int base = 0; base < rank; base += 32) {
+                const uint32_t p = base + lane < rank ? oppiv[base + lane] : kDead;
+                uint32_t todo = kFull;
+                for (;;) {
+                    __syncwarp();
+#pragma unroll
+                    for (int s = 0; s < NW; ++s) vsm[32 * s + lane] = vw[s];
+                    __syncwarp();
+                    const bool hit = p != kDead && ((vsm[p >> 5] >> (p & 31)) & 1u);
+                    const uint32_t mask = __ballot_sync(kFull, hit) & todo;
+                    if (!mask) break;
+                    const int i = __ffs(mask) - 1;
+#pragma unroll
+                    for (int s = 0; s < NW; ++s) vw[s] ^= opvec[(static_cast<size_t>(base + i) * NW + s) * 32 + lane];
+                    todo = i == 31 ? 0u : (kFull << (i + 1));
+                    if (!todo) break;
+                }
+            }
+            // pivot row: the first position >= rank of the oracle's row order whose row carries the reduced column
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < NW; ++s) vsm[32 * s + lane] = vw[s];
+            __syncwarp();
+            int pos = -1;
+            for (int base = rank; base < m && pos < 0; base += 32) {
+                const int i = base + lane;
+                const uint32_t r = i < m ? seq[i] : 0u;
+                const bool has = i < m && ((vsm[r >> 5] >> (r & 31)) & 1u);
+                const uint32_t hm = __ballot_sync(kFull, has);
+                if (hm) pos = base + __ffs(hm) - 1;
+            }
+            if (pos < 0) continue;                               // dependent on the columns before it
+            const int p = seq[pos];
+            __syncwarp();
+            if (lane == 0) {
+                seq[pos] = seq[rank];
+                seq[rank] = static_cast<uint16_t>(p);
+                oppiv[rank] = static_cast<uint16_t>(p);
+                opcol[rank] = static_cast<uint16_t>(j);
+            }
+            vec_set<NW>(vw, p, lane, false);                     // the row operation leaves the pivot row alone
+            vec_set<NW>(Pw, p, lane, true);
+#pragma unroll
+            for (int s = 0; s < NW; ++s) opvec[(static_cast<size_t>(rank) * NW + s) * 32 + lane] = vw[s];
+            if (vec_bit<NW>(zw, p)) {
+#pragma unroll
+                for (int s = 0; s < NW; ++s) zw[s] ^= vw[s];
+            }
+            ++rank;
+            __syncwarp();
+            done = satisfied();
+        }
+        // ---- solution on the pivots; commit (acc ^= L e, carry = U e)
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < NW; ++s) vsm[32 * s + lane] = zw[s];
+        __syncwarp();
+        for (int i = lane; i < rank; i += 32) {
+            const uint32_t p = oppiv[i];
+            if (!((vsm[p >> 5] >> (p & 31)) & 1u)) continue;
+            const int j = opcol[i];
+            if (b.ehat_out) atomicOr(&b.ehat_out[static_cast<size_t>(shot) * b.ehat_stride32 + (j >> 5)], 1u << (j & 31));
+            if (j < w.ncommit) {
+                for (int wd = 0; wd < w.KW; ++wd) {
+                    const uint64_t lm = __ldg(w.lmask + static_cast<size_t>(j) * w.KW + wd);
+                    if (static_cast<uint32_t>(lm)) atomicXor(&accs[2 * wd], static_cast<uint32_t>(lm));
+                    if (static_cast<uint32_t>(lm >> 32)) atomicXor(&accs[2 * wd + 1], static_cast<uint32_t>(lm >> 32));
+                }
+                if (w.carry_rows) {
+                    for (int q = __ldg(w.uptr + j); q < __ldg(w.uptr + j + 1); ++q) {
+                        const uint32_t ur = __ldg(w.uidx + q);
+                        atomicXor(&car[ur >> 5], 1u << (ur & 31));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < w.KW; i += 32) {
+            const uint64_t v = (static_cast<uint64_t>(accs[2 * i + 1]) << 32) | accs[2 * i];
+            b.acc[static_cast<size_t>(shot) * w.KW + i] ^= v;
+        }
+        for (int i = lane; i < carryW; i += 32) b.carry[static_cast<size_t>(shot) * b.carry_stride32 + i] = car[i];
+        if (lane == 0) {
+            atomicAdd(&b.stats[2], 1ull);
+            atomicAdd(&b.stats[3], static_cast<unsigned long long>(examined));
+            atomicAdd(&b.stats[4], static_cast<unsigned long long>(rank));
+            atomicMax(&b.stats[5], static_cast<unsigned long long>(examined));
+        }
+    }
+}
+
 inline int lsd_nw(const int rows) { return (rows + 1023) / 1024; }
 
 template <typename F>
@@ -542,6 +717,39 @@ cudaError_t launch_lsd(const WinDev& w, const BatchDev& b, int precision, int gr
     if (b.n_shots == 0) return cudaSuccess;
     const size_t smem = lsd_smem_bytes(w);
     return lsd_dispatch(w, precision, [&](auto kern) {
+        kern<<<grid, 32, smem, st>>>(w, b);
+        return cudaGetLastError();
+    });
+}
+
+size_t osd_big_smem_bytes(const WinDev& w) { return osd_big_layout(w).total; }
+size_t osd_big_slab_bytes(int max_rows) { return static_cast<size_t>((max_rows + 31) / 32 * 32) * 128 * lsd_nw(max_rows); }
+bool osd_big_supported(const WinDev& w) { return w.rows <= 3072 && w.ncols < 65535 && osd_big_smem_bytes(w) <= 200 * 1024; }
+
+template <typename F>
+static cudaError_t osd_big_dispatch(const WinDev& w, F&& f) {
+    const int nw = lsd_nw(w.rows);
+    return nw <= 1 ? f(osd_big_kernel<1>) : (nw == 2 ? f(osd_big_kernel<2>) : f(osd_big_kernel<3>));
+}
+
+cudaError_t osd_big_configure(const WinDev& w) {
+    static size_t have_d[kMaxDevices][4] = {};
+    size_t& have = have_d[device_slot()][lsd_nw(w.rows) & 3];
+    const size_t s = osd_big_smem_bytes(w);
+    if (s > have) {
+        cudaError_t e = osd_big_dispatch(w, [&](auto kern) {
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s));
+        });
+        if (e != cudaSuccess) return e;
+        have = s;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_osd_big(const WinDev& w, const BatchDev& b, int grid, cudaStream_t st) {
+    if (b.n_shots == 0) return cudaSuccess;
+    const size_t smem = osd_big_smem_bytes(w);
+    return osd_big_dispatch(w, [&](auto kern) {
         kern<<<grid, 32, smem, st>>>(w, b);
         return cudaGetLastError();
     });

@@ -42,9 +42,12 @@ __host__ __device__ inline size_t au(size_t x) { return (x + 15) / 16 * 16; }
 
 // ====================================================================================================== sort
 struct SortLayout {
-    size_t keys, idxA, idxB, hist, total;
+    size_t keys, idxA, idxB, hist, total;      // offsets; `total` = shared-memory bytes
+    size_t slab;                               // wide windows: keys / idxA / idxB live in a global slab of this size per CTA
     int n_pad;
 };
+
+constexpr size_t kSortSmemLimit = 200 * 1024;
 
 __host__ __device__ inline SortLayout sort_layout(const WinDev& w, int ksize) {
     SortLayout L;
@@ -53,6 +56,11 @@ __host__ __device__ inline SortLayout sort_layout(const WinDev& w, int ksize) {
     L.keys = o; o += au(static_cast<size_t>(L.n_pad) * ksize);
     L.idxA = o; o += au(static_cast<size_t>(L.n_pad) * 2);
     L.idxB = o; o += au(static_cast<size_t>(L.n_pad) * 2);
+    L.slab = 0;
+    if (o + au(kSortWarps * 256 * 4) > kSortSmemLimit) {      // too wide for shared memory: only the histograms stay there
+        L.slab = o;
+        o = 0;
+    }
     L.hist = o; o += au(kSortWarps * 256 * 4);
     L.total = o;
     return L;
@@ -74,9 +82,10 @@ __global__ void __launch_bounds__(kSortThreads) osd_sort_kernel(const WinDev w, 
     constexpr int kPasses = static_cast<int>(sizeof(KeyT));
     extern __shared__ __align__(16) unsigned char sm[];
     const SortLayout L = sort_layout(w, sizeof(KeyT));
-    KeyT* keys = reinterpret_cast<KeyT*>(sm + L.keys);
-    uint16_t* idxA = reinterpret_cast<uint16_t*>(sm + L.idxA);
-    uint16_t* idxB = reinterpret_cast<uint16_t*>(sm + L.idxB);
+    unsigned char* kbase = L.slab ? static_cast<unsigned char*>(b.sort_scratch) + static_cast<size_t>(blockIdx.x) * L.slab : sm;
+    KeyT* keys = reinterpret_cast<KeyT*>(kbase + L.keys);
+    uint16_t* idxA = reinterpret_cast<uint16_t*>(kbase + L.idxA);
+    uint16_t* idxB = reinterpret_cast<uint16_t*>(kbase + L.idxB);
     uint32_t* hist = reinterpret_cast<uint32_t*>(sm + L.hist);
     __shared__ int s_job;
     __shared__ uint32_t wsum[kSortWarps];
@@ -837,6 +846,7 @@ inline cudaError_t fast_dispatch(const WinDev& w, int precision, F&& f) {
 }  // namespace
 
 size_t osd_sort_smem_bytes(const WinDev& w, int precision) { return sort_layout(w, precision == 32 ? 4 : 8).total; }
+size_t osd_sort_slab_bytes(const WinDev& w, int precision) { return sort_layout(w, precision == 32 ? 4 : 8).slab; }
 size_t osd_elim_smem_bytes(const WinDev& w, bool hi) { return elim_layout(w, elim_nq(w), !w.full_row_rank, 0, hi).total; }
 size_t osd_fast_smem_bytes(const WinDev& w) { return elim_layout(w, elim_nq(w), !w.full_row_rank, kSelCap).total; }
 
@@ -845,15 +855,11 @@ bool osd_supported(const WinDev& w, int precision) {
            osd_elim_smem_bytes(w, true) <= 220 * 1024;
 }
 
-cudaError_t osd_configure(const WinDev& w, int precision) {
+cudaError_t osd_sort_configure(const WinDev& w, int precision) {
     // several windows may share one instantiation: the attributes only ever grow
-    static size_t sort_have_d[kMaxDevices][2] = {}, elim_have_d[kMaxDevices][2][2][8] = {}, fast_have_d[kMaxDevices][2][2][8] = {};
-    const int dev = device_slot();
-    auto& sort_have = sort_have_d[dev];
-    auto& elim_have = elim_have_d[dev];
-    auto& fast_have = fast_have_d[dev];
-    const size_t ss = osd_sort_smem_bytes(w, precision), fs = osd_fast_smem_bytes(w);
-    size_t& sh = sort_have[precision == 32 ? 0 : 1];
+    static size_t sort_have_d[kMaxDevices][2] = {};
+    const size_t ss = osd_sort_smem_bytes(w, precision);
+    size_t& sh = sort_have_d[device_slot()][precision == 32 ? 0 : 1];
     if (ss > sh) {
         cudaError_t e = precision == 32
             ? cudaFuncSetAttribute(osd_sort_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ss))
@@ -861,6 +867,17 @@ cudaError_t osd_configure(const WinDev& w, int precision) {
         if (e != cudaSuccess) return e;
         sh = ss;
     }
+    return cudaSuccess;
+}
+
+cudaError_t osd_configure(const WinDev& w, int precision) {
+    static size_t elim_have_d[kMaxDevices][2][2][8] = {}, fast_have_d[kMaxDevices][2][2][8] = {};
+    const int dev = device_slot();
+    auto& elim_have = elim_have_d[dev];
+    auto& fast_have = fast_have_d[dev];
+    const size_t fs = osd_fast_smem_bytes(w);
+    cudaError_t se = osd_sort_configure(w, precision);
+    if (se != cudaSuccess) return se;
     for (int hi = 0; hi < 2; ++hi) {
         const size_t es = osd_elim_smem_bytes(w, hi != 0);
         size_t& eh = elim_have[hi][w.full_row_rank ? 0 : 1][elim_nq(w) & 7];

@@ -66,6 +66,7 @@ struct WinDev {
     const double* osd_wt;     // [ncols] log(1/p_j): weights of the higher-order OSD sweeps
     double bin_scale;         // OSD fast path: LLR -> selection bin scale, 10 / (smallest prior LLR of the window)
     int full_row_rank;        // GF(2) rank of the window matrix == rows (then OSD's answer does not depend on pivot-row order)
+    int rank;                 // GF(2) rank of the window matrix
     const uint32_t* colE;     // [cw][ncols_pad]  (row << 8 | slot), kNoEdge when the column is shorter
     const float* llr0f;       // [ncols_pad]  prior LLRs log((1-p)/p), fp32 image (precision 32)
     const double* llr0d;      // [ncols_pad]  ... fp64 (precision 64)
@@ -134,6 +135,7 @@ struct BatchDev {
     void* lsd_scratch;        // LSD only: [grid] slabs of lsd_slab bytes (bit owners, column-order links, operation vectors)
     size_t lsd_slab;
     int lsd_cols;             // columns of the widest window (fixes the slab layout)
+    void* sort_scratch;       // wide windows: [grid] slabs of osd_sort_slab_bytes for the radix sort's keys and index buffers
 };
 
 struct BpParams {
@@ -154,10 +156,12 @@ cudaError_t launch_bp_serial(const WinDev& w, const BatchDev& b, const BpParams&
 cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, bool vglobal, int grid, cudaStream_t st);
 
 size_t osd_sort_smem_bytes(const WinDev& w, int precision);
+size_t osd_sort_slab_bytes(const WinDev& w, int precision);
 size_t osd_elim_smem_bytes(const WinDev& w, bool hi);
 size_t osd_fast_smem_bytes(const WinDev& w);
 bool osd_supported(const WinDev& w, int precision);
 cudaError_t osd_configure(const WinDev& w, int precision);
+cudaError_t osd_sort_configure(const WinDev& w, int precision);
 cudaError_t launch_osd_fast(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
 cudaError_t launch_osd_sort(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
 cudaError_t launch_osd_elim(const WinDev& w, const BatchDev& b, bool hi, int grid, cudaStream_t st);
@@ -168,6 +172,12 @@ size_t lsd_slab_bytes(int cols_cap, int max_rows);
 bool lsd_supported(const WinDev& w);
 cudaError_t lsd_configure(const WinDev& w, int precision);
 cudaError_t launch_lsd(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
+// OSD-0 for windows taller than the shared-memory elimination takes (768 < checks <= 3072): same slab machinery as LSD
+size_t osd_big_smem_bytes(const WinDev& w);
+size_t osd_big_slab_bytes(int max_rows);
+bool osd_big_supported(const WinDev& w);
+cudaError_t osd_big_configure(const WinDev& w);
+cudaError_t launch_osd_big(const WinDev& w, const BatchDev& b, int grid, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------- results
 // pred[n][K] int64 from acc bits; counts[0] += shots whose prediction differs from obs_rows in any observable,

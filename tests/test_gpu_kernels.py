@@ -520,7 +520,7 @@ def test_serial_schedule_on_a_tall_window_takes_the_cta_kernel(qb, bp_method):
             assert np.allclose(llr[i][fin], l[fin], rtol=1e-5, atol=1e-5), i
 
 
-def test_wide_tall_window_bp_and_lsd(qb):
+def test_wide_tall_window_bp_lsd_and_osd(qb):
     """A window of the size BASELINE config 5 produces (the 1020-qubit QLP code: 2250 checks x ~30000 faults, column weight up to
     15): BP takes the generic kernel with its messages in a global slab and its hard decisions in a bit array (more than 32
     columns per thread), LSD runs with three words per lane.  Per shot against the oracle, bit for bit."""
@@ -551,5 +551,13 @@ def test_wide_tall_window_bp_and_lsd(qb):
         assert np.array_equal(np.asarray(H @ ehat[i]).ravel() % 2, syn[i])
         n_lsd += orc.used_osd
     assert n_lsd >= 3
-    with pytest.raises(NotImplementedError):          # OSD still stops at 768 checks
-        qb.BpOsdDecoder(H, channel_probs=pri, osd_method="osd_0", **kw)
+    # OSD-0 at this size goes through the slab kernel (osd_big_kernel: wide radix sort in a global slab, row operations in a
+    # slab, pivot rows in the oracle's row order); higher orders stop at 768 checks
+    dec = qb.BpOsdDecoder(H, channel_probs=pri, osd_method="osd_0", **kw)
+    ehat, llr, iters, conv = dec.decode_batch(syn)
+    orc = cref.BpOsd(H, pri, osd_method="osd_0", **kw)
+    for i in range(n):
+        e, l, it, c = orc.decode(syn[i])
+        assert bool(conv[i]) == c and np.array_equal(ehat[i], e), (i, c, int(ehat[i].sum()), int(e.sum()))
+    with pytest.raises(NotImplementedError):
+        qb.BpOsdDecoder(H, channel_probs=pri, osd_method="osd_cs", osd_order=1, **kw)
