@@ -41,8 +41,13 @@ METRIC = "Monte-Carlo shots/sec, [[144,12,12]] BB 10-round window p=1e-3"
 
 def load_workload():
     g = os.path.join(ROOT, "tests", "golden", "circuits")
-    with open(os.path.join(g, WORKLOAD + ".stim")) as f:
-        text = f.read()
+    if os.path.exists(os.path.join(g, WORKLOAD + ".stim")):
+        with open(os.path.join(g, WORKLOAD + ".stim")) as f:
+            text = f.read()
+    else:                                                  # the large circuits are committed compressed
+        import gzip
+        with gzip.open(os.path.join(g, WORKLOAD + ".stim.gz"), "rb") as f:
+            text = f.read().decode()
     with open(os.path.join(g, WORKLOAD + ".json")) as f:
         meta = json.load(f)
     hz = np.zeros(meta["hz_shape"], dtype=np.uint8)
@@ -55,8 +60,8 @@ def load_workload():
 
 
 def config(shots, precision):
-    return {"workload": "%s custom circuit, W=%d F=%d, %s %s BP max_iter=%d + %s order %d" % (
-                WORKLOAD, W, F, BP_KW["bp_method"], "flooding" if BP_KW["schedule"] == "parallel" else "serial", BP_KW["max_iter"],
+    return {"workload": "%s %s, W=%d F=%d, %s %s BP max_iter=%d + %s order %d" % (
+                WORKLOAD, "custom circuit" if WORKLOAD.startswith("bb") else "circuit", W, F, BP_KW["bp_method"], "flooding" if BP_KW["schedule"] == "parallel" else "serial", BP_KW["max_iter"],
                 BP_KW["osd_method"], BP_KW["osd_order"]),
             "shots_per_step_per_gpu": int(shots), "precision": precision, "seed": SEED,
             "l2": "flushed between timed steps (256 MiB write); per-step message/LLR working set also exceeds L2"}
