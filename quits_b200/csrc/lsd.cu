@@ -292,7 +292,9 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
                 for (int q = 0; q < wt; ++q) {
                     const uint32_t r = __ldg(w.crow + q0 + q);
                     const uint32_t o = cown[r];
-                    if (lane == 0 && rbcol[r] == static_cast<uint32_t>(best)) rbcol[r] = static_cast<uint16_t>(kDirty);
+                    const bool stale = rbcol[r] == static_cast<uint32_t>(best);
+                    __syncwarp();                                    // every lane has read the owner before lane 0 changes it
+                    if (lane == 0 && stale) rbcol[r] = static_cast<uint16_t>(kDirty);
                     if (o == static_cast<uint32_t>(cid)) continue;
                     if (o == kNone) {
                         if (lane == 0) {

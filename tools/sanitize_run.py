@@ -36,6 +36,9 @@ def main():
             pred = dec.decode(det)
             print(kw["bp_method"], kw["schedule"], kw["osd_method"], kw["osd_order"], prec, "logical errors",
                   int(np.any((obs - pred) % 2, axis=1).sum()), flush=True)
+    for prec in ("f64", "f32"):                          # BP-LSD (lsd_kernel), few BP iterations so that LSD has work
+        dec = qb.SlidingWindowDecoder(c, hz.shape[0], 5, 3, precision=prec, **dict(base, osd_method="lsd_0", max_iter=3))
+        print("lsd_0", prec, "logical errors", int(np.any((obs - dec.decode(det)) % 2, axis=1).sum()), flush=True)
     mc = qb.MonteCarlo(c, hz.shape[0], 5, 3, capacity=192, **base)
     print("fused", mc.run(n(500), 9)[0][0], flush=True)
     c3 = circuit("bb144_r10_p3e-3")                      # OSD-heavy: second tier and overflow route
@@ -45,6 +48,23 @@ def main():
     dh, oh = qb.get_stim_mem_result(hg, n(100), seed=5)
     hzh, lzh = np.zeros((108, 225), dtype=np.uint8), np.zeros((9, 225), dtype=np.uint8)
     print("hgp", qb.sliding_window_bposd_circuit_mem(dh, hg, hzh, lzh, 3, 2, **base).sum(), flush=True)
+    from scipy.sparse import csc_matrix
+    rng = np.random.RandomState(2)                       # dense LSD merging on a tiny matrix (operation array compaction), and a
+    for rows, cols, rate, cls, kwx in ((30, 90, 0.3, qb.BpLsdDecoder, dict(lsd_order=0)),            # tall matrix: LSD / OSD slab kernels
+                                       (1100, 2600, 0.02, qb.BpLsdDecoder, dict(lsd_order=0)),
+                                       (1100, 2600, 0.02, qb.BpOsdDecoder, dict(osd_method="osd_0")),
+                                       (1100, 2600, 0.004, qb.BpOsdDecoder, dict(osd_method="off", schedule="serial"))):
+        indptr, indices = [0], []
+        for j in range(cols):
+            indices += list(np.sort(rng.choice(rows, size=3, replace=False)))
+            indptr.append(len(indices))
+        H = csc_matrix((np.ones(len(indices), dtype=np.uint8), np.array(indices), np.array(indptr)), shape=(rows, cols))
+        err = (rng.rand(n(48), cols) < rate).astype(np.uint8)
+        syn = np.asarray((H @ err.T).T % 2, dtype=np.uint8)
+        kw2 = dict(max_iter=2, bp_method="minimum_sum", schedule="parallel")
+        kw2.update(kwx)
+        e = cls(H, error_rate=0.02, **kw2).decode_batch(syn)[0]
+        print(cls.__name__, rows, cols, kwx, "weight", int(e.sum()), flush=True)
     rng = np.random.RandomState(1)
     print("phenom", qb.sliding_window_bposd_phenom_mem(rng.rand(n(64), 72 * 12) < 0.05, (rng.rand(72, 144) < 0.04).astype(int),
                                                        (rng.rand(12, 144) < 0.3).astype(int), 5, 3, error_rate=0.02, **base).sum(), flush=True)
