@@ -85,7 +85,8 @@ def lsd_engine_options(kw: dict) -> dict:
     kw = dict(kw)
     method = str(kw.pop("lsd_method", "lsd_0")).lower()
     order = int(kw.pop("lsd_order", 0))
-    kw.pop("bits_per_step", None)
+    if kw.pop("bits_per_step", 1) not in (None, 1):
+        raise NotImplementedError("BP-LSD with bits_per_step != 1 is not implemented on the GPU path")
     if method in ("off", "none"):
         kw["osd_method"] = "off"
         return kw

@@ -6,6 +6,7 @@ PYTHONHASHSEED=0 because the colouring-based strategies depend on set iteration 
 
   qt633_zxcol_r12_p1e-3   BASELINE config 4: the shipped 633 quantum-Tanner Hx/Hz pair through QldpcCode.from_parity_checks
                           (doc/01B_make_my_own_code.ipynb cells 3-5), zxcoloration circuit, 12 rounds
+  bpc90_card_r10_p5e-4    the reference's own sliding-window tests (tests/test_sliding_window.py): BPC code, cardinal circuit seed 1
   hgp225_r15_p1e-3        the notebooks' HGP run (doc/03, doc/06A): cardinal circuit seed 1, 15 rounds -- windows of
                           540 x 6480, the largest the shared-memory kernels take
 """
@@ -41,6 +42,15 @@ def main():
                              circuit_build_options=opts, seed=1)
     dump("hgp225_r15_p1e-3", hgp, circ, {"code": "HgpCode(h,h) n=12_dv=3_dc=4_dist=6", "strategy": "cardinal", "seed": 1, "rounds": 15,
                                          "p": p, "basis": "Z", "PYTHONHASHSEED": os.environ.get("PYTHONHASHSEED")})
+    # the code and circuit of the reference's own sliding-window tests (tests/test_sliding_window.py:10-33,47-52,106-111):
+    # BpcCode([0,1,5], [0,8,13], 15, 3), cardinal circuit seed 1, p = 5e-4, 10 rounds
+    from quits.qldpc_code import BpcCode
+    bpc = BpcCode([0, 1, 5], [0, 8, 13], 15, 3)
+    bpc.build_circuit(strategy="cardinal", seed=1)
+    p = 5e-4
+    circ = bpc.build_circuit(strategy="cardinal", error_model=ErrorModel(p, p, p, p), num_rounds=10, basis="Z", seed=1)
+    dump("bpc90_card_r10_p5e-4", bpc, circ, {"code": "BpcCode([0,1,5],[0,8,13],15,3)", "strategy": "cardinal", "seed": 1, "rounds": 10, "p": p,
+                                             "basis": "Z", "depth": int(bpc.depth), "PYTHONHASHSEED": os.environ.get("PYTHONHASHSEED")})
 
 
 if __name__ == "__main__":
