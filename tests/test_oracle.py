@@ -274,3 +274,88 @@ def test_lsd0_on_a_decoding_window():
         assert np.array_equal(H @ e % 2, s)
         used += dec.used_osd
     assert used >= 3
+
+
+# ---------------------------------------------------------------------------------------------- OSD, literally
+def _osd_literal(H, syn, llr, priors, method, order):
+    """OSD as published (Panteleev & Kalachev / Roffe et al.; ldpc's osd.hpp as far as remembered), written the slow obvious way
+    on dense numpy arrays: columns by ascending (LLR, index); row reduction with the first row at or below the current rank as
+    pivot; OSD-0 = solve on the pivots; osd_cs(w) = every single non-pivot column then every pair among the first w, osd_e(w) =
+    every non-empty subset of the first w; a candidate's weight is sum log(1/p_j) over its set bits in column-index order; the
+    first strictly lighter candidate wins."""
+    m, n = H.shape
+    order_idx = sorted(range(n), key=lambda j: (llr[j], j))
+    A = np.concatenate([H[:, order_idx], syn.reshape(-1, 1)], axis=1).astype(np.uint8)
+    piv, rank = [], 0
+    for k in range(n):
+        if rank == m:
+            break
+        nz = np.flatnonzero(A[rank:, k])
+        if nz.size == 0:
+            continue
+        p = rank + int(nz[0])
+        A[[rank, p]] = A[[p, rank]]
+        for i in range(m):
+            if i != rank and A[i, k]:
+                A[i] ^= A[rank]
+        piv.append(k)
+        rank += 1
+
+    def weight(x):
+        w = 0.0
+        for j in range(n):
+            if x[j]:
+                w += np.log(1.0 / priors[j])
+        return w
+
+    def solution(flips):
+        x = np.zeros(n, dtype=np.uint8)
+        for r, k in enumerate(piv):
+            b = A[r, n]
+            for f in flips:
+                b ^= A[r, f]
+            if b:
+                x[order_idx[k]] = 1
+        for f in flips:
+            x[order_idx[f]] = 1
+        return x
+
+    best = solution([])
+    if method == "osd_0" or order == 0:
+        return best
+    bw = weight(best)
+    nonpiv = [k for k in range(n) if k not in set(piv)]
+    w = min(order, len(nonpiv))
+    cands = []
+    if method == "osd_cs":
+        cands = [[k] for k in nonpiv] + [[nonpiv[i], nonpiv[j]] for i in range(w) for j in range(i + 1, w)]
+    else:
+        cands = [[nonpiv[b] for b in range(w) if (pat >> b) & 1] for pat in range(1, 1 << w)]
+    for fl in cands:
+        x = solution(fl)
+        cw = weight(x)
+        if cw < bw:
+            bw, best = cw, x
+    return best
+
+
+@pytest.mark.parametrize("method,order", [("osd_0", 0), ("osd_cs", 1), ("osd_cs", 4), ("osd_e", 3)])
+def test_osd_equals_the_literal_restatement(method, order):
+    """Pins the C oracle's packed-word elimination, stable sort and candidate sweeps against the obvious dense version,
+    including rank-deficient matrices and syndromes outside the image."""
+    rng = np.random.default_rng(17 + order)
+    n_osd = 0
+    for trial in range(60):
+        m = int(rng.integers(4, 24)); n = int(rng.integers(m, 3 * m + 4))
+        H = (rng.random((m, n)) < min(0.5, 3.0 / m)).astype(np.uint8)
+        if trial % 4 == 0 and m > 5:
+            H[m - 1] = H[0] ^ H[1]                       # rank deficient
+        p = rng.uniform(0.01, 0.2, n)
+        dec = cref.BpOsd(sp.csc_matrix(H), p, max_iter=int(rng.integers(1, 3)), bp_method="minimum_sum", osd_method=method, osd_order=order)
+        for t in range(3):
+            syn = ((H @ (rng.random(n) < 0.2)) % 2).astype(np.uint8) if t else rng.integers(0, 2, m).astype(np.uint8)   # t == 0: any syndrome
+            e, llr, it, conv = dec.decode(syn)
+            if not conv:
+                n_osd += 1
+                assert np.array_equal(_osd_literal(H, syn, llr, p, method, order), e), (trial, t)
+    assert n_osd > 60
