@@ -359,3 +359,90 @@ def test_osd_equals_the_literal_restatement(method, order):
                 n_osd += 1
                 assert np.array_equal(_osd_literal(H, syn, llr, p, method, order), e), (trial, t)
     assert n_osd > 60
+
+
+# ---------------------------------------------------------------------------------------------- BP, literally
+def _bp_literal(H, syn, priors, max_iter, method, schedule, alpha):
+    """ldpc v2's BP as published, on python dicts keyed by (row, column): flooding = all check->bit messages from the previous
+    bit->check messages, then all bits; serial = bit by bit in index order from the current messages.  Same floating-point
+    operation order as the statement in oracle/bp_impl.inc (prefix sums over a column in ascending row order, then the suffix)."""
+    import math
+    m, n = H.shape
+    rows = [list(np.flatnonzero(H[i])) for i in range(m)]
+    cols = [list(np.flatnonzero(H[:, j])) for j in range(n)]
+    l0 = [math.log((1.0 - p) / p) for p in priors]
+    v = {(i, j): l0[j] for j in range(n) for i in cols[j]}
+    llr = list(l0)
+
+    def check_to_bit(i, j, it):
+        others = [v[(i, g)] for g in rows[i] if g != j]
+        if method == "product_sum":
+            t = 1.0
+            for x in others:
+                t *= math.tanh(x / 2.0)
+            sign = -1.0 if syn[i] else 1.0
+            num, den = 1.0 + t, 1.0 - t
+            if den == 0.0:
+                return sign * math.inf
+            q = num / den
+            return sign * (-math.inf if q == 0.0 else (math.nan if q < 0.0 else math.log(q)))
+        a = alpha if alpha != 0.0 else 1.0 - 2.0 ** (-it)
+        mag = min([abs(x) for x in others], default=float(np.finfo(np.float64).max))
+        sgn = int(syn[i]) + sum(1 for x in others if x <= 0)
+        return (a if sgn % 2 == 0 else -a) * mag
+
+    for it in range(1, max_iter + 1):
+        e = np.zeros(n, dtype=np.uint8)
+        if schedule == "parallel":
+            c = {(i, j): check_to_bit(i, j, it) for j in range(n) for i in cols[j]}
+        for j in range(n):
+            if schedule == "serial":
+                c = {(i, j): check_to_bit(i, j, it) for i in cols[j]}
+            t = l0[j]
+            pre = []
+            for i in cols[j]:
+                pre.append(t)
+                t = t + c[(i, j)]
+            llr[j] = t
+            e[j] = 1 if t <= 0 else 0
+            if schedule == "serial" or True:
+                suf = 0.0
+                newv = {}
+                for k in range(len(cols[j]) - 1, -1, -1):
+                    i = cols[j][k]
+                    newv[(i, j)] = pre[k] + suf
+                    suf = suf + c[(i, j)]
+                if schedule == "serial":
+                    v.update(newv)
+                else:
+                    pending = newv if j == 0 else {**pending, **newv}
+        if schedule == "parallel":
+            v.update(pending)
+        if np.array_equal((H @ e) % 2, syn):
+            return e, np.array(llr), it, True
+    return e, np.array(llr), max_iter, False
+
+
+@pytest.mark.parametrize("method,schedule,alpha", [("minimum_sum", "parallel", 1.0), ("minimum_sum", "parallel", 0.0), ("minimum_sum", "serial", 0.75),
+                                                   ("product_sum", "parallel", 1.0), ("product_sum", "serial", 1.0)])
+def test_bp_equals_the_literal_restatement(method, schedule, alpha):
+    """Pins the C oracle's edge indexing, sweep order and scaling against the dictionary version: min-sum posteriors bit for bit,
+    product-sum to 1e-9 (same libm; the C version multiplies prefix x suffix instead of the others in one run)."""
+    rng = np.random.default_rng(41)
+    for trial in range(25):
+        m = int(rng.integers(4, 16)); n = int(rng.integers(m, 2 * m + 6))
+        H = (rng.random((m, n)) < min(0.5, 3.0 / m)).astype(np.uint8)
+        for j in range(n):
+            if not H[:, j].any():
+                H[rng.integers(m), j] = 1
+        p = rng.uniform(0.02, 0.2, n)
+        dec = cref.BpOsd(sp.csc_matrix(H), p, max_iter=4, bp_method=method, schedule=schedule, ms_scaling_factor=alpha, osd=False)
+        for t in range(3):
+            syn = ((H @ (rng.random(n) < 0.15)) % 2).astype(np.uint8)
+            e, llr, it, conv = dec.decode(syn)
+            e2, llr2, it2, conv2 = _bp_literal(H, syn, p, 4, method, schedule, alpha)
+            if method == "minimum_sum":
+                assert (it, conv) == (it2, conv2) and np.array_equal(llr, llr2) and np.array_equal(e, e2), (trial, t)
+            elif it == it2:
+                fin = np.isfinite(llr) & np.isfinite(llr2)
+                assert np.allclose(llr[fin], llr2[fin], rtol=1e-9, atol=1e-9), (trial, t)
