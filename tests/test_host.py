@@ -345,3 +345,46 @@ def test_baseline_config5_host_pipeline():
     assert shapes[6] == ((1800, 22170), 114184, 22170)
     assert plan.window(3)["U"].shape == (450, 18900)
     assert dt < 30.0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/quits"), reason="needs the reference tree (build container only)")
+def test_compat_runs_the_unmodified_reference_package():
+    """quits_b200.compat.install() registers the engine under the names the reference imports (stim, ldpc.bposd_decoder,
+    ldpc.bplsd_decoder); the UNMODIFIED reference package then builds its circuits into the engine's Circuit (C++ front end), walks
+    it with its own helpers, and its own detector_error_model_to_matrix / spacetime run on the engine's DEM.  Run in a subprocess:
+    the session's other tests keep the oracle's shims.  (No GPU: nothing is sampled or decoded here.)"""
+    import subprocess
+    import sys
+    code = r'''
+import sys, json, hashlib
+import numpy as np
+sys.path.insert(0, %r)
+import quits_b200.compat as compat
+assert compat.install(force=True)
+sys.path.insert(0, "/root/reference/src")
+import quits
+from quits import ErrorModel, CircuitBuildOptions
+from quits.qldpc_code import BbCode
+from quits.circuit import check_overlapping_CX
+from quits.decoder import spacetime, detector_error_model_to_matrix
+import stim, ldpc.bposd_decoder, ldpc.bplsd_decoder
+assert stim.Circuit is compat.StimCircuit and ldpc.bposd_decoder.BpOsdDecoder.__module__.startswith("quits_b200")
+code = BbCode(l=6, m=6, A_x_pows=[3], A_y_pows=[1, 2], B_x_pows=[1, 2], B_y_pows=[3])
+p = 1e-3
+circ = code.build_circuit(strategy="custom", error_model=ErrorModel(p, p, p, p), num_rounds=6, basis="Z",
+                          circuit_build_options=CircuitBuildOptions())
+assert isinstance(circ, compat.StimCircuit)
+assert check_overlapping_CX(circ, verbose=False) == []
+H, L, pri = detector_error_model_to_matrix(circ.detector_error_model(decompose_errors=False))
+checks, obs, priors, updates = spacetime(circ, code.hz, 5, 3, 1)
+print(json.dumps({"text_sha": hashlib.sha256(circ.text.encode()).hexdigest(), "n_instr": len(circ), "H": list(H.shape), "nnz": int(H.nnz),
+                  "sum": float(np.sum(pri)), "windows": [list(c.shape) for c in checks], "D": circ.num_detectors, "K": circ.num_observables}))
+''' % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = json.loads(out.stdout.strip().split("\n")[-1])
+    want_text = circuit_text("bb72_r6_p1e-3")
+    assert got["text_sha"] == hashlib.sha256(want_text.encode()).hexdigest()        # the frozen fixture IS what the reference builds
+    assert got["H"] == [288, 2592] and got["nnz"] == 9036 and abs(got["sum"] - 4.69) < 0.01       # SURVEY Appendix C, config 2
+    assert got["windows"] == [[180, 1764], [180, 1548]] and (got["D"], got["K"]) == (288, 12)
+    assert got["n_instr"] > 10
