@@ -388,3 +388,55 @@ print(json.dumps({"text_sha": hashlib.sha256(circ.text.encode()).hexdigest(), "n
     assert got["H"] == [288, 2592] and got["nnz"] == 9036 and abs(got["sum"] - 4.69) < 0.01
     assert got["windows"] == [[180, 1764], [180, 1548]] and (got["D"], got["K"]) == (288, 12)
     assert got["n_instr"] > 10
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/quits"), reason="needs the reference tree (build container only)")
+def test_every_code_family_of_the_reference_builds_into_the_engine():
+    """The code families and circuit strategies of the reference's own tests (tests/test_codes.py:159-414: HGP cardinal and
+    zxcoloration, QLP, BPC cardinal and cardinalNSmerge, LCS, BB custom), built by the UNMODIFIED reference on top of
+    quits_b200.compat: every text is accepted by the C++ front end, gives D = m (rounds + 1) detectors... and K observables, a DEM
+    whose matrix has the detectors' row count and no column heavier than the BP kernels take, and a W5/F3 window plan that covers
+    every detector row exactly once in its committed rows."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, json
+import numpy as np
+sys.path.insert(0, %r)
+import quits_b200.compat as compat
+compat.install(force=True)
+sys.path.insert(0, "/root/reference/src")
+from quits import ErrorModel
+from quits.qldpc_code import BbCode, BpcCode, HgpCode, LcsCode, QlpCode
+from quits.decoder import detector_error_model_to_matrix
+from quits_b200.decoder.base import WindowPlan
+h = np.loadtxt("/root/reference/parity_check_matrices/n=12_dv=3_dc=4_dist=6.txt", dtype=int)
+b = np.array([[0, 0, 0, 0, 0], [0, 2, 4, 7, 11], [0, 3, 10, 14, 15]])
+cases = [("hgp_cardinal", HgpCode(h, h), dict(strategy="cardinal", seed=1)), ("hgp_zxcol", HgpCode(h, h), dict(strategy="zxcoloration")),
+         ("bpc_cardinal", BpcCode([0, 1, 5], [0, 8, 13], 15, 3), dict(strategy="cardinal", seed=1)),
+         ("bpc_nsmerge", BpcCode([0, 1, 5], [0, 8, 13], 15, 3), dict(strategy="cardinalNSmerge", seed=1)),
+         ("lcs_cardinal", LcsCode(5, 3), dict(strategy="cardinal", seed=1)),
+         ("qlp_cardinal", QlpCode(b, b, 16), dict(strategy="cardinal", seed=1)),
+         ("bb_custom", BbCode(l=6, m=6, A_x_pows=[3], A_y_pows=[1, 2], B_x_pows=[1, 2], B_y_pows=[3]), dict(strategy="custom"))]
+out = {}
+for name, code, kw in cases:
+    p, rounds = 5e-4, 6
+    circ = code.build_circuit(error_model=ErrorModel(p, p, p, p), num_rounds=rounds, basis="Z", **kw)
+    m, K = code.hz.shape[0], code.lz.shape[0]
+    H, L, pri = detector_error_model_to_matrix(circ.detector_error_model(decompose_errors=False))
+    plan = WindowPlan(circ.detector_error_model(), m, 5, 3)
+    rows = [plan.window(k)["rows"] for k in range(plan.n_windows)]
+    out[name] = {"qubits": circ.num_qubits, "D": circ.num_detectors, "K": circ.num_observables, "m": m, "k": K, "rounds": rounds,
+                 "H": list(H.shape), "colw": int(np.diff(H.indptr).max()), "priors_ok": bool(((pri > 0) & (pri < 0.5)).all()),
+                 "windows": plan.n_windows, "rows": rows, "L_rows": int(L.shape[0])}
+print(json.dumps(out))
+''' % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, env=dict(os.environ, PYTHONHASHSEED="0"))
+    assert out.returncode == 0, out.stderr[-3000:]
+    got = json.loads(out.stdout.strip().split("\n")[-1])
+    assert len(got) == 7
+    for name, g in got.items():
+        assert g["D"] == g["m"] * (g["rounds"] + 2), name          # one detector layer per round, plus the first and the final data layer
+        assert g["K"] == g["k"] == g["L_rows"], name
+        assert g["H"][0] == g["D"] and g["colw"] <= 16 and g["priors_ok"], name
+        assert g["windows"] == 2 and g["rows"] == [5 * g["m"], 5 * g["m"]], name       # rounds + 2 = 8 layers: W5/F3 -> layers 0-4, 3-7
