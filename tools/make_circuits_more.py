@@ -51,6 +51,23 @@ def main():
     circ = bpc.build_circuit(strategy="cardinal", error_model=ErrorModel(p, p, p, p), num_rounds=10, basis="Z", seed=1)
     dump("bpc90_card_r10_p5e-4", bpc, circ, {"code": "BpcCode([0,1,5],[0,8,13],15,3)", "strategy": "cardinal", "seed": 1, "rounds": 10, "p": p,
                                              "basis": "Z", "depth": int(bpc.depth), "PYTHONHASHSEED": os.environ.get("PYTHONHASHSEED")})
+    # the other code families / strategies of the reference's tests (tests/test_codes.py:232-343), 6 rounds
+    from quits.qldpc_code import LcsCode, QlpCode
+    p = 1e-3
+    lcs = LcsCode(5, 3)
+    circ = lcs.build_circuit(strategy="cardinal", error_model=ErrorModel(p, p, p, p), num_rounds=6, basis="Z", seed=1)
+    dump("lcs_card_r6_p1e-3", lcs, circ, {"code": "LcsCode(5, 3)", "strategy": "cardinal", "seed": 1, "rounds": 6, "p": p, "basis": "Z",
+                                          "PYTHONHASHSEED": os.environ.get("PYTHONHASHSEED")})
+    circ = bpc.build_circuit(strategy="cardinalNSmerge", error_model=ErrorModel(p, p, p, p), num_rounds=6, basis="Z", seed=1)
+    dump("bpc90_nsmerge_r6_p1e-3", bpc, circ, {"code": "BpcCode([0,1,5],[0,8,13],15,3)", "strategy": "cardinalNSmerge", "seed": 1, "rounds": 6,
+                                               "p": p, "basis": "Z", "PYTHONHASHSEED": os.environ.get("PYTHONHASHSEED")})
+    p = 5e-4
+    b = np.array([[0, 0, 0, 0, 0], [0, 2, 4, 7, 11], [0, 3, 10, 14, 15]])
+    qlp = QlpCode(b, b, 16)
+    circ = qlp.build_circuit(strategy="cardinal", error_model=ErrorModel(p, p, p, p), num_rounds=6, basis="Z", seed=1)
+    # (committed gzip-compressed: gzip -9 tests/golden/circuits/qlp544_card_r6_p5e-4.stim)
+    dump("qlp544_card_r6_p5e-4", qlp, circ, {"code": "QlpCode(b, b, 16), [[544,80]]", "strategy": "cardinal", "seed": 1, "rounds": 6, "p": p,
+                                             "basis": "Z", "PYTHONHASHSEED": os.environ.get("PYTHONHASHSEED")})
 
 
 if __name__ == "__main__":

@@ -51,6 +51,9 @@ CASES = [
     ("toric3_zxcol_r3_p1e-3", 3, 2, 1024, 21),
     ("qt633_zxcol_r12_p1e-3", 5, 3, 128, 22),    # BASELINE config 4 (circuit from tools/make_circuits_more.py), BP-OSD inner decoder
     ("hgp225_r15_p1e-3", 5, 3, 48, 23),          # the notebooks' HGP run: 540 x 6480 windows
+    ("lcs_card_r6_p1e-3", 5, 3, 256, 24),        # the other code families / strategies of the reference's tests
+    ("bpc90_nsmerge_r6_p1e-3", 5, 3, 192, 25),
+    ("qlp544_card_r6_p5e-4", 5, 3, 48, 26),      # windows of 1200 checks: generic BP kernel + slab OSD
 ]
 
 
@@ -59,8 +62,14 @@ def sha(a):
 
 
 def load(name):
-    with open(os.path.join(G, "circuits", name + ".stim")) as f:
-        text = f.read()
+    path = os.path.join(G, "circuits", name + ".stim")
+    if os.path.exists(path):
+        with open(path) as f:
+            text = f.read()
+    else:                                              # the larger texts are committed compressed
+        import gzip
+        with gzip.open(path + ".gz", "rb") as f:
+            text = f.read().decode()
     with open(os.path.join(G, "circuits", name + ".json")) as f:
         meta = json.load(f)
     hz = np.zeros(meta["hz_shape"], dtype=np.uint8)
