@@ -17,7 +17,8 @@ import quits_b200 as qb
 from quits_b200 import _native as N
 from quits_b200.decoder.base import WindowPlan
 
-CIRCUITS = sorted(f[:-5] for f in os.listdir(os.path.join(GOLDEN, "circuits")) if f.endswith(".stim"))
+CIRCUITS = sorted(f[:-5] if f.endswith(".stim") else f[:-8] for f in os.listdir(os.path.join(GOLDEN, "circuits"))
+                  if f.endswith(".stim") or f.endswith(".stim.gz"))
 
 
 def sha(a):
