@@ -561,3 +561,22 @@ def test_wide_tall_window_bp_lsd_and_osd(qb):
         assert bool(conv[i]) == c and np.array_equal(ehat[i], e), (i, c, int(ehat[i].sum()), int(e.sum()))
     with pytest.raises(NotImplementedError):
         qb.BpOsdDecoder(H, channel_probs=pri, osd_method="osd_cs", osd_order=1, **kw)
+
+
+def test_frame_kernel_on_random_circuits(qb):
+    """K1 on 40 random circuits in the emitters' grammar (nested REPEAT blocks, RX / MX / MR, empty-target noise lines, detectors
+    on arbitrary earlier records, several observables): detection events and observable flips of 192 shots equal the oracle's
+    sampler bit for bit."""
+    from conftest import random_circuit_text
+    from oracle import cref, stimtext
+    rng = np.random.default_rng(99)
+    n_flips = 0
+    for trial in range(40):
+        text = random_circuit_text(rng, zbasis=bool(trial % 4))
+        fc = stimtext.parse_flat(text)
+        c = qb.Circuit(text)
+        det, obs = qb.get_stim_mem_result(c, 192, seed=1000 + trial)
+        odet, oobs = cref.sample(fc, 1000 + trial, 0, 192)
+        assert np.array_equal(det, odet.astype(bool)) and np.array_equal(obs, oobs.astype(bool)), text
+        n_flips += int(det.sum())
+    assert n_flips > 1000

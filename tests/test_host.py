@@ -10,7 +10,7 @@ import warnings
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT, circuit_meta, circuit_text
+from conftest import GOLDEN, ROOT, circuit_meta, circuit_text, random_circuit_text
 from oracle import cref, dem as odem, shims, stimtext
 
 import quits_b200 as qb
@@ -443,71 +443,6 @@ print(json.dumps(out))
         assert g["windows"] == 2 and g["rows"] == [5 * g["m"], 5 * g["m"]], name       # rounds + 2 = 8 layers: W5/F3 -> layers 0-4, 3-7
 
 
-def _random_circuit_text(rng):
-    """A random circuit in the grammar the reference's emitters produce (circuit.py:58-279) -- resets, H / CX layers with noise,
-    measurements with detectors on earlier records, nested REPEAT blocks, comments, blank lines, empty-target noise lines."""
-    nq = int(rng.integers(3, 10))
-    lines, n_meas, n_obs = [], [0], 0
-    zbasis = rng.random() < 0.7           # only Z-basis resets / measurements and CX: every detector is deterministic
-
-    def qubits(k=None):
-        k = int(rng.integers(1, nq + 1)) if k is None else k
-        return [int(x) for x in rng.choice(nq, size=min(k, nq), replace=False)]
-
-    def prob():
-        return float(rng.choice([0.001, 0.0123456789, 0.05, 0.2]))
-
-    def emit(indent, depth):
-        pad = "    " * indent
-        for _ in range(int(rng.integers(3, 9))):
-            kind = int(rng.integers(0, 10))
-            if kind == 0:
-                lines.append(pad + "%s %s" % ("R" if zbasis else rng.choice(["R", "RX"]), " ".join(map(str, qubits()))))
-                lines.append(pad + "%s(%.10f) %s" % (rng.choice(["X_ERROR", "Z_ERROR"]), prob(), " ".join(map(str, qubits()))))
-            elif kind == 1:
-                qs = qubits()
-                lines.append(pad + "H " + " ".join(map(str, qs)))
-                if zbasis:
-                    lines.append(pad + "H " + " ".join(map(str, qs)))        # back to the Z basis
-                lines.append(pad + "DEPOLARIZE1(%.10f) %s" % (prob(), " ".join(map(str, qubits()))))
-            elif kind in (2, 3):
-                qs = qubits(2 * int(rng.integers(1, nq // 2 + 1)))
-                qs = qs[:len(qs) // 2 * 2]
-                if qs:
-                    lines.append(pad + "CX " + " ".join(map(str, qs)))
-                    lines.append(pad + "DEPOLARIZE2(%.10f) %s" % (prob(), " ".join(map(str, qs))))
-            elif kind in (4, 5):
-                qs = qubits()
-                name = str(rng.choice(["M", "MR"])) if zbasis else str(rng.choice(["M", "MX", "MR"]))
-                lines.append(pad + "X_ERROR(%.10f) %s" % (prob(), " ".join(map(str, qs))))
-                lines.append(pad + name + " " + " ".join(map(str, qs)))
-                n_meas[0] += len(qs)
-                for _ in range(int(rng.integers(1, 3))):
-                    look = sorted(set(int(x) for x in rng.integers(1, min(n_meas[0], 6) + 1, size=int(rng.integers(1, 4)))))
-                    lines.append(pad + "DETECTOR " + " ".join("rec[-%d]" % k for k in look))
-            elif kind == 6:
-                lines.append(pad + "TICK")
-                lines.append("")
-                lines.append(pad + "# a comment")
-            elif kind == 7:
-                lines.append(pad + "DEPOLARIZE1(%.10f)" % prob())           # empty target list (circuit.py:106-124 on an empty layer)
-            elif kind == 8 and depth < 2 and n_meas[0] >= 1:
-                lines.append(pad + "REPEAT %d {" % int(rng.integers(1, 4)))
-                emit(indent + 1, depth + 1)
-                lines.append(pad + "}")
-            elif kind == 9 and n_meas[0] >= 1:
-                nonlocal_obs = int(rng.integers(0, 3))
-                lines.append(pad + "OBSERVABLE_INCLUDE(%d) %s" % (nonlocal_obs, " ".join("rec[-%d]" % int(k) for k in rng.integers(1, min(n_meas[0], 4) + 1, size=2))))
-
-    lines.append("R " + " ".join(map(str, range(nq))))
-    emit(0, 0)
-    lines.append("M " + " ".join(map(str, range(nq))))
-    n_meas[0] += nq
-    lines.append("DETECTOR rec[-1] rec[-%d]" % nq)
-    lines.append("OBSERVABLE_INCLUDE(0) rec[-1]")
-    return "\n".join(lines) + "\n"
-
-
 def test_front_end_and_dem_match_oracle_on_random_circuits():
     """400 random circuits in the emitters' grammar (those whose random detectors are not deterministic must be refused by both
     sides with the same message): the C++ parser's flattened op list and the C++ backward DEM analyser equal the
@@ -515,7 +450,7 @@ def test_front_end_and_dem_match_oracle_on_random_circuits():
     rng = np.random.default_rng(2024)
     n_rep = n_err = n_nondet = 0
     for trial in range(400):
-        text = _random_circuit_text(rng)
+        text = random_circuit_text(rng)
         c = qb.Circuit(text)
         fc = stimtext.parse_flat(text)
         assert (c.num_qubits, c.num_measurements, c.num_detectors, c.num_observables, c.num_flat_ops) == \
