@@ -580,3 +580,24 @@ def test_frame_kernel_on_random_circuits(qb):
         assert np.array_equal(det, odet.astype(bool)) and np.array_equal(obs, oobs.astype(bool)), text
         n_flips += int(det.sum())
     assert n_flips > 1000
+
+
+def test_code_capacity_loop_with_bplsd(qb):
+    """get_codecap_pL with the BP-LSD inner decoder (the reference hands ldpc's BpLsdDecoder and its kwargs to the same loop,
+    simulation.py:31-61): equals the per-trial loop over the oracle's BP + LSD-0."""
+    import types
+    from oracle import cref
+    _, hz, lz = circuit_meta("bb72_r6_p1e-3")
+    code = types.SimpleNamespace(hz=hz, lz=lz, hx=hz, lx=lz)
+    p, trials, seed = 0.04, 200, 321
+    kw = dict(bp_method="minimum_sum", schedule="parallel", max_iter=3, lsd_method="lsd_cs", lsd_order=0, error_rate=p)
+    got = qb.get_codecap_pL(code, p, trials, qb.BpLsdDecoder, dict(kw), basis="X", seed=seed)
+    np.random.seed(seed)
+    orc = cref.BpOsd(hz, np.full(hz.shape[1], p), max_iter=3, bp_method="minimum_sum", schedule="parallel", precision="f64", osd_method="lsd_0")
+    errs = used = 0
+    for _ in range(trials):
+        noise = np.random.binomial(1, p, hz.shape[1])
+        e, _, _, _ = orc.decode(hz @ noise % 2)
+        used += orc.used_osd
+        errs += int((lz @ ((e + noise) % 2) % 2).any())
+    assert got == errs / trials and used > 10
