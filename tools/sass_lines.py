@@ -16,12 +16,12 @@ import tempfile
 
 
 def main():
-    src, pattern = sys.argv[1], sys.argv[2]
+    src, pattern = os.path.abspath(sys.argv[1]), sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
     with tempfile.TemporaryDirectory() as td:
         cubin = os.path.join(td, "k.cubin")
         subprocess.run(["nvcc", "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--fmad=false", "-cubin",
-                        "-o", cubin, src], check=True, cwd=os.path.dirname(os.path.abspath(src)) or ".")
+                        "-o", cubin, src], check=True, cwd=os.path.dirname(src))
         txt = subprocess.run(["nvdisasm", "--print-line-info", cubin], check=True, capture_output=True, text=True).stdout
     lines = open(src).read().split("\n")
     base = os.path.basename(src)
