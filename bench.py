@@ -11,11 +11,17 @@ all-reduce of the error counters and a MAX of the device times.  Rank 0 prints O
   value     shots/s, whole job, CUDA-event time on the launching stream (max over ranks)
   e2e       same metric through the drop-in calls get_stim_mem_result -> sliding_window_bposd_circuit_mem with host
             numpy buffers (D2H of the detection events, H2D again for decoding, D2H of the predictions) inside the timed region
-  roofline  dominant kernel (BP): algorithmic message bytes per launch / CUDA-event duration, against the measured HBM peak
+  roofline  dominant kernel (BP).  Its messages never leave shared memory, so the binding roofline is the SM front end:
+            bound "issue" = warp-instructions issued per second (instructions per edge-iteration from the committed ncu
+            capture profiles/bp_inst_model.json x the edge-iterations this run executed / CUDA-event time of the BP launches)
+            against 148 SMs x 4 schedulers x the SM clock sampled during the run.  The HBM message-streaming model of
+            SURVEY 8(d) is kept beside it as hbm_model (frac > 1 there only says the messages are on chip), with the real
+            DRAM traffic per launch (ncu) and the compulsory I/O bytes.
   cpu_baseline  the oracle's C restatement of the same path (OpenMP, all host cores) on a bounded sample, rank 0, N=1
 
---impl reference times that CPU path alone (the reference's stim+ldpc wheels are not installable here, so the "reference
-arm" is the oracle port of its algorithm).
+--impl reference times the reference's CPU path alone: the real stim + ldpc wheels under the unmodified reference package
+(baseline/run_reference.py, kind "reference") when they import; on this image they do not exist (not in the wheelhouse, no
+network), so the arm falls back to the oracle's C port of the same algorithm (kind "port") and says so.
 """
 from __future__ import annotations
 
@@ -86,16 +92,67 @@ def cpu_arm(shots, nthreads=0):
     return shots / dt, dt, threads, fails
 
 
+REAL_REF_WHY = ["not probed"]
+
+
+def real_reference_arm(args):
+    """The unmodified reference on real stim + ldpc (baseline/run_reference.py), one process per host core; None when the
+    wheels are not importable (then REAL_REF_WHY says why)."""
+    script = os.path.join(ROOT, "baseline", "run_reference.py")
+    try:
+        pr = json.loads(subprocess.run([sys.executable, script, "--probe"], capture_output=True, text=True, timeout=300).stdout.strip().split("\n")[-1])
+    except Exception as e:
+        REAL_REF_WHY[0] = "probe failed: %r" % (e,)
+        return None
+    if not pr.get("available"):
+        REAL_REF_WHY[0] = pr.get("why", "unknown")
+        return None
+    procs = os.cpu_count() or 1
+    rates, times = [], []
+    shots = 16 * procs
+    for i in range(args.warmup + args.steps):
+        out = subprocess.run([sys.executable, script, "--workload", WORKLOAD, "--shots", str(shots), "--procs", str(procs)],
+                             capture_output=True, text=True, timeout=3600).stdout.strip().split("\n")[-1]
+        r = json.loads(out)
+        if i == 0:                               # size the sample for ~10 s per step
+            shots = int(max(procs, min(200000, r["shots_per_s"] * 10.0)) // procs * procs)
+        if i >= args.warmup:
+            rates.append(r["shots_per_s"])
+            times.append(r["wall_s"])
+    rate, ms = float(np.mean(rates)), float(np.mean(times) * 1e3)
+    sample = "%d shots per step, unmodified reference on stim+ldpc, one process per host core" % shots
+    return {"impl": "reference", "metric": METRIC, "value": rate, "unit": "shots/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config(shots, "f64"),
+            "cpu_baseline": {"value": rate, "unit": "shots/s", "cores": procs, "kind": "reference", "sample": sample},
+            "e2e": {"value": rate, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def calibrated_cpu_sample(budget_s=12.0):
     rate, dt, threads, _ = cpu_arm(256)
     shots = int(max(256, min(200000, rate * budget_s)) // 64 * 64)
     return shots
 
 
+def inst_model(precision):
+    """profiles/bp_inst_model.json: warp-instructions and shared-memory wavefronts per edge-iteration of the BP kernel, taken
+    from the committed ncu --set full capture (smsp__inst_executed.sum, l1tex__data_pipe_lsu_wavefronts_mem_shared.sum of one
+    launch / the edge-iterations that launch ran); None when no model for this precision / schedule is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "bp_inst_model.json")) as f:
+            m = json.load(f)
+        key = "%s_%s_%s" % (precision, BP_KW["bp_method"], BP_KW["schedule"])
+        return m.get(key)
+    except Exception:
+        return None
+
+
 def ncu_traffic(precision):
     """DRAM bytes of one BP launch (read + write) from the committed ncu --set full capture of the same launch geometry
     (65 536 shots per launch); None when no capture for this precision is committed."""
-    path = os.path.join(ROOT, "profiles", "r01_bp_kernel_%s_ncu_full.txt" % precision)
+    path = os.path.join(ROOT, "profiles", "r02_bp_kernel_%s_ncu_full.txt" % precision)
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r01_bp_kernel_%s_ncu_full.txt" % precision)
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     total, seen = 0.0, 0
     try:
@@ -108,6 +165,41 @@ def ncu_traffic(precision):
     except Exception:
         return None
     return total if seen == 2 else None
+
+
+def roofline(precision, agg, clocks, peaks):
+    """The BP kernel against the limit that binds it (issue slots), with the shared-memory pipe and the SURVEY 8(d) HBM model."""
+    bp_s = agg["bp_ms"] / 1e3
+    bp_launches = max(1, agg["bp_launches"])
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_ach = agg["bp_alg_bytes"] / bp_s / 1e9 if bp_s > 0 else 0.0
+    sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9              # G warp-instructions / s: one per scheduler and cycle
+    smem_peak = 148 * sm_mhz * 1e6 / 1e9                   # G shared-memory wavefronts / s: one per SM and cycle
+    m = inst_model(precision)
+    ei = agg.get("bp_edge_iters", 0.0)
+    out = {"kernel": "bp_kernel_compact", "bound": "issue", "unit": "Gwarp-inst/s", "peak": issue_peak,
+           "peak_source": "148 SMs x 4 schedulers x %.0f MHz (SM clock sampled during the timed region)" % sm_mhz,
+           "achieved": None, "frac": None, "edge_iters_per_s": ei / bp_s if bp_s > 0 else 0.0,
+           "ms_per_launch": agg["bp_ms"] / bp_launches, "traffic": ncu_traffic(precision),
+           "alg_io_bytes_per_launch": agg["bp_io_bytes"] / bp_launches if "bp_io_bytes" in agg else None,
+           "hbm_model": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "model_frac": hbm_ach / hbm_peak,
+                         "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650",
+                         "alg_bytes_per_launch": agg["bp_alg_bytes"] / bp_launches,
+                         "note": "SURVEY 8(d) message-streaming model (iterations x 4 x nnz x sizeof(msg) + syndrome in + commit/carry out). "
+                                 "The messages are shared-memory resident: model_frac > 1 is not an HBM figure, `traffic` is the DRAM bytes "
+                                 "one launch really moves (ncu)"}}
+    if m and bp_s > 0:
+        inst = m["warp_inst_per_edge_iter"] * ei
+        out["achieved"] = inst / bp_s / 1e9
+        out["frac"] = out["achieved"] / issue_peak
+        out["warp_inst_per_edge_iter"] = m["warp_inst_per_edge_iter"]
+        out["thread_inst_per_edge_iter"] = 32 * m["warp_inst_per_edge_iter"]
+        out["inst_source"] = m.get("source")
+        if m.get("smem_wavefronts_per_edge_iter"):
+            wf = m["smem_wavefronts_per_edge_iter"] * ei / bp_s / 1e9
+            out["smem"] = {"achieved": wf, "peak": smem_peak, "unit": "Gwavefront/s", "frac": wf / smem_peak}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -175,6 +267,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        real = real_reference_arm(args)
+        if real is not None:
+            print(json.dumps(real))
+            return
         shots = calibrated_cpu_sample(8.0)
         vals = []
         for i in range(args.warmup + args.steps):
@@ -189,7 +285,8 @@ def main():
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config(shots, "f64"),
                           "cpu_baseline": {"value": rate, "unit": "shots/s", "cores": threads, "kind": "port", "sample": sample},
                           "e2e": {"value": rate, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "note": "stim/ldpc wheels are not installable offline; this arm is the oracle's C port of the reference's CPU path"}))
+                          "note": "real stim/ldpc unavailable (%s); this arm is the oracle's C port of the reference's CPU path "
+                                  "(-O3 -march=x86-64-v3, OpenMP over shots, all host cores)" % REAL_REF_WHY[0]}))
         return
 
     import torch
@@ -253,16 +350,13 @@ def main():
                 peaks = json.load(f)
         except Exception:
             pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        bp_launches = max(1, agg["bp_launches"])
-        achieved = agg["bp_alg_bytes"] / (agg["bp_ms"] / 1e3) / 1e9 if agg["bp_ms"] > 0 else 0.0
         line = {"metric": METRIC, "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic", "config": config(S, args.precision), "clocks": clocks,
                 "gpu_launches": int(agg["bp_launches"] + agg["osd_launches"] + agg["frame_launches"] + agg["other_launches"]),
                 "wall_ms_per_step": wall_ms_max / args.steps,
                 "logical_errors": int(cnt[0].item()), "shots_total": int(total_shots),
-                "decoder_stats": {"bp_converged_frac": agg["bp_converged"] / max(1, agg["windows"]),
+                "decoder_stats": {"bp_edge_iters": agg.get("bp_edge_iters", 0.0), "bp_converged_frac": agg["bp_converged"] / max(1, agg["windows"]),
                                   "bp_iters_per_window": agg["bp_iterations"] / max(1, agg["windows"]),
                                   "osd_calls_per_shot": agg["osd_calls"] / max(1, agg["shots"]),
                                   "osd_columns_per_call": agg["osd_columns"] / max(1, agg["osd_calls"]),
@@ -270,15 +364,7 @@ def main():
                                   "osd_max_columns": agg["osd_max_columns"], "osd_fast_path_overflows": agg["osd_overflows"]},
                 "kernel_ms_per_step": {"frame": agg["frame_ms"] / args.steps, "bp": agg["bp_ms"] / args.steps,
                                        "osd": agg["osd_ms"] / args.steps},
-                "roofline": {"kernel": "bp_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": ncu_traffic(args.precision),
-                             "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650",
-                             "alg_bytes_per_launch": agg["bp_alg_bytes"] / bp_launches,
-                             "ms_per_launch": agg["bp_ms"] / bp_launches,
-                             "note": "HBM model of SURVEY 8(d): iterations x 4 x nnz x sizeof(msg) + syndrome in + commit/carry out per shot-window. The "
-                                     "messages are shared-memory resident, so frac > 1 against the HBM copy peak and the DRAM traffic (ncu, "
-                                     "profiles/r01_bp_kernel_f64_ncu_full.txt: LLR hand-off to OSD) is far below the model; the kernel's real ceiling "
-                                     "is the SM front end (ncu: issue slots 75 % busy, shared-memory pipe 54 %)"}}
+                "roofline": roofline(args.precision, agg, clocks, peaks)}
 
     # ---- e2e through the drop-in API with host buffers (same stream of work, smaller batch)
     if not args.no_e2e:
@@ -337,17 +423,18 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "shots/s", "cores": threads, "kind": "port",
                                     "sample": "%d shots of the same workload in %.1f s (oracle C port: frame sampler + window loop, fp64, OpenMP)" % (shots, dt)}
         print(json.dumps(line))
-    # orderly teardown: drop the engine objects while the CUDA context is alive, leave NCCL, then exit without running the
-    # interpreter's arbitrary-order finalisation (a rank that outlives its peers' NCCL teardown must not touch the device again)
+    # orderly teardown: drop the engine objects while the CUDA context is alive, leave NCCL, then return normally so that the
+    # interpreter's exit hooks (the driver records which shared libraries the process loaded) run
     sys.stdout.flush()
     del mc
+    qb.clear_decoder_cache()
     ctx.synchronize()
+    del flush
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -135,6 +135,7 @@ typedef struct {
     /* OSD work actually done (the elimination stops early, osd.cu): columns examined, pivots taken, worst case */
     int64_t osd_columns, osd_pivots, osd_max_columns;
     int64_t osd_overflows;      /* shots the fast OSD path handed to the full sort */
+    double bp_edge_iters;       /* sum over shot-windows of BP iterations run x edges of the window (the unit of BP work) */
 } qb_stats;
 
 /* Window plan (host only): spacetime() of decoder/base.py:134-190.  n_cor < 0 derives the number of sliding windows

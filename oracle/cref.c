@@ -255,6 +255,7 @@ typedef struct {
     int* rowptr; int* colidx;         /* CSR, ascending column inside a row; edge id = CSR position */
     int* colptr; int* coledge; int* colrow;   /* CSC view: edge ids / rows of column j in ascending row order */
     double* prior;
+    double* llr0;                     /* log((1-p_j)/p_j) */
     int max_iter; int method;         /* 0 = min-sum, 1 = product-sum */
     int schedule;                     /* 0 = parallel (flooding), 1 = serial */
     double alpha;                     /* ms_scaling_factor; 0 => 1 - 2^-it */
@@ -276,7 +277,8 @@ qo_bp* qo_bp_create(int m, int n, const int64_t* indptr /*csc n+1*/, const int32
     d->coledge = (int*)malloc((size_t)nnz * sizeof(int) + 4);
     d->colrow = (int*)malloc((size_t)nnz * sizeof(int) + 4);
     d->prior = (double*)malloc((size_t)n * sizeof(double) + 8);
-    for (int j = 0; j < n; ++j) { d->prior[j] = priors[j]; d->colptr[j] = (int)indptr[j]; }
+    d->llr0 = (double*)malloc((size_t)n * sizeof(double) + 8);
+    for (int j = 0; j < n; ++j) { d->prior[j] = priors[j]; d->llr0[j] = log((1.0 - priors[j]) / priors[j]); d->colptr[j] = (int)indptr[j]; }
     d->colptr[n] = nnz;
     for (int e = 0; e < nnz; ++e) d->rowptr[indices[e] + 1]++;
     for (int i = 0; i < m; ++i) d->rowptr[i + 1] += d->rowptr[i];
@@ -304,7 +306,7 @@ void qo_bp_set_osd(qo_bp* d, int osd_method, int osd_order)
 void qo_bp_free(qo_bp* d)
 {
     if (!d) return;
-    free(d->rowptr); free(d->colidx); free(d->colptr); free(d->coledge); free(d->colrow); free(d->prior); free(d);
+    free(d->rowptr); free(d->colidx); free(d->colptr); free(d->coledge); free(d->colrow); free(d->prior); free(d->llr0); free(d);
 }
 
 #define REAL double

@@ -19,10 +19,12 @@ OPK = {"R": 0, "RX": 1, "H": 2, "CX": 3, "M": 4, "MX": 5, "MR": 6, "X_ERROR": 7,
 
 
 def build(force: bool = False) -> str:
-    """gcc -O3 -fopenmp the C oracle into oracle/libqoracle.so (no -march=native, no FP contraction)."""
+    """gcc -O3 -fopenmp the C oracle into oracle/libqoracle.so.  -march=x86-64-v3 (AVX2 / BMI2) rather than -march=native: the
+    library is built in the build container and travels to the GPU box, whose host CPU may be another model; no FP contraction
+    (the GPU kernels are held bit-exact to this arithmetic)."""
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in _SRC):
         return _SO
-    cmd = ["gcc", "-O3", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-Wno-stringop-overflow", "-shared", "-fPIC", "-o", _SO, _SRC[0], "-lm"]
+    cmd = ["gcc", "-O3", "-march=x86-64-v3", "-mtune=generic", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-Wno-stringop-overflow", "-shared", "-fPIC", "-o", _SO, _SRC[0], "-lm"]
     subprocess.run(cmd, check=True, cwd=_HERE)
     return _SO
 

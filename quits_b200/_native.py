@@ -20,7 +20,8 @@ class QbStats(C.Structure):
                 ("frame_launches", C.c_int64), ("other_launches", C.c_int64),
                 ("frame_ms", C.c_double), ("bp_ms", C.c_double), ("osd_ms", C.c_double), ("total_ms", C.c_double),
                 ("bp_alg_bytes", C.c_double), ("osd_alg_bytes", C.c_double), ("frame_alg_bytes", C.c_double),
-                ("osd_columns", C.c_int64), ("osd_pivots", C.c_int64), ("osd_max_columns", C.c_int64), ("osd_overflows", C.c_int64)]
+                ("osd_columns", C.c_int64), ("osd_pivots", C.c_int64), ("osd_max_columns", C.c_int64), ("osd_overflows", C.c_int64),
+                ("bp_edge_iters", C.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

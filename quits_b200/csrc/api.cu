@@ -532,6 +532,7 @@ void finish_decoder(qb_sw* sw) {
         throw qb::unsupported_error("LSD post-processing beyond order 0 (lsd_order > 0) is not supported on the GPU path");
     int max_npad = 0, max_rowsW = 0, max_iter = 0, big_rows = 0;
     size_t max_slab = 0, sort_slab = 0;
+    int max_sort_grid = 0;
     bool any_big = false;
     for (auto& w : sw->wins) {
         // messages in shared memory when they fit, else in an L2-resident global slab per CTA
@@ -567,7 +568,6 @@ void finish_decoder(qb_sw* sw) {
             w->sort_grid = 148 * 4;
             any_big = true;
             big_rows = std::max(big_rows, w->dev.rows);
-            sort_slab = std::max(sort_slab, qb::osd_sort_slab_bytes(w->dev, prec));
         } else if (sw->use_osd) {
             CK(qb::osd_configure(w->dev, prec));
             const int sort_per_sm = static_cast<int>((227 * 1024) / (qb::osd_sort_smem_bytes(w->dev, prec) + 1024));
@@ -576,6 +576,12 @@ void finish_decoder(qb_sw* sw) {
             w->elim_grid = 148 * std::max(1, std::min(elim_per_sm, 16));
             const int fast_per_sm = static_cast<int>((227 * 1024) / (qb::osd_fast_smem_bytes(w->dev) + 1024));
             w->fast_grid = 148 * std::max(1, std::min(fast_per_sm, 16));
+        }
+        if (sw->use_osd) {
+            // windows too wide for the radix sort's shared memory keep its keys / index buffers in a global slab per CTA -- short, very
+            // wide windows that still take the shared-memory elimination included
+            sort_slab = std::max(sort_slab, qb::osd_sort_slab_bytes(w->dev, prec));
+            max_sort_grid = std::max(max_sort_grid, w->sort_grid);
         }
         if (sw->use_lsd) {
             if (!qb::lsd_supported(w->dev))
@@ -600,8 +606,8 @@ void finish_decoder(qb_sw* sw) {
         sw->use_slab = true;
         sw->lsd_slab = qb::osd_big_slab_bytes(big_rows);
         for (auto& w : sw->wins) if (w->osd_big) sw->lsd_grid = std::max(sw->lsd_grid, w->elim_grid);
-        if (sort_slab) sw->sort_scratch.ensure(sort_slab * 148 * 4 + 16);
     }
+    if (sort_slab) sw->sort_scratch.ensure(sort_slab * static_cast<size_t>(std::max(max_sort_grid, 1)) + 16);
     if (o.max_iter == 0 && sw->wins.size() > 1) {
         // ldpc's "0 => number of columns" differs per window; the kernel takes one value
         for (auto& w : sw->wins)
@@ -622,7 +628,7 @@ void finish_decoder(qb_sw* sw) {
     // LSD: a few shots grow clusters of hundreds of bits and keep one warp busy for milliseconds after the rest of the launch has
     // drained; with sub-batches on side streams the BP kernel of another sub-batch fills the machine meanwhile
     sw->lanes = o.lanes > 0 ? std::min(o.lanes, static_cast<int32_t>(qb_ctx::kMaxLanes)) : (sw->use_lsd ? static_cast<int>(qb_ctx::kMaxLanes) : 1);
-    if (max_slab || any_big) sw->lanes = 1;           // the global message / sort slabs are indexed by CTA, not by sub-batch
+    if (max_slab || any_big || sort_slab) sw->lanes = 1;           // the global message / sort slabs are indexed by CTA, not by sub-batch
     sw->DW = std::max(1, (sw->plan.D + 63) / 64);
     sw->KW = std::max(1, (sw->plan.K + 63) / 64);
     sw->carryW = (sw->plan.m + 31) / 32 + 1;
@@ -804,6 +810,7 @@ void collect_stats(qb_sw* sw, int n, qb_stats* stats) {        // stream must be
             const size_t s0 = static_cast<size_t>(n) * l / lanes, s1 = static_cast<size_t>(n) * (l + 1) / lanes;
             const double io = 8.0 * ((d.rows + 63) / 64) + 8.0 * sw->KW + 8.0 * ((d.carry_rows + 63) / 64);
             stats->bp_alg_bytes += static_cast<double>(hk[1]) * 4.0 * nnz * (sw->precision / 8) + io * static_cast<double>(s1 - s0);
+            stats->bp_edge_iters += static_cast<double>(hk[1]) * nnz;
             stats->osd_alg_bytes += static_cast<double>(hk[2]) * 2.0 * d.rows * 8.0 * ((d.ncols + 63) / 64);
         }
     if (sw->opts.profile) {

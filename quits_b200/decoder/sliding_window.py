@@ -23,13 +23,37 @@ from .inner import BpLsdDecoder, BpOsdDecoder, _GpuInnerDecoder, lsd_engine_opti
 # the reference rebuilds its ldpc decoders on every call (sliding_window.py:146-153), here that would mean re-analysing the
 # circuit and re-allocating the device batch buffers each time.  Small LRU; keyed by content, not identity.
 _DECODER_CACHE: "collections.OrderedDict" = collections.OrderedDict()
+_PHENOM_CACHE: "collections.OrderedDict" = collections.OrderedDict()
 _DECODER_CACHE_SIZE = 4
+
+
+def _freeze(v):
+    """Hashable image of an option value; arrays by content (numpy's repr elides the middle of long arrays)."""
+    if isinstance(v, np.ndarray):
+        return ("ndarray", v.dtype.str, v.shape, hashlib.sha1(np.ascontiguousarray(v).tobytes()).hexdigest())
+    if isinstance(v, (list, tuple)):
+        return (type(v).__name__,) + tuple(_freeze(x) for x in v)
+    return repr(v)
+
+
+def _options_key(kw: dict):
+    return tuple(sorted((k, _freeze(v)) for k, v in kw.items()))
+
+
+def _device_key():
+    from ..circuit import Context
+    return Context.default().device
+
+
+def clear_decoder_cache():
+    """Drop the cached sliding-window decoders (and with them their device buffers)."""
+    _DECODER_CACHE.clear()
+    _PHENOM_CACHE.clear()
 
 
 def _cached_decoder(circuit, m, W, F, num_cor_rounds, kw) -> SlidingWindowDecoder:
     c = Circuit.of(circuit)
-    key = (hashlib.sha1(c.text.encode()).hexdigest(), int(m), int(W), int(F), int(num_cor_rounds),
-           tuple(sorted((k, repr(v)) for k, v in kw.items())))
+    key = (_device_key(), hashlib.sha1(c.text.encode()).hexdigest(), int(m), int(W), int(F), int(num_cor_rounds), _options_key(kw))
     dec = _DECODER_CACHE.get(key)
     if dec is None:
         dec = SlidingWindowDecoder(c, m, W, F, num_cor_rounds, **kw)
@@ -76,7 +100,7 @@ def sliding_window_circuit_mem(zcheck_samples, circuit, hz, lz, W, F, decoder1, 
                 "BpLsdDecoder); got %r. There is no per-shot CPU fallback." % (cls,))
     kw1 = _engine_kwargs(decoder1, dict1, error_rate_name1)
     kw2 = _engine_kwargs(decoder2, dict2, error_rate_name2)
-    if kw1 != kw2 or function_name1 != "decode" or function_name2 != "decode":
+    if _options_key(kw1) != _options_key(kw2) or function_name1 != "decode" or function_name2 != "decode":
         raise NotImplementedError("different inner decoders for the sliding windows and the last window are not supported on the GPU path")
     dec = _cached_decoder(circuit, m, W, F, num_cor_rounds, kw1)
     # the reference leaves the priors of the last constructed decoders in the caller's dicts (sliding_window.py:148,151)
@@ -127,9 +151,6 @@ def _phenom_priors(params: dict):
     raise ValueError("the inner decoder needs error_rate, error_channel or channel_probs")
 
 
-_PHENOM_CACHE: "collections.OrderedDict" = collections.OrderedDict()
-
-
 def sliding_window_phenom_mem(zcheck_samples, hz, lz, W, F, decoder1, decoder2, dict1: dict, dict2: dict,
                               function_name1: str, function_name2: str, tqdm_on=False):
     """Phenomenological sliding window (reference ``sliding_window.py:14-101``) on the batched GPU kernels: same window
@@ -159,13 +180,13 @@ def sliding_window_phenom_mem(zcheck_samples, hz, lz, W, F, decoder1, decoder2, 
     rate_names = ("error_rate", "error_channel", "channel_probs")
     kw1 = _engine_kwargs(decoder1, {k: v for k, v in dict1.items() if k not in rate_names}, "")
     kw2 = _engine_kwargs(decoder2, {k: v for k, v in dict2.items() if k not in rate_names}, "")
-    if kw1 != kw2 or function_name1 != "decode" or function_name2 != "decode":
+    if _options_key(kw1) != _options_key(kw2) or function_name1 != "decode" or function_name2 != "decode":
         raise NotImplementedError("different inner decoders for the sliding windows and the last window are not supported on the GPU path")
     p1, p2 = _phenom_priors(dict1), _phenom_priors(dict2)
-    key = (hashlib.sha1(np.ascontiguousarray(hz % 2, dtype=np.uint8).tobytes()).hexdigest(), hz.shape,
+    key = (_device_key(), hashlib.sha1(np.ascontiguousarray(hz % 2, dtype=np.uint8).tobytes()).hexdigest(), hz.shape,
            hashlib.sha1(np.ascontiguousarray(lz % 2, dtype=np.uint8).tobytes()).hexdigest(), int(W), int(F), int(num_rounds),
            hashlib.sha1(np.asarray(p1, dtype=np.float64).tobytes()).hexdigest(), hashlib.sha1(np.asarray(p2, dtype=np.float64).tobytes()).hexdigest(),
-           tuple(sorted((k, repr(v)) for k, v in kw1.items())))
+           _options_key(kw1))
     dec = _PHENOM_CACHE.get(key)
     if dec is None:
         plan = _phenom_plan(hz, lz, W, F, num_cor_rounds, W_last, m * (num_rounds + 2), p1, p2)
@@ -178,4 +199,4 @@ def sliding_window_phenom_mem(zcheck_samples, hz, lz, W, F, decoder1, decoder2, 
     return dec.decode(zcheck_samples[:, :m * (num_rounds + 2)])
 
 
-__all__ = ["sliding_window_phenom_mem", "sliding_window_circuit_mem"]
+__all__ = ["sliding_window_phenom_mem", "sliding_window_circuit_mem", "clear_decoder_cache"]

@@ -25,15 +25,29 @@ _OSD_METHODS = {"osd_0": 0, "osd0": 0, "osd_e": 1, "osde": 1, "exhaustive": 1, "
 def bp_options(bp_method="minimum_sum", max_iter=0, schedule="parallel", osd_method="osd_0", osd_order=0, ms_scaling_factor=1.0,
                precision="f64", capacity=0, profile=False, lanes=0, **unknown) -> N.QbBpOpts:
     """Translate ldpc.BpOsdDecoder-style kwargs (reference decoder/bposd.py:74-83) into the C option block."""
-    for k in unknown:
+    for k, v in unknown.items():
         if k not in ("channel_probs", "error_rate", "error_channel", "input_vector_type", "omp_thread_count",
                      "random_schedule_seed", "serial_schedule_order", "osd_on"):
             raise TypeError("unexpected decoder option %r" % k)
+        # options ldpc accepts that would change what is decoded: only their defaults are implemented (no silent ignoring)
+        if k == "serial_schedule_order" and v is not None:
+            raise NotImplementedError("serial_schedule_order: only the default order (column index) runs on the GPU path")
+        if k == "random_schedule_seed" and v not in (None, 0, -1):
+            raise NotImplementedError("random_schedule_seed: randomised serial schedules are not implemented on the GPU path")
+        if k == "input_vector_type" and str(v).lower() not in ("syndrome", "auto", "0", "none"):
+            raise NotImplementedError("input_vector_type=%r: only syndrome input is implemented on the GPU path" % (v,))
+        if k == "osd_on" and not v:
+            osd_method = "off"
+    # ldpc also accepts small integers here, with its own numbering (bp_method 0 = product_sum there); an integer passed on from
+    # ldpc-style code would silently select another algorithm through the engine's enums, so only names are taken
+    for name, v in (("bp_method", bp_method), ("schedule", schedule), ("osd_method", osd_method)):
+        if isinstance(v, (int, np.integer)) and not isinstance(v, bool):
+            raise ValueError("%s must be given by name (e.g. 'minimum_sum', 'parallel', 'osd_cs'), got the integer %r" % (name, v))
     o = N.QbBpOpts()
     try:
-        o.bp_method = bp_method if isinstance(bp_method, int) else _BP_METHODS[str(bp_method).lower()]
-        o.schedule = schedule if isinstance(schedule, int) else _SCHEDULES[str(schedule).lower()]
-        o.osd_method = osd_method if isinstance(osd_method, int) else _OSD_METHODS[str(osd_method).lower()]
+        o.bp_method = _BP_METHODS[str(bp_method).lower()]
+        o.schedule = _SCHEDULES[str(schedule).lower()]
+        o.osd_method = _OSD_METHODS[str(osd_method).lower()]
     except KeyError as e:
         raise ValueError("unknown decoder option value %s" % e) from None
     if precision not in ("f64", "f32", 64, 32):
