@@ -249,7 +249,7 @@ int gf2_rank(const qb::Window& hw) {
     return rank;
 }
 
-void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinOwned& wo) {
+void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, int method, WinOwned& wo) {
     qb::WinDev& d = wo.dev;
     const int rows = hw.rows, ncols = hw.ncols;
     if (rows <= 0) throw qb::value_error("a decoding window has no detector rows");
@@ -271,7 +271,8 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
     // gathers are bank-conflict free (layout.cpp); any choice gives the same arithmetic
     qb::BpLayout layout;
     if (cw <= 6) {
-        qb::optimize_bp_layout(hw, rs, precision, layout);
+        // flooding min-sum runs bp_kernel_ms2, whose row summaries are single values (bank classes as for the messages)
+        qb::optimize_bp_layout(hw, rs, precision, layout, method == 0 && qb::bp_ms2_enabled() ? (precision == 32 ? 32 : 16) : 0);
     } else {
         layout.order.resize(static_cast<size_t>(ncols));
         std::iota(layout.order.begin(), layout.order.end(), 0);
@@ -314,7 +315,7 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
             if (k == ptab.size()) { if (ptab.size() > 4096) break; ptab.push_back(llr0d[j]); }
             pidx[j] = static_cast<int>(k);
         }
-        const bool fits = cw <= 6 && static_cast<long long>(rows) * rs + 512 + 2 * rs < 65535 && ncols < 65535 && ptab.size() <= 4096 && rs <= 255;
+        const bool fits = cw <= 6 && static_cast<long long>(rows) * rs + 512 + 2 * rs < 65535 && ncols < 65535 && ptab.size() < 4095 && rs <= 255;
         if (fits) {
             const uint32_t magic = static_cast<uint32_t>((1ull << 32) / static_cast<uint64_t>(rs)) + 1u;
             for (uint32_t a = 0; a <= static_cast<uint32_t>(rows) * rs + 512 + static_cast<uint32_t>(rs); ++a)
@@ -324,13 +325,15 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
             // handles record r), then w = original column | prior index << 16 | weight of the heaviest column of the record's warp << 28
             const uint32_t dummy0 = static_cast<uint32_t>(rows) * static_cast<uint32_t>(rs);
             const uint32_t nthreads = precision == 32 ? 256u : 512u;          // threads of bp_kernel_compact (bp.cu)
-            const int nrec = std::max(npad, 1024);           // the kernel prefetches record `tid` before it tests tid < npad
+            const int nrec = std::max(npad, 512) + 1024;     // the kernels prefetch up to two records per thread past the last chunk
             std::vector<uint32_t> rec(static_cast<size_t>(nrec) * 4, 0);
             for (int r = 0; r < nrec; ++r) {
                 uint32_t* o = &rec[static_cast<size_t>(r) * 4];
                 const uint32_t dummy = dummy0 + static_cast<uint32_t>(r) % nthreads;
                 uint32_t e[6] = {dummy, dummy, dummy, dummy, dummy, dummy};
-                uint32_t word3 = 0xFFFFu;                     // padding record: no column
+                // padding record: no column, dummy edges only, and a positive prior (the extra last entry of the prior table) so
+                // that its posterior is never <= 0
+                uint32_t word3 = 0xFFFFu | (static_cast<uint32_t>(ptab.size()) << 16);
                 if (r < ncols) {
                     const int j = order[r];
                     const int wt = static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]);
@@ -362,9 +365,11 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
                     float& f1 = s0f[2 * r]; float& f2 = s0f[2 * r + 1];
                     f2 = std::min(f2, std::max(f1, af)); f1 = std::min(f1, af);
                 }
-            std::vector<float> ptf(ptab.begin(), ptab.end());
+            std::vector<double> ptab_x(ptab);
+            ptab_x.push_back(1.0);                            // prior LLR of the padding records
+            std::vector<float> ptf(ptab_x.begin(), ptab_x.end());
             upload(wo.colrec, rec, ctx->stream);
-            upload(wo.ptabd, ptab, ctx->stream);
+            upload(wo.ptabd, ptab_x, ctx->stream);
             upload(wo.ptabf, ptf, ctx->stream);
             upload(wo.rlen, rlen, ctx->stream);
             upload(wo.neg0, neg0, ctx->stream);
@@ -458,8 +463,18 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, WinO
                 d.ser_pairs = wo.ser_pairs.as<uint2>();
                 d.ser_cols = wo.ser_cols.as<uint2>();
             }
+            // chunks of 32 records by the weight of their heaviest (= first) column, for the segment loops of bp_kernel_ms2
+            {
+                const int nch = npad / 32;
+                for (int wt = 0; wt <= 6; ++wt) d.chunk_end[wt] = 0;
+                for (int ch = 0; ch < nch; ++ch) {
+                    const int lead = ch * 32;
+                    const int wmax = lead < ncols ? static_cast<int>(hw.cptr[order[lead] + 1] - hw.cptr[order[lead]]) : 0;
+                    for (int wt = 0; wt <= wmax; ++wt) d.chunk_end[wt] = ch + 1;
+                }
+            }
             d.compact = 1;
-            d.n_ptab = static_cast<int>(ptab.size());
+            d.n_ptab = static_cast<int>(ptab_x.size());
             d.rs_magic = magic;
             d.colrec = wo.colrec.as<uint4>();
             d.ptabf = wo.ptabf.as<float>(); d.ptabd = wo.ptabd.as<double>();
@@ -541,6 +556,7 @@ void finish_decoder(qb_sw* sw) {
                 throw qb::unsupported_error("schedule 'serial' needs a window that fits the compact shared-memory layout (column weight <= 6, messages <= 227 KB)");
             CK(qb::bp_serial_configure(w->dev, prec, o.bp_method));
         }
+        w->dev.unit_alpha = o.ms_scaling_factor == 1.0 ? 1 : 0;
         w->vglobal = qb::bp_smem_bytes(w->dev, prec, false) > 227 * 1024;
         w->bp_smem = qb::bp_smem_bytes(w->dev, prec, w->vglobal);
         if (w->bp_smem > 227 * 1024)
@@ -1214,7 +1230,7 @@ int qb_sw_create(qb_ctx* ctx, const qb_plan* plan, const qb_bp_opts* opts, qb_sw
         for (const qb::Window& hw : sw->plan.windows) {
             if (hw.urows != 0 && hw.urows != sw->plan.m) throw qb::value_error("carry block of a window is not m rows tall");
             sw->wins.emplace_back(new WinOwned());
-            build_window(ctx, hw, KW, sw->opts.precision == 32 ? 32 : 64, *sw->wins.back());
+            build_window(ctx, hw, KW, sw->opts.precision == 32 ? 32 : 64, (sw->opts.bp_method == 0 && sw->opts.schedule == 0) ? 0 : 1, *sw->wins.back());
         }
         finish_decoder(sw.get());
         *out = sw.release();
@@ -1250,7 +1266,7 @@ int qb_sw_create_single(qb_ctx* ctx, int32_t rows, int32_t cols, const int64_t* 
         sw->plan.m = rows; sw->plan.K = 0; sw->plan.D = rows; sw->plan.W = 1; sw->plan.F = 1; sw->plan.n_cor = 0;
         sw->plan.windows.push_back(hw);
         sw->wins.emplace_back(new WinOwned());
-        build_window(ctx, sw->plan.windows[0], 1, sw->opts.precision == 32 ? 32 : 64, *sw->wins.back());
+        build_window(ctx, sw->plan.windows[0], 1, sw->opts.precision == 32 ? 32 : 64, (sw->opts.bp_method == 0 && sw->opts.schedule == 0) ? 0 : 1, *sw->wins.back());
         finish_decoder(sw.get());
         *out = sw.release();
     });

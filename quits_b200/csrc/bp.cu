@@ -20,7 +20,9 @@
 // reads 128 contiguous bytes) and the prior LLRs are shared by all shots and stream from L2.
 // Windows whose messages do not fit in shared memory run the same code with V in a per-CTA global scratch slab
 // that stays L2 resident (VGLOBAL).
+#include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 #include "qb_device.h"
 
@@ -631,6 +633,303 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_compact(const WinDev w, co
 }
 
 // =====================================================================================================================
+// Flooding min-sum, second form (bp_kernel_ms2; the headline path).  Same arithmetic and data as bp_kernel_compact<.., false>,
+// half the instructions per edge and iteration and fewer shared-memory wavefronts:
+//   * messages are stored with a CANONICAL SIGN: the sign bit of a stored message is set exactly when v <= 0 (a message that
+//     is exactly +0 is stored as -0; |v| and every comparison are unchanged).  The row parity is then the XOR of the high words
+//     (one LOP3 per edge instead of a compare and an add) and the sign of a check->bit message is one LOP3 on the high word;
+//   * |.| comparisons use the compare instruction's operand modifiers (DSETP |a|, |b|) and the running minima of a row are kept
+//     as SIGNED values (the one with the smallest magnitude): no per-edge integer masking, no register-pair copies;
+//   * the row summary is two arrays, min1[row] and min2[row], both carrying the row parity in their sign bit: the bit sweep loads
+//     min1 (8 bytes instead of a 16-byte pair) and only the edge that holds the minimum -- one in ~30 -- loads min2, predicated;
+//   * ms_scaling_factor == 1 (ldpc's and the reference's default; the wrappers do not plumb the option) skips the multiply
+//     (x * 1.0 == x exactly);
+//   * the backward pass starts from t = c[W-1] instead of 0 + c[W-1] and the last edge's message is the prefix itself: the two
+//     forms differ only in the sign of an exact zero, which the canonical sign absorbs;
+//   * column records are walked in warp chunks (32 records) by weight segment -- `chunk_end[W]` -- so the code path of a chunk
+//     is selected by loop structure, not by a per-record switch; hard decisions are one ballot word per chunk.
+// =====================================================================================================================
+template <typename R> struct Bits;
+template <> struct Bits<float> {
+    static __device__ __forceinline__ uint32_t hi(float x) { return __float_as_uint(x); }
+    static __device__ __forceinline__ float with_hi(float, uint32_t h) { return __uint_as_float(h); }
+};
+template <> struct Bits<double> {
+    static __device__ __forceinline__ uint32_t hi(double x) { return static_cast<uint32_t>(__double2hiint(x)); }
+    static __device__ __forceinline__ double with_hi(double x, uint32_t h) { return __hiloint2double(static_cast<int>(h), __double2loint(x)); }
+};
+
+// sign bit set <=> x <= 0  (x == +0 becomes -0)
+template <typename R>
+__device__ __forceinline__ R canonical_sign(const R x) {
+    return Bits<R>::with_hi(x, x == R(0) ? 0x80000000u : Bits<R>::hi(x));
+}
+
+// off: rm1, rm2, V, syn, cand, accs, car, ptab, hist, ebits
+__host__ __device__ inline size_t bpm_layout(const WinDev& w, int rsize, size_t* off /*[10]*/) {
+    size_t o = 0;
+    const size_t rrows = static_cast<size_t>(w.rows + bp_dummy_rows(w, rsize));
+    off[0] = o; o += align_up(rrows * rsize, 16);
+    off[1] = o; o += align_up(rrows * rsize, 16);
+    off[2] = o; o += align_up((static_cast<size_t>(w.rows) * w.RS + bp_dummy_slots(rsize)) * rsize, 16);
+    off[3] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 4, 16);
+    off[4] = o; o += align_up(static_cast<size_t>(w.rowsW32) * 2 * 4, 16);          // candidate syndrome, double-buffered
+    off[5] = o; o += align_up(static_cast<size_t>(w.KW) * 8, 16);
+    off[6] = o; o += align_up(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4, 16);
+    off[7] = o; o += align_up(static_cast<size_t>(w.n_ptab) * rsize, 16);
+    off[8] = o; o += kSelWords * 4;
+    off[9] = o; o += align_up(static_cast<size_t>(w.nW32) * 4, 16);
+    return o;
+}
+
+// one element of a row scan: (m1, m2) = the two entries of smallest magnitude seen so far, signed; par ^= sign word
+template <typename R>
+__device__ __forceinline__ void min2_signed(const R v, R& m1, R& m2, uint32_t& par) {
+    par ^= Bits<R>::hi(v);
+    const bool p = fabs(v) < fabs(m1), q = fabs(v) < fabs(m2);
+    m2 = p ? m1 : (q ? v : m2);
+    m1 = p ? v : m1;
+}
+
+// shared-memory accesses by 32-bit shared-window address (the bit sweep does its own address arithmetic on byte offsets)
+template <typename R> struct Sh;
+template <> struct Sh<double> {
+    static constexpr uint32_t kOffMask = 0x7FFF8u;      // byte offset of a u16 slot index
+    static __device__ __forceinline__ uint32_t off_lo(uint32_t w) { return (w << 3) & kOffMask; }
+    static __device__ __forceinline__ uint32_t off_hi(uint32_t w) { return (w >> 13) & kOffMask; }
+    static __device__ __forceinline__ uint32_t ptab_off(uint32_t w) { return (w >> 13) & 0x7FF8u; }
+    static __device__ __forceinline__ double ld(uint32_t a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+    static __device__ __forceinline__ void st(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+    // m = [a1]; if |v| == |m| then m = [a2]   (the second load is predicated: one edge in ~30 takes it)
+    static __device__ __forceinline__ double row_msg(uint32_t a1, uint32_t a2, double v) {
+        double m;
+        asm volatile("{\n .reg .pred p;\n .reg .f64 av, am;\n ld.shared.f64 %0, [%1];\n abs.f64 av, %3;\n abs.f64 am, %0;\n"
+                     " setp.eq.f64 p, av, am;\n @p ld.shared.f64 %0, [%2];\n}"
+                     : "=&d"(m) : "r"(a1), "r"(a2), "d"(v));
+        return m;
+    }
+};
+template <> struct Sh<float> {
+    static constexpr uint32_t kOffMask = 0x3FFFCu;
+    static __device__ __forceinline__ uint32_t off_lo(uint32_t w) { return (w << 2) & kOffMask; }
+    static __device__ __forceinline__ uint32_t off_hi(uint32_t w) { return (w >> 14) & kOffMask; }
+    static __device__ __forceinline__ uint32_t ptab_off(uint32_t w) { return (w >> 14) & 0x3FFCu; }
+    static __device__ __forceinline__ float ld(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+    static __device__ __forceinline__ void st(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+    static __device__ __forceinline__ float row_msg(uint32_t a1, uint32_t a2, float v) {
+        float m;
+        asm volatile("{\n .reg .pred p;\n .reg .f32 av, am;\n ld.shared.f32 %0, [%1];\n abs.f32 av, %3;\n abs.f32 am, %0;\n"
+                     " setp.eq.f32 p, av, am;\n @p ld.shared.f32 %0, [%2];\n}"
+                     : "=&f"(m) : "r"(a1), "r"(a2), "f"(v));
+        return m;
+    }
+};
+
+struct Ms2Ctx {
+    uint32_t vbase, r1base, r2base;      // shared-window addresses of V, min1, min2
+    uint32_t magic;                      // umulhi(byte offset of a slot, magic) & ~(sizeof(R)-1) = byte offset of its row in min1 / min2
+};
+
+// MODE 0: first iteration (every bit->check message is the column's prior, V is only written)   1: later iterations
+template <typename R, int W, int MODE, bool UNIT>
+__device__ __forceinline__ R column_ms2(const uint4 rec, const R l0, const R alpha, const Ms2Ctx& x) {
+    using RT = Real<R>;
+    using SH = Sh<R>;
+    const uint32_t vo[6] = {SH::off_lo(rec.x), SH::off_hi(rec.x), SH::off_lo(rec.y), SH::off_hi(rec.y), SH::off_lo(rec.z), SH::off_hi(rec.z)};
+    R c[W], vn[W];
+    const R l0c = MODE == 0 ? canonical_sign<R>(l0) : l0;
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        const R v = MODE == 0 ? l0c : SH::ld(x.vbase + vo[q]);
+        const uint32_t ro = __umulhi(vo[q], x.magic) & ~static_cast<uint32_t>(sizeof(R) - 1);
+        R m = SH::row_msg(x.r1base + ro, x.r2base + ro, v);
+        if (!UNIT) m = RT::mul(m, alpha);
+        c[q] = Bits<R>::with_hi(m, Bits<R>::hi(m) ^ (Bits<R>::hi(v) & 0x80000000u));
+    }
+    R t = l0;
+#pragma unroll
+    for (int q = 0; q < W; ++q) { vn[q] = t; t = RT::add(t, c[q]); }
+    const R llr = t;
+    t = c[W - 1];
+#pragma unroll
+    for (int q = W - 2; q >= 0; --q) {
+        vn[q] = RT::add(vn[q], t);
+        if (q > 0) t = RT::add(t, c[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < W; ++q) SH::st(x.vbase + vo[q], canonical_sign<R>(vn[q]));
+    return llr;
+}
+
+// one bit sweep: warp chunks of 32 records, heaviest first; chunk c is handled by warp c % NWARPS.
+// CM 0: first iteration, 1: later iterations.  WRITE: posteriors are written out (last iteration, or the caller wants them every iteration)
+// One bit sweep: warp chunks of 32 records, heaviest first; chunk c is handled by warp c % NWARPS.  Padding records carry a
+// positive prior (an extra entry of the prior table) and dummy edges only, so their posterior is never <= 0.
+template <typename R, int NWARPS, int CM, bool WRITE, bool UNIT>
+__device__ __forceinline__ void sweep_ms2(const WinDev& w, const Ms2Ctx& x, const R alpha, const uint32_t ptab_s, uint32_t* ebits,
+                                          uint32_t* cand, uint32_t* hist, R* llr_row, const bool last, const int warp, const int lane) {
+    using SH = Sh<R>;
+    constexpr int S = NWARPS * 32;
+    int c = warp;
+    const uint4* rp = w.colrec + warp * 32 + lane;          // colrec is padded by two chunks per warp past the last chunk
+    uint4 ra = __ldg(rp), rb;
+#define QB_CHUNK(WT, REC)                                                                                                \
+    {                                                                                                                    \
+        const R l0 = SH::ld(ptab_s + SH::ptab_off(REC.w));                                                               \
+        const R llr = column_ms2<R, WT, CM, UNIT>(REC, l0, alpha, x);                                                    \
+        if (llr <= R(0)) {                                    /* hard decision 1: record bit, candidate syndrome */      \
+            atomicOr(&ebits[c], 1u << lane);                                                                             \
+            const uint32_t e[6] = {REC.x & 0xFFFFu, REC.x >> 16, REC.y & 0xFFFFu, REC.y >> 16, REC.z & 0xFFFFu, REC.z >> 16}; \
+            _Pragma("unroll") for (int q = 0; q < WT; ++q) {                                                             \
+                const uint32_t row = __umulhi(e[q], w.rs_magic);                                                         \
+                if (row < static_cast<uint32_t>(w.rows)) atomicXor(&cand[row >> 5], 1u << (row & 31u));                  \
+            }                                                                                                            \
+        }                                                                                                                \
+        if (WRITE) {                                                                                                     \
+            const uint32_t j = REC.w & 0xFFFFu;               /* original column; 0xFFFF marks a padding record */       \
+            if (j != 0xFFFFu) {                                                                                          \
+                llr_row[j] = llr;                                                                                        \
+                if (last) atomicAdd(&hist[llr_bin<R>(llr, static_cast<R>(w.bin_scale))], 1u);                            \
+            }                                                                                                            \
+        }                                                                                                                \
+    }
+    // two records in flight (ra: chunk c, rb: chunk c + NWARPS) so that the prefetch needs no register copies in steady state
+#define QB_SEGMENT(WT)                                                                                                   \
+    while (c < w.chunk_end[WT]) {                                                                                        \
+        rb = __ldg(rp + S);                                                                                              \
+        QB_CHUNK(WT, ra)                                                                                                 \
+        c += NWARPS; rp += S;                                                                                            \
+        if (c >= w.chunk_end[WT]) { ra = rb; break; }                                                                    \
+        ra = __ldg(rp + S);                                                                                              \
+        QB_CHUNK(WT, rb)                                                                                                 \
+        c += NWARPS; rp += S;                                                                                            \
+    }
+    QB_SEGMENT(6) QB_SEGMENT(5) QB_SEGMENT(4) QB_SEGMENT(3) QB_SEGMENT(2) QB_SEGMENT(1)
+#undef QB_SEGMENT
+#undef QB_CHUNK
+    if (WRITE) {
+        for (; c < w.nW32; c += NWARPS, rp += S) {            // weight-0 chunks: columns without a check (posterior = prior)
+            const uint4 cur = __ldg(rp);
+            const R l0 = SH::ld(ptab_s + SH::ptab_off(cur.w));
+            const uint32_t j = cur.w & 0xFFFFu;
+            if (j != 0xFFFFu) {
+                if (l0 <= R(0)) atomicOr(&ebits[c], 1u << lane);
+                llr_row[j] = l0;
+                if (last) atomicAdd(&hist[llr_bin<R>(l0, static_cast<R>(w.bin_scale))], 1u);
+            }
+        }
+    } else {
+        for (; c < w.nW32; c += NWARPS, rp += S) {
+            const uint4 cur = __ldg(rp);
+            if ((cur.w & 0xFFFFu) != 0xFFFFu && SH::ld(ptab_s + SH::ptab_off(cur.w)) <= R(0)) atomicOr(&ebits[c], 1u << lane);
+        }
+    }
+}
+
+template <typename R, int NT, int MINB, bool UNIT>
+__global__ void __launch_bounds__(NT, MINB) bp_kernel_ms2(const WinDev w, const BatchDev b, const BpParams p) {
+    using RT = Real<R>;
+    using CT = Compact<R>;
+    using BT = Bits<R>;
+    constexpr int NWARPS = NT / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    size_t off[10];
+    bpm_layout(w, sizeof(R), off);
+    R* rm1 = reinterpret_cast<R*>(smem_raw + off[0]);
+    R* rm2 = reinterpret_cast<R*>(smem_raw + off[1]);
+    R* V = reinterpret_cast<R*>(smem_raw + off[2]);
+    uint32_t* syn = reinterpret_cast<uint32_t*>(smem_raw + off[3]);
+    uint32_t* cand = reinterpret_cast<uint32_t*>(smem_raw + off[4]);
+    uint32_t* accs = reinterpret_cast<uint32_t*>(smem_raw + off[5]);
+    uint32_t* car = reinterpret_cast<uint32_t*>(smem_raw + off[6]);
+    R* ptab = reinterpret_cast<R*>(smem_raw + off[7]);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw + off[8]);
+    uint32_t* ebits = reinterpret_cast<uint32_t*>(smem_raw + off[9]);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rows = w.rows, RS = w.RS;
+    const int nchunks = w.nW32;
+    Ms2Ctx x;
+    x.r1base = static_cast<uint32_t>(__cvta_generic_to_shared(rm1));
+    x.r2base = static_cast<uint32_t>(__cvta_generic_to_shared(rm2));
+    x.vbase = static_cast<uint32_t>(__cvta_generic_to_shared(V));
+    x.magic = w.rs_magic;
+    const uint32_t ptab_s = static_cast<uint32_t>(__cvta_generic_to_shared(ptab));
+    for (int i = tid; i < w.n_ptab; i += NT) ptab[i] = CT::ptab(w)[i];
+    if (tid < bp_dummy_rows(w, sizeof(R))) { rm1[rows + tid] = R(0); rm2[rows + tid] = R(0); }
+    V[rows * RS + tid] = R(0);
+
+    for (int shot = blockIdx.x; shot < b.n_shots; shot += gridDim.x) {
+        __syncthreads();
+        load_syndrome(w, b, shot, tid, syn, accs, car);
+        __syncthreads();
+        R* const llr_row = reinterpret_cast<R*>(b.llr_buf) + static_cast<size_t>(shot) * b.llr_stride;
+        bool conv = false;
+        int it = 1;
+        for (; it <= p.max_iter; ++it) {
+            const R alpha = static_cast<R>(__ldg(p.alpha + it));
+            const bool first = it == 1;
+            const bool last = it == p.max_iter;
+            // ---- check sweep: one thread per row -> min1[row], min2[row], both signed by the row parity
+            for (int i = tid; i < rows; i += NT) {
+                uint32_t par = ((syn[i >> 5] >> (i & 31)) & 1u) << 31;
+                R m1, m2;
+                if (first) {
+                    const typename RT::pair s0 = CT::sum0(w, i);
+                    m1 = s0.x; m2 = s0.y;
+                    par ^= static_cast<uint32_t>(__ldg(w.neg0 + i)) << 31;
+                } else {
+                    const R* vr = V + i * RS;
+                    const int len = __ldg(w.rlen + i);
+                    R m1a = RT::big(), m2a = RT::big(), m1b = RT::big(), m2b = RT::big();
+                    int q = 0;
+                    for (; q + 7 < len; q += 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; u += 2) {
+                            min2_signed<R>(vr[q + u], m1a, m2a, par);
+                            min2_signed<R>(vr[q + u + 1], m1b, m2b, par);
+                        }
+                    }
+                    for (; q + 1 < len; q += 2) {
+                        min2_signed<R>(vr[q], m1a, m2a, par);
+                        min2_signed<R>(vr[q + 1], m1b, m2b, par);
+                    }
+                    if (q < len) min2_signed<R>(vr[q], m1a, m2a, par);
+                    const bool lo = fabs(m1b) < fabs(m1a);
+                    m1 = lo ? m1b : m1a;
+                    const R mo = lo ? m1a : m1b;                                  // the larger of the two chain minima
+                    const R m2c = fabs(m2b) < fabs(m2a) ? m2b : m2a;
+                    m2 = fabs(m2c) < fabs(mo) ? m2c : mo;
+                }
+                par &= 0x80000000u;
+                rm1[i] = BT::with_hi(m1, (BT::hi(m1) & 0x7FFFFFFFu) | par);
+                rm2[i] = BT::with_hi(m2, (BT::hi(m2) & 0x7FFFFFFFu) | par);
+            }
+            // the candidate syndrome is double-buffered by iteration parity: every warp evaluates the stop test itself right after
+            // the barrier that ends the bit sweep, and a fast warp may already be clearing the other buffer for the next iteration
+            uint32_t* const cnd = cand + (it & 1) * w.rowsW32;
+            for (int i = tid; i < w.rowsW32; i += NT) cnd[i] = 0;
+            for (int i = tid; i < nchunks; i += NT) ebits[i] = 0;
+            if (last && tid < 32) hist[tid] = 0;
+            __syncthreads();
+            // ---- bit sweep
+            const bool wr = last || b.write_llr_always;
+            if (first && !wr) sweep_ms2<R, NWARPS, 0, false, UNIT>(w, x, alpha, ptab_s, ebits, cnd, hist, llr_row, last, warp, lane);
+            else if (first) sweep_ms2<R, NWARPS, 0, true, UNIT>(w, x, alpha, ptab_s, ebits, cnd, hist, llr_row, last, warp, lane);
+            else if (!wr) sweep_ms2<R, NWARPS, 1, false, UNIT>(w, x, alpha, ptab_s, ebits, cnd, hist, llr_row, last, warp, lane);
+            else sweep_ms2<R, NWARPS, 1, true, UNIT>(w, x, alpha, ptab_s, ebits, cnd, hist, llr_row, last, warp, lane);
+            // ---- stop test H e == s, by every warp for itself (no second barrier)
+            __syncthreads();
+            int mismatch = 0;
+            for (int i = lane; i < w.rowsW32; i += 32) mismatch |= cnd[i] != syn[i];
+            if (!__any_sync(0xFFFFFFFFu, mismatch)) { conv = true; break; }
+        }
+        if (it > p.max_iter) it = p.max_iter;
+        finish_shot<R, NT, true>(w, b, shot, tid, conv, it, 0u, syn, accs, car, hist, ebits);
+    }
+}
+
+// =====================================================================================================================
 // Serial schedule (ldpc schedule='serial', the reference wrappers' default, decoder/bposd.py:54): the columns are updated one
 // after the other in index order, each from the CURRENT messages of its rows (oracle/bp_impl.inc, serial branch).  Columns
 // that share no row commute, so the host cuts the column sequence into dependency levels (api.cu, serial tables) and the
@@ -1072,6 +1371,23 @@ Variant& compact_variant(int prec, int method) {
 
 inline bool use_compact(const WinDev& w, bool vglobal) { return w.compact && !vglobal; }
 
+// flooding min-sum on the compact layout: second form unless QB_BP_MS2=0 (A/B measurements)
+inline bool ms2_enabled() {
+    static const int on = [] { const char* e = getenv("QB_BP_MS2"); return e ? atoi(e) : 1; }();
+    return on != 0;
+}
+inline bool use_ms2(const WinDev& w, bool vglobal, int method) { return use_compact(w, vglobal) && method == 0 && ms2_enabled(); }
+
+Variant& ms2_variant(int prec, bool unit) {
+    static Variant table[2][2] = {};
+    Variant& v = table[prec == 32 ? 0 : 1][unit ? 1 : 0];
+    if (!v.fn) {
+        if (prec == 32) { v.fn = unit ? bp_kernel_ms2<float, 256, 4, true> : bp_kernel_ms2<float, 256, 4, false>; v.threads = 256; }
+        else { v.fn = unit ? bp_kernel_ms2<double, 512, 2, true> : bp_kernel_ms2<double, 512, 2, false>; v.threads = 512; }
+    }
+    return v;
+}
+
 }  // namespace
 
 // the warp-per-shot form needs everything its single warp indexes by lane to fit 32 lanes
@@ -1115,12 +1431,14 @@ cudaError_t launch_bp_serial(const WinDev& w, const BatchDev& b, const BpParams&
 }
 
 size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal) {
-    size_t off[9];
-    if (use_compact(w, vglobal)) return bpc_layout(w, precision == 32 ? 4 : 8, off);
+    size_t off[10];
+    if (use_compact(w, vglobal)) return std::max(bpc_layout(w, precision == 32 ? 4 : 8, off), bpm_layout(w, precision == 32 ? 4 : 8, off));
     return bp_layout(w, precision == 32 ? 4 : 8, vglobal, off);
 }
 
 int bp_threads(int precision) { return precision == 32 ? 256 : 512; }
+
+bool bp_ms2_enabled() { return ms2_enabled(); }
 
 bool bp_supports(const WinDev& w, int method, bool vglobal) { return method == 0 || use_compact(w, vglobal); }
 
@@ -1129,7 +1447,8 @@ cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal, int metho
     if (!bp_supports(w, method, vglobal)) return cudaErrorInvalidValue;
     const size_t smem = bp_smem_bytes(w, precision, vglobal);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    Variant& v = use_compact(w, vglobal) ? compact_variant(precision, method) : variant(precision, w.cw, vglobal);
+    Variant& v = use_ms2(w, vglobal, method) ? ms2_variant(precision, w.unit_alpha != 0)
+                 : (use_compact(w, vglobal) ? compact_variant(precision, method) : variant(precision, w.cw, vglobal));
     size_t& have = v.configured[device_slot()];
     if (smem <= have) return cudaSuccess;                   // the attribute only ever grows (decoders of different sizes coexist)
     cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -1139,7 +1458,8 @@ cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal, int metho
 
 cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, bool vglobal, int grid, cudaStream_t st) {
     if (b.n_shots == 0) return cudaSuccess;
-    Variant& v = use_compact(w, vglobal) ? compact_variant(precision, p.method) : variant(precision, w.cw, vglobal);
+    Variant& v = use_ms2(w, vglobal, p.method) ? ms2_variant(precision, w.unit_alpha != 0)
+                 : (use_compact(w, vglobal) ? compact_variant(precision, p.method) : variant(precision, w.cw, vglobal));
     const size_t smem = bp_smem_bytes(w, precision, vglobal);
     v.fn<<<grid, v.threads, smem, st>>>(w, b, p);
     return cudaGetLastError();

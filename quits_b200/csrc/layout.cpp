@@ -12,6 +12,8 @@
 //                            message V                       row summary rsum
 //   fp64   8-byte accesses:  half-warp of 16, (addr) mod 16  16-byte accesses: quarter-warp of 8, row mod 8
 //   fp32   4-byte accesses:  warp of 32,      (addr) mod 32   8-byte accesses: half-warp of 16,  row mod 16
+// (bp_kernel_ms2 keeps min1 / min2 in two arrays of single values: its row-summary gather has the message geometry -- `rb`
+// overrides the row-summary class count: 16 in fp64, 32 in fp32)
 // Step 1 groups columns of equal weight so that, at every edge position, the rows of a sub-group are distinct modulo the
 // class count (greedy seed-and-extend, then plateau-walking swaps).  Step 2 assigns slots so that the message addresses
 // of a sub-group are distinct modulo the class count (first-fit, then plateau-walking slot swaps inside a row).
@@ -73,30 +75,30 @@ int group_cost(const Cols& c, const int* members, int nm, int RB, int dummy_row)
 
 }  // namespace
 
-static void search_bp_layout(const Window& hw, int rs, int precision, BpLayout& out);
+static void search_bp_layout(const Window& hw, int rs, int precision, int rb, BpLayout& out);
 
 // The search is deterministic, so its result is cached per process by window structure: decoders are rebuilt for every
 // call of the drop-in functions, and consecutive sliding windows usually have identical structure.
-void optimize_bp_layout(const Window& hw, int rs, int precision, BpLayout& out) {
-    struct Entry { std::vector<int64_t> cptr; std::vector<int32_t> crow; int rs, precision; BpLayout lay; };
+void optimize_bp_layout(const Window& hw, int rs, int precision, BpLayout& out, int rb) {
+    struct Entry { std::vector<int64_t> cptr; std::vector<int32_t> crow; int rs, precision, rb; BpLayout lay; };
     static std::mutex mu;
     static std::vector<std::unique_ptr<Entry>> cache;
     {
         std::lock_guard<std::mutex> lk(mu);
         for (auto& e : cache)
-            if (e->rs == rs && e->precision == precision && e->crow == hw.crow && e->cptr == hw.cptr) { out = e->lay; return; }
+            if (e->rs == rs && e->precision == precision && e->rb == rb && e->crow == hw.crow && e->cptr == hw.cptr) { out = e->lay; return; }
     }
-    search_bp_layout(hw, rs, precision, out);
+    search_bp_layout(hw, rs, precision, rb, out);
     std::lock_guard<std::mutex> lk(mu);
     if (cache.size() >= 64) cache.erase(cache.begin());
-    std::unique_ptr<Entry> e(new Entry{hw.cptr, hw.crow, rs, precision, out});
+    std::unique_ptr<Entry> e(new Entry{hw.cptr, hw.crow, rs, precision, rb, out});
     cache.push_back(std::move(e));
 }
 
-static void search_bp_layout(const Window& hw, int rs, int precision, BpLayout& out) {
+static void search_bp_layout(const Window& hw, int rs, int precision, int rb, BpLayout& out) {
     const Cols c(hw);
     const int n = c.n, rows = hw.rows;
-    const int RB = precision == 32 ? 16 : 8;        // row-summary classes = sub-group size
+    const int RB = rb > 0 ? rb : (precision == 32 ? 16 : 8);        // row-summary classes = sub-group size
     const int VB = precision == 32 ? 32 : 16;       // message classes = sub-group size
     const char* env = std::getenv("QB_LAYOUT_OPT");
     const bool enabled = !(env && env[0] == '0');
@@ -121,8 +123,8 @@ static void search_bp_layout(const Window& hw, int rs, int precision, BpLayout& 
             size_t first_free = 0, left = pool.size();
             while (left) {
                 while (used[first_free]) ++first_free;
-                int classrow[6][16];
-                for (int q = 0; q < 6; ++q) std::fill(classrow[q], classrow[q] + 16, -1);
+                int classrow[6][32];
+                for (int q = 0; q < 6; ++q) std::fill(classrow[q], classrow[q] + 32, -1);
                 auto add = [&](int j) {
                     for (int q = 0; q < wc; ++q) {
                         int& slot = classrow[q][c.row(j, q) % RB];
@@ -285,10 +287,10 @@ static void search_bp_layout(const Window& hw, int rs, int precision, BpLayout& 
 // Predicted shared-memory passes of one bit sweep relative to the conflict-free minimum, for the message gather
 // (v_ratio; the scatter is the same) and the row-summary gather (r_ratio).  Same model ncu confirms on the device
 // ("L1 Wavefronts Shared" / "Ideal" per source line).
-void layout_wavefronts(const Window& hw, int rs, int precision, const BpLayout& lay, double* v_ratio, double* r_ratio) {
+void layout_wavefronts(const Window& hw, int rs, int precision, const BpLayout& lay, double* v_ratio, double* r_ratio, int rb) {
     const Cols c(hw);
     const int n = c.n, rows = hw.rows;
-    const int RB = precision == 32 ? 16 : 8, VB = precision == 32 ? 32 : 16;
+    const int RB = rb > 0 ? rb : (precision == 32 ? 16 : 8), VB = precision == 32 ? 32 : 16;
     const int npad = (n + 31) / 32 * 32;
     const long long dummy = static_cast<long long>(rows) * rs;
     long vw = 0, vi = 0, rw = 0, ri = 0;

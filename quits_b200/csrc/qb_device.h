@@ -89,6 +89,8 @@ struct WinDev {
     const float2* rsum0f;     // [rows] iteration-1 row summaries (min1, min2 of the prior LLRs along the row)
     const double2* rsum0d;
     const uint8_t* neg0;      // [rows] parity of #{prior LLR <= 0} along the row
+    int chunk_end[7];         // bp_kernel_ms2: chunk_end[W] = first 32-record chunk whose heaviest column is lighter than W
+    int unit_alpha;           // every iteration's min-sum scaling factor is exactly 1 (the multiply is skipped)
     // serial schedule (bp_kernel_serial): steps of independent (column, row) pairs in column order
     int ser_nsteps;
     const uint32_t* ser_steps;// [ser_nsteps + 1] n_pairs | n_cols << 8
@@ -149,6 +151,7 @@ constexpr uint32_t kNoAddr = 0xFFFFu;
 size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal);
 int bp_threads(int precision);
 bool bp_supports(const WinDev& w, int method, bool vglobal);
+bool bp_ms2_enabled();       // flooding min-sum through bp_kernel_ms2 (default) or bp_kernel_compact (QB_BP_MS2=0, A/B measurements)
 cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal, int method);
 size_t bp_serial_smem_bytes(const WinDev& w, int precision);
 cudaError_t bp_serial_configure(const WinDev& w, int precision, int method);

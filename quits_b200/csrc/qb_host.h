@@ -115,8 +115,9 @@ struct BpLayout {
     long rsum_excess = 0, v_excess = 0; // residual bank-class collisions after the search (0 = conflict free)
 };
 // rs: row stride of the message array; precision 32 / 64 selects the bank-class geometry
-void optimize_bp_layout(const Window& hw, int rs, int precision, BpLayout& out);
-void layout_wavefronts(const Window& hw, int rs, int precision, const BpLayout& lay, double* v_ratio, double* r_ratio);
+// rb > 0 overrides the number of row-summary bank classes (default: 8 in fp64, 16 in fp32 -- the (min1, min2) pairs of bp_kernel_compact)
+void optimize_bp_layout(const Window& hw, int rs, int precision, BpLayout& out, int rb = 0);
+void layout_wavefronts(const Window& hw, int rs, int precision, const BpLayout& lay, double* v_ratio, double* r_ratio, int rb = 0);
 
 // n_cor_override < 0: derive the number of sliding windows as sliding_window.py:130-141 does
 void plan_windows(const CheckMatrix& cm, int m, int W, int F, int n_cor_override, WindowPlan& plan);
