@@ -11,7 +11,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libquits_b200.so")
+SO_PATH = os.environ.get("QB_LIB") or os.path.join(_HERE, "libquits_b200.so")      # QB_LIB: A/B builds of the same ABI (development)
 
 
 class QbStats(C.Structure):

@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "libquits_b200.so")
-SOURCES = ["qb_host.cpp", "layout.cpp", "frame.cu", "bp.cu", "osd.cu", "lsd.cu", "api.cu"]
-HEADERS = ["qb_host.h", "qb_device.h", os.path.join(ROOT, "include", "quits_b200.h")]
+SOURCES = ["qb_host.cpp", "layout.cpp", "frame.cu", "bp.cu", "bp_serial.cu", "osd.cu", "lsd.cu", "api.cu"]
+HEADERS = ["qb_host.h", "qb_device.h", "bp_common.cuh", os.path.join(ROOT, "include", "quits_b200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall", "--fmad=false"]
 

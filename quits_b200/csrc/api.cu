@@ -149,7 +149,8 @@ namespace {
 
 struct WinOwned {
     qb::WinDev dev{};
-    DevBuf ser_steps, ser_pairs, ser_cols, ser32_rec;
+    DevBuf ss_rec, ss_v0, ss_s0, ss_rsum0, ss_neg0;
+    bool serial_slab = false;
     DevBuf colE, llr0f, llr0d, osd_wt, lmask, uptr, uidx, cptr, crow, rptr, rcol, colrec, ptabf, ptabd, rlen, rsum0f, rsum0d, neg0;
     size_t bp_smem = 0;
     bool vglobal = false;
@@ -181,6 +182,8 @@ struct qb_sw {
     size_t llr_stride = 0;
     DevBuf det_rows, det_bytes, det_bytes_alt, carry, acc, llr, syn, fail_list, ovf_list, order, sel_key, sel_idx, sel_cnt, counters, stats, pred, ehat, iters, conv, vscratch, lsd_scratch, sort_scratch;
     size_t lsd_slab = 0;
+    size_t serial_slab = 0;       // serial schedule: bytes of one CTA's message slab, CTAs of the persistent grid
+    int serial_grid = 0;
     int lsd_cols = 0;
     int lsd_grid = 0, lsd_slabs_per_lane = 0;
     EventTimer t_bp, t_osd;
@@ -247,6 +250,105 @@ int gf2_rank(const qb::Window& hw) {
         ++rank;
     }
     return rank;
+}
+
+// ---- serial schedule on the message slab (bp_serial.cu): dependency levels of the column sequence, steps of independent columns
+void build_serial_slab(qb_ctx* ctx, const qb::Window& hw, int precision, int method, WinOwned& wo) {
+    qb::WinDev& d = wo.dev;
+    const int rows = hw.rows, ncols = hw.ncols;
+    const size_t nnz = hw.crow.size();
+    int cw = 0;
+    for (int j = 0; j < ncols; ++j) cw = std::max(cw, static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]));
+    if (cw > 16 || rows >= 65535 || ncols >= 65535) return;
+    const int lpc = cw <= 6 ? 6 : (cw <= 8 ? 8 : 16), ng = 32 / lpc;
+    // CSR position of every CSC edge (rows ascending, columns ascending inside a row: the order the serial sweep visits a row in)
+    std::vector<int32_t> rptr(static_cast<size_t>(rows) + 1, 0);
+    for (int32_t r : hw.crow) rptr[static_cast<size_t>(r) + 1]++;
+    for (int r = 0; r < rows; ++r) rptr[r + 1] += rptr[r];
+    std::vector<uint32_t> csr_of(nnz);
+    {
+        std::vector<int32_t> fill(rptr.begin(), rptr.end() - 1);
+        for (int j = 0; j < ncols; ++j)
+            for (int64_t e = hw.cptr[j]; e < hw.cptr[j + 1]; ++e) csr_of[static_cast<size_t>(e)] = static_cast<uint32_t>(fill[hw.crow[e]]++);
+    }
+    // level of a column = 1 + the highest level among the earlier columns it shares a row with
+    std::vector<int> lastlvl(static_cast<size_t>(rows), 0);
+    std::vector<std::vector<int>> bylevel(1);
+    for (int j = 0; j < ncols; ++j) {
+        int l = 1;
+        for (int64_t e = hw.cptr[j]; e < hw.cptr[j + 1]; ++e) l = std::max(l, lastlvl[hw.crow[e]] + 1);
+        for (int64_t e = hw.cptr[j]; e < hw.cptr[j + 1]; ++e) lastlvl[hw.crow[e]] = l;
+        if (static_cast<size_t>(l) >= bylevel.size()) bylevel.resize(static_cast<size_t>(l) + 1);
+        bylevel[l].push_back(j);
+    }
+    std::vector<uint32_t> rec;                                // uint2 per lane
+    int nsteps = 0;
+    auto push_step = [&](const int* cj, int n) {
+        for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane / lpc, q = lane % lpc;
+            uint32_t x = static_cast<uint32_t>(nnz) + static_cast<uint32_t>(lane), row = static_cast<uint32_t>(rows), extra = q == 0 ? 0xFFFFu : 0u;
+            if (g < ng && g < n) {
+                const int j = cj[g];
+                const int wt = static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]);
+                if (q < wt) { x = csr_of[static_cast<size_t>(hw.cptr[j] + q)]; row = static_cast<uint32_t>(hw.crow[hw.cptr[j] + q]); }
+                if (q == 0) extra = static_cast<uint32_t>(j);
+            }
+            rec.push_back(x);
+            rec.push_back(row | (extra << 16));
+        }
+        ++nsteps;
+    };
+    for (size_t l = 1; l < bylevel.size(); ++l)
+        for (size_t i = 0; i < bylevel[l].size(); i += static_cast<size_t>(ng))
+            push_step(bylevel[l].data() + i, static_cast<int>(std::min<size_t>(static_cast<size_t>(ng), bylevel[l].size() - i)));
+    const int real_steps = nsteps;
+    for (int k = 0; k < 4; ++k) push_step(nullptr, 0);        // the records in flight past the last step land here
+    upload(wo.ss_rec, rec, ctx->stream, 2);
+    // initial messages per CSR edge and iteration-0 row summaries
+    std::vector<double> v0d(nnz), s0sum(static_cast<size_t>(rows) * 2, DBL_MAX);
+    std::vector<float> v0f(nnz), s0sumf(static_cast<size_t>(rows) * 2, FLT_MAX);
+    std::vector<uint8_t> neg0(static_cast<size_t>(rows), 0);
+    for (int j = 0; j < ncols; ++j) {
+        const double l0 = std::log((1.0 - hw.priors[j]) / hw.priors[j]);
+        const float l0f = static_cast<float>(l0);
+        for (int64_t e = hw.cptr[j]; e < hw.cptr[j + 1]; ++e) {
+            const int r = hw.crow[e];
+            v0d[csr_of[static_cast<size_t>(e)]] = l0;
+            v0f[csr_of[static_cast<size_t>(e)]] = l0f;
+            if (l0 <= 0.0) neg0[r] ^= 1;
+            const double ad = std::fabs(l0);
+            const float af = std::fabs(l0f);
+            double& m1 = s0sum[2 * r]; double& m2 = s0sum[2 * r + 1];
+            m2 = std::min(m2, std::max(m1, ad)); m1 = std::min(m1, ad);
+            float& f1 = s0sumf[2 * r]; float& f2 = s0sumf[2 * r + 1];
+            f2 = std::min(f2, std::max(f1, af)); f1 = std::min(f1, af);
+        }
+    }
+    const size_t esz = precision == 32 ? 4 : 8;
+    wo.ss_v0.ensure((nnz + 32) * esz + 16);
+    wo.ss_s0.ensure((nnz + 32) * esz + 16);
+    if (precision == 32) {
+        if (nnz) CK(cudaMemcpyAsync(wo.ss_v0.p, v0f.data(), nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+        upload(wo.ss_rsum0, s0sumf, ctx->stream, 2);
+    } else {
+        if (nnz) CK(cudaMemcpyAsync(wo.ss_v0.p, v0d.data(), nnz * 8, cudaMemcpyHostToDevice, ctx->stream));
+        upload(wo.ss_rsum0, s0sum, ctx->stream, 2);
+    }
+    upload(wo.ss_neg0, neg0, ctx->stream, 2);
+    CK(cudaStreamSynchronize(ctx->stream));
+    d.nnz = static_cast<int>(nnz);
+    d.ss_nsteps = real_steps;
+    d.ss_lpc = lpc;
+    d.ss_rec = wo.ss_rec.as<uint2>();
+    d.ss_v0f = wo.ss_v0.as<float>(); d.ss_v0d = wo.ss_v0.as<double>();
+    d.ss_s0f = wo.ss_s0.as<float>(); d.ss_s0d = wo.ss_s0.as<double>();
+    d.ss_rsum0f = wo.ss_rsum0.as<float2>(); d.ss_rsum0d = wo.ss_rsum0.as<double2>();
+    d.ss_neg0 = wo.ss_neg0.as<uint8_t>();
+    if (method == 1) {                                        // product-sum: tanh(LLR / 2) per edge and its suffix products, by the device
+        CK(qb::launch_serial_slab_ps_tables(d, precision, wo.ss_v0.p, wo.ss_s0.p, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    wo.serial_slab = true;
 }
 
 void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, int method, WinOwned& wo) {
@@ -375,94 +477,6 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, int 
             upload(wo.neg0, neg0, ctx->stream);
             upload(wo.rsum0d, s0d, ctx->stream);
             upload(wo.rsum0f, s0f, ctx->stream);
-            // ---- serial schedule: dependency levels of the column sequence, cut into steps of <= 16 (column, row) pairs
-            {
-                constexpr int kPairs = 16, kCols = 128;
-                std::vector<int> lastlvl(static_cast<size_t>(rows), 0), lvl(static_cast<size_t>(ncols), 1);
-                int nlev = 1;
-                for (int j = 0; j < ncols; ++j) {
-                    int l = 1;
-                    for (int64_t e2 = hw.cptr[j]; e2 < hw.cptr[j + 1]; ++e2) l = std::max(l, lastlvl[hw.crow[e2]] + 1);
-                    lvl[j] = l;
-                    for (int64_t e2 = hw.cptr[j]; e2 < hw.cptr[j + 1]; ++e2) lastlvl[hw.crow[e2]] = l;
-                    nlev = std::max(nlev, l);
-                }
-                std::vector<std::vector<int>> bylevel(static_cast<size_t>(nlev) + 1);
-                for (int j = 0; j < ncols; ++j) bylevel[lvl[j]].push_back(j);
-                // fixed-stride tables so that the kernel can prefetch step s+1 without a dependent load:
-                // steps[s] = n_pairs | n_cols << 8; pairs[s][16] = (address | row << 16, row length); cols[s][16] = (column | prior
-                // index << 16, first pair | weight << 8)
-                std::vector<uint32_t> steps, pairs, cols;
-                for (int l = 1; l <= nlev; ++l) {
-                    size_t i = 0;
-                    const std::vector<int>& cl = bylevel[l];
-                    while (i < cl.size()) {
-                        const size_t pbase = pairs.size(), cbase = cols.size();
-                        pairs.resize(pbase + 2 * kPairs, 0u);
-                        cols.resize(cbase + 2 * kPairs, 0u);
-                        int np = 0, nc = 0;
-                        while (i < cl.size() && nc < kPairs) {
-                            const int j = cl[i];
-                            const int wt = static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]);
-                            if (np + wt > kPairs) break;
-                            cols[cbase + 2 * nc] = static_cast<uint32_t>(j) | (static_cast<uint32_t>(pidx[j]) << 16);
-                            cols[cbase + 2 * nc + 1] = static_cast<uint32_t>(np) | (static_cast<uint32_t>(wt) << 8);
-                            for (int64_t e2 = hw.cptr[j]; e2 < hw.cptr[j + 1]; ++e2, ++np) {
-                                const uint32_t r = static_cast<uint32_t>(hw.crow[e2]);
-                                pairs[pbase + 2 * np] = (r * static_cast<uint32_t>(rs) + static_cast<uint32_t>(layout.slot[e2])) | (r << 16);
-                                pairs[pbase + 2 * np + 1] = static_cast<uint32_t>(fillr[r]);
-                            }
-                            ++nc; ++i;
-                        }
-                        steps.push_back(static_cast<uint32_t>(np) | (static_cast<uint32_t>(nc) << 8));
-                    }
-                }
-                // warp-per-shot form: steps of <= 5 columns of one level, lane 6g + q = edge q of column g; lighter columns and
-                // the empty places of a step point at the private dummy slot of the lane (rows*rs + lane)
-                {
-                    std::vector<uint32_t> rec32;
-                    int nsteps32 = 0;
-                    const uint32_t realN = static_cast<uint32_t>(rows) * static_cast<uint32_t>(rs);
-                    auto push_step = [&](const int* cj, int n) {
-                        for (int lane = 0; lane < 32; ++lane) {
-                            const int g = lane / 6, q = lane % 6;
-                            uint32_t addr = realN + static_cast<uint32_t>(lane), hi = q == 0 ? 0xFFFFu : 0u;
-                            if (g < n) {
-                                const int j = cj[g];
-                                const int wt = static_cast<int>(hw.cptr[j + 1] - hw.cptr[j]);
-                                if (q < wt) {
-                                    const int64_t e2 = hw.cptr[j] + q;
-                                    addr = static_cast<uint32_t>(hw.crow[e2]) * static_cast<uint32_t>(rs) + static_cast<uint32_t>(layout.slot[e2]);
-                                }
-                                if (q == 0) hi = static_cast<uint32_t>(j);
-                                if (q == 1) hi = static_cast<uint32_t>(pidx[j]);
-                            }
-                            rec32.push_back(addr | (hi << 16));
-                        }
-                        ++nsteps32;
-                    };
-                    for (int l = 1; l <= nlev; ++l) {
-                        const std::vector<int>& cl = bylevel[l];
-                        for (size_t i = 0; i < cl.size(); i += 5) push_step(cl.data() + i, static_cast<int>(std::min<size_t>(5, cl.size() - i)));
-                    }
-                    const int real_steps = nsteps32;
-                    for (int k = 0; k < 4; ++k) push_step(nullptr, 0);       // the rows in flight past the last step land here
-                    upload(wo.ser32_rec, rec32, ctx->stream, 4);
-                    d.ser32_nsteps = real_steps;
-                    d.ser32_rec = wo.ser32_rec.as<uint32_t>();
-                }
-                (void)kCols;
-                steps.push_back(0u);                                 // the prefetch of the step after the last one lands here
-                pairs.resize(pairs.size() + 2 * kPairs, 0u);
-                cols.resize(cols.size() + 2 * kPairs, 0u);
-                upload(wo.ser_steps, steps, ctx->stream, 4);
-                upload(wo.ser_pairs, pairs, ctx->stream, 2);
-                upload(wo.ser_cols, cols, ctx->stream, 2);
-                d.ser_nsteps = static_cast<int>(steps.size()) - 1;
-                d.ser_steps = wo.ser_steps.as<uint32_t>();
-                d.ser_pairs = wo.ser_pairs.as<uint2>();
-                d.ser_cols = wo.ser_cols.as<uint2>();
-            }
             // chunks of 32 records by the weight of their heaviest (= first) column, for the segment loops of bp_kernel_ms2
             {
                 const int nch = npad / 32;
@@ -524,8 +538,6 @@ void build_window(qb_ctx* ctx, const qb::Window& hw, int KW, int precision, int 
     d.rptr = wo.rptr.as<int32_t>(); d.rcol = wo.rcol.as<uint16_t>();
 }
 
-static bool rows_fit_serial(const qb::WinDev& d, int prec) { return qb::bp_serial_smem_bytes(d, prec) <= 227 * 1024; }
-
 void finish_decoder(qb_sw* sw) {
     qb_ctx* ctx = sw->ctx;
     const qb_bp_opts& o = sw->opts;
@@ -546,18 +558,27 @@ void finish_decoder(qb_sw* sw) {
     if (sw->use_lsd && o.osd_order != 0)
         throw qb::unsupported_error("LSD post-processing beyond order 0 (lsd_order > 0) is not supported on the GPU path");
     int max_npad = 0, max_rowsW = 0, max_iter = 0, big_rows = 0;
-    size_t max_slab = 0, sort_slab = 0;
-    int max_sort_grid = 0;
+    size_t max_slab = 0, sort_slab = 0, serial_slab = 0;
+    int max_sort_grid = 0, serial_grid = 0;
     bool any_big = false;
     for (auto& w : sw->wins) {
         // messages in shared memory when they fit, else in an L2-resident global slab per CTA
-        if (sw->serial) {
-            if (!w->dev.compact || rows_fit_serial(w->dev, prec) == false)
-                throw qb::unsupported_error("schedule 'serial' needs a window that fits the compact shared-memory layout (column weight <= 6, messages <= 227 KB)");
-            CK(qb::bp_serial_configure(w->dev, prec, o.bp_method));
-        }
         w->dev.unit_alpha = o.ms_scaling_factor == 1.0 ? 1 : 0;
-        w->vglobal = qb::bp_smem_bytes(w->dev, prec, false) > 227 * 1024;
+        if (sw->serial) {
+            // one warp per shot, messages in a global slab per persistent CTA, row summaries in shared memory (bp_serial.cu)
+            if (!w->serial_slab || !qb::bp_serial_slab_supported(w->dev, prec, o.bp_method))
+                throw qb::unsupported_error("schedule 'serial': window of " + std::to_string(w->dev.rows) + " x " + std::to_string(w->dev.ncols) +
+                                            " exceeds what the serial kernel handles (column weight <= 16, rows < 65535, row summaries in shared memory)");
+            CK(qb::bp_serial_slab_configure(w->dev, prec, o.bp_method));
+            w->bp_grid = 148 * qb::bp_serial_slab_ctas_per_sm(w->dev, prec, o.bp_method);
+            serial_slab = std::max(serial_slab, qb::bp_serial_slab_bytes(w->dev, prec, o.bp_method));
+            serial_grid = std::max(serial_grid, w->bp_grid);
+            max_npad = std::max(max_npad, w->dev.ncols_pad);
+            max_rowsW = std::max(max_rowsW, w->dev.rowsW32);
+            max_iter = std::max(max_iter, o.max_iter > 0 ? o.max_iter : w->dev.ncols);
+        }
+        w->vglobal = !sw->serial && qb::bp_smem_bytes(w->dev, prec, false) > 227 * 1024;
+        if (!sw->serial) {
         w->bp_smem = qb::bp_smem_bytes(w->dev, prec, w->vglobal);
         if (w->bp_smem > 227 * 1024)
             throw qb::unsupported_error("window of " + std::to_string(w->dev.rows) + " rows is too tall for the BP kernel's per-row shared-memory state");
@@ -567,6 +588,7 @@ void finish_decoder(qb_sw* sw) {
         if (w->vglobal) {
             w->bp_grid = 148 * 2;
             max_slab = std::max(max_slab, static_cast<size_t>(w->dev.rows) * w->dev.RS * (prec / 8));
+        }
         }
         max_npad = std::max(max_npad, w->dev.ncols_pad);
         max_rowsW = std::max(max_rowsW, w->dev.rowsW32);
@@ -609,6 +631,8 @@ void finish_decoder(qb_sw* sw) {
         }
     }
     if (max_slab) sw->vscratch.ensure(max_slab * 148 * 2 + 16);
+    sw->serial_slab = serial_slab;
+    sw->serial_grid = serial_grid;
     if (sw->use_lsd) {
         // one slab per persistent warp: bit owners (0xFFFF = none between shots), column-order links, operation vectors
         int max_rows = 0;
@@ -676,6 +700,7 @@ void ensure_batch(qb_sw* sw, int n) {
             sw->lsd_slabs_per_lane = per_lane;
         }
     }
+    if (sw->serial_slab) sw->vscratch.ensure(sw->serial_slab * static_cast<size_t>(sw->serial_grid) * static_cast<size_t>(std::max(sw->lanes, 1)) + 64);
     const size_t nw = sw->wins.size() * qb_ctx::kMaxLanes;
     sw->counters.ensure(nw * kCounterSlots * sizeof(int) + 16);
     sw->stats.ensure(nw * kStatSlots * sizeof(unsigned long long) + 16);
@@ -726,7 +751,8 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.llr_esize = sw->precision / 8;
             b.order_alt = (want_llr && sw->use_osd) ? sw->order.as<uint16_t>() + s0 * sw->llr_stride : nullptr;   // keep the posteriors intact for the caller
             b.llr_buf = static_cast<unsigned char*>(sw->llr.p) + s0 * sw->llr_stride * esz;
-            b.vscratch = sw->vscratch.p;
+            b.vscratch = sw->serial_slab ? static_cast<void*>(static_cast<unsigned char*>(sw->vscratch.p) + static_cast<size_t>(l) * sw->serial_slab * sw->serial_grid)
+                                         : sw->vscratch.p;
             b.syn_stride32 = sw->synW;
             b.syn_buf = sw->syn.as<uint32_t>() + s0 * sw->synW;
             b.fail_list = sw->fail_list.as<int>() + s0;          // shot indices local to the sub-batch
@@ -755,8 +781,9 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.iters_out = want_ehat ? sw->iters.as<int32_t>() : nullptr;
             b.conv_out = want_ehat ? sw->conv.as<uint8_t>() : nullptr;
             b.write_llr_always = want_llr ? 1 : 0;
+            b.commit_unconverged = (!sw->use_osd && !sw->use_lsd) ? 1 : 0;
             if (sw->opts.profile) sw->t_bp.begin(ls);
-            if (sw->serial) CK(qb::launch_bp_serial(w.dev, b, bp, sw->precision, nl, ls));
+            if (sw->serial) CK(qb::launch_bp_serial_slab(w.dev, b, bp, sw->precision, std::min(w.bp_grid, nl), ls));
             else CK(qb::launch_bp(w.dev, b, bp, sw->precision, w.vglobal, w.vglobal ? std::min(w.bp_grid, nl) : nl, ls));
             if (sw->opts.profile) sw->t_bp.end(ls);
             if (stats) stats->bp_launches++;
@@ -1231,6 +1258,7 @@ int qb_sw_create(qb_ctx* ctx, const qb_plan* plan, const qb_bp_opts* opts, qb_sw
             if (hw.urows != 0 && hw.urows != sw->plan.m) throw qb::value_error("carry block of a window is not m rows tall");
             sw->wins.emplace_back(new WinOwned());
             build_window(ctx, hw, KW, sw->opts.precision == 32 ? 32 : 64, (sw->opts.bp_method == 0 && sw->opts.schedule == 0) ? 0 : 1, *sw->wins.back());
+            if (sw->opts.schedule == 1) build_serial_slab(ctx, hw, sw->opts.precision == 32 ? 32 : 64, sw->opts.bp_method, *sw->wins.back());
         }
         finish_decoder(sw.get());
         *out = sw.release();
@@ -1267,6 +1295,7 @@ int qb_sw_create_single(qb_ctx* ctx, int32_t rows, int32_t cols, const int64_t* 
         sw->plan.windows.push_back(hw);
         sw->wins.emplace_back(new WinOwned());
         build_window(ctx, sw->plan.windows[0], 1, sw->opts.precision == 32 ? 32 : 64, (sw->opts.bp_method == 0 && sw->opts.schedule == 0) ? 0 : 1, *sw->wins.back());
+        if (sw->opts.schedule == 1) build_serial_slab(ctx, sw->plan.windows[0], sw->opts.precision == 32 ? 32 : 64, sw->opts.bp_method, *sw->wins.back());
         finish_decoder(sw.get());
         *out = sw.release();
     });

@@ -89,17 +89,21 @@ struct WinDev {
     const float2* rsum0f;     // [rows] iteration-1 row summaries (min1, min2 of the prior LLRs along the row)
     const double2* rsum0d;
     const uint8_t* neg0;      // [rows] parity of #{prior LLR <= 0} along the row
+    // serial schedule on a global message slab (bp_serial.cu, bp_kernel_serial_slab): any column weight <= 16
+    int nnz;
+    int ss_nsteps, ss_lpc;    // steps of one sweep; lanes per column (6, 8 or 16 => 5, 4 or 2 independent columns per step)
+    const uint2* ss_rec;      // [ss_nsteps + 4][32]  x = CSR position of the lane's edge (no edge: the lane's dummy slot nnz + lane),
+                              //   y = row (no edge: the dummy row `rows`) | extra << 16, extra = column index on the first lane of a
+                              //   column's group (0xFFFF: no column)
+    const float* ss_v0f;      // [nnz] initial message of every CSR edge: the prior LLR of its column (product-sum: tanh(LLR / 2))
+    const double* ss_v0d;
+    const float* ss_s0f;      // product-sum: [nnz] suffix products of the initial factors along each row
+    const double* ss_s0d;
+    const float2* ss_rsum0f;  // min-sum: [rows] (min1, min2) of the prior LLRs' magnitudes along the row, and the parity of #{LLR <= 0}
+    const double2* ss_rsum0d;
+    const uint8_t* ss_neg0;
     int chunk_end[7];         // bp_kernel_ms2: chunk_end[W] = first 32-record chunk whose heaviest column is lighter than W
     int unit_alpha;           // every iteration's min-sum scaling factor is exactly 1 (the multiply is skipped)
-    // serial schedule (bp_kernel_serial): steps of independent (column, row) pairs in column order
-    int ser_nsteps;
-    const uint32_t* ser_steps;// [ser_nsteps + 1] n_pairs | n_cols << 8
-    const uint2* ser_pairs;   // [ser_nsteps + 1][16] (message address | row << 16, row length); a column's pairs contiguous, ascending rows
-    const uint2* ser_cols;    // [ser_nsteps + 1][16] (column | prior index << 16, first pair of the step | weight << 8)
-    // serial schedule, warp-per-shot form (bp_kernel_serial_warp): steps of <= 5 independent columns, one lane per edge
-    int ser32_nsteps;
-    const uint32_t* ser32_rec;// [ser32_nsteps + 4][32] lane 6g+q: message address of edge q of the step's column g (the lane's private dummy
-                              // slot rows*RS + lane when there is none) | (q == 0: column, 0xFFFF = no column; q == 1: prior index) << 16
 };
 
 struct BatchDev {
@@ -133,6 +137,7 @@ struct BatchDev {
     int32_t* iters_out;       // optional [n]
     uint8_t* conv_out;        // optional [n]
     int write_llr_always;
+    int commit_unconverged;   // no OSD / LSD behind BP: commit BP's hard decision of unconverged shots too (ldpc's BpDecoder semantics)
     int osd_method, osd_order; // 0 osd_0 | 1 osd_e | 2 osd_cs; order 0 = OSD-0 | 3 lsd_0
     void* lsd_scratch;        // LSD only: [grid] slabs of lsd_slab bytes (bit owners, column-order links, operation vectors)
     size_t lsd_slab;
@@ -153,10 +158,16 @@ int bp_threads(int precision);
 bool bp_supports(const WinDev& w, int method, bool vglobal);
 bool bp_ms2_enabled();       // flooding min-sum through bp_kernel_ms2 (default) or bp_kernel_compact (QB_BP_MS2=0, A/B measurements)
 cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal, int method);
-size_t bp_serial_smem_bytes(const WinDev& w, int precision);
-cudaError_t bp_serial_configure(const WinDev& w, int precision, int method);
-cudaError_t launch_bp_serial(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, int grid, cudaStream_t st);
 cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, bool vglobal, int grid, cudaStream_t st);
+
+// serial schedule, one warp per shot, messages in a global slab per CTA (b.vscratch: [grid] slabs of bp_serial_slab_bytes)
+size_t bp_serial_slab_smem_bytes(const WinDev& w, int precision, int method);
+size_t bp_serial_slab_bytes(const WinDev& w, int precision, int method);
+bool bp_serial_slab_supported(const WinDev& w, int precision, int method);
+cudaError_t bp_serial_slab_configure(const WinDev& w, int precision, int method);
+int bp_serial_slab_ctas_per_sm(const WinDev& w, int precision, int method);
+cudaError_t launch_bp_serial_slab(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, int grid, cudaStream_t st);
+cudaError_t launch_serial_slab_ps_tables(const WinDev& w, int precision, void* v0, void* s0, cudaStream_t st);
 
 size_t osd_sort_smem_bytes(const WinDev& w, int precision);
 size_t osd_sort_slab_bytes(const WinDev& w, int precision);
