@@ -250,6 +250,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="concurrent sub-batches per device batch (0 = engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fanout", action="store_true", help="single process, e2e through the drop-in calls spread over every visible GPU")
     args = ap.parse_args()
     globals()["WORKLOAD"] = args.workload
     if args.bp_method:
@@ -297,6 +298,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     text, hz, lz = load_workload()
+    # --gpus N means N devices, one per rank: the drop-in calls of this process stay on this rank's device (left alone they would
+    # spread a call over every visible GPU; --fanout measures exactly that, from one process)
+    qb.set_devices(None if args.fanout else [local])
     ctx = qb.Context.default(local)
     circuit = qb.Circuit(text)
     mc = qb.MonteCarlo(circuit, hz.shape[0], W, F, ctx=ctx, precision=args.precision, profile=True, lanes=args.lanes, **BP_KW)
@@ -413,6 +417,8 @@ def main():
                                   "d2h_bytes_per_step": Se * (DW + KW) * 8 + Se * KW * 8,
                                   "path": "Circuit.sample(packed=True) -> SlidingWindowDecoder.decode_packed (qb_sample_packed / qb_sw_decode_packed, "
                                           "u64 bit rows in host memory)"}
+            if args.fanout:
+                line["e2e_devices"] = qb.active_devices()
             line["e2e"] = {"value": Se * n_e2e * world / float(te.item()), "unit": "shots/s", "h2d_bytes_per_step": Se * D,
                            "d2h_bytes_per_step": Se * (D + K) + Se * K * 8, "shots_per_step_per_gpu": Se, "steps": n_e2e,
                            "path": "get_stim_mem_result -> sliding_window_bposd_circuit_mem (numpy host buffers, host wall clock)"}

@@ -15,6 +15,7 @@ from .decoder import (BpLsdDecoder, BpOsdDecoder, detector_error_model_to_matrix
                       sliding_window_bplsd_phenom_mem, sliding_window_bposd_circuit_mem, sliding_window_bposd_phenom_mem,
                       sliding_window_circuit_mem, sliding_window_phenom_mem, spacetime)
 from .decoder.sliding_window import clear_decoder_cache  # noqa: E402
+from .devices import active_devices, set_devices  # noqa: E402
 from .engine import MonteCarlo, SlidingWindowDecoder, run_sharded, shard_range  # noqa: E402
 from .simulation import get_codecap_pL, get_stim_mem_result  # noqa: E402
 

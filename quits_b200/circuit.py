@@ -55,6 +55,12 @@ class Context:
             pass
 
 
+def _default_ctx() -> "Context":
+    """The context calls without an explicit one run on: slot 0 of quits_b200.devices."""
+    from . import devices as dv
+    return dv.slot_context(0)
+
+
 def circuit_text(circuit) -> str:
     """Stim text of whatever the caller holds: our Circuit, a str, or a stim.Circuit (``str()`` prints Stim text)."""
     if isinstance(circuit, Circuit):
@@ -89,6 +95,7 @@ class Circuit:
         self.num_noise_sites = info.n_noise_sites
         self.ring = info.ring
         self._dem = None
+        self._clones = {}         # slot -> Circuit: the device tape of a parsed circuit belongs to one device at a time
 
     @classmethod
     def of(cls, circuit) -> "Circuit":
@@ -124,24 +131,44 @@ class Circuit:
             self._dem = DetectorErrorModel(self)
         return self._dem
 
+    def for_slot(self, slot: int) -> "Circuit":
+        """This circuit for device slot ``slot`` (quits_b200.devices): slot 0 is the object itself, later slots get a parsed copy."""
+        if slot == 0:
+            return self
+        c = self._clones.get(slot)
+        if c is None:
+            c = self._clones[slot] = Circuit(self.text)
+        return c
+
     # ---- sampling (reference simulation.py:22-27)
     def sample(self, shots, seed, shot0=0, ctx=None, packed=False):
-        ctx = ctx or Context.default()
+        """Shots [shot0, shot0 + shots) of ``seed``.  Without an explicit context the shots are spread over every device of
+        quits_b200.devices (contiguous ranges; shot s is the same bits wherever it is sampled)."""
+        from . import devices as dv
         shots = int(shots)
         D, K = self.num_detectors, self.num_observables
         if packed:
             det = N.empty((shots, max(1, (D + 63) // 64)), np.uint64)
             obs = N.empty((shots, max(1, (K + 63) // 64)), np.uint64)
-            N.check(N.lib().qb_sample_packed(ctx._h, self._h, int(seed), int(shot0), shots, N.ptr(det), N.ptr(obs)))
+            fn = N.lib().qb_sample_packed
+        else:
+            det = N.empty((shots, D), np.bool_)
+            obs = N.empty((shots, K), np.bool_)
+            fn = N.lib().qb_sample
+        if ctx is not None or int(shot0) % 64:
+            N.check(fn((ctx or _default_ctx())._h, self._h, int(seed), int(shot0), shots, N.ptr(det), N.ptr(obs)))
             return det, obs
-        det = N.empty((shots, D), np.bool_)
-        obs = N.empty((shots, K), np.bool_)
-        N.check(N.lib().qb_sample(ctx._h, self._h, int(seed), int(shot0), shots, N.ptr(det), N.ptr(obs)))
+
+        def part(slot, lo, hi):
+            c = self.for_slot(slot)
+            N.check(fn(dv.slot_context(slot)._h, c._h, int(seed), int(shot0) + lo, hi - lo, N.ptr(det[lo:hi]), N.ptr(obs[lo:hi])))
+
+        dv.run_split(shots, part)
         return det, obs
 
     def inject(self, op_idx, tgt_idx, codes, shots=None, n_shots=None, ctx=None):
         """Explicit-fault propagation: fault f goes into shot ``shots[f]`` (default: one fault per shot)."""
-        ctx = ctx or Context.default()
+        ctx = ctx or _default_ctx()
         op_idx = np.ascontiguousarray(op_idx, dtype=np.int32)
         tgt_idx = np.ascontiguousarray(tgt_idx, dtype=np.int32)
         codes = np.ascontiguousarray(codes, dtype=np.int32)

@@ -12,7 +12,7 @@ import numpy as np
 from scipy.sparse import csc_matrix
 
 from .. import _native as N
-from ..circuit import Context
+from ..circuit import Context, _default_ctx
 from ..engine import bp_options
 
 
@@ -37,7 +37,7 @@ class _GpuInnerDecoder:
             raise ValueError("need one prior per column")
         self.options = dict(kw)
         opts = bp_options(osd_method=kw.pop(self._method_key, self._default_method), osd_order=kw.pop(self._order_key, 0), **kw)
-        self.ctx = ctx or Context.default()
+        self.ctx = ctx or _default_ctx()
         indptr = np.ascontiguousarray(pcm.indptr, dtype=np.int64)
         indices = np.ascontiguousarray(pcm.indices if pcm.nnz else [0], dtype=np.int32)
         h = C.c_void_p()

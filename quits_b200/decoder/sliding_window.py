@@ -41,8 +41,8 @@ def _options_key(kw: dict):
 
 
 def _device_key():
-    from ..circuit import Context
-    return Context.default().device
+    from .. import devices as dv
+    return tuple(dv.active_devices())
 
 
 def clear_decoder_cache():

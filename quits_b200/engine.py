@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 from . import _native as N
-from .circuit import Circuit, Context
+from .circuit import Circuit, Context, _default_ctx
 from .decoder.base import WindowPlan
 
 _BP_METHODS = {"minimum_sum": 0, "min_sum": 0, "ms": 0, "msl": 0, "product_sum": 1, "prod_sum": 1, "ps": 1, "psl": 1}
@@ -63,26 +63,36 @@ def bp_options(bp_method="minimum_sum", max_iter=0, schedule="parallel", osd_met
 
 
 class SlidingWindowDecoder:
-    """All windows of one circuit resident on one GPU; decodes batches of shots (K3/K4 kernels)."""
+    """All windows of one circuit resident on a GPU; decodes batches of shots (K3/K4 kernels).
+
+    Built without an explicit context the decoder belongs to the default device and, for large calls, spreads the shots over
+    every device of ``quits_b200.devices``: each further device gets its own copy of the device tables on first use (the window
+    plan is host data and is shared)."""
 
     def __init__(self, circuit, m: int, W: int, F: int, num_cor_rounds: int = -1, ctx: Context = None, **bp_kwargs):
-        self.ctx = ctx or Context.default()
+        self._fanout = ctx is None
+        self.ctx = ctx or _default_ctx()
         self.circuit = Circuit.of(circuit)
         self.plan = WindowPlan(self.circuit.detector_error_model(), m, W, F, num_cor_rounds)
+        self._bp_kwargs = dict(bp_kwargs)
         self.opts = bp_options(**bp_kwargs)
         h = C.c_void_p()
         N.check(N.lib().qb_sw_create(self.ctx._h, self.plan._h, C.byref(self.opts), C.byref(h)))
         self._h = h
         self.K, self.D = self.plan.K, self.plan.D
         self.stats = N.QbStats()
+        self._peers = {}
 
     @classmethod
     def from_plan(cls, plan: WindowPlan, ctx: Context = None, **bp_kwargs) -> "SlidingWindowDecoder":
         """Decoder over an explicit window plan (``WindowPlan.explicit``), e.g. the phenomenological windows."""
         self = cls.__new__(cls)
-        self.ctx = ctx or Context.default()
+        self._fanout = ctx is None
+        self.ctx = ctx or _default_ctx()
         self.circuit = None
         self.plan = plan
+        self._bp_kwargs = dict(bp_kwargs)
+        self._peers = {}
         self.opts = bp_options(**bp_kwargs)
         h = C.c_void_p()
         N.check(N.lib().qb_sw_create(self.ctx._h, plan._h, C.byref(self.opts), C.byref(h)))
@@ -99,6 +109,27 @@ class SlidingWindowDecoder:
         except Exception:
             pass
 
+    def _peer(self, slot: int) -> "SlidingWindowDecoder":
+        """The same decoder on the device of slot ``slot`` (slot 0: this object)."""
+        if slot == 0:
+            return self
+        from . import devices as dv
+        d = self._peers.get(slot)
+        if d is None:
+            d = self._peers[slot] = SlidingWindowDecoder.from_plan(self.plan, ctx=dv.slot_context(slot), **self._bp_kwargs)
+        return d
+
+    def _split(self, n, call):
+        """Run ``call(decoder, lo, hi)`` over the shot ranges of the device split (one range on this decoder when it was built on
+        an explicit context)."""
+        if not self._fanout:
+            return call(self, 0, n)
+        from . import devices as dv
+        parts = dv.plan_split(n)
+        for slot, _, _ in parts:                       # device tables are set up on the calling thread, one device after the other
+            self._peer(slot)
+        dv.run_split(n, lambda slot, lo, hi: call(self._peer(slot), lo, hi))
+
     def decode(self, det) -> np.ndarray:
         """det: [N, D] array of 0/1 (bool or integer) on the host -> int64 [N, K] predictions."""
         det = np.asarray(det)
@@ -110,18 +141,29 @@ class SlidingWindowDecoder:
         pred = N.empty((det.shape[0], self.K), np.int64)
         if self.K == 0 or det.shape[0] == 0:
             pred[...] = 0
-        N.check(N.lib().qb_sw_decode(self._h, N.ptr(det), det.shape[0], N.ptr(pred), C.byref(self.stats)))
+
+        def call(dec, lo, hi):
+            N.check(N.lib().qb_sw_decode(dec._h, N.ptr(det[lo:hi]), hi - lo, N.ptr(pred[lo:hi]), C.byref(dec.stats)))
+
+        self._split(det.shape[0], call)
         return pred
 
     def decode_packed(self, det_rows: np.ndarray) -> np.ndarray:
         det_rows = np.ascontiguousarray(det_rows, dtype=np.uint64)
         out = np.zeros((det_rows.shape[0], max(1, (self.K + 63) // 64)), dtype=np.uint64)
-        N.check(N.lib().qb_sw_decode_packed(self._h, N.ptr(det_rows), det_rows.shape[0], N.ptr(out), C.byref(self.stats)))
+
+        def call(dec, lo, hi):
+            N.check(N.lib().qb_sw_decode_packed(dec._h, N.ptr(det_rows[lo:hi]), hi - lo, N.ptr(out[lo:hi]), C.byref(dec.stats)))
+
+        self._split(det_rows.shape[0], call)
         return out
 
 
 class MonteCarlo:
-    """sample -> decode -> count on one GPU; ``run`` covers global shots [shot0, shot0 + shots)."""
+    """sample -> decode -> count on the device(s); ``run`` covers global shots [shot0, shot0 + shots).
+
+    With an explicit context everything runs on that device (one process per GPU: bench.py, ``run_sharded``); without one the
+    shots of a call are spread over every device of ``quits_b200.devices``."""
 
     def __init__(self, circuit, m: int, W: int, F: int, ctx: Context = None, **bp_kwargs):
         self.decoder = SlidingWindowDecoder(circuit, m, W, F, ctx=ctx, **bp_kwargs)
@@ -131,11 +173,28 @@ class MonteCarlo:
 
     def run(self, shots: int, seed: int, shot0: int = 0):
         """Returns (counts uint64 [1+K], stats dict): counts[0] = shots with any observable mispredicted."""
-        counts = np.zeros(1 + self.K, dtype=np.uint64)
-        st = N.QbStats()
-        N.check(N.lib().qb_mc_run(self.ctx._h, self.circuit._h, self.decoder._h, int(seed), int(shot0), int(shots), N.ptr(counts),
-                                  C.byref(st)))
-        return counts, st.as_dict()
+        from . import devices as dv
+        shots, shot0 = int(shots), int(shot0)
+
+        def call(slot, lo, hi):
+            dec = self.decoder._peer(slot)
+            counts = np.zeros(1 + self.K, dtype=np.uint64)
+            st = N.QbStats()
+            N.check(N.lib().qb_mc_run(dec.ctx._h, self.circuit.for_slot(slot)._h, dec._h, int(seed), shot0 + lo, hi - lo, N.ptr(counts),
+                                      C.byref(st)))
+            return counts, st.as_dict()
+
+        if not self.decoder._fanout or shot0 % 64:
+            return call(0, 0, shots)
+        for slot, _, _ in dv.plan_split(shots):
+            self.decoder._peer(slot)
+        parts = dv.run_split(shots, call)
+        counts, stats = parts[0]
+        for c, st in parts[1:]:
+            counts = counts + c
+            for k, v in st.items():                   # times: the slowest device; everything else adds up
+                stats[k] = max(stats[k], v) if k.endswith("_ms") or k == "osd_max_columns" else stats[k] + v
+        return counts, stats
 
 
 def shard_range(total: int, rank: int, world: int, align: int = 64):
