@@ -558,8 +558,8 @@ void finish_decoder(qb_sw* sw) {
     if (sw->use_lsd && o.osd_order != 0)
         throw qb::unsupported_error("LSD post-processing beyond order 0 (lsd_order > 0) is not supported on the GPU path");
     int max_npad = 0, max_rowsW = 0, max_iter = 0, big_rows = 0;
-    size_t max_slab = 0, sort_slab = 0, serial_slab = 0;
-    int max_sort_grid = 0, serial_grid = 0;
+    size_t max_slab = 0, sort_slab = 0, serial_slab = 0, tall_hi_slab = 0;
+    int max_sort_grid = 0, serial_grid = 0, tall_hi_grid = 0;
     bool any_big = false;
     for (auto& w : sw->wins) {
         // messages in shared memory when they fit, else in an L2-resident global slab per CTA
@@ -593,11 +593,22 @@ void finish_decoder(qb_sw* sw) {
         max_npad = std::max(max_npad, w->dev.ncols_pad);
         max_rowsW = std::max(max_rowsW, w->dev.rowsW32);
         max_iter = std::max(max_iter, o.max_iter > 0 ? o.max_iter : w->dev.ncols);
-        if (sw->use_osd && !qb::osd_supported(w->dev, prec)) {
-            // taller than the shared-memory elimination takes: OSD-0 through the slab kernel (lsd.cu, osd_big_kernel)
-            if (sw->osd_hi || !qb::osd_big_supported(w->dev))
+        if (sw->use_osd && !qb::osd_supported(w->dev, prec) && sw->osd_hi) {
+            // taller than the shared-memory elimination takes, higher-order sweeps: the same elimination with T in a global slab
+            if (!qb::osd_tall_hi_supported(w->dev, prec))
                 throw qb::unsupported_error("window of " + std::to_string(w->dev.rows) + " x " + std::to_string(w->dev.ncols) +
-                                            " exceeds what the OSD kernels handle (order 0: rows <= 3072; higher orders: rows <= 768)");
+                                            " exceeds what the higher-order OSD kernels handle (rows <= 2304)");
+            CK(qb::osd_tall_hi_configure(w->dev, prec));
+            const int per_sm = static_cast<int>((227 * 1024) / (qb::osd_elim_smem_bytes(w->dev, true) + 1024));
+            w->elim_grid = 148 * std::max(1, std::min(per_sm, 4));
+            w->sort_grid = 148 * 4;
+            tall_hi_slab = std::max(tall_hi_slab, qb::osd_tall_hi_slab_bytes(w->dev));
+            tall_hi_grid = std::max(tall_hi_grid, w->elim_grid);
+        } else if (sw->use_osd && !qb::osd_supported(w->dev, prec)) {
+            // taller than the shared-memory elimination takes: OSD-0 through the slab kernel (lsd.cu, osd_big_kernel)
+            if (!qb::osd_big_supported(w->dev))
+                throw qb::unsupported_error("window of " + std::to_string(w->dev.rows) + " x " + std::to_string(w->dev.ncols) +
+                                            " exceeds what the OSD kernels handle (order 0: rows <= 3072; higher orders: rows <= 2304)");
             w->osd_big = true;
             CK(qb::osd_sort_configure(w->dev, prec));
             CK(qb::osd_big_configure(w->dev));
@@ -647,6 +658,12 @@ void finish_decoder(qb_sw* sw) {
         sw->lsd_slab = qb::osd_big_slab_bytes(big_rows);
         for (auto& w : sw->wins) if (w->osd_big) sw->lsd_grid = std::max(sw->lsd_grid, w->elim_grid);
     }
+    if (tall_hi_slab) {
+        // higher-order OSD on tall windows: one T slab per persistent warp (shares the LSD / slab-OSD scratch buffer)
+        sw->use_slab = true;
+        sw->lsd_slab = std::max(sw->lsd_slab, tall_hi_slab);
+        sw->lsd_grid = std::max(sw->lsd_grid, tall_hi_grid);
+    }
     if (sort_slab) sw->sort_scratch.ensure(sort_slab * static_cast<size_t>(std::max(max_sort_grid, 1)) + 16);
     if (o.max_iter == 0 && sw->wins.size() > 1) {
         // ldpc's "0 => number of columns" differs per window; the kernel takes one value
@@ -668,7 +685,7 @@ void finish_decoder(qb_sw* sw) {
     // LSD: a few shots grow clusters of hundreds of bits and keep one warp busy for milliseconds after the rest of the launch has
     // drained; with sub-batches on side streams the BP kernel of another sub-batch fills the machine meanwhile
     sw->lanes = o.lanes > 0 ? std::min(o.lanes, static_cast<int32_t>(qb_ctx::kMaxLanes)) : (sw->use_lsd ? static_cast<int>(qb_ctx::kMaxLanes) : 1);
-    if (max_slab || any_big || sort_slab) sw->lanes = 1;           // the global message / sort slabs are indexed by CTA, not by sub-batch
+    if (max_slab || any_big || sort_slab || tall_hi_slab) sw->lanes = 1;           // the global message / sort slabs are indexed by CTA, not by sub-batch
     sw->DW = std::max(1, (sw->plan.D + 63) / 64);
     sw->KW = std::max(1, (sw->plan.K + 63) / 64);
     sw->carryW = (sw->plan.m + 31) / 32 + 1;

@@ -47,9 +47,12 @@ __host__ __device__ inline size_t bp_layout(const WinDev& w, int rsize, bool vgl
     return o;
 }
 
-template <typename R, int CW, int NT, int MINB, bool VGLOBAL>
+// PS: product-sum (the message array holds tanh(v/2); the row summary is (signed product of the non-zero factors, number of
+// zero factors) and "the others" is the row product divided by the edge's own factor -- as in bp_kernel_compact<.., true>)
+template <typename R, int CW, int NT, int MINB, bool VGLOBAL, bool PS = false>
 __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const BatchDev b, const BpParams p) {
     using RT = Real<R>;
+    using TT = Trans<R>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     size_t off[9];
     bp_layout(w, sizeof(R), VGLOBAL, off);
@@ -72,10 +75,10 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
     for (int shot = blockIdx.x; shot < b.n_shots; shot += gridDim.x) {
         __syncthreads();
         load_syndrome(w, b, shot, tid, syn, accs, car);
-        for (int i = tid; i < rows * RS; i += NT) V[i] = RT::big();       // padding slots: never the minimum, never negative
+        for (int i = tid; i < rows * RS; i += NT) V[i] = PS ? R(1) : RT::big();       // padding slots: never the minimum, never negative (product-sum: a factor 1)
         __syncthreads();
         for (int j = tid; j < ncols; j += NT) {
-            const R l0 = RT::prior(w, j);
+            const R l0 = PS ? TT::th(RT::mul(RT::prior(w, j), R(0.5))) : RT::prior(w, j);
 #pragma unroll
             for (int q = 0; q < CW; ++q) {
                 const uint32_t e = __ldg(w.colE + static_cast<size_t>(q) * npad + j);
@@ -94,6 +97,17 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
                 const R* vr = V + i * RS;
                 R m1 = RT::big(), m2 = RT::big();
                 uint32_t arg = 0, neg = (syn[i >> 5] >> (i & 31)) & 1u;
+                if (PS) {
+                    R prod = (neg & 1u) ? R(-1) : R(1);
+                    int zc = 0;
+                    for (int s = 0; s < RS; ++s) {
+                        const R t = vr[s];
+                        if (t == R(0)) ++zc;
+                        else prod = RT::mul(prod, t);
+                    }
+                    rsum[i] = RT::mk(prod, static_cast<R>(zc));
+                    continue;
+                }
 #pragma unroll 5
                 for (int s = 0; s < RS; ++s) {
                     const R v = vr[s];
@@ -129,10 +143,17 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
                         addr[q] = static_cast<int>(row) * RS + static_cast<int>(slot);
                         const R v = V[addr[q]];
                         const typename RT::pair s = rsum[row];
-                        const uint32_t meta = rmeta[row];
-                        const R mag = slot == (meta & 0x7FFFFFFFu) ? s.y : s.x;
-                        const uint32_t odd = (meta >> 31) ^ (v <= R(0) ? 1u : 0u);
-                        c[q] = RT::mul(mag, odd ? -alpha : alpha);
+                        if (PS) {
+                            R x = R(0);
+                            if (s.y == R(0)) x = TT::div(s.x, v);
+                            else if (s.y == R(1) && v == R(0)) x = s.x;
+                            c[q] = TT::lg(TT::div(RT::add(R(1), x), RT::add(R(1), -x)));
+                        } else {
+                            const uint32_t meta = rmeta[row];
+                            const R mag = slot == (meta & 0x7FFFFFFFu) ? s.y : s.x;
+                            const uint32_t odd = (meta >> 31) ^ (v <= R(0) ? 1u : 0u);
+                            c[q] = RT::mul(mag, odd ? -alpha : alpha);
+                        }
                     }
                 }
                 R t = l0;
@@ -144,7 +165,7 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
                 for (int q = CW - 1; q >= 0; --q) { vn[q] = RT::add(vn[q], t); t = RT::add(t, c[q]); }
 #pragma unroll
                 for (int q = 0; q < CW; ++q)
-                    if (e[q] != kNoEdge) V[addr[q]] = vn[q];
+                    if (e[q] != kNoEdge) V[addr[q]] = PS ? TT::th(RT::mul(vn[q], R(0.5))) : vn[q];
                 if (llr <= R(0)) {
                     if (wide) atomicOr(&ebits[j >> 5], 1u << (j & 31));
                     else hmask |= 1u << k;
@@ -726,21 +747,22 @@ struct Variant {
     size_t configured[kMaxDevices];
 };
 
-template <typename R, int CW, bool VG>
+template <typename R, int CW, bool VG, bool PS>
 KernelPtr pick_kernel(int* threads) {
-    // fp32: 256 threads x 4 CTAs/SM (64 regs); fp64: 512 threads x 2 CTAs/SM; wide columns get more registers
+    // fp32: 256 threads x 4 CTAs/SM (64 regs); fp64: 512 threads x 2 CTAs/SM; wide columns and product-sum get more registers
     constexpr int NT = sizeof(R) == 4 ? 256 : 512;
-    constexpr int MINB = CW <= 8 ? (sizeof(R) == 4 ? 4 : 2) : 1;
+    constexpr int MINB = (CW <= 8 && !PS) ? (sizeof(R) == 4 ? 4 : 2) : 1;
     *threads = NT;
-    return bp_kernel<R, CW, NT, MINB, VG>;
+    return bp_kernel<R, CW, NT, MINB, VG, PS>;
 }
 
-Variant& variant(int prec, int cw, bool vg) {
-    static Variant table[2][3][2] = {};
+Variant& variant(int prec, int cw, bool vg, int method = 0) {
+    static Variant table[2][3][2][2] = {};
     const int pi = prec == 32 ? 0 : 1, ci = cw <= 6 ? 0 : (cw <= 8 ? 1 : 2), gi = vg ? 1 : 0;
-    Variant& v = table[pi][ci][gi];
+    Variant& v = table[pi][ci][gi][method ? 1 : 0];
     if (!v.fn) {
-#define QB_PICK(R, CWV) (vg ? pick_kernel<R, CWV, true>(&v.threads) : pick_kernel<R, CWV, false>(&v.threads))
+#define QB_PICK(R, CWV) (method ? (vg ? pick_kernel<R, CWV, true, true>(&v.threads) : pick_kernel<R, CWV, false, true>(&v.threads)) \
+                                : (vg ? pick_kernel<R, CWV, true, false>(&v.threads) : pick_kernel<R, CWV, false, false>(&v.threads)))
         if (pi == 0) v.fn = ci == 0 ? QB_PICK(float, 6) : (ci == 1 ? QB_PICK(float, 8) : QB_PICK(float, 16));
         else v.fn = ci == 0 ? QB_PICK(double, 6) : (ci == 1 ? QB_PICK(double, 8) : QB_PICK(double, 16));
 #undef QB_PICK
@@ -792,7 +814,7 @@ int bp_threads(int precision) { return precision == 32 ? 256 : 512; }
 
 bool bp_ms2_enabled() { return ms2_enabled(); }
 
-bool bp_supports(const WinDev& w, int method, bool vglobal) { return method == 0 || use_compact(w, vglobal); }
+bool bp_supports(const WinDev& w, int method, bool vglobal) { (void)w; (void)vglobal; return method == 0 || method == 1; }
 
 cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal, int method) {
     if (w.cw > 16) return cudaErrorInvalidValue;
@@ -800,7 +822,7 @@ cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal, int metho
     const size_t smem = bp_smem_bytes(w, precision, vglobal);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     Variant& v = use_ms2(w, vglobal, method) ? ms2_variant(precision, w.unit_alpha != 0)
-                 : (use_compact(w, vglobal) ? compact_variant(precision, method) : variant(precision, w.cw, vglobal));
+                 : (use_compact(w, vglobal) ? compact_variant(precision, method) : variant(precision, w.cw, vglobal, method));
     size_t& have = v.configured[device_slot()];
     if (smem <= have) return cudaSuccess;                   // the attribute only ever grows (decoders of different sizes coexist)
     cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -811,7 +833,7 @@ cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal, int metho
 cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, bool vglobal, int grid, cudaStream_t st) {
     if (b.n_shots == 0) return cudaSuccess;
     Variant& v = use_ms2(w, vglobal, p.method) ? ms2_variant(precision, w.unit_alpha != 0)
-                 : (use_compact(w, vglobal) ? compact_variant(precision, p.method) : variant(precision, w.cw, vglobal));
+                 : (use_compact(w, vglobal) ? compact_variant(precision, p.method) : variant(precision, w.cw, vglobal, p.method));
     const size_t smem = bp_smem_bytes(w, precision, vglobal);
     v.fn<<<grid, v.threads, smem, st>>>(w, b, p);
     return cudaGetLastError();

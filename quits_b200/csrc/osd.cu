@@ -180,11 +180,11 @@ struct ElimLayout {
     int TS;
 };
 
-__host__ __device__ inline ElimLayout elim_layout(const WinDev& w, int NQ, bool exact, int selcap, bool hi = false) {
+__host__ __device__ inline ElimLayout elim_layout(const WinDev& w, int NQ, bool exact, int selcap, bool hi = false, bool tglobal = false) {
     ElimLayout L;
     L.TS = (w.rows + 31) / 32 * 32;
     size_t o = 0;
-    L.T = o; o += static_cast<size_t>(NQ) * L.TS * 16;
+    L.T = o; o += tglobal ? 0 : static_cast<size_t>(NQ) * L.TS * 16;      // tall windows keep T in a global slab per warp
     L.rvec = o; o += static_cast<size_t>(NQ) * 16;
     L.freem = o; o += static_cast<size_t>(NQ) * 16;
     L.svec = o; o += static_cast<size_t>(NQ) * 16;
@@ -240,10 +240,10 @@ __device__ __forceinline__ void gather_reduced(const WinDev& w, const uint4* T4,
 }
 
 template <int NQ>
-__device__ void osd_higher(const WinDev& w, const BatchDev& b, unsigned char* sm, const ElimLayout& L, const int rank,
+__device__ void osd_higher(const WinDev& w, const BatchDev& b, unsigned char* sm, const ElimLayout& L, uint4* Tbase, const int rank,
                            const uint16_t* order, const int n, const int lane) {
     constexpr int YS = 4 * NQ + 1;
-    const uint4* T4 = reinterpret_cast<const uint4*>(sm + L.T);
+    const uint4* T4 = Tbase;
     const int TS = L.TS;
     uint4* svec = reinterpret_cast<uint4*>(sm + L.svec);
     uint32_t* svec32 = reinterpret_cast<uint32_t*>(svec);
@@ -300,7 +300,7 @@ __device__ void osd_higher(const WinDev& w, const BatchDev& b, unsigned char* sm
         __syncwarp();
         for (int t = lane; t < rank; t += 32) t_of_row[rowperm[t]] = static_cast<uint16_t>(t);
         __syncwarp();
-        uint4* T4w = reinterpret_cast<uint4*>(sm + L.T);
+        uint4* T4w = Tbase;
         auto permute = [&](uint4* vec, const int stride) {                        // in place, through this lane's ybuf row
             for (int i = 0; i < 4 * NQ; ++i) ybuf[i] = 0;
             for (int i = 0; i < NQ; ++i) {
@@ -499,10 +499,10 @@ __device__ void osd_higher(const WinDev& w, const BatchDev& b, unsigned char* sm
 // One shot, one warp: eliminate over `order[0 .. n_avail)` (the first n_avail columns of the OSD order out of n).  Returns
 // false -- and commits nothing -- when those columns ran out before the answer was final although more columns exist.
 template <int NQ, bool EXACT, bool HI = false>
-__device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, unsigned char* sm, const ElimLayout& L, const int shot,
-                                         const uint16_t* order, const int n, const int n_total) {
-    uint4* T4 = reinterpret_cast<uint4*>(sm + L.T);
-    const uint32_t* T32 = reinterpret_cast<const uint32_t*>(sm + L.T);
+__device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, unsigned char* sm, const ElimLayout& L, uint4* Tbase,
+                                         const int shot, const uint16_t* order, const int n, const int n_total) {
+    uint4* T4 = Tbase;
+    const uint32_t* T32 = reinterpret_cast<const uint32_t*>(Tbase);
     uint4* rvec = reinterpret_cast<uint4*>(sm + L.rvec);
     uint4* freem = reinterpret_cast<uint4*>(sm + L.freem);
     uint4* svec = reinterpret_cast<uint4*>(sm + L.svec);
@@ -589,10 +589,16 @@ __device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, uns
                 __syncwarp();
                 int prow;
                 if (!EXACT) {
-                    const uint32_t x = lane < 4 * NQ ? (rvec32[lane] & freem32[lane]) : 0u;
-                    const uint32_t bal = __ballot_sync(kFull, x != 0u);
-                    const int wl = __ffs(bal) - 1;
-                    prow = 32 * wl + __shfl_sync(kFull, __ffs(x) - 1, wl);
+                    prow = -1;
+#pragma unroll
+                    for (int w0 = 0; w0 < 4 * NQ; w0 += 32) {             // the first free row that carries the candidate
+                        const uint32_t x = w0 + lane < 4 * NQ ? (rvec32[w0 + lane] & freem32[w0 + lane]) : 0u;
+                        const uint32_t bal = __ballot_sync(kFull, x != 0u);
+                        if (bal && prow < 0) {
+                            const int wl = __ffs(bal) - 1;
+                            prow = 32 * (w0 + wl) + __shfl_sync(kFull, __ffs(x) - 1, wl);
+                        }
+                    }
                 } else {
                     // rank-deficient window (inconsistent syndromes are possible): follow the oracle's row order exactly,
                     // i.e. the first free row in position order that has a 1
@@ -625,7 +631,8 @@ __device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, uns
                     slot_of_row[prow] = static_cast<uint16_t>(rank);
                 }
                 __syncwarp();
-                if (sbit && lane < 4 * NQ) svec32[lane] ^= rvec32[lane];
+                if (sbit)
+                    for (int i = lane; i < 4 * NQ; i += 32) svec32[i] ^= rvec32[i];
                 uint4 r[NQ];
 #pragma unroll
                 for (int i = 0; i < NQ; ++i) r[i] = rvec[i];
@@ -664,7 +671,8 @@ __device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, uns
                 // (an operation only acts on a vector that has the pivot row's bit, and pivot rows are taken from the
                 // free rows), and every later pivot gets solution bit 0.
                 if (!HI) {
-                    const uint32_t y = lane < 4 * NQ ? (svec32[lane] & freem32[lane]) : 0u;
+                    uint32_t y = 0u;
+                    for (int i = lane; i < 4 * NQ; i += 32) y |= svec32[i] & freem32[i];
                     if (!__any_sync(kFull, y != 0u)) { done = true; break; }
                 }
             }
@@ -675,7 +683,7 @@ __device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, uns
         int nflip = 0;
         const uint32_t* flips = reinterpret_cast<const uint32_t*>(sm + L.flips);
         if (HI) {
-            osd_higher<NQ>(w, b, sm, L, rank, order, n, lane);
+            osd_higher<NQ>(w, b, sm, L, Tbase, rank, order, n, lane);
             nflip = static_cast<int>(flips[0]);
         }
         auto commit_column = [&](const int j) {
@@ -721,10 +729,14 @@ __device__ __forceinline__ bool elim_job(const WinDev& w, const BatchDev& b, uns
     return true;
 }
 
-template <int NQ, bool EXACT, bool HI>
+// TG: the accumulated row transformation T (m x m bits) lives in a global slab per warp instead of shared memory -- windows of
+// more than 768 checks (BASELINE config 5: 2250 checks => 633 KB), higher-order OSD only (OSD-0 at that size is osd_big_kernel).
+template <int NQ, bool EXACT, bool HI, bool TG = false>
 __global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const BatchDev b) {
     extern __shared__ __align__(16) unsigned char sm[];
-    const ElimLayout L = elim_layout(w, NQ, EXACT, 0, HI);
+    const ElimLayout L = elim_layout(w, NQ, EXACT, 0, HI, TG);
+    uint4* const Tbase = TG ? reinterpret_cast<uint4*>(static_cast<unsigned char*>(b.lsd_scratch) + static_cast<size_t>(blockIdx.x) * b.lsd_slab)
+                            : reinterpret_cast<uint4*>(sm + L.T);
     const int lane = threadIdx.x;
     const int count = *b.fail_count;
     for (;;) {
@@ -736,7 +748,7 @@ __global__ void __launch_bounds__(32) osd_elim_kernel(const WinDev w, const Batc
         const uint16_t* order = b.order_alt ? b.order_alt + static_cast<size_t>(shot) * b.llr_stride
                                             : reinterpret_cast<const uint16_t*>(static_cast<const unsigned char*>(b.llr_buf) +
                                                                                 static_cast<size_t>(shot) * b.llr_stride * b.llr_esize);
-        elim_job<NQ, EXACT, HI>(w, b, sm, L, shot, order, w.ncols, w.ncols);
+        elim_job<NQ, EXACT, HI>(w, b, sm, L, Tbase, shot, order, w.ncols, w.ncols);
     }
 }
 
@@ -794,7 +806,7 @@ __global__ void __launch_bounds__(32) osd_fast_kernel(const WinDev w, const Batc
                     __syncwarp();
                 }
             }
-            finished = elim_job<NQ, EXACT>(w, b, sm, L, shot, selidx, S, n);
+            finished = elim_job<NQ, EXACT>(w, b, sm, L, reinterpret_cast<uint4*>(sm + L.T), shot, selidx, S, n);
         }
         if (!finished && lane == 0) {
             b.ovf_list[atomicAdd(b.ovf_count, 1)] = shot;
@@ -819,8 +831,22 @@ inline cudaError_t elim_dispatch_h(const WinDev& w, F&& f) {
     return cudaErrorInvalidValue;
 }
 
+// tall windows (768 < checks <= 2304), higher-order OSD: T in the global slab, NQ in steps of three 128-row groups
+template <typename F>
+inline cudaError_t elim_dispatch_tall(const WinDev& w, F&& f) {
+    const bool exact = !w.full_row_rank;
+    const int nq = elim_nq(w);
+    if (nq <= 9) return exact ? f(osd_elim_kernel<9, true, true, true>) : f(osd_elim_kernel<9, false, true, true>);
+    if (nq <= 12) return exact ? f(osd_elim_kernel<12, true, true, true>) : f(osd_elim_kernel<12, false, true, true>);
+    if (nq <= 15) return exact ? f(osd_elim_kernel<15, true, true, true>) : f(osd_elim_kernel<15, false, true, true>);
+    if (nq <= 18) return exact ? f(osd_elim_kernel<18, true, true, true>) : f(osd_elim_kernel<18, false, true, true>);
+    return cudaErrorInvalidValue;
+}
+inline int elim_tall_nq(const WinDev& w) { const int nq = elim_nq(w); return nq <= 9 ? 9 : (nq <= 12 ? 12 : (nq <= 15 ? 15 : 18)); }
+
 template <typename F>
 inline cudaError_t elim_dispatch(const WinDev& w, bool hi, F&& f) {
+    if (hi && w.rows > 768) return elim_dispatch_tall(w, f);
     return hi ? elim_dispatch_h<true>(w, f) : elim_dispatch_h<false>(w, f);
 }
 
@@ -847,7 +873,23 @@ inline cudaError_t fast_dispatch(const WinDev& w, int precision, F&& f) {
 
 size_t osd_sort_smem_bytes(const WinDev& w, int precision) { return sort_layout(w, precision == 32 ? 4 : 8).total; }
 size_t osd_sort_slab_bytes(const WinDev& w, int precision) { return sort_layout(w, precision == 32 ? 4 : 8).slab; }
-size_t osd_elim_smem_bytes(const WinDev& w, bool hi) { return elim_layout(w, elim_nq(w), !w.full_row_rank, 0, hi).total; }
+size_t osd_elim_smem_bytes(const WinDev& w, bool hi) {
+    if (hi && w.rows > 768) return elim_layout(w, elim_tall_nq(w), !w.full_row_rank, 0, true, true).total;
+    return elim_layout(w, elim_nq(w), !w.full_row_rank, 0, hi).total;
+}
+// higher-order OSD on a window taller than the shared-memory elimination takes: T in a global slab of this many bytes per warp
+bool osd_tall_hi_supported(const WinDev& w, int precision) {
+    return w.rows > 768 && w.rows <= 2304 && w.ncols <= 65535 && osd_elim_smem_bytes(w, true) <= 200 * 1024;
+}
+size_t osd_tall_hi_slab_bytes(const WinDev& w) { return static_cast<size_t>(elim_tall_nq(w)) * ((w.rows + 31) / 32 * 32) * 16; }
+cudaError_t osd_tall_hi_configure(const WinDev& w, int precision) {
+    cudaError_t se = osd_sort_configure(w, precision);
+    if (se != cudaSuccess) return se;
+    const size_t es = osd_elim_smem_bytes(w, true);
+    return elim_dispatch_tall(w, [&](auto kern) {
+        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(es));
+    });
+}
 size_t osd_fast_smem_bytes(const WinDev& w) { return elim_layout(w, elim_nq(w), !w.full_row_rank, kSelCap).total; }
 
 bool osd_supported(const WinDev& w, int precision) {

@@ -174,6 +174,9 @@ size_t osd_sort_slab_bytes(const WinDev& w, int precision);
 size_t osd_elim_smem_bytes(const WinDev& w, bool hi);
 size_t osd_fast_smem_bytes(const WinDev& w);
 bool osd_supported(const WinDev& w, int precision);
+bool osd_tall_hi_supported(const WinDev& w, int precision);      // osd_e / osd_cs of order > 0 on 768 < checks <= 2304: T in a global slab
+size_t osd_tall_hi_slab_bytes(const WinDev& w);
+cudaError_t osd_tall_hi_configure(const WinDev& w, int precision);
 cudaError_t osd_configure(const WinDev& w, int precision);
 cudaError_t osd_sort_configure(const WinDev& w, int precision);
 cudaError_t launch_osd_fast(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);

@@ -83,6 +83,41 @@ def test_product_sum_matches_oracle_within_tolerance(qb, case, window, precision
     assert checked >= n - 2
 
 
+@pytest.mark.parametrize("kind", ["hgp225_r15_window", "weight9", "weight15_tall"])
+def test_product_sum_flooding_on_general_windows(qb, kind):
+    """Flooding product-sum outside the compact shared-memory layout (bp_kernel<.., PS>): the 540 x 6480 windows of the 15-round
+    HGP circuit in fp64 (233 KB of padded messages: global slab), column weights above 6.  Same bar as the compact kernel."""
+    from oracle import cref
+    rng = np.random.RandomState(11)
+    if kind == "hgp225_r15_window":
+        g = decode_case("hgp225_r15_p1e-3_W5F3")
+        w = _oracle_windows("hgp225_r15_p1e-3", g["m"], g["W"], g["F"])[1]
+        H, pri = w["H"], w["priors"]
+        syn = g["det"][:32, w["row0"]:w["row0"] + H.shape[0]].astype(np.uint8)
+    else:
+        rows, cols, cw = (300, 900, 9) if kind == "weight9" else (2250, 6000, 15)
+        H = _random_ldpc(rng, rows, cols, cw)
+        pri = rng.choice([0.004, 0.006, 0.01], size=cols)
+        err = (rng.rand(24, cols) < pri[None, :]).astype(np.uint8)
+        syn = (err @ H.T.toarray() % 2).astype(np.uint8)
+    n = syn.shape[0]
+    kw = dict(max_iter=8, bp_method="product_sum", schedule="parallel")
+    dec = qb.BpOsdDecoder(H, channel_probs=pri, osd_method="off", **kw)
+    ehat, llr, iters, conv = dec.decode_batch(syn)
+    orc = cref.BpOsd(H, pri, osd=False, **kw)
+    checked = 0
+    for i in range(n):
+        e, l, it, c = orc.decode(syn[i])
+        if int(iters[i]) != it:
+            continue
+        fin = np.isfinite(l) & np.isfinite(llr[i])
+        lo = fin & (np.abs(l) < 30)           # beyond ~30 tanh(v/2) is within a few ulps of 1 and log((1+x)/(1-x)) amplifies one ulp of x
+        assert np.allclose(llr[i][lo], l[lo], rtol=1e-5, atol=1e-5), (i, np.max(np.abs(llr[i][lo] - l[lo])))
+        assert np.allclose(llr[i][fin], l[fin], rtol=1e-4, atol=1e-5), (i, np.max(np.abs(llr[i][fin] - l[fin])))
+        checked += 1
+    assert checked >= n - 2
+
+
 def test_product_sum_sliding_window_agrees_with_oracle(qb):
     """Whole sliding-window decode with product-sum BP: predictions agree with the oracle loop on (nearly) every shot."""
     from oracle import cref
@@ -595,8 +630,16 @@ def test_wide_tall_window_bp_lsd_and_osd(qb):
     for i in range(n):
         e, l, it, c = orc.decode(syn[i])
         assert bool(conv[i]) == c and np.array_equal(ehat[i], e), (i, c, int(ehat[i].sum()), int(e.sum()))
-    with pytest.raises(NotImplementedError):
-        qb.BpOsdDecoder(H, channel_probs=pri, osd_method="osd_cs", osd_order=1, **kw)
+    # higher-order OSD at this height keeps the accumulated row transformation (2250 x 2250 bits) in a global slab per warp
+    dec = qb.BpOsdDecoder(H, channel_probs=pri, osd_method="osd_cs", osd_order=1, **kw)
+    ehat, llr, iters, conv = dec.decode_batch(syn[:6])
+    orc = cref.BpOsd(H, pri, osd_method="osd_cs", osd_order=1, **kw)
+    used = 0
+    for i in range(6):
+        e, l, it, c = orc.decode(syn[i])
+        assert bool(conv[i]) == c and np.array_equal(ehat[i], e), (i, c, int(ehat[i].sum()), int(e.sum()))
+        used += orc.used_osd
+    assert used >= 2
 
 
 def test_frame_kernel_on_random_circuits(qb):
