@@ -193,6 +193,7 @@ namespace {
 
 constexpr size_t kStatSlots = 8;
 constexpr size_t kCounterSlots = 8;
+constexpr size_t kBatchSlots = 4;          // batches of one fused-run chunk in flight
 
 void use_device(qb_ctx* ctx) { CK(cudaSetDevice(ctx->device)); }
 
@@ -718,7 +719,9 @@ void ensure_batch(qb_sw* sw, int n) {
         }
     }
     if (sw->serial_slab) sw->vscratch.ensure(sw->serial_slab * static_cast<size_t>(sw->serial_grid) * static_cast<size_t>(std::max(sw->lanes, 1)) + 64);
-    const size_t nw = sw->wins.size() * qb_ctx::kMaxLanes;
+    // counters and statistics: one set per (batch slot, sub-batch lane, window); batch slots let the fused run queue several
+    // batches before it reads anything back
+    const size_t nw = sw->wins.size() * qb_ctx::kMaxLanes * kBatchSlots;
     sw->counters.ensure(nw * kCounterSlots * sizeof(int) + 16);
     sw->stats.ensure(nw * kStatSlots * sizeof(unsigned long long) + 16);
 }
@@ -726,7 +729,7 @@ void ensure_batch(qb_sw* sw, int n) {
 // decode n (<= cap) shots whose packed detector rows are on the device; leaves acc[n][KW] on the device.
 // The batch is cut into `lanes` contiguous sub-batches, each walking the windows on its own stream (the windows of one
 // shot are sequential -- carry dependency, sliding_window.py:169,174 -- but shots are independent).
-void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, bool want_llr, qb_stats* stats) {
+void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, bool want_llr, qb_stats* stats, int batch_slot = 0) {
     qb_ctx* ctx = sw->ctx;
     cudaStream_t st = ctx->stream;
     ensure_batch(sw, n);
@@ -737,8 +740,9 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
     sw->lanes_used = lanes;
     CK(cudaMemsetAsync(sw->acc.p, 0, static_cast<size_t>(n) * sw->KW * 8, st));
     CK(cudaMemsetAsync(sw->carry.p, 0, static_cast<size_t>(n) * sw->carryW * 4, st));
-    CK(cudaMemsetAsync(sw->counters.p, 0, nw * lanes * kCounterSlots * sizeof(int), st));
-    CK(cudaMemsetAsync(sw->stats.p, 0, nw * lanes * kStatSlots * sizeof(unsigned long long), st));
+    const size_t slot0 = static_cast<size_t>(batch_slot) * nw * qb_ctx::kMaxLanes;          // first (lane, window) set of this batch slot
+    CK(cudaMemsetAsync(sw->counters.as<int>() + kCounterSlots * slot0, 0, nw * lanes * kCounterSlots * sizeof(int), st));
+    CK(cudaMemsetAsync(sw->stats.as<unsigned long long>() + kStatSlots * slot0, 0, nw * lanes * kStatSlots * sizeof(unsigned long long), st));
     if (lanes > 1) {
         for (int l = 1; l < lanes; ++l) ctx->lane_stream(l);
         CK(cudaEventRecord(ctx->ev_fork, st));
@@ -773,7 +777,7 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.syn_stride32 = sw->synW;
             b.syn_buf = sw->syn.as<uint32_t>() + s0 * sw->synW;
             b.fail_list = sw->fail_list.as<int>() + s0;          // shot indices local to the sub-batch
-            const size_t slot = static_cast<size_t>(l) * nw + k;
+            const size_t slot = slot0 + static_cast<size_t>(l) * nw + k;
             int* ctr = sw->counters.as<int>() + kCounterSlots * slot;
             b.fail_count = ctr;
             b.fast_next = ctr + 1;
@@ -847,12 +851,13 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
     }
 }
 
-void collect_stats(qb_sw* sw, int n, qb_stats* stats) {        // stream must be synchronised
+void collect_stats(qb_sw* sw, int n, qb_stats* stats, int batch_slot = 0) {        // stream must be synchronised
     if (!stats) return;
     const size_t nw = sw->wins.size();
     const int lanes = sw->lanes_used;
     std::vector<unsigned long long> h(nw * lanes * kStatSlots);
-    CK(cudaMemcpy(h.data(), sw->stats.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h.data(), sw->stats.as<unsigned long long>() + kStatSlots * static_cast<size_t>(batch_slot) * nw * qb_ctx::kMaxLanes,
+                  h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     stats->shots += n;
     stats->windows += static_cast<int64_t>(nw) * n;
     for (int l = 0; l < lanes; ++l)
@@ -1506,9 +1511,12 @@ int qb_mc_run(qb_ctx* ctx, qb_circuit* c, qb_sw* sw, uint64_t seed, uint64_t sho
         CK(cudaMemsetAsync(ctx->counts.p, 0, (1 + static_cast<size_t>(a.KW) * 64) * 8, st));
         const bool prof = sw->opts.profile != 0;
         if (prof) ctx->t_total.begin(st);
-        for (uint64_t done = 0; done < n_shots; done += static_cast<uint64_t>(sw->cap)) {
-            const uint64_t n = std::min<uint64_t>(sw->cap, n_shots - done);
-            const uint64_t nwords = (n + 63) / 64;
+        // One frame launch samples a chunk of up to kBatchSlots decoder batches (65536 shots give the frame kernel 1024 warps, a
+        // tenth of the machine); the batches of the chunk are then decoded back to back and their statistics read once.
+        const uint64_t chunk_cap = static_cast<uint64_t>(sw->cap) * kBatchSlots;
+        for (uint64_t done = 0; done < n_shots; done += chunk_cap) {
+            const uint64_t nc = std::min<uint64_t>(chunk_cap, n_shots - done);
+            const uint64_t nwords = (nc + 63) / 64;
             ctx->det_rows.ensure(nwords * 64 * a.DW * 8 + 16);
             ctx->obs_rows.ensure(nwords * 64 * a.KW * 8 + 16);
             a.word0 = (shot0 + done) / 64;
@@ -1518,12 +1526,18 @@ int qb_mc_run(qb_ctx* ctx, qb_circuit* c, qb_sw* sw, uint64_t seed, uint64_t sho
             if (prof) ctx->t_frame.begin(st);
             CK(qb::launch_frame(a, st));
             if (prof) ctx->t_frame.end(st);
-            decode_batch(sw, a.det_rows, static_cast<int>(n), false, false, stats);
-            CK(qb::launch_count(sw->acc.as<uint64_t>(), a.obs_rows, a.KW, K, n, ctx->counts.as<unsigned long long>(), st));
-            if (stats) { stats->frame_launches++; stats->other_launches++; stats->frame_alg_bytes += static_cast<double>(n) * 8.0 * (a.DW + a.KW); }
-            // per-batch statistics are read back after the batch: the counters are reused by the next one
+            if (stats) { stats->frame_launches++; stats->frame_alg_bytes += static_cast<double>(nc) * 8.0 * (a.DW + a.KW); }
+            int slot = 0;
+            std::vector<int> sizes;
+            for (uint64_t off = 0; off < nc; off += static_cast<uint64_t>(sw->cap), ++slot) {
+                const uint64_t n = std::min<uint64_t>(sw->cap, nc - off);
+                decode_batch(sw, a.det_rows + off * a.DW, static_cast<int>(n), false, false, stats, slot);
+                CK(qb::launch_count(sw->acc.as<uint64_t>(), a.obs_rows + off * a.KW, a.KW, K, n, ctx->counts.as<unsigned long long>(), st));
+                if (stats) stats->other_launches++;
+                sizes.push_back(static_cast<int>(n));
+            }
             CK(cudaStreamSynchronize(st));
-            collect_stats(sw, static_cast<int>(n), stats);
+            for (int b2 = 0; b2 < slot; ++b2) collect_stats(sw, sizes[b2], stats, b2);
         }
         if (prof) { ctx->t_total.end(st); }
         std::vector<unsigned long long> h(1 + static_cast<size_t>(K));

@@ -34,6 +34,12 @@ __device__ __forceinline__ Ph4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t 
 __device__ __forceinline__ void sm_xor(uint64_t* p, uint64_t m) {
     if (m) atomicXor(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(m));
 }
+// the lane is the only one of the warp that touches *p during this tape op (targets of the op are distinct qubits)
+__device__ __forceinline__ void sm_xor_owned(uint64_t* p, uint64_t m, bool owned) {
+    if (!m) return;
+    if (owned) *p ^= m;
+    else atomicXor(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(m));
+}
 
 // levels 2 and 3 of the sampling scheme: how many of the 64 shots of this word are hit at this site, which
 // ones, and with which Pauli.  m[0..3] = masks to XOR into x_a, z_a, x_b, z_b.
@@ -156,6 +162,7 @@ __global__ void __launch_bounds__(128) frame_kernel(const FrameArgs a, const int
             const int fixed = kind == OP_XERR ? 1 : (kind == OP_ZERR ? 2 : 0);
             const uint64_t* ctab = a.ctab + static_cast<size_t>(h1.y) * 64;
             const int groups = (n + 3) >> 2;
+            const bool owned = h1.w != 0;
             for (int g = lane; g < groups; g += 32) {
                 const uint32_t s0 = aux + 4u * static_cast<uint32_t>(g);
                 const Ph4 r = philox4x32_10(k0, k1, s0 >> 2, wl, wh, 0u);
@@ -167,12 +174,12 @@ __global__ void __launch_bounds__(128) frame_kernel(const FrameArgs a, const int
                     uint64_t m[4];
                     site_faults(k0, k1, s0 + static_cast<uint32_t>(l), wl, wh, ctab, npauli, fixed, m);
                     const uint32_t qa = __ldg(tg + (two ? 2 * j : j));
-                    sm_xor(&x[qa], m[0]);
-                    sm_xor(&z[qa], m[1]);
+                    sm_xor_owned(&x[qa], m[0], owned);
+                    sm_xor_owned(&z[qa], m[1], owned);
                     if (two) {
                         const uint32_t qb = __ldg(tg + 2 * j + 1);
-                        sm_xor(&x[qb], m[2]);
-                        sm_xor(&z[qb], m[3]);
+                        sm_xor_owned(&x[qb], m[2], owned);
+                        sm_xor_owned(&z[qb], m[3], owned);
                     }
                 }
             }

@@ -298,6 +298,12 @@ void build_tape(const FlatCircuit& fc, Tape& tape) {
             uint64_t dummy[64];
             noise_tables(op.arg, &t1, dummy);
             t.thr = t1;
+            // foff = 1: no qubit occurs twice among the targets (what the reference's emitters produce), so the lanes of the frame
+            // kernel own their qubits' frame words and update them without atomics
+            ++cur_stamp;
+            bool distinct = true;
+            for (int32_t q : op.targets) { if (stamp[q] == cur_stamp) distinct = false; stamp[q] = cur_stamp; }
+            t.foff = distinct ? 1 : 0;
             for (int32_t q : op.targets) tape.targets.push_back(static_cast<uint32_t>(q));
             site += ns;
             tape.ops.push_back(t);      // kept even when thr == 0 so that explicit-fault injection can address it
