@@ -588,7 +588,7 @@ void finish_decoder(qb_sw* sw) {
         CK(qb::bp_configure(w->dev, prec, w->vglobal, o.bp_method));
         if (w->vglobal) {
             w->bp_grid = 148 * 2;
-            max_slab = std::max(max_slab, static_cast<size_t>(w->dev.rows) * w->dev.RS * (prec / 8));
+            max_slab = std::max(max_slab, qb::bp_slab_bytes(w->dev, prec));
         }
         }
         max_npad = std::max(max_npad, w->dev.ncols_pad);

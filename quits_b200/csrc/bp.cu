@@ -31,9 +31,39 @@ namespace qb {
 
 namespace {
 
+// ---- bulk-asynchronous staging (TMA engine, 1-D form): cp.async.bulk global -> shared, completion on an mbarrier.
+// Used by the global-slab flooding kernel: its check sweep walks every row of the message slab, one thread per row -- 32 lanes
+// touching 32 different 32-byte sectors per load, four times the bytes the rows hold.  Staging tiles of whole rows through the
+// copy engine reads each byte once, in 128-byte lines, while the threads work on the previous tile.
+constexpr int kTileRows = 32;                   // rows per staged tile (16 lanes per row with 512 threads)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (spin > (1u << 26)) __trap();        // a lost copy must not hang the device
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // shared-memory layout; returns the total.  off: V, rsum, rmeta, syn, cand, accs, car, hist, ebits (hard decisions as a bit array:
 // windows wider than 32 columns per thread, where the per-thread mask runs out)
-__host__ __device__ inline size_t bp_layout(const WinDev& w, int rsize, bool vglobal, size_t* off /*[9]*/) {
+__host__ __device__ inline size_t bp_tile_bytes(const WinDev& w, int rsize) { return static_cast<size_t>(kTileRows) * w.RS * rsize; }
+__host__ __device__ inline size_t bp_slab_elems(const WinDev& w) {
+    return static_cast<size_t>((w.rows + kTileRows - 1) / kTileRows * kTileRows) * w.RS;
+}
+__host__ __device__ inline size_t bp_layout(const WinDev& w, int rsize, bool vglobal, size_t* off /*[11]*/, bool staged = false) {
     size_t o = 0;
     off[0] = o; o += vglobal ? 0 : align_up(static_cast<size_t>(w.rows) * w.RS * rsize, 16);
     off[1] = o; o += align_up(static_cast<size_t>(w.rows) * 2 * rsize, 16);
@@ -44,20 +74,33 @@ __host__ __device__ inline size_t bp_layout(const WinDev& w, int rsize, bool vgl
     off[6] = o; o += align_up(static_cast<size_t>((w.carry_rows + 31) / 32 + 1) * 4, 16);
     off[7] = o; o += kSelWords * 4;
     off[8] = o; o += align_up(static_cast<size_t>(w.nW32) * 4, 16);
+    off[9] = o; o += (vglobal && staged) ? 2 * align_up(bp_tile_bytes(w, rsize), 128) : 0;      // two row tiles in flight
+    off[10] = o; o += (vglobal && staged) ? 16 : 0;                                               // their mbarriers
     return o;
 }
 
 // PS: product-sum (the message array holds tanh(v/2); the row summary is (signed product of the non-zero factors, number of
 // zero factors) and "the others" is the row product divided by the edge's own factor -- as in bp_kernel_compact<.., true>)
-template <typename R, int CW, int NT, int MINB, bool VGLOBAL, bool PS = false>
+template <typename R, int CW, int NT, int MINB, bool VGLOBAL, bool PS = false, bool STAGED = false>
 __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const BatchDev b, const BpParams p) {
     using RT = Real<R>;
     using TT = Trans<R>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    size_t off[9];
-    bp_layout(w, sizeof(R), VGLOBAL, off);
-    R* V = VGLOBAL ? reinterpret_cast<R*>(b.vscratch) + static_cast<size_t>(blockIdx.x) * (static_cast<size_t>(w.rows) * w.RS)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    size_t off[11];
+    bp_layout(w, sizeof(R), VGLOBAL, off, STAGED);
+    // the slab of a CTA holds whole tiles of kTileRows rows (the staged check sweep copies the last tile in full)
+    R* V = VGLOBAL ? reinterpret_cast<R*>(b.vscratch) + static_cast<size_t>(blockIdx.x) * bp_slab_elems(w)
                    : reinterpret_cast<R*>(smem_raw + off[0]);
+    R* const tile = reinterpret_cast<R*>(smem_raw + off[9]);
+    uint64_t* const tbar = reinterpret_cast<uint64_t*>(smem_raw + off[10]);
+    const uint32_t tile_bytes = static_cast<uint32_t>(bp_tile_bytes(w, sizeof(R)));
+    const size_t tile_stride = align_up(tile_bytes, 128) / sizeof(R);
+    uint32_t tphase0 = 0, tphase1 = 0;           // parity of the next completion of each tile barrier
+    if (STAGED && VGLOBAL) {
+        if (threadIdx.x == 0) { mbar_init(&tbar[0], 1); mbar_init(&tbar[1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
     typename RT::pair* rsum = reinterpret_cast<typename RT::pair*>(smem_raw + off[1]);
     uint32_t* rmeta = reinterpret_cast<uint32_t*>(smem_raw + off[2]);
     uint32_t* syn = reinterpret_cast<uint32_t*>(smem_raw + off[3]);
@@ -92,7 +135,72 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel(const WinDev w, const Batc
         int it = 1;
         for (; it <= p.max_iter; ++it) {
             const R alpha = static_cast<R>(__ldg(p.alpha + it));
-            // ---- check sweep: one thread per row
+            // ---- check sweep
+            if (STAGED && VGLOBAL) {
+                // tiles of kTileRows whole rows come in through the copy engine (two in flight); NT / kTileRows lanes share a row
+                constexpr int LPR = NT / kTileRows;
+                const int ntiles = (rows + kTileRows - 1) / kTileRows;
+                const int tr = tid / LPR, tl = tid - tr * LPR;
+                fence_proxy_async();                                  // this CTA's message stores (bit sweep) before the engine reads them
+                __syncthreads();
+                if (tid == 0) {
+                    mbar_expect_tx(&tbar[0], tile_bytes);
+                    bulk_load(tile, V, tile_bytes, &tbar[0]);
+                }
+                for (int t = 0; t < ntiles; ++t) {
+                    const int cur = t & 1;
+                    if (tid == 0 && t + 1 < ntiles) {                 // next tile into the other buffer (released by the barrier below)
+                        mbar_expect_tx(&tbar[cur ^ 1], tile_bytes);
+                        bulk_load(tile + (cur ^ 1) * tile_stride, V + static_cast<size_t>(t + 1) * kTileRows * RS, tile_bytes, &tbar[cur ^ 1]);
+                    }
+                    mbar_wait(&tbar[cur], cur ? tphase1 : tphase0);
+                    if (cur) tphase1 ^= 1u; else tphase0 ^= 1u;
+                    const int i = t * kTileRows + tr;
+                    const R* vr = tile + cur * tile_stride + tr * RS;
+                    if (PS) {
+                        R prod = R(1);
+                        int zc = 0;
+                        for (int sl = tl; sl < RS; sl += LPR) {
+                            const R f = vr[sl];
+                            if (f == R(0)) ++zc;
+                            else prod = RT::mul(prod, f);
+                        }
+#pragma unroll
+                        for (int o = LPR / 2; o > 0; o >>= 1) {
+                            prod = RT::mul(prod, __shfl_xor_sync(0xFFFFFFFFu, prod, o, LPR));
+                            zc += __shfl_xor_sync(0xFFFFFFFFu, zc, o, LPR);
+                        }
+                        if (tl == 0 && i < rows) {
+                            const uint32_t sb = (syn[i >> 5] >> (i & 31)) & 1u;
+                            rsum[i] = RT::mk(sb ? -prod : prod, static_cast<R>(zc));
+                        }
+                    } else {
+                        R m1 = RT::big(), m2 = RT::big();
+                        uint32_t arg = 0, neg = 0;
+                        for (int sl = tl; sl < RS; sl += LPR) {
+                            const R v = vr[sl];
+                            const R a = RT::abs(v);
+                            neg += v <= R(0) ? 1u : 0u;
+                            if (a < m1) { m2 = m1; m1 = a; arg = static_cast<uint32_t>(sl); }
+                            else if (a < m2) { m2 = a; }
+                        }
+#pragma unroll
+                        for (int o = LPR / 2; o > 0; o >>= 1) {
+                            const R o1 = __shfl_xor_sync(0xFFFFFFFFu, m1, o, LPR), o2 = __shfl_xor_sync(0xFFFFFFFFu, m2, o, LPR);
+                            const uint32_t oa = __shfl_xor_sync(0xFFFFFFFFu, arg, o, LPR);
+                            neg += __shfl_xor_sync(0xFFFFFFFFu, neg, o, LPR);
+                            if (o1 < m1) { m2 = m1 < o2 ? m1 : o2; m1 = o1; arg = oa; }
+                            else { m2 = o1 < m2 ? o1 : m2; }
+                        }
+                        if (tl == 0 && i < rows) {
+                            neg += (syn[i >> 5] >> (i & 31)) & 1u;
+                            rsum[i] = RT::mk(m1, m2);
+                            rmeta[i] = arg | (neg << 31);
+                        }
+                    }
+                    __syncthreads();                                  // the tile is consumed: its buffer may be refilled
+                }
+            } else
             for (int i = tid; i < rows; i += NT) {
                 const R* vr = V + i * RS;
                 R m1 = RT::big(), m2 = RT::big();
@@ -747,13 +855,22 @@ struct Variant {
     size_t configured[kMaxDevices];
 };
 
+// QB_BP_STAGE=1: the global-slab variant stages its check sweep through cp.async.bulk (UBLKCP).  Measured on BASELINE config 5
+// (2250 x 31500 windows, fp64, 16384 shots): BP 3141 ms staged vs 3095 ms direct -- the sweep that binds that kernel is the bit
+// sweep's scattered 8-byte gathers over a 232 MB working set, not the row walk -- so it is off by default.
+inline bool staged_enabled() {
+    static const int on = [] { const char* e = getenv("QB_BP_STAGE"); return e ? atoi(e) : 0; }();
+    return on != 0;
+}
+
 template <typename R, int CW, bool VG, bool PS>
 KernelPtr pick_kernel(int* threads) {
     // fp32: 256 threads x 4 CTAs/SM (64 regs); fp64: 512 threads x 2 CTAs/SM; wide columns and product-sum get more registers
     constexpr int NT = sizeof(R) == 4 ? 256 : 512;
-    constexpr int MINB = (CW <= 8 && !PS) ? (sizeof(R) == 4 ? 4 : 2) : 1;
+    constexpr int MINB = (CW <= 8 && !PS) ? (sizeof(R) == 4 ? 4 : 2) : 1;       // (two CTAs per SM at 64 registers: 27 % slower on config 5 -- spills, and twice the slabs competing for L2)
     *threads = NT;
-    return bp_kernel<R, CW, NT, MINB, VG, PS>;
+    if (VG && staged_enabled()) return bp_kernel<R, CW, NT, MINB, VG, PS, true>;
+    return bp_kernel<R, CW, NT, MINB, VG, PS, false>;
 }
 
 Variant& variant(int prec, int cw, bool vg, int method = 0) {
@@ -804,10 +921,12 @@ Variant& ms2_variant(int prec, bool unit) {
 
 }  // namespace
 
+size_t bp_slab_bytes(const WinDev& w, int precision) { return bp_slab_elems(w) * (precision == 32 ? 4 : 8); }
+
 size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal) {
-    size_t off[10];
+    size_t off[11];
     if (use_compact(w, vglobal)) return std::max(bpc_layout(w, precision == 32 ? 4 : 8, off), bpm_layout(w, precision == 32 ? 4 : 8, off));
-    return bp_layout(w, precision == 32 ? 4 : 8, vglobal, off);
+    return bp_layout(w, precision == 32 ? 4 : 8, vglobal, off, staged_enabled());
 }
 
 int bp_threads(int precision) { return precision == 32 ? 256 : 512; }

@@ -154,6 +154,7 @@ struct BpParams {
 // precision: 32 or 64 (message / posterior type).  vglobal: messages in a global scratch slab instead of shared memory.
 constexpr uint32_t kNoAddr = 0xFFFFu;
 size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal);
+size_t bp_slab_bytes(const WinDev& w, int precision);       // bytes of one CTA's global message slab (VGLOBAL)
 int bp_threads(int precision);
 bool bp_supports(const WinDev& w, int method, bool vglobal);
 bool bp_ms2_enabled();       // flooding min-sum through bp_kernel_ms2 (default) or bp_kernel_compact (QB_BP_MS2=0, A/B measurements)
