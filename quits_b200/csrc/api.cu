@@ -1465,7 +1465,7 @@ int qb_bp_decode_batch(qb_sw* sw, const uint8_t* syndromes, uint64_t n, uint8_t*
             CK(cudaMemcpyAsync(sw->det_bytes.p, syndromes + done * rows, static_cast<size_t>(nb) * rows, cudaMemcpyHostToDevice, st));
             CK(qb::launch_pack_bits(sw->det_bytes.as<uint8_t>(), rows, nb, sw->det_rows.as<uint64_t>(), sw->DW, st));
             CK(cudaMemsetAsync(sw->ehat.p, 0, static_cast<size_t>(nb) * w.nW32 * 4, st));
-            decode_batch(sw, sw->det_rows.as<uint64_t>(), nb, true, true, nullptr);
+            decode_batch(sw, sw->det_rows.as<uint64_t>(), nb, true, llr != nullptr, nullptr);
             if (ehat) {
                 // ehat bit rows are u32 words; widen through the u64 unpacker when the stride is even, else via a u32 view
                 // (nW32 words per shot) -> unpack treats rows as u64 with words_per_row = nW32/2 only if even; use byte path below

@@ -56,14 +56,15 @@ class _GpuInnerDecoder:
         except Exception:
             pass
 
-    def decode_batch(self, syndromes):
-        """syndromes [N, m] -> (ehat uint8 [N, n], llr float64 [N, n], iters int32 [N], converged bool [N])."""
+    def decode_batch(self, syndromes, want_llr=True):
+        """syndromes [N, m] -> (ehat uint8 [N, n], llr float64 [N, n] or None, iters int32 [N], converged bool [N]).
+        ``want_llr=False`` skips the N x n posterior array (8 bytes per column and shot) on the device and on the host."""
         s = np.ascontiguousarray(np.asarray(syndromes) % 2, dtype=np.uint8)
         if s.ndim != 2 or s.shape[1] != self.m:
             raise ValueError("expected syndromes of shape (N, %d)" % self.m)
         n = s.shape[0]
         ehat = np.zeros((n, self.n), dtype=np.uint8)
-        llr = np.zeros((n, self.n), dtype=np.float64)
+        llr = np.zeros((n, self.n), dtype=np.float64) if want_llr else None
         iters = np.zeros(n, dtype=np.int32)
         conv = np.zeros(n, dtype=np.uint8)
         N.check(N.lib().qb_bp_decode_batch(self._h, N.ptr(s), n, N.ptr(ehat), N.ptr(llr), N.ptr(iters), N.ptr(conv)))

@@ -93,21 +93,68 @@ def sliding_window_circuit_mem(zcheck_samples, circuit, hz, lz, W, F, decoder1, 
         warnings.warn("Window size larger than the syndrome extraction rounds: Doing whole history correction")
     if F == 0:
         raise ValueError("Input parameter F cannot be zero.")
-    for cls in (decoder1, decoder2):
-        if not (isinstance(cls, type) and issubclass(cls, _GpuInnerDecoder)):
-            raise NotImplementedError(
-                "the GPU sliding-window path runs the engine's own inner decoders only (quits_b200.decoder.BpOsdDecoder / "
-                "BpLsdDecoder); got %r. There is no per-shot CPU fallback." % (cls,))
-    kw1 = _engine_kwargs(decoder1, dict1, error_rate_name1)
-    kw2 = _engine_kwargs(decoder2, dict2, error_rate_name2)
-    if _options_key(kw1) != _options_key(kw2) or function_name1 != "decode" or function_name2 != "decode":
-        raise NotImplementedError("different inner decoders for the sliding windows and the last window are not supported on the GPU path")
+    gpu_classes = all(isinstance(cls, type) and issubclass(cls, _GpuInnerDecoder) for cls in (decoder1, decoder2))
+    fused = gpu_classes and function_name1 == "decode" and function_name2 == "decode"
+    if fused:
+        kw1 = _engine_kwargs(decoder1, dict1, error_rate_name1)
+        kw2 = _engine_kwargs(decoder2, dict2, error_rate_name2)
+        fused = _options_key(kw1) == _options_key(kw2)
+    if not fused:
+        # the plug-in seam as the reference defines it (sliding_window.py:146-153,171,182): any decoder class, different classes or
+        # options for the last window, any decode-function name.  Windows one after the other; the engine's own inner decoders
+        # take all shots of a window in one batch, a foreign decoder is called once per shot like the reference calls it.
+        return _plugin_window_loop(zcheck_samples, circuit, hz, lz, W, F, num_cor_rounds, decoder1, decoder2, dict1, dict2,
+                                   error_rate_name1, error_rate_name2, function_name1, function_name2)
     dec = _cached_decoder(circuit, m, W, F, num_cor_rounds, kw1)
     # the reference leaves the priors of the last constructed decoders in the caller's dicts (sliding_window.py:148,151)
     if dec.plan.n_windows > 1:
         dict1[error_rate_name1] = dec.plan.window(dec.plan.n_windows - 2)["priors"]
     dict2[error_rate_name2] = dec.plan.window(dec.plan.n_windows - 1)["priors"]
     return dec.decode(zcheck_samples)
+
+
+def _decode_window(dec, fname, syn):
+    """All shots of one window through one inner decoder: ehat uint8 [N, n]."""
+    if isinstance(dec, _GpuInnerDecoder) and fname == "decode":
+        return dec.decode_batch(syn, want_llr=False)[0]
+    fn = getattr(dec, fname)
+    return np.stack([np.asarray(fn(syn[i])).astype(np.uint8) % 2 for i in range(syn.shape[0])]) if syn.shape[0] else \
+        np.zeros((0, 0), dtype=np.uint8)
+
+
+def _window_loop(z, m, windows, decs, fnames):
+    """The reference's window loop (sliding_window.py:162-186 / :72-99) with the shot loop inside: windows = dicts with row0, H,
+    L (observables x committed columns), U (carry rows x committed columns, None for the last window)."""
+    n = z.shape[0]
+    acc = np.zeros((n, windows[0]["L"].shape[0]), dtype=np.int64)
+    carry = np.zeros((n, m), dtype=np.int64)
+    for k, w in enumerate(windows):
+        rows = w["H"].shape[0]
+        syn = z[:, w["row0"]:w["row0"] + rows].astype(np.int64)
+        syn[:, :m] = (syn[:, :m] + carry) % 2
+        ehat = _decode_window(decs[k], fnames[k], syn.astype(np.uint8))
+        e = ehat[:, :w["L"].shape[1]].astype(np.int64)
+        acc = (acc + np.asarray((w["L"] @ e.T).T)) % 2
+        if w.get("U") is not None:
+            carry = np.asarray((w["U"] @ e.T).T) % 2
+    return np.asarray(acc, dtype=np.int64)
+
+
+def _plugin_window_loop(zcheck_samples, circuit, hz, lz, W, F, num_cor_rounds, decoder1, decoder2, dict1, dict2, error_rate_name1,
+                        error_rate_name2, function_name1, function_name2):
+    from .base import spacetime
+    m = hz.shape[0]
+    checks, observables, priors, updates = spacetime(circuit, hz, W, F, num_cor_rounds)
+    decs = []
+    for k in range(len(checks) - 1):
+        dict1[error_rate_name1] = priors[k]
+        decs.append(decoder1(checks[k], **dict1))
+    dict2[error_rate_name2] = priors[-1]
+    decs.append(decoder2(checks[-1], **dict2))
+    windows = [{"row0": F * k * m, "H": checks[k], "L": observables[k], "U": updates[k] if k < num_cor_rounds else None}
+               for k in range(num_cor_rounds + 1)]
+    z = np.asarray(zcheck_samples) % 2
+    return _window_loop(z, m, windows, decs, [function_name1] * num_cor_rounds + [function_name2])
 
 
 def _phenom_plan(hz, lz, W, F, num_cor_rounds, W_last, D, priors1, priors2) -> WindowPlan:
@@ -141,7 +188,7 @@ def _phenom_plan(hz, lz, W, F, num_cor_rounds, W_last, D, priors1, priors2) -> W
 
     windows = [window(k, W, False, priors1) for k in range(num_cor_rounds)]
     windows.append(window(num_cor_rounds, W_last, True, priors2))
-    return WindowPlan.explicit(m, K, D, windows)
+    return windows if D is None else WindowPlan.explicit(m, K, D, windows)
 
 
 def _phenom_priors(params: dict):
@@ -172,16 +219,20 @@ def sliding_window_phenom_mem(zcheck_samples, hz, lz, W, F, decoder1, decoder2, 
     W_last = num_rounds + 2 - F * num_cor_rounds
     if num_cor_rounds and F > W:
         raise ValueError("cannot reshape the first F data-error blocks out of a window of W < F rounds")
-    for cls in (decoder1, decoder2):
-        if not (isinstance(cls, type) and issubclass(cls, _GpuInnerDecoder)):
-            raise NotImplementedError(
-                "the GPU sliding-window path runs the engine's own inner decoders only (quits_b200.decoder.BpOsdDecoder / "
-                "BpLsdDecoder); got %r. There is no per-shot CPU fallback." % (cls,))
     rate_names = ("error_rate", "error_channel", "channel_probs")
-    kw1 = _engine_kwargs(decoder1, {k: v for k, v in dict1.items() if k not in rate_names}, "")
-    kw2 = _engine_kwargs(decoder2, {k: v for k, v in dict2.items() if k not in rate_names}, "")
-    if _options_key(kw1) != _options_key(kw2) or function_name1 != "decode" or function_name2 != "decode":
-        raise NotImplementedError("different inner decoders for the sliding windows and the last window are not supported on the GPU path")
+    gpu_classes = all(isinstance(cls, type) and issubclass(cls, _GpuInnerDecoder) for cls in (decoder1, decoder2))
+    fused = gpu_classes and function_name1 == "decode" and function_name2 == "decode"
+    if fused:
+        kw1 = _engine_kwargs(decoder1, {k: v for k, v in dict1.items() if k not in rate_names}, "")
+        kw2 = _engine_kwargs(decoder2, {k: v for k, v in dict2.items() if k not in rate_names}, "")
+        fused = _options_key(kw1) == _options_key(kw2)
+    if not fused:
+        # the plug-in seam (sliding_window.py:56-69,84,94): any decoder classes / options / function names; the window matrices are
+        # the reference's, the inner decoders are constructed and called as the reference constructs and calls them
+        wins = _phenom_plan(hz, lz, W, F, num_cor_rounds, W_last, None, 0.5, 0.5)
+        decs = [decoder1(w["H"], **dict1) for w in wins[:-1]] + [decoder2(wins[-1]["H"], **dict2)]
+        z = zcheck_samples[:, :m * (num_rounds + 2)] % 2
+        return _window_loop(z, m, wins, decs, [function_name1] * num_cor_rounds + [function_name2])
     p1, p2 = _phenom_priors(dict1), _phenom_priors(dict2)
     key = (_device_key(), hashlib.sha1(np.ascontiguousarray(hz % 2, dtype=np.uint8).tobytes()).hexdigest(), hz.shape,
            hashlib.sha1(np.ascontiguousarray(lz % 2, dtype=np.uint8).tobytes()).hexdigest(), int(W), int(F), int(num_rounds),

@@ -45,11 +45,15 @@ def get_codecap_pL(code, p, num_trials, decoder, dict, basis='Z', seed=-1, tqdm_
     Lg = np.asarray(logical_codewords) % 2
     bpd = decoder(H, **dict)
     num_trials = int(num_trials)
-    noise = np.random.binomial(1, p, (num_trials, H.shape[1]))
-    syndromes = (noise @ H.T % 2).astype(np.uint8)
-    decoded, _, _, _ = bpd.decode_batch(syndromes)
-    residual = (decoded.astype(np.int64) + noise) % 2
-    num_errors = int(np.any(residual @ Lg.T % 2, axis=1).sum())
+    num_errors = 0
+    Ht, Lt = H.T.astype(np.int64), Lg.T.astype(np.int64)
+    for lo in range(0, num_trials, 65536):                   # chunks: memory stays O(chunk x n) whatever num_trials is
+        n = min(65536, num_trials - lo)
+        noise = np.random.binomial(1, p, (n, H.shape[1])).astype(np.uint8)      # same stream as one draw of all trials
+        syndromes = (noise.astype(np.int64) @ Ht % 2).astype(np.uint8)
+        decoded, _, _, _ = bpd.decode_batch(syndromes, want_llr=False)
+        residual = decoded ^ noise
+        num_errors += int(np.any(residual.astype(np.int64) @ Lt % 2, axis=1).sum())
     return num_errors / num_trials
 
 

@@ -10,7 +10,7 @@ import warnings
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT, circuit_meta, circuit_text, random_circuit_text
+from conftest import GOLDEN, ROOT, case_circuit, circuit_meta, circuit_text, decode_case, random_circuit_text
 from oracle import cref, dem as odem, shims, stimtext
 
 import quits_b200 as qb
@@ -288,8 +288,15 @@ def test_phenom_argument_errors():
             fn(det, hz, lz, 3, 0, error_rate=0.05)
         with pytest.raises(ValueError, match="cannot be zero"):
             fn(det, hz, lz, 3, 0, eff_error_rate_per_fault=0.05)
-    with pytest.raises(NotImplementedError):            # foreign inner decoder classes are not run per shot
-        qb.sliding_window_phenom_mem(det, hz, lz, 3, 2, dict, dict, {"error_rate": 0.1}, {"error_rate": 0.1}, "decode", "decode")
+    # a foreign inner decoder class goes through the plug-in loop (one object per window, one call per shot and window)
+    class Zero:
+        def __init__(self, pcm, error_rate=None):
+            self.n = pcm.shape[1]
+
+        def decode(self, s):
+            return np.zeros(self.n, dtype=int)
+    pred = qb.sliding_window_phenom_mem(det, hz, lz, 3, 2, Zero, Zero, {"error_rate": 0.1}, {"error_rate": 0.1}, "decode", "decode")
+    assert pred.shape == (2, 1) and pred.dtype == np.int64 and not pred.any()
 
 
 def test_lsd_option_mapping():
@@ -472,3 +479,35 @@ def test_front_end_and_dem_match_oracle_on_random_circuits():
         assert e["det_idx"].tolist() == [x for ds in od.dets for x in ds] and e["obs_idx"].tolist() == [x for ds in od.obs for x in ds], text
         n_err += len(od.probs)
     assert n_rep > 30 and n_err > 1000 and 10 < n_nondet < 300, (n_rep, n_err, n_nondet)
+
+
+class _ForeignDecoder:
+    """A decoder class this engine knows nothing about, with the call shape the reference's plug-in seam expects
+    (decoder(pcm, **params) then a named decode method, sliding_window.py:146-153,171,182): the oracle's BP + OSD behind it."""
+
+    def __init__(self, pcm, my_rates=None, **kw):
+        from oracle import cref
+        self._d = cref.BpOsd(pcm, my_rates, **kw)
+        self.calls = 0
+
+    def run_it(self, syndrome):
+        self.calls += 1
+        return self._d.decode(syndrome)[0]
+
+
+def test_plugin_seam_runs_foreign_decoder_classes_per_shot():
+    """sliding_window_circuit_mem with a decoder class of the caller's own, its own rate-keyword and method name (the reference's
+    real plug point, doc/05 cells 10-11): window matrices from the C++ planner, one decoder object per window, one call per shot
+    and window -- equal to the fixture the reference's own loop produced with the same inner decoder.  No GPU involved."""
+    import quits_b200 as qb
+    case = "bb72_r6_p3e-3_W5F3"
+    g = decode_case(case)
+    name = case_circuit(case)
+    _, hz, lz = circuit_meta(name)
+    n = 24
+    params = dict(max_iter=10, bp_method="minimum_sum", schedule="parallel", osd_method="osd_0", osd_order=0, precision="f64")
+    d1, d2 = dict(params), dict(params)
+    pred = qb.sliding_window_circuit_mem(g["det"][:n], qb.Circuit(circuit_text(name)), hz, lz, g["W"], g["F"], _ForeignDecoder,
+                                         _ForeignDecoder, d1, d2, "my_rates", "my_rates", "run_it", "run_it")
+    assert pred.dtype == np.int64 and np.array_equal(pred, g["pred_f64"][:n])
+    assert "my_rates" in d1 and "my_rates" in d2           # the reference leaves the last priors in the caller's dicts

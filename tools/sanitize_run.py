@@ -65,6 +65,29 @@ def main():
         kw2.update(kwx)
         e = cls(H, error_rate=0.02, **kw2).decode_batch(syn)[0]
         print(cls.__name__, rows, cols, kwx, "weight", int(e.sum()), flush=True)
+    # round-2 kernels: serial slab kernel with 8 / 16 lanes per column, product-sum in the generic flooding kernel, higher-order OSD
+    # with the row transformation in a global slab, the device fan-out (three contexts on one GPU)
+    for rows, cols, cw, kwx in ((300, 900, 9, dict(osd_method="off", schedule="serial")),
+                                (300, 900, 9, dict(osd_method="off", schedule="serial", bp_method="product_sum")),
+                                (300, 900, 15, dict(osd_method="off", schedule="serial")),
+                                (300, 900, 9, dict(osd_method="off", bp_method="product_sum")),
+                                (1100, 2600, 3, dict(osd_method="osd_cs", osd_order=1))):
+        indptr, indices = [0], []
+        for j in range(cols):
+            indices += list(np.sort(rng.choice(rows, size=cw, replace=False)))
+            indptr.append(len(indices))
+        H = csc_matrix((np.ones(len(indices), dtype=np.uint8), np.array(indices), np.array(indptr)), shape=(rows, cols))
+        err = (rng.rand(n(24), cols) < 0.01).astype(np.uint8)
+        syn = np.asarray((H @ err.T).T % 2, dtype=np.uint8)
+        kw2 = dict(max_iter=3, bp_method="minimum_sum", schedule="parallel")
+        kw2.update(kwx)
+        e = qb.BpOsdDecoder(H, error_rate=0.01, **kw2).decode_batch(syn)[0]
+        print("round2", rows, cols, cw, kwx, "weight", int(e.sum()), flush=True)
+    qb.set_devices([0, 0, 0])
+    qb.devices.MIN_SHOTS_PER_DEVICE = 64
+    det3, obs3 = qb.get_stim_mem_result(c, n(300), seed=3)
+    print("fan-out", np.array_equal(det3, det), int(qb.sliding_window_bposd_circuit_mem(det3, c, hz, lz, 5, 3, **base).sum()), flush=True)
+    qb.set_devices(None)
     rng = np.random.RandomState(1)
     print("phenom", qb.sliding_window_bposd_phenom_mem(rng.rand(n(64), 72 * 12) < 0.05, (rng.rand(72, 144) < 0.04).astype(int),
                                                        (rng.rand(12, 144) < 0.3).astype(int), 5, 3, error_rate=0.02, **base).sum(), flush=True)
