@@ -178,11 +178,15 @@ def roofline(precision, agg, clocks, peaks):
     smem_peak = 148 * sm_mhz * 1e6 / 1e9                   # G shared-memory wavefronts / s: one per SM and cycle
     m = inst_model(precision)
     ei = agg.get("bp_edge_iters", 0.0)
-    out = {"kernel": "bp_kernel_compact", "bound": "issue", "unit": "Gwarp-inst/s", "peak": issue_peak,
+    esz = 4 if precision == "f32" else 8
+    io_bytes = max(0.0, agg["bp_alg_bytes"] - 4.0 * esz * ei)           # syndrome in + commit / carry out: the compulsory HBM bytes
+    kernel = {("minimum_sum", "parallel"): "bp_kernel_ms2", ("product_sum", "parallel"): "bp_kernel_compact<PS>"}.get(
+        (BP_KW["bp_method"], BP_KW["schedule"]), "bp_kernel_serial_slab")
+    out = {"kernel": kernel, "bound": "issue", "unit": "Gwarp-inst/s", "peak": issue_peak,
            "peak_source": "148 SMs x 4 schedulers x %.0f MHz (SM clock sampled during the timed region)" % sm_mhz,
            "achieved": None, "frac": None, "edge_iters_per_s": ei / bp_s if bp_s > 0 else 0.0,
            "ms_per_launch": agg["bp_ms"] / bp_launches, "traffic": ncu_traffic(precision),
-           "alg_io_bytes_per_launch": agg["bp_io_bytes"] / bp_launches if "bp_io_bytes" in agg else None,
+           "alg_io_bytes_per_launch": io_bytes / bp_launches,
            "hbm_model": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "model_frac": hbm_ach / hbm_peak,
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650",
                          "alg_bytes_per_launch": agg["bp_alg_bytes"] / bp_launches,

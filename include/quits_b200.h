@@ -104,9 +104,10 @@ int qb_dem_matrix(const qb_dem* d, int64_t* h_ptr, int32_t* h_idx, int64_t* l_pt
  * (:130-141 + decoder/base.py:149-188), one BP(+OSD) decoder per window (:146-153) and the per-shot loop (:162-186)
  * with ldpc.BpOsdDecoder.decode inside (:171,182).  Option names follow the reference's kwargs (decoder/bposd.py:74-83;
  * decoder/bplsd.py:74-83 for osd_method 3 = ldpc.BpLsdDecoder's post-processing).
- * Window sizes: BP up to 8192 checks and 65534 fault columns (messages in shared memory when they fit, else in an L2-resident
- * slab); OSD-0 and LSD-0 up to 3072 checks; osd_e / osd_cs with order > 0 up to 768 checks; schedule 'serial' and
- * bp_method 'product_sum' need column weight <= 6 and messages that fit shared memory.  Anything beyond: QB_ENOTIMPL. */
+ * Window sizes: BP up to 8192 checks and 65534 fault columns, column weight <= 16, both bp_methods and both schedules (flooding:
+ * messages in shared memory when they fit, else in a global slab; serial: messages in a global slab, row summaries in shared
+ * memory); OSD-0 and LSD-0 up to 3072 checks; osd_e / osd_cs with order > 0 up to 2304 checks; lsd_order > 0 and anything beyond
+ * these sizes: QB_ENOTIMPL. */
 typedef struct {
     int32_t bp_method;          /* 0 'minimum_sum' | 1 'product_sum' */
     int32_t schedule;           /* 0 'parallel' (flooding) | 1 'serial' (columns in index order, no random reshuffle) */
