@@ -585,11 +585,10 @@ template <> struct Bits<double> {
     static __device__ __forceinline__ double with_hi(double x, uint32_t h) { return __hiloint2double(static_cast<int>(h), __double2loint(x)); }
 };
 
-// sign bit set <=> x <= 0  (x == +0 becomes -0)
-template <typename R>
-__device__ __forceinline__ R canonical_sign(const R x) {
-    return Bits<R>::with_hi(x, x == R(0) ? 0x80000000u : Bits<R>::hi(x));
-}
+// sign bit set <=> x <= 0  (x == +0 becomes -0): one addition of -0 in round-down mode -- x + (-0) is x for every non-zero x in
+// any rounding mode, (+0) + (-0) is -0 when rounding down, (-0) + (-0) is -0
+__device__ __forceinline__ float canonical_sign(const float x) { return __fadd_rd(x, -0.0f); }
+__device__ __forceinline__ double canonical_sign(const double x) { return __dadd_rd(x, -0.0); }
 
 // off: rm1, rm2, V, syn, cand, accs, car, ptab, hist, ebits
 __host__ __device__ inline size_t bpm_layout(const WinDev& w, int rsize, size_t* off /*[10]*/) {
@@ -663,7 +662,7 @@ __device__ __forceinline__ R column_ms2(const uint4 rec, const R l0, const R alp
     using SH = Sh<R>;
     const uint32_t vo[6] = {SH::off_lo(rec.x), SH::off_hi(rec.x), SH::off_lo(rec.y), SH::off_hi(rec.y), SH::off_lo(rec.z), SH::off_hi(rec.z)};
     R c[W], vn[W];
-    const R l0c = MODE == 0 ? canonical_sign<R>(l0) : l0;
+    const R l0c = MODE == 0 ? canonical_sign(l0) : l0;
 #pragma unroll
     for (int q = 0; q < W; ++q) {
         const R v = MODE == 0 ? l0c : SH::ld(x.vbase + vo[q]);
@@ -683,7 +682,7 @@ __device__ __forceinline__ R column_ms2(const uint4 rec, const R l0, const R alp
         if (q > 0) t = RT::add(t, c[q]);
     }
 #pragma unroll
-    for (int q = 0; q < W; ++q) SH::st(x.vbase + vo[q], canonical_sign<R>(vn[q]));
+    for (int q = 0; q < W; ++q) SH::st(x.vbase + vo[q], canonical_sign(vn[q]));
     return llr;
 }
 
