@@ -56,6 +56,12 @@ def load_workload():
             text = f.read().decode()
     with open(os.path.join(g, WORKLOAD + ".json")) as f:
         meta = json.load(f)
+    if RATE[0] is not None:
+        # threshold sweeps: the builders write every noise rate as "%.10f" of the one p of ErrorModel(p, p, p, p), so another rate
+        # of the same circuit is a substitution of that literal
+        old, new = "(%.10f)" % float(meta["p"]), "(%.10f)" % RATE[0]
+        assert old in text, "fixture rate literal not found"
+        text = text.replace(old, new)
     hz = np.zeros(meta["hz_shape"], dtype=np.uint8)
     for i, r in enumerate(meta["hz_rows"]):
         hz[i, r] = 1
@@ -69,7 +75,7 @@ def config(shots, precision):
     return {"workload": "%s %s, W=%d F=%d, %s %s BP max_iter=%d + %s order %d" % (
                 WORKLOAD, "custom circuit" if WORKLOAD.startswith("bb") else "circuit", W, F, BP_KW["bp_method"], "flooding" if BP_KW["schedule"] == "parallel" else "serial", BP_KW["max_iter"],
                 BP_KW["osd_method"], BP_KW["osd_order"]),
-            "shots_per_step_per_gpu": int(shots), "precision": precision, "seed": SEED,
+            "shots_per_step_per_gpu": int(shots), "precision": precision, "seed": SEED, "rate_override": RATE[0],
             "l2": "flushed between timed steps (256 MiB write); per-step message/LLR working set also exceeds L2"}
 
 
@@ -93,6 +99,7 @@ def cpu_arm(shots, nthreads=0):
 
 
 REAL_REF_WHY = ["not probed"]
+RATE = [None]
 
 
 def real_reference_arm(args):
@@ -254,9 +261,11 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="concurrent sub-batches per device batch (0 = engine default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--rate", type=float, default=None, help="noise rate substituted for the fixture's (threshold sweeps)")
     ap.add_argument("--fanout", action="store_true", help="single process, e2e through the drop-in calls spread over every visible GPU")
     args = ap.parse_args()
     globals()["WORKLOAD"] = args.workload
+    RATE[0] = args.rate
     if args.bp_method:
         BP_KW["bp_method"] = args.bp_method
     if args.schedule:
