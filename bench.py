@@ -393,8 +393,9 @@ def main():
             det, obs = qb.get_stim_mem_result(circuit, Se, seed=shot_seed)
             pred = qb.sliding_window_bposd_circuit_mem(det, circuit, hz, lz, W, F, **BP_KW) if dec32 is None else dec32.decode(det)
             # the caller's pL reduction.  The reference's idiom np.any((obs - pred) % 2, axis=1) (tests/test_sliding_window.py:83) costs
-            # 32 ms on 262144 x 12 int64 -- a fifth of the step -- for an integer modulo of 0/1 values; this is the same predicate
-            return int(np.any(obs != pred.astype(np.bool_), axis=1).sum())
+            # 32 ms on 262144 x 12 int64 -- a fifth of the step -- for an integer modulo of 0/1 values; count_logical_errors is the
+            # same predicate over row blocks on the host's cores
+            return qb.count_logical_errors(obs, pred)
         e2e_step(0)
         barrier()
         t0 = time.perf_counter()

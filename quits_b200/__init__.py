@@ -17,6 +17,6 @@ from .decoder import (BpLsdDecoder, BpOsdDecoder, detector_error_model_to_matrix
 from .decoder.sliding_window import clear_decoder_cache  # noqa: E402
 from .devices import active_devices, set_devices  # noqa: E402
 from .engine import MonteCarlo, SlidingWindowDecoder, run_sharded, shard_range  # noqa: E402
-from .simulation import get_codecap_pL, get_stim_mem_result  # noqa: E402
+from .simulation import count_logical_errors, get_codecap_pL, get_stim_mem_result  # noqa: E402
 
 __version__ = "0.1.0"

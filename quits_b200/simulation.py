@@ -57,4 +57,44 @@ def get_codecap_pL(code, p, num_trials, decoder, dict, basis='Z', seed=-1, tqdm_
     return num_errors / num_trials
 
 
-__all__ = ["get_stim_mem_result", "get_codecap_pL"]
+def count_logical_errors(observable_flips, logical_pred, threads=None):
+    """Number of shots whose prediction differs from the observed flips in any observable -- the caller's reduction
+    ``np.sum(np.any((observable_flips - logical_pred) % 2, axis=1))`` (reference ``tests/test_sliding_window.py:83``,
+    ``doc/06B`` cell 5) without the int64 temporaries, over row blocks on a thread pool (numpy releases the GIL in these loops):
+    at eight GPUs the single-threaded idiom costs more than the decode it follows."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    obs = np.asarray(observable_flips)
+    pred = np.asarray(logical_pred)
+    n = obs.shape[0]
+    if pred.shape != obs.shape:
+        raise ValueError("observable flips %r and predictions %r differ in shape" % (obs.shape, pred.shape))
+    threads = max(1, min(int(threads or os.cpu_count() or 1), 32, (n + 65535) // 65536))
+
+    def bits(a):                                      # 0/1 bytes of a boolean / integer array (integers reduced mod 2)
+        if a.dtype == np.bool_:
+            return a.view(np.uint8)
+        if a.dtype.kind in "iu":
+            return a.astype(np.uint8) & np.uint8(1)     # truncation keeps the low byte, whose low bit is the parity
+        return (a % 2 != 0).view(np.uint8)
+
+    def block(i):
+        lo, hi = n * i // threads, n * (i + 1) // threads
+        x = np.ascontiguousarray(bits(obs[lo:hi]) ^ bits(pred[lo:hi]))          # [rows, K] bytes, non-zero where they differ
+        k = x.shape[1]
+        if k == 0 or hi == lo:
+            return 0
+        if k % 4 == 0:                                # OR the row's bytes through a few wide column passes (an axis-1 reduction
+            x = x.view(np.uint32)                     # over K = 12 short elements is an order of magnitude slower)
+        acc = x[:, 0].copy()
+        for c in range(1, x.shape[1]):
+            acc |= x[:, c]
+        return int(np.count_nonzero(acc))
+
+    if threads == 1:
+        return block(0)
+    with ThreadPoolExecutor(threads) as ex:
+        return int(sum(ex.map(block, range(threads))))
+
+
+__all__ = ["get_stim_mem_result", "get_codecap_pL", "count_logical_errors"]

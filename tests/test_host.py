@@ -511,3 +511,22 @@ def test_plugin_seam_runs_foreign_decoder_classes_per_shot():
                                          _ForeignDecoder, d1, d2, "my_rates", "my_rates", "run_it", "run_it")
     assert pred.dtype == np.int64 and np.array_equal(pred, g["pred_f64"][:n])
     assert "my_rates" in d1 and "my_rates" in d2           # the reference leaves the last priors in the caller's dicts
+
+
+def test_count_logical_errors_equals_the_reference_idiom():
+    """quits_b200.count_logical_errors == np.sum(np.any((obs - pred) % 2, axis=1)) (reference tests/test_sliding_window.py:83) for
+    boolean flips against int64 predictions, odd K, negative / even integers, empty input, one thread or many."""
+    import quits_b200 as qb
+    rng = np.random.default_rng(3)
+    for n, K in ((0, 12), (1, 1), (1000, 12), (70001, 7), (5000, 136)):
+        obs = rng.random((n, K)) < 0.02
+        pred = (obs ^ (rng.random((n, K)) < 0.003)).astype(np.int64)
+        if n > 10:
+            pred[3, 0] = -3
+            pred[4, K - 1] = 2
+        want = int(np.any((obs - pred) % 2, axis=1).sum())
+        assert qb.count_logical_errors(obs, pred) == want
+        assert qb.count_logical_errors(obs, pred, threads=1) == want
+        assert qb.count_logical_errors(obs.astype(np.int64), pred.astype(np.bool_) if n == 0 else pred, threads=3) == want
+    with pytest.raises(ValueError):
+        qb.count_logical_errors(np.zeros((3, 2), bool), np.zeros((3, 3), np.int64))
