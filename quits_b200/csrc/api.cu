@@ -96,6 +96,7 @@ struct qb_ctx {
     cudaStream_t stream = nullptr;
     // sampler scratch
     DevBuf det_rows, obs_rows, det_bytes, obs_bytes, inj_start, inj_tgt, inj_code, inj_shot, counts;
+    DevBuf det_words;          // frame kernel scratch (qb::frame_scratch_bytes)
     EventTimer t_frame, t_total;
     // side streams of the decoder: a batch is decoded as kMaxLanes independent sub-batches so that the latency-bound OSD
     // kernel of one sub-batch shares the SMs with the BP kernel of another
@@ -199,7 +200,11 @@ void use_device(qb_ctx* ctx) { CK(cudaSetDevice(ctx->device)); }
 
 void circuit_to_device(qb_ctx* ctx, qb_circuit* c) {
     if (c->dev == ctx->device) return;
-    upload(c->d_ops, c->tape.ops, ctx->stream);
+    {
+        std::vector<qb::TapeOp> ops(c->tape.ops);
+        ops.push_back(qb::TapeOp{});                     // the frame kernel reads one op header ahead
+        upload(c->d_ops, ops, ctx->stream);
+    }
     upload(c->d_targets, c->tape.targets, ctx->stream, 2);
     upload(c->d_detptr, c->tape.detptr, ctx->stream, 2);
     upload(c->d_detidx, c->tape.detidx, ctx->stream);
@@ -1052,7 +1057,7 @@ static void sample_impl(qb_ctx* ctx, qb_circuit* c, uint64_t seed, uint64_t shot
         a.n_words = nwords;
         a.det_rows = rows_d.as<uint64_t>();
         a.obs_rows = rows_o.as<uint64_t>();
-        CK(qb::launch_frame(a, ctx->stream));
+        ctx->det_words.ensure(qb::frame_scratch_bytes(a)); a.det_words = ctx->det_words.as<uint64_t>(); CK(qb::launch_frame(a, ctx->stream));
         if (det || obs) {
             bytes_d.ensure(std::min<uint64_t>(chunk, n_shots) * std::max(D, 1) + 16);
             bytes_o.ensure(std::min<uint64_t>(chunk, n_shots) * std::max(K, 1) + 16);
@@ -1127,7 +1132,7 @@ int qb_sample_faults(qb_ctx* ctx, qb_circuit* c, int64_t n_faults, const int32_t
         a.inj_tgt = ctx->inj_tgt.as<int32_t>();
         a.inj_code = ctx->inj_code.as<int32_t>();
         a.inj_shot = ctx->inj_shot.as<int64_t>();
-        CK(qb::launch_frame(a, ctx->stream));
+        ctx->det_words.ensure(qb::frame_scratch_bytes(a)); a.det_words = ctx->det_words.as<uint64_t>(); CK(qb::launch_frame(a, ctx->stream));
         ctx->det_bytes.ensure(n_shots * std::max(D, 1) + 16);
         ctx->obs_bytes.ensure(n_shots * std::max(K, 1) + 16);
         CK(qb::launch_unpack_bits(a.det_rows, a.DW, D, n_shots, ctx->det_bytes.as<uint8_t>(), ctx->stream));
@@ -1524,7 +1529,7 @@ int qb_mc_run(qb_ctx* ctx, qb_circuit* c, qb_sw* sw, uint64_t seed, uint64_t sho
             a.det_rows = ctx->det_rows.as<uint64_t>();
             a.obs_rows = ctx->obs_rows.as<uint64_t>();
             if (prof) ctx->t_frame.begin(st);
-            CK(qb::launch_frame(a, st));
+            ctx->det_words.ensure(qb::frame_scratch_bytes(a)); a.det_words = ctx->det_words.as<uint64_t>(); CK(qb::launch_frame(a, st));
             if (prof) ctx->t_frame.end(st);
             if (stats) { stats->frame_launches++; stats->frame_alg_bytes += static_cast<double>(nc) * 8.0 * (a.DW + a.KW); }
             int slot = 0;

@@ -86,15 +86,23 @@ __global__ void __launch_bounds__(128) frame_kernel(const FrameArgs a, const int
     uint64_t* x = smem + static_cast<size_t>(warp) * words_per_warp_smem;
     uint64_t* z = x + nq;
     uint64_t* ring = z + nq;
-    uint64_t* det = ring + a.ring;
-    uint64_t* obs = det + DW * 64;
+    uint64_t* obs = ring + a.ring;
+    // detector words go straight to a global scratch row of this 64-shot word (each is written exactly once, 32 lanes x 8 bytes
+    // coalesced) instead of 7.7 KB of shared memory per warp: shared memory per warp is what bounds this kernel's occupancy
+    uint64_t* det = a.det_words + widx * static_cast<uint64_t>(DW) * 64ull;
     for (int i = lane; i < 2 * nq; i += 32) x[i] = 0;
-    for (int i = lane; i < (DW + KW) * 64; i += 32) det[i] = 0;
+    for (int i = lane; i < KW * 64; i += 32) obs[i] = 0;
+    for (int i = a.n_det + lane; i < DW * 64; i += 32) det[i] = 0;       // padding detectors of the last word
     __syncwarp();
 
+    // the 32-byte op headers are read one op ahead (the tape is the same for every warp: L1 / L2 resident, but its latency would
+    // otherwise sit between every two ops of the dependent chain); the tape is padded by one no-op
+    int4 n0 = __ldg(reinterpret_cast<const int4*>(a.ops));
+    int4 n1 = __ldg(reinterpret_cast<const int4*>(a.ops) + 1);
     for (int i = 0; i < a.n_ops; ++i) {
-        const int4 h0 = __ldg(reinterpret_cast<const int4*>(a.ops + i));
-        const int4 h1 = __ldg(reinterpret_cast<const int4*>(a.ops + i) + 1);
+        const int4 h0 = n0, h1 = n1;
+        n0 = __ldg(reinterpret_cast<const int4*>(a.ops + i + 1));
+        n1 = __ldg(reinterpret_cast<const int4*>(a.ops + i + 1) + 1);
         const int kind = h0.x, n = h0.y;
         const uint32_t t0 = static_cast<uint32_t>(h0.z), aux = static_cast<uint32_t>(h0.w);
         const uint32_t thr = static_cast<uint32_t>(h1.x);
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(128) frame_kernel(const FrameArgs a, const int
                 const uint32_t b = __ldg(a.detptr + t0 + j), e = __ldg(a.detptr + t0 + j + 1);
                 uint64_t acc = 0;
                 for (uint32_t q = b; q < e; ++q) acc ^= ring[__ldg(a.detidx + q) & rmask];
-                det[aux + j] = acc;
+                __stcg(det + aux + j, acc);
             }
             break;
         case OP_OBS: {
@@ -188,10 +196,25 @@ __global__ void __launch_bounds__(128) frame_kernel(const FrameArgs a, const int
         __syncwarp();
     }
 
-    // In-place 64x64 bit transposes: det[c*64 + d] (bit b = shot b)  ->  det[c*64 + b] (bit d = detector c*64+d);
-    // the observable words follow the detector words in shared memory and are handled by the same loop.
-    for (int c = 0; c < DW + KW; ++c) {
-        uint64_t* blk = det + c * 64;
+    // 64x64 bit transposes: word d of block c (bit b = shot b) -> word c of shot b (bit d = detector c*64 + d).  The detector words
+    // come back from the scratch row (L2: this warp wrote them; every lane reads the same word), the shot rows are written in place.
+    __syncwarp();
+    uint64_t* drow = a.det_rows + widx * 64ull * DW;
+    for (int c = 0; c < DW; ++c) {
+        const uint64_t* blk = det + c * 64;
+        uint64_t o0 = 0, o1 = 0;
+#pragma unroll 16
+        for (int d = 0; d < 64; ++d) {
+            const uint64_t v = __ldcg(blk + d);
+            o0 |= ((v >> lane) & 1ull) << d;
+            o1 |= ((v >> (lane + 32)) & 1ull) << d;
+        }
+        drow[static_cast<size_t>(lane) * DW + c] = o0;
+        drow[static_cast<size_t>(lane + 32) * DW + c] = o1;
+    }
+    uint64_t* orow = a.obs_rows + widx * 64ull * KW;
+    for (int c = 0; c < KW; ++c) {
+        const uint64_t* blk = obs + c * 64;
         uint64_t o0 = 0, o1 = 0;
 #pragma unroll 8
         for (int d = 0; d < 64; ++d) {
@@ -199,15 +222,9 @@ __global__ void __launch_bounds__(128) frame_kernel(const FrameArgs a, const int
             o0 |= ((v >> lane) & 1ull) << d;
             o1 |= ((v >> (lane + 32)) & 1ull) << d;
         }
-        __syncwarp();
-        blk[lane] = o0;
-        blk[lane + 32] = o1;
+        orow[static_cast<size_t>(lane) * KW + c] = o0;
+        orow[static_cast<size_t>(lane + 32) * KW + c] = o1;
     }
-    __syncwarp();
-    uint64_t* drow = a.det_rows + widx * 64ull * DW;
-    for (int idx = lane; idx < 64 * DW; idx += 32) drow[idx] = det[(idx % DW) * 64 + idx / DW];
-    uint64_t* orow = a.obs_rows + widx * 64ull * KW;
-    for (int idx = lane; idx < 64 * KW; idx += 32) orow[idx] = obs[(idx % KW) * 64 + idx / KW];
 }
 
 __global__ void unpack_bits_kernel(const uint64_t* __restrict__ rows, int wpr, int nbits, uint64_t n_rows, uint8_t* __restrict__ out) {
@@ -270,16 +287,18 @@ __global__ void count_kernel(const uint64_t* __restrict__ acc, const uint64_t* _
 }  // namespace
 
 size_t frame_smem_per_warp(const FrameArgs& a) {
-    return (static_cast<size_t>(2) * a.n_qubits + a.ring + static_cast<size_t>(a.DW + a.KW) * 64) * sizeof(uint64_t);
+    return (static_cast<size_t>(2) * a.n_qubits + a.ring + static_cast<size_t>(a.KW) * 64) * sizeof(uint64_t);
 }
+size_t frame_scratch_bytes(const FrameArgs& a) { return static_cast<size_t>(a.n_words) * a.DW * 64 * sizeof(uint64_t) + 64; }
 
 cudaError_t launch_frame(const FrameArgs& a, cudaStream_t st) {
     if (a.n_words == 0) return cudaSuccess;
     const size_t per_warp = frame_smem_per_warp(a);
     const size_t budget = 200 * 1024;
     if (per_warp > budget) return cudaErrorInvalidValue;
+    if (!a.det_words) return cudaErrorInvalidValue;
     int wpb = 4;
-    while (wpb > 1 && per_warp * wpb > budget / 3) --wpb;          // keep >= 3 CTAs per SM when possible
+    while (wpb > 1 && per_warp * wpb > budget / 6) --wpb;          // keep >= 6 CTAs per SM when possible
     const size_t smem = per_warp * wpb;
     static size_t configured_dev[kMaxDevices] = {};
     size_t& configured = configured_dev[device_slot()];

@@ -36,6 +36,8 @@ struct FrameArgs {
     uint64_t seed;
     uint64_t word0;           // global index of the first 64-shot word of this launch
     uint64_t n_words;
+    uint64_t* det_words;      // scratch [n_words][DW*64]: word d of a 64-shot word holds detector d of its 64 shots (written once per
+                              // detector by the frame kernel, transposed into det_rows at the end of the same launch)
     uint64_t* det_rows;       // [n_words*64][DW]   bit d of shot s = det_rows[s*DW + d/64] >> (d%64)
     uint64_t* obs_rows;       // [n_words*64][KW]
     // explicit-fault mode (noise instructions are replaced by the listed faults)
@@ -46,6 +48,7 @@ struct FrameArgs {
     const int64_t* inj_shot;  // shot index local to this launch
 };
 size_t frame_smem_per_warp(const FrameArgs& a);
+size_t frame_scratch_bytes(const FrameArgs& a);       // bytes of the detector-word scratch a launch of a.n_words words needs
 cudaError_t launch_frame(const FrameArgs& a, cudaStream_t st);
 
 // bit rows <-> byte matrices (the reference API works on numpy bool arrays)
