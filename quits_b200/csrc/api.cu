@@ -789,6 +789,7 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.ovf_count = ctr + 2;
             b.sort_next = ctr + 3;
             b.osd_next = ctr + 4;
+            b.bp_next = ctr + 5;
             b.ovf_list = sw->use_osd ? sw->ovf_list.as<int>() + s0 : nullptr;
             b.osd_method = sw->opts.osd_method;
             b.osd_order = sw->opts.osd_order;
@@ -810,7 +811,11 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.commit_unconverged = (!sw->use_osd && !sw->use_lsd) ? 1 : 0;
             if (sw->opts.profile) sw->t_bp.begin(ls);
             if (sw->serial) CK(qb::launch_bp_serial_slab(w.dev, b, bp, sw->precision, std::min(w.bp_grid, nl), ls));
-            else CK(qb::launch_bp(w.dev, b, bp, sw->precision, w.vglobal, w.vglobal ? std::min(w.bp_grid, nl) : nl, ls));
+            else {
+                const int pg = qb::bp_persistent_grid(w.dev, sw->precision, w.vglobal, bp.method);
+                if (!pg) b.bp_next = nullptr;
+                CK(qb::launch_bp(w.dev, b, bp, sw->precision, w.vglobal, w.vglobal ? std::min(w.bp_grid, nl) : (pg ? std::min(pg, nl) : nl), ls));
+            }
             if (sw->opts.profile) sw->t_bp.end(ls);
             if (stats) stats->bp_launches++;
             if (sw->use_lsd) {

@@ -783,9 +783,18 @@ __global__ void __launch_bounds__(NT, MINB) bp_kernel_ms2(const WinDev w, const 
     for (int i = tid; i < w.n_ptab; i += NT) ptab[i] = CT::ptab(w)[i];
     if (tid < bp_dummy_rows(w, sizeof(R))) { rm1[rows + tid] = R(0); rm2[rows + tid] = R(0); }
     for (int i = tid; i < bp_dummy_slots(sizeof(R)); i += NT) V[rows * RS + i] = R(0);
+    bool s_first = true;
 
-    for (int shot = blockIdx.x; shot < b.n_shots; shot += gridDim.x) {
+    // persistent grid: CTAs pull shots from a queue (shots run 1 to 10 iterations: a static stride would leave a tail, one CTA
+    // per shot pays the CTA set-up -- prior table, dummy slots -- and the launch's drain for every shot)
+    __shared__ int s_shot;
+    for (;;) {
         __syncthreads();
+        if (tid == 0) s_shot = b.bp_next ? atomicAdd(b.bp_next, 1) : (s_first ? static_cast<int>(blockIdx.x) : b.n_shots);
+        s_first = false;
+        __syncthreads();
+        const int shot = s_shot;
+        if (shot >= b.n_shots) break;
         load_syndrome(w, b, shot, tid, syn, accs, car);
         __syncthreads();
         R* const llr_row = reinterpret_cast<R*>(b.llr_buf) + static_cast<size_t>(shot) * b.llr_stride;
@@ -931,6 +940,13 @@ size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal) {
 int bp_threads(int precision) { return precision == 32 ? 256 : 512; }
 
 bool bp_ms2_enabled() { return ms2_enabled(); }
+
+// CTAs of the persistent grid the flooding min-sum kernel is launched with (0: the window takes another kernel, one CTA per shot)
+int bp_persistent_grid(const WinDev& w, int precision, bool vglobal, int method) {
+    static const int on = [] { const char* e = getenv("QB_BP_PERSIST"); return e ? atoi(e) : 1; }();
+    if (!on || !use_ms2(w, vglobal, method)) return 0;
+    return 148 * (precision == 32 ? 4 : 2);
+}
 
 bool bp_supports(const WinDev& w, int method, bool vglobal) { (void)w; (void)vglobal; return method == 0 || method == 1; }
 

@@ -134,6 +134,7 @@ struct BatchDev {
     int* ovf_count;           // [1]
     int* sort_next;           // [1] work counter of the persistent OSD sort grid
     int* osd_next;            // [1] work counter of the persistent OSD elimination grid
+    int* bp_next;             // [1] shot queue of the persistent bp_kernel_ms2 grid (NULL: one CTA per shot, shot = blockIdx.x)
     unsigned long long* stats;// [8] converged windows, BP iterations, OSD calls, OSD columns examined, OSD pivots, max OSD columns, fast-path overflows
     uint32_t* ehat_out;       // optional [n][ehat_stride32]  (pre-zeroed)
     int ehat_stride32;
@@ -160,6 +161,7 @@ size_t bp_smem_bytes(const WinDev& w, int precision, bool vglobal);
 size_t bp_slab_bytes(const WinDev& w, int precision);       // bytes of one CTA's global message slab (VGLOBAL)
 int bp_threads(int precision);
 bool bp_supports(const WinDev& w, int method, bool vglobal);
+int bp_persistent_grid(const WinDev& w, int precision, bool vglobal, int method);
 bool bp_ms2_enabled();       // flooding min-sum through bp_kernel_ms2 (default) or bp_kernel_compact (QB_BP_MS2=0, A/B measurements)
 cudaError_t bp_configure(const WinDev& w, int precision, bool vglobal, int method);
 cudaError_t launch_bp(const WinDev& w, const BatchDev& b, const BpParams& p, int precision, bool vglobal, int grid, cudaStream_t st);
