@@ -1,4 +1,10 @@
-// quits_b200/csrc/bp.cu -- K3 (+K2/K5 fused): flooding min-sum BP of one sliding window, one shot per CTA (sm_100a).
+// quits_b200/csrc/bp.cu -- K3 (+K2/K5 fused): flooding BP of one sliding window, one shot per CTA (sm_100a).
+//
+// Three kernels, one arithmetic:
+//   bp_kernel_ms2        flooding min-sum on the compact layout (column weight <= 6, messages in shared memory): the headline path
+//   bp_kernel_compact    the same layout, kept for product-sum (and as round 1's min-sum kernel for A/B runs, QB_BP_MS2=0)
+//   bp_kernel            any window (column weight <= 16; messages in shared memory or, VGLOBAL, in a global slab per CTA), both methods
+// (the serial schedule is bp_serial.cu).
 //
 // Replaces the BP stage of ldpc.BpOsdDecoder.decode() as the reference calls it once per shot and window
 // (reference src/quits/decoder/sliding_window.py:171,182) together with the glue around it:

@@ -23,6 +23,8 @@
 // Arithmetic: min-sum is bit-exact with the oracle (same operations in the same order: a minimum does not depend on the order it
 // is taken in, the column's prefix / suffix sums are formed as the oracle forms them); product-sum agrees to rounding (the
 // association of the row product differs, and CUDA's tanh / log are not libm's).
+#include <cstdlib>
+
 #include "bp_common.cuh"
 #include "qb_device.h"
 
@@ -344,6 +346,8 @@ int bp_serial_slab_ctas_per_sm(const WinDev& w, int precision, int method) {
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, slab_kernel(precision, method, w.ss_lpc), 32,
                                                       bp_serial_slab_smem_bytes(w, precision, method)) != cudaSuccess) return 1;
+    static const int cap = [] { const char* e = getenv("QB_SERIAL_CTAS"); return e ? atoi(e) : 0; }();      // experiments
+    if (cap > 0 && n > cap) n = cap;
     return n > 0 ? n : 1;
 }
 

@@ -1,8 +1,10 @@
 // quits_b200/csrc/qb_device.h -- argument blocks of the CUDA kernels (sm_100a) and their launch wrappers.
 //
 //   K1  frame_kernel   per-shot Pauli-frame propagation, 64 shots per bit-word      (frame.cu)
-//   K3  bp_kernel      flooding min-sum BP of one window, one shot per CTA, messages in shared memory (bp.cu)
-//   K4  osd_sort_kernel / osd_elim_kernel   OSD-0: LLR radix sort (CTA per shot), GF(2) Gauss-Jordan (warp per shot) (osd.cu)
+//   K3  bp_kernel_ms2 / bp_kernel_compact / bp_kernel   flooding BP of one window, one shot per CTA (bp.cu)
+//   K3s bp_kernel_serial_slab   serial-schedule BP, one warp per shot, messages in a global slab (bp_serial.cu)
+//   K4  osd_fast_kernel / osd_sort_kernel / osd_elim_kernel   OSD: selection or radix sort, GF(2) Gauss-Jordan, candidate sweeps (osd.cu)
+//   K4L lsd_kernel, K4b osd_big_kernel   localized statistics decoding / OSD-0 of tall windows, one warp per shot (lsd.cu)
 //   K2/K5 are fused into K3/K4: syndrome = slice(det) ^ carry on entry, H e == s as the stop test, L e / U e on exit.
 #pragma once
 #include <cuda_runtime.h>
