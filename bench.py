@@ -397,22 +397,33 @@ def main():
         Se = args.e2e_shots
         dec32 = qb.SlidingWindowDecoder(circuit, hz.shape[0], W, F, ctx=ctx, precision="f32", **BP_KW) if args.precision == "f32" else None
 
+        phase = [0.0, 0.0, 0.0]                      # host wall clock of the three calls over the timed e2e steps (this rank)
+
         def e2e_step(i):
             shot_seed = SEED + 1000 + i * world + rank
+            ta = time.perf_counter()
             det, obs = qb.get_stim_mem_result(circuit, Se, seed=shot_seed)
+            tb = time.perf_counter()
             pred = qb.sliding_window_bposd_circuit_mem(det, circuit, hz, lz, W, F, **BP_KW) if dec32 is None else dec32.decode(det)
-            # the caller's pL reduction.  The reference's idiom np.any((obs - pred) % 2, axis=1) (tests/test_sliding_window.py:83) costs
-            # 32 ms on 262144 x 12 int64 -- a fifth of the step -- for an integer modulo of 0/1 values; count_logical_errors is the
-            # same predicate over row blocks on the host's cores
-            return qb.count_logical_errors(obs, pred)
+            tc = time.perf_counter()
+            n_bad = qb.count_logical_errors(obs, pred)
+            td = time.perf_counter()
+            phase[0] += tb - ta; phase[1] += tc - tb; phase[2] += td - tc
+            return n_bad
+        # the caller's pL reduction: the reference's idiom np.any((obs - pred) % 2, axis=1) (tests/test_sliding_window.py:83) costs
+        # 32 ms on 262144 x 12 int64 -- a fifth of the step -- for an integer modulo of 0/1 values; count_logical_errors is the
+        # same predicate over row blocks on the host's cores
         e2e_step(0)
         barrier()
+        phase[:] = [0.0, 0.0, 0.0]
         t0 = time.perf_counter()
         n_e2e = max(1, min(args.steps, 3))
         for i in range(n_e2e):
             e2e_step(1 + i)
         barrier()
         dt = time.perf_counter() - t0
+        print("e2e rank %d host ms per step: sample %.1f decode %.1f reduce %.1f" % (rank, 1e3 * phase[0] / n_e2e, 1e3 * phase[1] / n_e2e,
+                                                                                     1e3 * phase[2] / n_e2e), file=sys.stderr)
         te = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -444,6 +455,8 @@ def main():
                 line["e2e_devices"] = qb.active_devices()
             line["e2e"] = {"value": Se * n_e2e * world / float(te.item()), "unit": "shots/s", "h2d_bytes_per_step": Se * D,
                            "d2h_bytes_per_step": Se * (D + K) + Se * K * 8, "shots_per_step_per_gpu": Se, "steps": n_e2e,
+                           "host_ms_per_step": {"get_stim_mem_result": 1e3 * phase[0] / n_e2e, "sliding_window_bposd_circuit_mem": 1e3 * phase[1] / n_e2e,
+                                                "count_logical_errors": 1e3 * phase[2] / n_e2e, "rank": 0},
                            "path": "get_stim_mem_result -> sliding_window_bposd_circuit_mem (numpy host buffers, host wall clock)"}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
