@@ -106,15 +106,15 @@ int qb_dem_matrix(const qb_dem* d, int64_t* h_ptr, int32_t* h_idx, int64_t* l_pt
  * decoder/bplsd.py:74-83 for osd_method 3 = ldpc.BpLsdDecoder's post-processing).
  * Window sizes: BP up to 8192 checks and 65534 fault columns, column weight <= 16, both bp_methods and both schedules (flooding:
  * messages in shared memory when they fit, else in a global slab; serial: messages in a global slab, row summaries in shared
- * memory); OSD-0 and LSD-0 up to 3072 checks; osd_e / osd_cs with order > 0 up to 2304 checks; lsd_order > 0 and anything beyond
- * these sizes: QB_ENOTIMPL. */
+ * memory); OSD-0 and LSD (any order) up to 3072 checks; osd_e / osd_cs with order > 0 up to 2304 checks; anything beyond these
+ * sizes: QB_ENOTIMPL. */
 typedef struct {
     int32_t bp_method;          /* 0 'minimum_sum' | 1 'product_sum' */
     int32_t schedule;           /* 0 'parallel' (flooding) | 1 'serial' (columns in index order, no random reshuffle) */
     int32_t max_iter;           /* 0 => number of columns (ldpc convention) */
     double ms_scaling_factor;   /* 0.0 => 1 - 2^-iteration */
-    int32_t osd_method;         /* 0 'osd_0' | 1 'osd_e' | 2 'osd_cs' | 3 'lsd_0' (BpLsdDecoder, order 0) | -1 no post-processing */
-    int32_t osd_order;          /* 0 = OSD-0 whatever the method; osd_e: <= 12, osd_cs: <= 32 */
+    int32_t osd_method;         /* 0 'osd_0' | 1 'osd_e' | 2 'osd_cs' | 3 'lsd_0' | 4 'lsd_e' | 5 'lsd_cs' (BpLsdDecoder) | -1 no post-processing */
+    int32_t osd_order;          /* 0 = OSD-0 / LSD-0 whatever the method; osd_e, lsd_e: <= 12; osd_cs, lsd_cs: <= 32 (for LSD this is lsd_order) */
     int32_t precision;          /* 64 (default when 0): messages in fp64 as ldpc computes; 32: fp32 messages */
     int32_t capacity;           /* shots per device batch; 0 => default */
     int32_t profile;            /* 1: time the kernel classes with CUDA events on the launching stream */

@@ -261,7 +261,7 @@ typedef struct {
     double alpha;                     /* ms_scaling_factor; 0 => 1 - 2^-it */
     int precision;                    /* 64 or 32 */
     int osd;                          /* 1: OSD when BP fails; 0: return BP output */
-    int osd_method;                   /* 0 osd_0 | 1 osd_e (exhaustive) | 2 osd_cs (combination sweep) | 3 lsd_0 */
+    int osd_method;                   /* 0 osd_0 | 1 osd_e (exhaustive) | 2 osd_cs (combination sweep) | 3 lsd_0 | 4 lsd_e | 5 lsd_cs */
     int osd_order;
 } qo_bp;
 
@@ -296,11 +296,12 @@ qo_bp* qo_bp_create(int m, int n, const int64_t* indptr /*csc n+1*/, const int32
     return d;
 }
 
-/* osd_method: 0 osd_0 | 1 osd_e | 2 osd_cs (order 0 is OSD-0 whatever the method) | 3 lsd_0 (LSD post-processing, order 0) */
+/* osd_method: 0 osd_0 | 1 osd_e | 2 osd_cs (order 0 is OSD-0 whatever the method) | 3 lsd_0 (LSD post-processing, order 0) |
+ * 4 lsd_e | 5 lsd_cs (LSD with the per-cluster candidate sweep below; order 0 is LSD-0) */
 void qo_bp_set_osd(qo_bp* d, int osd_method, int osd_order)
 {
     d->osd_method = osd_method;
-    d->osd_order = osd_order < 0 ? 0 : (osd_method == 1 && osd_order > 20 ? 20 : (osd_order > 64 ? 64 : osd_order));
+    d->osd_order = osd_order < 0 ? 0 : ((osd_method == 1 || osd_method == 4) && osd_order > 20 ? 20 : (osd_order > 64 ? 64 : osd_order));
 }
 
 void qo_bp_free(qo_bp* d)
@@ -468,6 +469,87 @@ static void lsd_push(int** a, int* n, int* cap, int v)
 static _Thread_local int64_t lsd_diag[3];
 void qo_lsd_diag(int64_t* out) { out[0] = lsd_diag[0]; out[1] = lsd_diag[1]; out[2] = lsd_diag[2]; }
 
+/* --------------------------------------------------------------------------------------------
+ * LSD beyond order 0 (lsd_method = lsd_e / lsd_cs, lsd_order = w > 0).  PARITY UNPINNED: the published description ("the
+ * higher-order reprocessing of OSD applied inside every cluster") fixes the idea, not ldpc's tie-breaking details, and ldpc is
+ * not available here.  This restatement applies the candidate sweep of osd_decode above to each final cluster on its own:
+ *   - columns of the cluster in column-list order b_0 .. b_{nb-1}; pivots = the first independent ones (as in LSD-0); the other
+ *     columns, in list order, are the non-pivots np_0 .. np_{t-1}
+ *   - candidates, in this order -- lsd_cs: {np_i} for every i, then {np_i, np_j} for i < j < min(w, t); lsd_e: every non-empty
+ *     subset of the first min(w, t) non-pivots, as the bit patterns 1, 2, 3, ...
+ *   - a candidate sets its non-pivot columns to 1 and solves the pivots for the cluster's syndrome
+ *   - weight of a solution = sum over its set columns, in list order, of log(1 / p_j) (sequential double additions from 0);
+ *     the first candidate strictly lighter than everything before it (LSD-0's solution included) wins
+ * ldpc additionally lets clusters with fewer than w non-pivots grow by further bits first; that step is not restated.
+ * -------------------------------------------------------------------------------------------- */
+static void lsd_reduce(const lsd_cl* B, uint64_t* v, int nw)
+{
+    for (int o = 0; o < B->nops; ++o) {
+        int p = B->oprow[o];
+        if ((v[p >> 6] >> (p & 63)) & 1ull)
+            for (int q = 0; q < nw; ++q) v[q] ^= B->opvec[(size_t)o * nw + q];
+    }
+}
+
+static double lsd_cl_weight(const qo_bp* d, const lsd_cl* B, const int* prow, const uint64_t* y, const uint8_t* inF)
+{
+    double w = 0.0;
+    for (int k = 0; k < B->nbits; ++k) {
+        int on = prow[k] >= 0 ? (int)((y[prow[k] >> 6] >> (prow[k] & 63)) & 1ull) : inF[k];
+        if (on) w += log(1.0 / d->prior[B->cols[k]]);
+    }
+    return w;
+}
+
+/* z: the cluster's reduced syndrome.  Writes the cluster's part of ehat. */
+static void lsd_cluster_higher(const qo_bp* d, const lsd_cl* B, const uint64_t* z, int nw, int* posof, uint8_t* ehat)
+{
+    const int nb = B->nbits;
+    int* prow = (int*)malloc((size_t)nb * sizeof(int) + 4);
+    int* np = (int*)malloc((size_t)nb * sizeof(int) + 4);
+    uint8_t* inF = (uint8_t*)calloc((size_t)nb + 1, 1);
+    uint64_t* v = (uint64_t*)malloc((size_t)nw * 8);
+    uint64_t* ybest = (uint64_t*)malloc((size_t)nw * 8);
+    int bestF[64], nbestF = 0, flip[64];
+    for (int k = 0; k < nb; ++k) { prow[k] = -1; posof[B->cols[k]] = k; }
+    for (int o = 0; o < B->nops; ++o) prow[posof[B->opcol[o]]] = B->oprow[o];
+    int nnp = 0;
+    for (int k = 0; k < nb; ++k) if (prow[k] < 0) np[nnp++] = k;
+    memcpy(ybest, z, (size_t)nw * 8);
+    double best = lsd_cl_weight(d, B, prow, z, inF);
+    const int w = d->osd_order < nnp ? d->osd_order : nnp;
+    #define QO_LSD_TRY(NF)                                                                            \
+        do {                                                                                          \
+            memset(v, 0, (size_t)nw * 8);                                                             \
+            for (int f_ = 0; f_ < (NF); ++f_) {                                                       \
+                int j_ = B->cols[flip[f_]];                                                           \
+                inF[flip[f_]] = 1;                                                                    \
+                for (int q_ = d->colptr[j_]; q_ < d->colptr[j_ + 1]; ++q_) v[d->colrow[q_] >> 6] ^= 1ull << (d->colrow[q_] & 63); \
+            }                                                                                         \
+            lsd_reduce(B, v, nw);                                                                     \
+            for (int q_ = 0; q_ < nw; ++q_) v[q_] ^= z[q_];                                           \
+            double cw_ = lsd_cl_weight(d, B, prow, v, inF);                                           \
+            if (cw_ < best) { best = cw_; memcpy(ybest, v, (size_t)nw * 8); nbestF = (NF); memcpy(bestF, flip, sizeof(int) * (size_t)(NF)); } \
+            for (int f_ = 0; f_ < (NF); ++f_) inF[flip[f_]] = 0;                                      \
+        } while (0)
+    if (d->osd_method == 5) {
+        for (int i = 0; i < nnp; ++i) { flip[0] = np[i]; QO_LSD_TRY(1); }
+        for (int i = 0; i < w; ++i)
+            for (int j = i + 1; j < w; ++j) { flip[0] = np[i]; flip[1] = np[j]; QO_LSD_TRY(2); }
+    } else {
+        for (uint32_t pat = 1; pat < (1u << w); ++pat) {
+            int nf = 0;
+            for (int b = 0; b < w; ++b) if ((pat >> b) & 1u) flip[nf++] = np[b];
+            QO_LSD_TRY(nf);
+        }
+    }
+    #undef QO_LSD_TRY
+    for (int k = 0; k < nb; ++k)
+        if (prow[k] >= 0 && ((ybest[prow[k] >> 6] >> (prow[k] & 63)) & 1ull)) ehat[B->cols[k]] = 1;
+    for (int f = 0; f < nbestF; ++f) ehat[B->cols[bestF[f]]] = 1;
+    free(prow); free(np); free(inF); free(v); free(ybest);
+}
+
 static void lsd_decode(const qo_bp* d, const uint8_t* syn, const double* llr, uint8_t* ehat)
 {
     lsd_diag[0] = lsd_diag[1] = lsd_diag[2] = 0;
@@ -602,6 +684,9 @@ static void lsd_decode(const qo_bp* d, const uint8_t* syn, const double* llr, ui
         lsd_cl* B = &cl[c];
         if (B->active) {
             LSD_REDUCED_SYNDROME(B);
+            if (d->osd_method >= 4 && d->osd_order > 0 && B->nbits > 0) {
+                lsd_cluster_higher(d, B, z, nw, bit_owner /* scratch from here on */, ehat);
+            } else
             for (int o = 0; o < B->nops; ++o) {
                 int p = B->oprow[o];
                 if ((z[p >> 6] >> (p & 63)) & 1ull) ehat[B->opcol[o]] = 1;
@@ -622,7 +707,7 @@ int qo_bp_decode(const qo_bp* d, const uint8_t* syn, uint8_t* ehat, double* llr_
     if (d->precision == 32) conv = bp_run_f32(d, syn, ehat, llr, iters_out);
     else conv = bp_run_f64(d, syn, ehat, llr, iters_out);
     int used = 0;
-    if (!conv && d->osd) { if (d->osd_method == 3) lsd_decode(d, syn, llr, ehat); else osd_decode(d, syn, llr, ehat); used = 1; }
+    if (!conv && d->osd) { if (d->osd_method >= 3) lsd_decode(d, syn, llr, ehat); else osd_decode(d, syn, llr, ehat); used = 1; }
     if (used_osd_out) *used_osd_out = used;
     if (!llr_out) free(llr);
     return conv;

@@ -125,7 +125,7 @@ class BpOsd:
     SCHEDULES = {"parallel": 0, "serial": 1, 0: 0, 1: 1}
 
     OSD_METHODS = {"osd_0": 0, "osd0": 0, "osd_e": 1, "osde": 1, "exhaustive": 1, "osd_cs": 2, "osdcs": 2, "combination_sweep": 2,
-                   "lsd_0": 3, "lsd0": 3, 0: 0, 1: 1, 2: 2, 3: 3}
+                   "lsd_0": 3, "lsd0": 3, "lsd_e": 4, "lsd_cs": 5, 0: 0, 1: 1, 2: 2, 3: 3, 4: 4, 5: 5}
 
     def __init__(self, pcm, priors, max_iter, bp_method="minimum_sum", ms_scaling_factor=1.0, schedule="parallel",
                  precision="f64", osd=True, osd_method="osd_0", osd_order=0):

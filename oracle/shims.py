@@ -207,8 +207,9 @@ class _OracleBpDecoderBase:
         if method.startswith("lsd"):
             # ldpc's lsd_method only matters for lsd_order > 0 (the order-0 solve is the same for lsd_0 / lsd_cs / lsd_e)
             if order != 0 and method != "lsd0":
-                raise NotImplementedError("oracle implements order-0 LSD post-processing only (got %s order %d)" % (method, order))
-            osd_method, order = "lsd_0", 0
+                osd_method = "lsd_cs" if method == "lsdcs" else "lsd_e"         # per-cluster candidate sweep (cref.c, parity unpinned)
+            else:
+                osd_method, order = "lsd_0", 0
         else:
             osd_method = {"osd0": "osd_0", "osde": "osd_e", "exhaustive": "osd_e", "osdcs": "osd_cs", "combinationsweep": "osd_cs"}.get(method, "osd_0")
         self._dec = cref.BpOsd(pcm, priors, max_iter=max_iter if max_iter > 0 else n, bp_method=bp_method,

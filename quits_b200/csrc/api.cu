@@ -168,7 +168,8 @@ struct qb_sw {
     qb_bp_opts opts{};
     bool single = false;
     bool use_osd = true;
-    bool use_lsd = false;         // BpLsdDecoder post-processing (lsd_0) instead of OSD
+    bool use_lsd = false;         // BpLsdDecoder post-processing (LSD) instead of OSD
+    bool lsd_hi = false;          // lsd_e / lsd_cs with order > 0: candidate sweep inside every cluster
     bool use_slab = false;        // some window runs OSD-0 through the slab kernel (more than 768 checks)
     bool serial = false;          // ldpc schedule='serial'
     bool osd_hi = false;          // osd_e / osd_cs with order > 0: full elimination + candidate sweeps
@@ -553,16 +554,18 @@ void finish_decoder(qb_sw* sw) {
     if (o.osd_order < 0) throw qb::value_error("osd_order must be >= 0");
     if (o.osd_method == 1 && o.osd_order > 12) throw qb::unsupported_error("osd_e beyond order 12 (4095 patterns per shot) is not supported on the GPU path");
     if (o.osd_method == 2 && o.osd_order > 32) throw qb::unsupported_error("osd_cs beyond order 32 is not supported on the GPU path");
-    sw->osd_hi = o.osd_method > 0 && o.osd_order > 0;
+    if (o.osd_method == 4 && o.osd_order > 12) throw qb::unsupported_error("lsd_e beyond order 12 (4095 patterns per cluster) is not supported on the GPU path");
+    if (o.osd_method == 5 && o.osd_order > 32) throw qb::unsupported_error("lsd_cs beyond order 32 is not supported on the GPU path");
+    sw->osd_hi = (o.osd_method == 1 || o.osd_method == 2) && o.osd_order > 0;
     if (o.ms_scaling_factor < 0) throw qb::value_error("ms_scaling_factor must be >= 0");
     if (o.precision != 0 && o.precision != 32 && o.precision != 64) throw qb::value_error("precision must be 32 or 64");
     sw->precision = o.precision == 32 ? 32 : 64;
     const int prec = sw->precision;
-    if (o.osd_method > 3) throw qb::value_error("osd_method must be -1 (off), 0 (osd_0), 1 (osd_e), 2 (osd_cs) or 3 (lsd_0)");
+    if (o.osd_method > 5)
+        throw qb::value_error("osd_method must be -1 (off), 0 (osd_0), 1 (osd_e), 2 (osd_cs), 3 (lsd_0), 4 (lsd_e) or 5 (lsd_cs)");
     sw->use_osd = o.osd_method >= 0 && o.osd_method <= 2;
-    sw->use_lsd = o.osd_method == 3;
-    if (sw->use_lsd && o.osd_order != 0)
-        throw qb::unsupported_error("LSD post-processing beyond order 0 (lsd_order > 0) is not supported on the GPU path");
+    sw->use_lsd = o.osd_method >= 3;
+    sw->lsd_hi = o.osd_method >= 4 && o.osd_order > 0;          // order 0 is LSD-0 whatever the method
     int max_npad = 0, max_rowsW = 0, max_iter = 0, big_rows = 0;
     size_t max_slab = 0, sort_slab = 0, serial_slab = 0, tall_hi_slab = 0;
     int max_sort_grid = 0, serial_grid = 0, tall_hi_grid = 0;
@@ -642,7 +645,7 @@ void finish_decoder(qb_sw* sw) {
             if (!qb::lsd_supported(w->dev))
                 throw qb::unsupported_error("window of " + std::to_string(w->dev.rows) + " x " + std::to_string(w->dev.ncols) +
                                             " exceeds what the LSD kernel handles (rows <= 3072, columns < 65535)");
-            CK(qb::lsd_configure(w->dev, prec));
+            CK(qb::lsd_configure(w->dev, prec, sw->lsd_hi));
             const int per_sm = static_cast<int>((227 * 1024) / (qb::lsd_smem_bytes(w->dev) + 1024));
             w->lsd_grid = 148 * std::max(1, std::min(per_sm, 16));
         }
@@ -796,6 +799,8 @@ void decode_batch(qb_sw* sw, const uint64_t* d_det_rows, int n, bool want_ehat, 
             b.lsd_scratch = sw->lsd_scratch.p ? static_cast<unsigned char*>(sw->lsd_scratch.p) + static_cast<size_t>(l) * sw->lsd_slab * sw->lsd_slabs_per_lane : nullptr;
             b.lsd_slab = sw->lsd_slab;
             b.lsd_cols = sw->lsd_cols;
+            b.lsd_method = sw->lsd_hi ? (sw->opts.osd_method == 4 ? 1 : 2) : 0;
+            b.lsd_order = sw->lsd_hi ? sw->opts.osd_order : 0;
             b.sort_scratch = sw->sort_scratch.p;
             if (sw->use_osd && !sw->osd_hi && !w.osd_big) {
                 b.sel_key = static_cast<unsigned char*>(sw->sel_key.p) + s0 * qb::kOsdSelCap * esz;

@@ -33,6 +33,7 @@ constexpr uint32_t kNone = 0xFFFFu;
 constexpr uint32_t kDead = 0xFFFFu;
 constexpr uint32_t kDirty = 0xFFFEu;      // row cache: best candidate not computed / no longer free
 constexpr uint32_t kActive = 1u, kValid = 2u;
+constexpr int kLsdColBytes = 12;          // slab bytes per column: owner, successor + the four u16 arrays of the higher-order sweep
 
 __host__ __device__ inline size_t al16(size_t x) { return (x + 15) / 16 * 16; }
 
@@ -101,7 +102,20 @@ __device__ __forceinline__ void vec_set(uint32_t (&v)[NW], const int r, const in
         if (slot == s) v[s] = on ? (v[s] | bit) : (v[s] & ~bit);
 }
 
-template <typename R, int NW>
+template <int NW>
+__device__ __forceinline__ void vec_xor(uint32_t (&v)[NW], const int r, const int lane) {
+    const int wi = r >> 5, slot = wi >> 5;
+    if (lane != (wi & 31)) return;
+    const uint32_t bit = 1u << (r & 31);
+#pragma unroll
+    for (int s = 0; s < NW; ++s)
+        if (slot == s) v[s] ^= bit;
+}
+
+// HI: lsd_order > 0 -- after the growth every cluster runs the candidate sweep oracle/cref.c lsd_cluster_higher states (lsd_e /
+// lsd_cs over the cluster's non-pivot columns, weights summed in column-list order with __dadd_rn: the same additions in the same
+// order as the oracle, so ties resolve identically)
+template <typename R, int NW, bool HI>
 __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev b) {
     extern __shared__ __align__(16) unsigned char sm[];
     const LsdLayout L = lsd_layout(w);
@@ -134,7 +148,13 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
     // (the owner array sits at the same place for every window of the decoder: b.lsd_cols = widest window)
     uint16_t* bown = reinterpret_cast<uint16_t*>(slab);                                   // 0xFFFF between shots
     uint16_t* bnext = bown + b.lsd_cols;
-    uint32_t* opvec = reinterpret_cast<uint32_t*>(slab + al16(static_cast<size_t>(b.lsd_cols) * 4));          // [opcap][NW][32]
+    // higher order only: the cluster being swept as arrays -- its columns in list order, pivot row (or none) and non-pivot rank
+    // of each position, position of a column
+    uint16_t* clist = bnext + b.lsd_cols;
+    uint16_t* cprow = clist + b.lsd_cols;
+    uint16_t* crank = cprow + b.lsd_cols;
+    uint16_t* bpos = crank + b.lsd_cols;
+    uint32_t* opvec = reinterpret_cast<uint32_t*>(slab + al16(static_cast<size_t>(b.lsd_cols) * kLsdColBytes));      // [opcap][NW][32]
     const int count = *b.fail_count;
     for (;;) {
         int job = 0;
@@ -459,6 +479,147 @@ __global__ void __launch_bounds__(32) lsd_kernel(const WinDev w, const BatchDev 
             ninv = k;
             __syncwarp();
         }
+        if (HI) {
+            // ---- higher order: candidate sweep inside every cluster; the winner's non-pivot columns are committed here, its pivot
+            // part by folding the reduced candidate vector into z
+            const double* const wt = w.osd_wt;
+            const int ord = b.lsd_order;
+            auto reduce_ops = [&](uint32_t (&vw)[NW]) {
+                for (int base = 0; base < nops; base += 32) {
+                    const uint32_t p = base + lane < nops ? oppiv[base + lane] : kDead;
+                    uint32_t todo = kFull;
+                    for (;;) {
+                        __syncwarp();
+#pragma unroll
+                        for (int s = 0; s < NW; ++s) vsm[32 * s + lane] = vw[s];
+                        __syncwarp();
+                        const bool hit = p != kDead && ((vsm[p >> 5] >> (p & 31)) & 1u);
+                        const uint32_t mask = __ballot_sync(kFull, hit) & todo;
+                        if (!mask) break;
+                        const int i = __ffs(mask) - 1;
+#pragma unroll
+                        for (int s = 0; s < NW; ++s) vw[s] ^= opvec[(static_cast<size_t>(base + i) * NW + s) * 32 + lane];
+                        todo = i == 31 ? 0u : (kFull << (i + 1));
+                        if (!todo) break;
+                    }
+                }
+            };
+            auto commit_col = [&](const int j) {                 // one lane
+                if (b.ehat_out) atomicOr(&b.ehat_out[static_cast<size_t>(shot) * b.ehat_stride32 + (j >> 5)], 1u << (j & 31));
+                if (j < w.ncommit) {
+                    for (int wd = 0; wd < w.KW; ++wd) {
+                        const uint64_t lm = __ldg(w.lmask + static_cast<size_t>(j) * w.KW + wd);
+                        if (static_cast<uint32_t>(lm)) atomicXor(&accs[2 * wd], static_cast<uint32_t>(lm));
+                        if (static_cast<uint32_t>(lm >> 32)) atomicXor(&accs[2 * wd + 1], static_cast<uint32_t>(lm >> 32));
+                    }
+                    if (w.carry_rows) {
+                        for (int q = __ldg(w.uptr + j); q < __ldg(w.uptr + j + 1); ++q) {
+                            const uint32_t ur = __ldg(w.uidx + q);
+                            atomicXor(&car[ur >> 5], 1u << (ur & 31));
+                        }
+                    }
+                }
+            };
+            for (int id = 0; id < nc; ++id) {
+                if (!(flag[id] & kActive) || nbits[id] == 0) continue;
+                const int nb = nbits[id];
+                __syncwarp();
+                if (lane == 0) {
+                    int k = 0;
+                    for (uint32_t j = bhead[id]; j != kNone; j = bnext[j], ++k) {
+                        clist[k] = static_cast<uint16_t>(j); bpos[j] = static_cast<uint16_t>(k); cprow[k] = static_cast<uint16_t>(kNone);
+                    }
+                }
+                __syncwarp();
+                for (int i = lane; i < nops; i += 32) {
+                    const uint32_t p = oppiv[i];
+                    if (p != kDead && cown[p] == id) cprow[bpos[opcol[i]]] = static_cast<uint16_t>(p);
+                }
+                __syncwarp();
+                int nnp = 0;                                     // non-pivot ranks; the first 32 non-pivot positions go to ml[]
+                for (int base = 0; base < nb; base += 32) {
+                    const int k = base + lane;
+                    const bool np = k < nb && cprow[k] == kNone;
+                    const uint32_t mk = __ballot_sync(kFull, np);
+                    const int rk = nnp + __popc(mk & ((1u << lane) - 1u));
+                    if (k < nb) crank[k] = static_cast<uint16_t>(np ? rk : 0xFFFF);
+                    if (np && rk < 32) ml[rk] = static_cast<uint16_t>(k);
+                    nnp += __popc(mk);
+                }
+                __syncwarp();
+                if (nnp == 0) continue;
+                const int wsub = ord < nnp ? ord : nnp;         // candidates beyond singles range over the first wsub non-pivots (<= 32)
+                // candidate = one position (or -1) plus a pattern over the first 32 non-pivot ranks
+                auto cand_vec = [&](const int single, const uint32_t pat, uint32_t (&vw)[NW]) {
+#pragma unroll
+                    for (int s = 0; s < NW; ++s) vw[s] = 0u;
+                    auto add_col = [&](const int k) {
+                        const int j = clist[k];
+                        const int c0 = __ldg(w.cptr + j), c1 = __ldg(w.cptr + j + 1);
+                        for (int q = c0; q < c1; ++q) vec_xor<NW>(vw, static_cast<int>(__ldg(w.crow + q)), lane);
+                    };
+                    if (single >= 0) add_col(single);
+                    for (uint32_t x = pat; x; x &= x - 1) add_col(ml[__ffs(x) - 1]);
+                    reduce_ops(vw);
+                };
+                auto weigh = [&](const uint32_t (&yw)[NW], const int single, const uint32_t pat) -> double {
+                    __syncwarp();
+#pragma unroll
+                    for (int s = 0; s < NW; ++s) vsm[32 * s + lane] = yw[s];
+                    __syncwarp();
+                    double ws = 0.0;
+                    for (int base = 0; base < nb; base += 32) {
+                        const int k = base + lane;
+                        bool on = false;
+                        double wk = 0.0;
+                        if (k < nb) {
+                            const uint32_t pr = cprow[k];
+                            if (pr != kNone) on = (vsm[pr >> 5] >> (pr & 31)) & 1u;
+                            else { const uint32_t rk = crank[k]; on = k == single || (rk < 32u && ((pat >> rk) & 1u)); }
+                            if (on) wk = __ldg(wt + clist[k]);
+                        }
+                        uint32_t mask = __ballot_sync(kFull, on);
+                        while (mask) {
+                            const int src = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            ws = __dadd_rn(ws, __shfl_sync(kFull, wk, src));
+                        }
+                    }
+                    return ws;
+                };
+                double best = weigh(zw, -1, 0u);
+                int best_single = -1;
+                uint32_t best_pat = 0u;
+                bool found = false;
+                auto try_cand = [&](const int single, const uint32_t pat) {
+                    uint32_t vw[NW], yw[NW];
+                    cand_vec(single, pat, vw);
+#pragma unroll
+                    for (int s = 0; s < NW; ++s) yw[s] = zw[s] ^ vw[s];
+                    const double cw = weigh(yw, single, pat);
+                    if (cw < best) { best = cw; best_single = single; best_pat = pat; found = true; }
+                };
+                if (b.lsd_method == 2) {                         // lsd_cs
+                    for (int k = 0; k < nb; ++k)
+                        if (cprow[k] == kNone) try_cand(k, 0u);
+                    for (int i = 0; i < wsub; ++i)
+                        for (int j = i + 1; j < wsub; ++j) try_cand(-1, (1u << i) | (1u << j));
+                } else {                                         // lsd_e
+                    for (uint32_t pat = 1; pat < (1u << wsub); ++pat) try_cand(-1, pat);
+                }
+                if (found) {
+                    uint32_t vw[NW];
+                    cand_vec(best_single, best_pat, vw);
+#pragma unroll
+                    for (int s = 0; s < NW; ++s) zw[s] ^= vw[s];
+                    if (lane == 0) {
+                        if (best_single >= 0) commit_col(clist[best_single]);
+                        for (uint32_t x = best_pat; x; x &= x - 1) commit_col(clist[ml[__ffs(x) - 1]]);
+                    }
+                }
+                __syncwarp();
+            }
+        }
         // ---- solution: pivot column i is set iff the reduced syndrome has its pivot row; commit (acc ^= L e, carry = U e)
         __syncwarp();
 #pragma unroll
@@ -687,26 +848,30 @@ __global__ void __launch_bounds__(32) osd_big_kernel(const WinDev w, const Batch
 inline int lsd_nw(const int rows) { return (rows + 1023) / 1024; }
 
 template <typename F>
-inline cudaError_t lsd_dispatch(const WinDev& w, int precision, F&& f) {
+inline cudaError_t lsd_dispatch(const WinDev& w, int precision, bool hi, F&& f) {
     const int nw = lsd_nw(w.rows);
-    if (precision == 32) return nw <= 1 ? f(lsd_kernel<float, 1>) : (nw == 2 ? f(lsd_kernel<float, 2>) : f(lsd_kernel<float, 3>));
-    return nw <= 1 ? f(lsd_kernel<double, 1>) : (nw == 2 ? f(lsd_kernel<double, 2>) : f(lsd_kernel<double, 3>));
+    if (hi) {
+        if (precision == 32) return nw <= 1 ? f(lsd_kernel<float, 1, true>) : (nw == 2 ? f(lsd_kernel<float, 2, true>) : f(lsd_kernel<float, 3, true>));
+        return nw <= 1 ? f(lsd_kernel<double, 1, true>) : (nw == 2 ? f(lsd_kernel<double, 2, true>) : f(lsd_kernel<double, 3, true>));
+    }
+    if (precision == 32) return nw <= 1 ? f(lsd_kernel<float, 1, false>) : (nw == 2 ? f(lsd_kernel<float, 2, false>) : f(lsd_kernel<float, 3, false>));
+    return nw <= 1 ? f(lsd_kernel<double, 1, false>) : (nw == 2 ? f(lsd_kernel<double, 2, false>) : f(lsd_kernel<double, 3, false>));
 }
 
 }  // namespace
 
 size_t lsd_smem_bytes(const WinDev& w) { return lsd_layout(w).total; }
 size_t lsd_slab_bytes(int cols_cap, int max_rows) {
-    return al16(static_cast<size_t>(cols_cap) * 4) + static_cast<size_t>(lsd_opcap(max_rows)) * 128 * lsd_nw(max_rows);
+    return al16(static_cast<size_t>(cols_cap) * kLsdColBytes) + static_cast<size_t>(lsd_opcap(max_rows)) * 128 * lsd_nw(max_rows);
 }
 bool lsd_supported(const WinDev& w) { return w.rows <= 3072 && w.ncols < 65535 && lsd_smem_bytes(w) <= 200 * 1024; }
 
-cudaError_t lsd_configure(const WinDev& w, int precision) {
-    static size_t have_d[kMaxDevices][2][4] = {};
-    size_t& have = have_d[device_slot()][precision == 32 ? 0 : 1][lsd_nw(w.rows) & 3];
+cudaError_t lsd_configure(const WinDev& w, int precision, bool hi) {
+    static size_t have_d[kMaxDevices][2][2][4] = {};
+    size_t& have = have_d[device_slot()][hi ? 1 : 0][precision == 32 ? 0 : 1][lsd_nw(w.rows) & 3];
     const size_t s = lsd_smem_bytes(w);
     if (s > have) {
-        cudaError_t e = lsd_dispatch(w, precision, [&](auto kern) {
+        cudaError_t e = lsd_dispatch(w, precision, hi, [&](auto kern) {
             return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(s));
         });
         if (e != cudaSuccess) return e;
@@ -718,7 +883,7 @@ cudaError_t lsd_configure(const WinDev& w, int precision) {
 cudaError_t launch_lsd(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st) {
     if (b.n_shots == 0) return cudaSuccess;
     const size_t smem = lsd_smem_bytes(w);
-    return lsd_dispatch(w, precision, [&](auto kern) {
+    return lsd_dispatch(w, precision, b.lsd_order > 0, [&](auto kern) {
         kern<<<grid, 32, smem, st>>>(w, b);
         return cudaGetLastError();
     });

@@ -148,6 +148,7 @@ struct BatchDev {
     void* lsd_scratch;        // LSD only: [grid] slabs of lsd_slab bytes (bit owners, column-order links, operation vectors)
     size_t lsd_slab;
     int lsd_cols;             // columns of the widest window (fixes the slab layout)
+    int lsd_method, lsd_order; // beyond order 0: 1 = lsd_e, 2 = lsd_cs candidate sweep inside every cluster
     void* sort_scratch;       // wide windows: [grid] slabs of osd_sort_slab_bytes for the radix sort's keys and index buffers
 };
 
@@ -195,7 +196,7 @@ cudaError_t launch_osd_elim(const WinDev& w, const BatchDev& b, bool hi, int gri
 size_t lsd_smem_bytes(const WinDev& w);
 size_t lsd_slab_bytes(int cols_cap, int max_rows);
 bool lsd_supported(const WinDev& w);
-cudaError_t lsd_configure(const WinDev& w, int precision);
+cudaError_t lsd_configure(const WinDev& w, int precision, bool hi);
 cudaError_t launch_lsd(const WinDev& w, const BatchDev& b, int precision, int grid, cudaStream_t st);
 // OSD-0 for windows taller than the shared-memory elimination takes (768 < checks <= 3072): same slab machinery as LSD
 size_t osd_big_smem_bytes(const WinDev& w);

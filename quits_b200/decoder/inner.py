@@ -82,7 +82,8 @@ class BpOsdDecoder(_GpuInnerDecoder):
 
 def lsd_engine_options(kw: dict) -> dict:
     """ldpc BpLsdDecoder keywords -> engine keywords.  ``lsd_method`` only matters beyond order 0 (the order-0 solve of a
-    cluster is the same for lsd_0 / lsd_cs / lsd_e), and only order 0 runs on the GPU."""
+    cluster is the same for lsd_0 / lsd_cs / lsd_e); beyond it the engine runs the per-cluster candidate sweep that
+    ``oracle/cref.c`` restates (not pinned against ldpc -- DESIGN.md section 2)."""
     kw = dict(kw)
     method = str(kw.pop("lsd_method", "lsd_0")).lower()
     order = int(kw.pop("lsd_order", 0))
@@ -91,19 +92,23 @@ def lsd_engine_options(kw: dict) -> dict:
     if method in ("off", "none"):
         kw["osd_method"] = "off"
         return kw
-    if method.replace("_", "") not in ("lsd0", "lsdcs", "lsde"):
+    short = method.replace("_", "")
+    if short not in ("lsd0", "lsdcs", "lsde"):
         raise ValueError("unknown lsd_method %r" % method)
-    if order != 0 and method.replace("_", "") != "lsd0":
-        raise NotImplementedError("BP-LSD post-processing beyond order 0 (lsd_method=%r, lsd_order=%d) is not implemented on the "
-                                  "GPU path" % (method, order))
-    kw["osd_method"] = "lsd_0"
-    kw["osd_order"] = 0
+    if order < 0:
+        raise ValueError("lsd_order must be >= 0")
+    if order == 0 or short == "lsd0":
+        kw["osd_method"] = "lsd_0"
+        kw["osd_order"] = 0
+    else:
+        kw["osd_method"] = "lsd_cs" if short == "lsdcs" else "lsd_e"
+        kw["osd_order"] = order
     return kw
 
 
 class BpLsdDecoder(_GpuInnerDecoder):
     """ldpc.bplsd_decoder.BpLsdDecoder-shaped (kwargs as in reference decoder/bplsd.py:74-84): BP, then localized statistics
-    decoding of order 0 on the shots BP leaves unconverged (``csrc/lsd.cu``)."""
+    decoding on the shots BP leaves unconverged (``csrc/lsd.cu``; ``lsd_order`` > 0 adds the per-cluster candidate sweep)."""
     _order_key = "osd_order"
     _method_key = "osd_method"
     _default_method = "lsd_0"

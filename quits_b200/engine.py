@@ -19,7 +19,7 @@ from .decoder.base import WindowPlan
 _BP_METHODS = {"minimum_sum": 0, "min_sum": 0, "ms": 0, "msl": 0, "product_sum": 1, "prod_sum": 1, "ps": 1, "psl": 1}
 _SCHEDULES = {"parallel": 0, "p": 0, "serial": 1, "s": 1}
 _OSD_METHODS = {"osd_0": 0, "osd0": 0, "osd_e": 1, "osde": 1, "exhaustive": 1, "osd_cs": 2, "osdcs": 2, "combination_sweep": 2,
-                "lsd_0": 3, "lsd0": 3, "off": -1, "none": -1}
+                "lsd_0": 3, "lsd0": 3, "lsd_e": 4, "lsde": 4, "lsd_cs": 5, "lsdcs": 5, "off": -1, "none": -1}
 
 
 def bp_options(bp_method="minimum_sum", max_iter=0, schedule="parallel", osd_method="osd_0", osd_order=0, ms_scaling_factor=1.0,

@@ -479,8 +479,8 @@ def test_lsd_on_random_matrices(qb, rows, cols, col_w, rate):
 
 
 def test_lsd_sliding_window(qb):
-    """sliding_window_bplsd_circuit_mem (reference decoder/bplsd.py:54-86) equals the oracle's window loop with LSD-0 bit for bit;
-    orders beyond 0 are refused loudly."""
+    """sliding_window_bplsd_circuit_mem (reference decoder/bplsd.py:54-86) equals the oracle's window loop bit for bit, at order 0
+    and beyond."""
     from oracle import cref
     case = "bb72_r6_p3e-3_W5F3"
     g = decode_case(case)
@@ -494,9 +494,72 @@ def test_lsd_sliding_window(qb):
                                precision="f64", osd_method="lsd_0")
     assert pred.dtype == np.int64 and np.array_equal(pred, opred.astype(np.int64))
     assert st[:, 2].sum() > 0
-    with pytest.raises(NotImplementedError):
-        qb.sliding_window_bplsd_circuit_mem(g["det"][:4], circ, hz, lz, g["W"], g["F"], max_iter=3, lsd_order=2, bp_method="minimum_sum",
-                                            schedule="parallel", lsd_method="lsd_cs")
+    # beyond order 0 (the reference's LSD test and doc/05 ask for lsd_order=1): the per-cluster candidate sweep, against the oracle
+    for method, order in (("lsd_cs", 1), ("lsd_cs", 3), ("lsd_e", 2)):
+        pred = qb.sliding_window_bplsd_circuit_mem(g["det"], circ, hz, lz, g["W"], g["F"], max_iter=3, lsd_order=order, bp_method="minimum_sum",
+                                                   schedule="parallel", lsd_method=method)
+        opred, st = cref.sw_decode(wins, g["m"], g["K"], g["det"].astype(np.uint8), max_iter=3, bp_method="minimum_sum", schedule="parallel",
+                                   precision="f64", osd_method=method, osd_order=order)
+        assert np.array_equal(pred, opred.astype(np.int64)), (method, order)
+    dflt = qb.sliding_window_bplsd_circuit_mem(g["det"][:64], circ, hz, lz, g["W"], g["F"], max_iter=10, lsd_order=1)     # product_sum, serial, lsd_cs
+    oprd, _ = cref.sw_decode(wins, g["m"], g["K"], g["det"][:64].astype(np.uint8), max_iter=10, bp_method="product_sum", schedule="serial",
+                             precision="f64", osd_method="lsd_cs", osd_order=1)
+    assert int(np.any(dflt != oprd.astype(np.int64), axis=1).sum()) <= 1          # product-sum: libm vs CUDA tanh/log
+
+
+@pytest.mark.parametrize("method,order", [("lsd_cs", 1), ("lsd_cs", 5), ("lsd_e", 3), ("lsd_e", 12)])
+@pytest.mark.parametrize("case,window,max_iter", [("bb72_r6_p3e-3_W5F3", 0, 3), ("bb144_r10_p3e-3_W5F3", 1, 2), ("hgp225_r3_p1e-2_W3F2", 0, 2)])
+def test_lsd_higher_order_matches_oracle_per_shot(qb, case, window, max_iter, method, order):
+    """BpLsdDecoder with lsd_order > 0: the GPU's per-cluster candidate sweep returns the oracle's error estimate bit for bit (same
+    candidates in the same order, weights added in column-list order), satisfies the syndrome and is never heavier than LSD-0's."""
+    from oracle import cref
+    g = decode_case(case)
+    w = _oracle_windows(case_circuit(case), g["m"], g["W"], g["F"])[window]
+    H, pri = w["H"], w["priors"]
+    n = min(g["shots"], 96)
+    syn = g["det"][:n, w["row0"]:w["row0"] + H.shape[0]].astype(np.uint8)
+    kw = dict(max_iter=max_iter, bp_method="minimum_sum", schedule="parallel")
+    ehat, llr, iters, conv = qb.BpLsdDecoder(H, channel_probs=pri, lsd_method=method, lsd_order=order, **kw).decode_batch(syn)
+    ehat0 = qb.BpLsdDecoder(H, channel_probs=pri, lsd_order=0, **kw).decode_batch(syn)[0]
+    orc = cref.BpOsd(H, pri, osd_method=method, osd_order=order, **kw)
+    Hd = H.toarray()
+    wt = np.log(1.0 / pri)
+    n_lsd = n_diff = 0
+    for i in range(n):
+        e, l, it, c = orc.decode(syn[i])
+        assert bool(conv[i]) == c and int(iters[i]) == it
+        assert np.array_equal(ehat[i], e), (i, c, int(ehat[i].sum()), int(e.sum()))
+        assert np.array_equal(Hd @ ehat[i] % 2, Hd @ ehat0[i] % 2)
+        assert wt[ehat[i].astype(bool)].sum() <= wt[ehat0[i].astype(bool)].sum() + 1e-9
+        n_lsd += orc.used_osd
+        n_diff += not np.array_equal(ehat[i], ehat0[i])
+    assert n_lsd >= 3
+
+
+@pytest.mark.parametrize("rows,cols,col_w,rate", [(24, 60, 3, 0.08), (60, 150, 8, 0.03), (700, 2600, 6, 0.02), (30, 90, 3, 0.3), (1200, 3000, 4, 0.03)])
+def test_lsd_higher_order_on_random_matrices(qb, rows, cols, col_w, rate):
+    """Dense merging, few distinct priors (weight ties between candidates everywhere), clusters with many non-pivot columns, and a
+    matrix with more than 1024 checks (two vector words per lane)."""
+    from oracle import cref
+    rng = np.random.RandomState(rows + 7 * col_w)
+    H = _random_ldpc(rng, rows, cols, col_w)
+    pri = rng.choice([0.01, 0.02, 0.03], size=cols)
+    n = 48
+    err = (rng.rand(n, cols) < rate).astype(np.uint8)
+    syn = (err @ H.T.toarray() % 2).astype(np.uint8)
+    kw = dict(max_iter=2, bp_method="minimum_sum", schedule="parallel", ms_scaling_factor=0.75)
+    Hd = H.toarray()
+    for method, order in (("lsd_cs", 2), ("lsd_e", 4)):
+        ehat, llr, iters, conv = qb.BpLsdDecoder(H, channel_probs=pri, lsd_method=method, lsd_order=order, **kw).decode_batch(syn)
+        orc = cref.BpOsd(H, pri, osd_method=method, osd_order=order, **kw)
+        n_lsd = 0
+        for i in range(n):
+            e, l, it, c = orc.decode(syn[i])
+            assert bool(conv[i]) == c
+            assert np.array_equal(ehat[i], e), (method, i, c, int(ehat[i].sum()), int(e.sum()))
+            assert np.array_equal(Hd @ ehat[i] % 2, syn[i])
+            n_lsd += orc.used_osd
+        assert n_lsd >= 8
 
 
 def test_lsd_edge_cases(qb):

@@ -301,7 +301,7 @@ def test_phenom_argument_errors():
 
 def test_lsd_option_mapping():
     """BpLsdDecoder keywords (reference decoder/bplsd.py:38-49,74-83): order 0 maps onto the engine's lsd_0 whatever lsd_method says;
-    higher orders are refused loudly (no CPU fallback)."""
+    beyond order 0 lsd_cs / lsd_e select the per-cluster candidate sweep with lsd_order as its order."""
     from quits_b200.decoder.inner import lsd_engine_options
     from quits_b200.engine import bp_options
     kw = lsd_engine_options({"bp_method": "product_sum", "max_iter": 2, "schedule": "serial", "lsd_method": "lsd_cs", "lsd_order": 0})
@@ -309,10 +309,18 @@ def test_lsd_option_mapping():
     o = bp_options(**kw)
     assert (o.osd_method, o.osd_order, o.bp_method, o.schedule) == (3, 0, 1, 1)
     assert lsd_engine_options({"lsd_method": "off"})["osd_method"] == "off"
-    with pytest.raises(NotImplementedError):
-        lsd_engine_options({"lsd_method": "lsd_cs", "lsd_order": 1})
+    o = bp_options(**lsd_engine_options({"lsd_method": "lsd_cs", "lsd_order": 1}))          # the reference's own LSD test: order 1
+    assert (o.osd_method, o.osd_order) == (5, 1)
+    o = bp_options(**lsd_engine_options({"lsd_method": "lsd_e", "lsd_order": 3}))
+    assert (o.osd_method, o.osd_order) == (4, 3)
+    o = bp_options(**lsd_engine_options({"lsd_method": "lsd_0", "lsd_order": 7}))            # lsd_0 is order 0 whatever lsd_order says
+    assert (o.osd_method, o.osd_order) == (3, 0)
     with pytest.raises(ValueError):
         lsd_engine_options({"lsd_method": "osd_cs"})
+    with pytest.raises(ValueError):
+        lsd_engine_options({"lsd_method": "lsd_cs", "lsd_order": -1})
+    with pytest.raises(NotImplementedError):
+        lsd_engine_options({"lsd_method": "lsd_cs", "lsd_order": 1, "bits_per_step": 2})
 
 
 def test_drop_in_signatures_equal_the_reference():

@@ -181,7 +181,7 @@ def _gf2_greedy_solve(A, s):
             z ^= bv; x ^= bc
     return (not z.any()), sorted(x)
 
-def _lsd0_literal(H, syn, llr):
+def _lsd0_literal(H, syn, llr, clusters_out=None):
     m, n = H.shape
     rows = [np.flatnonzero(H[i]) for i in range(m)]
     cols = [np.flatnonzero(H[:, j]) for j in range(n)]
@@ -233,6 +233,79 @@ def _lsd0_literal(H, syn, llr):
     for k in cl:
         if cl[k]['active']:
             for j in validate(cl[k])[1]: e[j] = 1
+            if clusters_out is not None:
+                clusters_out.append((list(cl[k]['bits']), list(cl[k]['checks'])))
+    return e
+
+
+def _gf2_solve_unique(A, t):
+    """x with A x = t for A of full column rank and t in its image (plain Gauss-Jordan; the answer does not depend on pivoting)."""
+    A = A.copy().astype(np.uint8); t = t.copy().astype(np.uint8)
+    r, c = A.shape
+    where = []
+    row = 0
+    for j in range(c):
+        nz = [i for i in range(row, r) if A[i, j]]
+        assert nz, "dependent column"
+        i = nz[0]
+        A[[row, i]] = A[[i, row]]; t[[row, i]] = t[[i, row]]
+        for k in range(r):
+            if k != row and A[k, j]:
+                A[k] ^= A[row]; t[k] ^= t[row]
+        where.append(row); row += 1
+    assert not t[row:].any(), "outside the image"
+    return np.array([t[w] for w in where], dtype=np.uint8)
+
+
+def _lsdw_literal(H, syn, llr, priors, method, order):
+    """LSD beyond order 0 as oracle/cref.c lsd_cluster_higher states it, written per cluster from scratch: local matrix, greedy
+    first-independent pivots in column-list order, every candidate solved by a plain elimination, weights summed in list order."""
+    import math
+    clusters = []
+    e = _lsd0_literal(H, syn, llr, clusters)
+    for bits, checks in clusters:
+        if not bits:
+            continue
+        A = H[np.ix_(checks, bits)].astype(np.uint8)
+        s = syn[checks].astype(np.uint8)
+        piv = []                                     # greedy first independent columns
+        basis = []
+        for k in range(len(bits)):
+            v = A[:, k].copy()
+            for bv, pr in basis:
+                if v[pr]:
+                    v ^= bv
+            nz = np.flatnonzero(v)
+            if nz.size:
+                basis.append((v, int(nz[0]))); piv.append(k)
+        nonpiv = [k for k in range(len(bits)) if k not in piv]
+        wt = [math.log(1.0 / priors[j]) for j in bits]
+
+        def solution(F):
+            t = s.copy()
+            for k in F:
+                t ^= A[:, k]
+            x = np.zeros(len(bits), np.uint8)
+            x[piv] = _gf2_solve_unique(A[:, piv], t)
+            for k in F:
+                x[k] = 1
+            w = 0.0
+            for k in range(len(bits)):
+                if x[k]:
+                    w += wt[k]
+            return w, x
+        best_w, best_x = solution([])
+        w = min(order, len(nonpiv))
+        if method == "lsd_cs":
+            cands = [[k] for k in nonpiv] + [[nonpiv[i], nonpiv[j]] for i in range(w) for j in range(i + 1, w)]
+        else:
+            cands = [[nonpiv[b] for b in range(w) if (pat >> b) & 1] for pat in range(1, 1 << w)]
+        for F in cands:
+            cw, cx = solution(F)
+            if cw < best_w:
+                best_w, best_x = cw, cx
+        for k, j in enumerate(bits):
+            e[j] = best_x[k]
     return e
 
 
@@ -256,6 +329,37 @@ def test_lsd0_equals_the_literal_restatement():
                 n_lsd += 1
                 assert np.array_equal(_lsd0_literal(H, syn, llr), e)
     assert n_lsd > 200
+
+
+@pytest.mark.parametrize("method,order", [("lsd_cs", 1), ("lsd_cs", 4), ("lsd_e", 3)])
+def test_lsd_higher_order_equals_the_literal_per_cluster_restatement(method, order):
+    """lsd_order > 0 (the reference's phenomenological LSD test asks for order 1, tests/test_decoders.py:124-159): the C
+    oracle's incremental version against the literal per-cluster one.  PARITY UNPINNED against ldpc (oracle/cref.c header)."""
+    rng = np.random.default_rng(11)
+    n_lsd = n_better = 0
+    for trial in range(90):
+        m = int(rng.integers(4, 30)); n = int(rng.integers(m, 3 * m + 5))
+        H = (rng.random((m, n)) < min(0.5, 3.0 / m)).astype(np.uint8)
+        for j in range(n):
+            if not H[:, j].any():
+                H[rng.integers(m), j] = 1
+        p = rng.choice([0.02, 0.05, 0.11], n) if trial % 2 else rng.uniform(0.01, 0.2, n)      # few distinct priors: ties everywhere
+        kw = dict(max_iter=int(rng.integers(1, 4)), bp_method="minimum_sum")
+        dec = cref.BpOsd(sp.csc_matrix(H), p, osd_method=method, osd_order=order, **kw)
+        dec0 = cref.BpOsd(sp.csc_matrix(H), p, osd_method="lsd_0", **kw)
+        for t in range(4):
+            err = (rng.random(n) < 0.15).astype(np.uint8)
+            syn = (H @ err % 2).astype(np.uint8)
+            e, llr, it, conv = dec.decode(syn)
+            assert np.array_equal(H @ e % 2, syn)
+            if not conv:
+                n_lsd += 1
+                assert np.array_equal(_lsdw_literal(H, syn, llr, p, method, order), e)
+                e0 = dec0.decode(syn)[0]
+                w = lambda x: float(np.log(1.0 / p[x.astype(bool)]).sum())
+                assert w(e) <= w(e0) + 1e-9
+                n_better += not np.array_equal(e, e0)
+    assert n_lsd > 150 and n_better > 5
 
 
 def test_lsd0_on_a_decoding_window():

@@ -7,7 +7,8 @@ behind the ``ldpc.bplsd_decoder.BpLsdDecoder`` shim.  Build container only (need
 
 Writes tests/golden/decode_lsd/<case>.npz = {pred_f32, pred_f64, max_iter}; the inputs are tests/golden/decode/<case>.npz.
 The same for the phenomenological twin ``sliding_window_bplsd_phenom_mem`` (decoder/bplsd.py:10-51) on the inputs of
-tests/golden/phenom/<case>.npz -> tests/golden/phenom_lsd/<case>.npz.
+tests/golden/phenom/<case>.npz -> tests/golden/phenom_lsd/<case>.npz.  Each file also carries ``pred_f64_cs1``: the same call with
+``lsd_order=1`` (what the reference's own LSD test and doc/05 ask for), over the oracle's per-cluster candidate sweep.
 """
 import os
 import sys
@@ -51,11 +52,16 @@ def main():
                 preds[prec] = sliding_window_bplsd_circuit_mem(g["det"], circ, hz, lz, g["W"], g["F"], max_iter=max_iter, lsd_order=0,
                                                                bp_method="minimum_sum", schedule="parallel", lsd_method="lsd_cs")
         shims.DEFAULT_PRECISION = "f64"
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            cs1 = sliding_window_bplsd_circuit_mem(g["det"], circ, hz, lz, g["W"], g["F"], max_iter=max_iter, lsd_order=1,
+                                                   bp_method="minimum_sum", schedule="parallel", lsd_method="lsd_cs")
         pl = {k: float(np.mean(np.any((g["obs"].astype(int) - v) % 2, axis=1))) for k, v in preds.items()}
         np.savez_compressed(os.path.join(G, "decode_lsd", case + ".npz"), max_iter=np.int64(max_iter),
-                            pred_f32=preds["f32"].astype(np.uint8), pred_f64=preds["f64"].astype(np.uint8))
-        print("%-30s shots %d  pL(f32) %.4f  pL(f64) %.4f  (BP-OSD-0 fixture: %.4f)" % (
-            case, g["shots"], pl["f32"], pl["f64"], float(np.mean(np.any((g["obs"].astype(int) - g["pred_f64"]) % 2, axis=1)))))
+                            pred_f32=preds["f32"].astype(np.uint8), pred_f64=preds["f64"].astype(np.uint8), pred_f64_cs1=cs1.astype(np.uint8))
+        print("%-30s shots %d  pL(f32) %.4f  pL(f64) %.4f  (BP-OSD-0 fixture: %.4f)  lsd_cs 1: pL %.4f, differs from LSD-0 on %d shots" % (
+            case, g["shots"], pl["f32"], pl["f64"], float(np.mean(np.any((g["obs"].astype(int) - g["pred_f64"]) % 2, axis=1))),
+            float(np.mean(np.any((g["obs"].astype(int) - cs1) % 2, axis=1))), int(np.any(cs1 != preds["f64"], axis=1).sum())))
     os.makedirs(os.path.join(G, "phenom_lsd"), exist_ok=True)
     for case, max_iter in PHENOM_CASES:
         z = np.load(os.path.join(G, "phenom", case + ".npz"))
@@ -70,8 +76,12 @@ def main():
                 preds[prec] = sliding_window_bplsd_phenom_mem(det, hz, lz, int(z["W"]), int(z["F"]), float(z["error_rate"]), max_iter=max_iter,
                                                               lsd_order=0, bp_method="minimum_sum", schedule="parallel", lsd_method="lsd_cs")
         shims.DEFAULT_PRECISION = "f64"
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            cs1 = sliding_window_bplsd_phenom_mem(det, hz, lz, int(z["W"]), int(z["F"]), float(z["error_rate"]), max_iter=max_iter,
+                                                  lsd_order=1, bp_method="minimum_sum", schedule="parallel", lsd_method="lsd_cs")
         np.savez_compressed(os.path.join(G, "phenom_lsd", case + ".npz"), max_iter=np.int64(max_iter),
-                            pred_f32=preds["f32"].astype(np.uint8), pred_f64=preds["f64"].astype(np.uint8))
+                            pred_f32=preds["f32"].astype(np.uint8), pred_f64=preds["f64"].astype(np.uint8), pred_f64_cs1=cs1.astype(np.uint8))
         print("phenom %-30s shots %d  differs from the BP-OSD-0 fixture on %d shots" % (
             case, det.shape[0], int(np.any(preds["f64"] != z["pred_f64"], axis=1).sum())))
 

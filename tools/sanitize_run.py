@@ -39,6 +39,9 @@ def main():
     for prec in ("f64", "f32"):                          # BP-LSD (lsd_kernel), few BP iterations so that LSD has work
         dec = qb.SlidingWindowDecoder(c, hz.shape[0], 5, 3, precision=prec, **dict(base, osd_method="lsd_0", max_iter=3))
         print("lsd_0", prec, "logical errors", int(np.any((obs - dec.decode(det)) % 2, axis=1).sum()), flush=True)
+        for m_, o_ in (("lsd_cs", 2), ("lsd_e", 3)):     # per-cluster candidate sweep (lsd_kernel<.., HI>)
+            dec = qb.SlidingWindowDecoder(c, hz.shape[0], 5, 3, precision=prec, **dict(base, osd_method=m_, osd_order=o_, max_iter=3))
+            print(m_, o_, prec, "logical errors", int(np.any((obs - dec.decode(det)) % 2, axis=1).sum()), flush=True)
     mc = qb.MonteCarlo(c, hz.shape[0], 5, 3, capacity=192, **base)
     print("fused", mc.run(n(500), 9)[0][0], flush=True)
     c3 = circuit("bb144_r10_p3e-3")                      # OSD-heavy: second tier and overflow route
@@ -51,7 +54,9 @@ def main():
     from scipy.sparse import csc_matrix
     rng = np.random.RandomState(2)                       # dense LSD merging on a tiny matrix (operation array compaction), and a
     for rows, cols, rate, cls, kwx in ((30, 90, 0.3, qb.BpLsdDecoder, dict(lsd_order=0)),            # tall matrix: LSD / OSD slab kernels
+                                       (30, 90, 0.3, qb.BpLsdDecoder, dict(lsd_method="lsd_cs", lsd_order=2)),
                                        (1100, 2600, 0.02, qb.BpLsdDecoder, dict(lsd_order=0)),
+                                       (1100, 2600, 0.02, qb.BpLsdDecoder, dict(lsd_method="lsd_e", lsd_order=2)),
                                        (1100, 2600, 0.02, qb.BpOsdDecoder, dict(osd_method="osd_0")),
                                        (1100, 2600, 0.004, qb.BpOsdDecoder, dict(osd_method="off", schedule="serial"))):
         indptr, indices = [0], []
