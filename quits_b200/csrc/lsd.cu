@@ -1,4 +1,5 @@
-// quits_b200/csrc/lsd.cu -- K4L: localized statistics decoding, order 0: the post-processing stage of ldpc's BpLsdDecoder
+// quits_b200/csrc/lsd.cu -- K4L: localized statistics decoding (order 0, and the per-cluster lsd_cs / lsd_e candidate sweep beyond it):
+// the post-processing stage of ldpc's BpLsdDecoder
 // (reference src/quits/decoder/bplsd.py:38-50,74-86 constructs it; sliding_window.py:171,182 calls decode()).  sm_100a.
 //
 // The algorithm is the one oracle/cref.c lsd_decode restates (Hillmann et al., "Localized statistics decoding"):
