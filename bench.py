@@ -224,11 +224,39 @@ def roofline(precision, agg, clocks, peaks):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU, sampled while the timed region runs: through NVML every 10 ms when pynvml is
+    importable (a 0.6 s region gives ~50 samples), else through nvidia-smi (the profiling recipe's clocks line; ~5 samples / s)."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x.strip() for x in vis.split(",") if x.strip()]
+        if ids and all(x.isdigit() for x in ids) and index < len(ids):
+            index = int(ids[index])                   # NVML / nvidia-smi count physical devices
+        self.index, self.rows, self._halt, self.source = index, [], threading.Event(), "nvidia-smi"
+
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+        nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)          # fails here, before the first sample, if NVML cannot serve this GPU
+        self.source = "nvml"
+        while not self._halt.is_set():
+            r = int(get_reasons(h))
+            self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
+            self._halt.wait(0.01)
 
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            self.source = "nvidia-smi"
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self._halt.is_set():
@@ -246,10 +274,9 @@ class ClockSampler(threading.Thread):
         self.join(timeout=5)
         sm = [int(r[0]) for r in self.rows if r[0].isdigit()]
         mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        reasons = sorted({n for r in self.rows for n, v in zip(self.NAMES, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------ main

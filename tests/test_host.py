@@ -538,3 +538,44 @@ def test_count_logical_errors_equals_the_reference_idiom():
         assert qb.count_logical_errors(obs.astype(np.int64), pred.astype(np.bool_) if n == 0 else pred, threads=3) == want
     with pytest.raises(ValueError):
         qb.count_logical_errors(np.zeros((3, 2), bool), np.zeros((3, 3), np.int64))
+
+
+def _load_bench():
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("qb_bench_module", os.path.join(root, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_bench_roofline_object_follows_the_committed_instruction_model():
+    """bench.py's roofline: `achieved` = warp-instructions per edge-iteration (profiles/bp_inst_model.json, an ncu count) x the
+    edge-iterations of the run / BP event time, against 148 x 4 x SM clock; the model is used only for the workload and decoder
+    setting it was captured on, and the SURVEY 8(d) HBM figure stays beside it as hbm_model."""
+    b = _load_bench()
+    agg = {"bp_ms": 102.2 * 5, "bp_launches": 80, "bp_alg_bytes": 1.0e12, "bp_edge_iters": 2.69e11}
+    clocks = {"sm_mhz": 1965}
+    r = b.roofline("f64", agg, clocks, {"hbm_gbs": 6538.6})
+    m = json.load(open(os.path.join(os.path.dirname(b.__file__), "profiles", "bp_inst_model.json")))["f64_minimum_sum_parallel"]
+    assert r["bound"] == "issue" and r["kernel"] == "bp_kernel_ms2"
+    assert abs(r["peak"] - 148 * 4 * 1.965) < 1e-6
+    want = m["warp_inst_per_edge_iter"] * agg["bp_edge_iters"] / (agg["bp_ms"] / 1e3) / 1e9
+    assert abs(r["achieved"] - want) < 1e-6 * want and abs(r["frac"] - want / r["peak"]) < 1e-9 and 0 < r["frac"] < 1
+    assert r["hbm_model"]["bound"] == "hbm" and r["smem"]["frac"] < 1
+    # another workload, or a decoder setting without a capture: no instruction model, no issue fraction
+    b.WORKLOAD = "qlp1020_zxcol_r20_p5e-4"
+    r = b.roofline("f64", agg, clocks, {"hbm_gbs": 6538.6})
+    assert r["frac"] is None and r["achieved"] is None and "note" in r and r["traffic"] is None
+    b.WORKLOAD = b.HEADLINE_WORKLOAD
+    b.BP_KW["schedule"] = "serial"
+    r = b.roofline("f64", agg, clocks, {"hbm_gbs": 6538.6})
+    assert r["kernel"] == "bp_kernel_serial_slab" and r["frac"] is None
+
+
+def test_bench_clock_sampler_degrades_without_a_gpu():
+    b = _load_bench()
+    s = b.ClockSampler(0)
+    s.start()
+    out = s.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples", "source"} and out["reasons"] == []
