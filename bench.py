@@ -198,7 +198,7 @@ def roofline(precision, agg, clocks, peaks):
            "peak_source": "148 SMs x 4 schedulers x %.0f MHz (SM clock sampled during the timed region)" % sm_mhz,
            "achieved": None, "frac": None, "edge_iters_per_s": ei / bp_s if bp_s > 0 else 0.0,
            "ms_per_launch": agg["bp_ms"] / bp_launches,
-           "traffic": ncu_traffic(precision) if (m and BP_KW["schedule"] == "parallel") else None,
+           "traffic": None,
            "alg_io_bytes_per_launch": io_bytes / bp_launches,
            "hbm_model": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "model_frac": hbm_ach / hbm_peak,
                          "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650",
@@ -206,6 +206,11 @@ def roofline(precision, agg, clocks, peaks):
                          "note": "SURVEY 8(d) message-streaming model (iterations x 4 x nnz x sizeof(msg) + syndrome in + commit/carry out). "
                                  "The messages are shared-memory resident: model_frac > 1 is not an HBM figure, `traffic` is the DRAM bytes "
                                  "one launch really moves (ncu)"}}
+    if m and BP_KW["schedule"] == "parallel":
+        # the committed capture ran 65 536 shots per BP launch; the posterior rows and syndromes a launch moves scale with its shots
+        t, spl = ncu_traffic(precision), agg.get("windows", 0) / bp_launches
+        out["traffic"] = t * spl / 65536.0 if (t and spl) else t
+        out["traffic_note"] = "dram__bytes_read + write of a 65 536-shot BP launch (ncu --set full, profiles/) x shots per launch of this run / 65 536"
     if m and bp_s > 0:
         inst = m["warp_inst_per_edge_iter"] * ei
         out["achieved"] = inst / bp_s / 1e9
@@ -295,6 +300,7 @@ def main():
     ap.add_argument("--osd-method", default=None, help="secondary points: osd_0 (headline) | osd_cs | osd_e")
     ap.add_argument("--osd-order", type=int, default=None)
     ap.add_argument("--lanes", type=int, default=0, help="concurrent sub-batches per device batch (0 = engine default)")
+    ap.add_argument("--capacity", type=int, default=0, help="shots per device batch of the decoder (0 = engine default, 262144)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--rate", type=float, default=None, help="noise rate substituted for the fixture's (threshold sweeps)")
@@ -352,7 +358,7 @@ def main():
     qb.set_devices(None if args.fanout else [local])
     ctx = qb.Context.default(local)
     circuit = qb.Circuit(text)
-    mc = qb.MonteCarlo(circuit, hz.shape[0], W, F, ctx=ctx, precision=args.precision, profile=True, lanes=args.lanes, **BP_KW)
+    mc = qb.MonteCarlo(circuit, hz.shape[0], W, F, ctx=ctx, precision=args.precision, profile=True, lanes=args.lanes, capacity=args.capacity, **BP_KW)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     S = args.shots
 

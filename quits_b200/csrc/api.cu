@@ -684,11 +684,13 @@ void finish_decoder(qb_sw* sw) {
     for (int it = 1; it <= max_iter; ++it) alpha[it] = o.ms_scaling_factor == 0.0 ? 1.0 - std::pow(2.0, -1.0 * it) : o.ms_scaling_factor;
     upload(sw->alpha, alpha, ctx->stream);
     // batches start on 64-shot word boundaries (the sampler numbers shots by word): capacity is rounded down to a multiple of 64
-    sw->cap = o.capacity > 0 ? std::max(64, o.capacity / 64 * 64) : 65536;
+    static const int env_cap = [] { const char* e = getenv("QB_CAPACITY"); return e ? atoi(e) : 0; }();      // tuning knob
+    const int want_cap = o.capacity > 0 ? o.capacity : (env_cap > 0 ? env_cap : 262144);
+    sw->cap = std::max(64, want_cap / 64 * 64);
     {
-        // the posterior scratch is capacity x widest window: keep it under 4 GiB for very wide windows
+        // the posterior scratch is capacity x widest window: keep it under 8 GiB for very wide windows
         const size_t per_shot = static_cast<size_t>(max_npad) * (prec / 8);
-        const size_t fit = (size_t(4) << 30) / std::max<size_t>(per_shot, 1);
+        const size_t fit = (size_t(8) << 30) / std::max<size_t>(per_shot, 1);
         if (static_cast<size_t>(sw->cap) > fit) sw->cap = static_cast<int>(std::max<size_t>(64, fit / 64 * 64));
     }
     // LSD: a few shots grow clusters of hundreds of bits and keep one warp busy for milliseconds after the rest of the launch has
@@ -1413,25 +1415,32 @@ int qb_sw_decode(qb_sw* sw, const uint8_t* det, uint64_t n, int64_t* pred, qb_st
         // the host-to-device copy of batch k+1 runs on the copy stream while batch k is decoded (two staging buffers; the stream
         // is synchronised at the end of every batch, so a buffer is free again two batches later)
         cudaStream_t cs = ctx->copy_stream();
-        const size_t cap = static_cast<size_t>(std::min<uint64_t>(sw->cap, n));
-        sw->det_bytes.ensure(cap * D + 16);
-        if (n > static_cast<uint64_t>(sw->cap)) sw->det_bytes_alt.ensure(cap * D + 16);
-        auto stage = [&](uint64_t first, int which) {
-            const size_t nb = static_cast<size_t>(std::min<uint64_t>(sw->cap, n - first));
-            DevBuf& buf = which ? sw->det_bytes_alt : sw->det_bytes;
-            CK(cudaMemcpyAsync(buf.p, det + first * D, nb * D, cudaMemcpyHostToDevice, cs));
-            CK(cudaEventRecord(ctx->ev_ready[which], cs));
+        // batches: a short first one, so that decoding starts after a small copy and the rest of the input arrives underneath it,
+        // then full device batches (the fewer the batches, the fewer post-processing launches with a handful of warps each)
+        const uint64_t cap = static_cast<uint64_t>(sw->cap);
+        std::vector<uint64_t> cut(1, 0);
+        if (n > 32768) cut.push_back(std::min<uint64_t>(cap, std::max<uint64_t>(16384, n / 8 / 64 * 64)));
+        while (cut.back() < n) cut.push_back(std::min<uint64_t>(n, cut.back() + cap));
+        const size_t nbat = cut.size() - 1;
+        size_t big = 0;
+        for (size_t k = 0; k < nbat; ++k) big = std::max<size_t>(big, static_cast<size_t>(cut[k + 1] - cut[k]));
+        sw->det_bytes.ensure(big * D + 16);
+        if (nbat > 1) sw->det_bytes_alt.ensure(big * D + 16);
+        auto stage = [&](size_t k) {
+            DevBuf& buf = (k & 1) ? sw->det_bytes_alt : sw->det_bytes;
+            CK(cudaMemcpyAsync(buf.p, det + cut[k] * D, static_cast<size_t>(cut[k + 1] - cut[k]) * D, cudaMemcpyHostToDevice, cs));
+            CK(cudaEventRecord(ctx->ev_ready[k & 1], cs));
         };
-        if (n) stage(0, 0);
-        int kb = 0;
-        for (uint64_t done = 0; done < n; done += static_cast<uint64_t>(sw->cap), ++kb) {
-            const int nb = static_cast<int>(std::min<uint64_t>(sw->cap, n - done));
-            const int which = kb & 1;
+        if (nbat) stage(0);
+        for (size_t k = 0; k < nbat; ++k) {
+            const uint64_t done = cut[k];
+            const int nb = static_cast<int>(cut[k + 1] - cut[k]);
+            const int which = static_cast<int>(k & 1);
             sw->det_rows.ensure(static_cast<size_t>(nb) * sw->DW * 8 + 16);
             sw->pred.ensure(static_cast<size_t>(nb) * std::max(K, 1) * 8 + 16);
             CK(cudaStreamWaitEvent(st, ctx->ev_ready[which], 0));
             CK(qb::launch_pack_bits((which ? sw->det_bytes_alt : sw->det_bytes).as<uint8_t>(), D, nb, sw->det_rows.as<uint64_t>(), sw->DW, st));
-            if (done + static_cast<uint64_t>(sw->cap) < n) stage(done + static_cast<uint64_t>(sw->cap), which ^ 1);
+            if (k + 1 < nbat) stage(k + 1);
             decode_batch(sw, sw->det_rows.as<uint64_t>(), nb, false, false, stats);
             CK(qb::launch_expand_pred(sw->acc.as<uint64_t>(), sw->KW, K, nb, sw->pred.as<int64_t>(), st));
             if (K) CK(cudaMemcpyAsync(pred + done * K, sw->pred.p, static_cast<size_t>(nb) * K * 8, cudaMemcpyDeviceToHost, st));

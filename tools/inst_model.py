@@ -41,8 +41,8 @@ def main():
     model[key] = {"warp_inst_per_edge_iter": tot["smsp__inst_executed.sum"] / ei,
                   "smem_wavefronts_per_edge_iter": tot.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", 0.0) / ei,
                   "launches": len(launches), "edge_iters": ei, "warp_inst": tot["smsp__inst_executed.sum"],
-                  "source": "ncu smsp__inst_executed.sum over the %d BP launches of one 65536-shot batch (%s), %s" % (
-                      len(launches), os.path.basename(csv_path), line["config"]["workload"])}
+                  "source": "ncu smsp__inst_executed.sum over the %d BP launches of one %d-shot step (%s), %s" % (
+                      len(launches), int(line["config"].get("shots_per_step_per_gpu", 0)), os.path.basename(csv_path), line["config"]["workload"])}
     json.dump(model, open(out_path, "w"), indent=1, sort_keys=True)
     print(json.dumps(model[key], indent=1))
 
