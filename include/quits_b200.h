@@ -35,6 +35,9 @@ typedef struct qb_sw qb_sw;
 
 const char* qb_last_error(void);
 int qb_version(void);
+/* "quits_b200 abi=.. arch=sm_100a nvcc=X.Y.Z fmad=off lineinfo=on src=<hash>": how this library was built; <hash> is the sha256
+ * prefix of the sources it was compiled from (quits_b200/build.py source_hash()), so a loaded .so can be matched to a source tree. */
+const char* qb_build_info(void);
 /* number of CUDA devices visible (0 without a GPU; never fails) */
 int qb_device_count(void);
 

@@ -39,7 +39,7 @@ class QbCircuitInfo(C.Structure):
 
 
 # every symbol include/quits_b200.h declares (tests check the library exports all of them)
-SYMBOLS = ["qb_last_error", "qb_version", "qb_device_count", "qb_host_alloc", "qb_host_free", "qb_ctx_create", "qb_ctx_destroy", "qb_ctx_synchronize",
+SYMBOLS = ["qb_last_error", "qb_version", "qb_build_info", "qb_device_count", "qb_host_alloc", "qb_host_free", "qb_ctx_create", "qb_ctx_destroy", "qb_ctx_synchronize",
            "qb_circuit_parse", "qb_circuit_free", "qb_circuit_get_info", "qb_circuit_flat", "qb_sample", "qb_sample_packed",
            "qb_sample_faults", "qb_dem_from_circuit", "qb_dem_free", "qb_dem_sizes", "qb_dem_errors", "qb_dem_matrix",
            "qb_dem_from_errors", "qb_plan_create", "qb_plan_create_explicit", "qb_plan_free", "qb_plan_info", "qb_plan_window", "qb_plan_layout",
@@ -74,9 +74,14 @@ def lib():
             "quits_b200: %s is missing. Build it with `python -m quits_b200.build` (needs nvcc); "
             "there is no CPU fallback." % SO_PATH)
     L = C.CDLL(SO_PATH)
+    stale = [name for name in SYMBOLS if not hasattr(L, name)]
+    if stale:
+        raise ImportError("quits_b200: %s does not export %s -- it was built from older sources. Rebuild it with "
+                          "`python -m quits_b200.build`; there is no CPU fallback." % (SO_PATH, ", ".join(stale)))
     vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
     L.qb_last_error.restype = C.c_char_p
     L.qb_version.restype = C.c_int
+    L.qb_build_info.restype = C.c_char_p
     L.qb_device_count.restype = C.c_int
     L.qb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.qb_host_free.argtypes = [vp]

@@ -28,6 +28,18 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: the quits_b200 engine cannot be built")
 
 
+def source_hash() -> str:
+    """sha256 over the CUDA / C++ sources and headers the library is built from (in build order): compiled into the library
+    (`qb_build_info()`), so a test can tell whether the `.so` that was loaded belongs to the source tree next to it."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in [os.path.join(CSRC, s) for s in SOURCES] + [x if os.path.isabs(x) else os.path.join(CSRC, x) for x in HEADERS]:
+        h.update(os.path.basename(f).encode() + b"\0")
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def _stale(target: str, deps) -> bool:
     if not os.path.exists(target):
         return True
@@ -41,6 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale(SO, srcs + hdrs + [os.path.abspath(__file__)]):
         return SO
     nvcc = _nvcc()
+    src_hash = source_hash()
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
@@ -49,6 +62,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(objdir, os.path.basename(s) + ".o")
         objs.append(o)
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", s, "-o", o]
+        if os.path.basename(s) == "api.cu":
+            cmd.insert(1, '-DQB_SRC_HASH="%s"' % src_hash)
         procs.append((cmd, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()

@@ -930,6 +930,16 @@ extern "C" {
 const char* qb_last_error(void) { return g_err.c_str(); }
 int qb_version(void) { return 100; }
 
+#ifndef QB_SRC_HASH
+#define QB_SRC_HASH "unknown"
+#endif
+#define QB_STR2(x) #x
+#define QB_STR(x) QB_STR2(x)
+const char* qb_build_info(void) {
+    return "quits_b200 abi=100 arch=sm_100a nvcc=" QB_STR(__CUDACC_VER_MAJOR__) "." QB_STR(__CUDACC_VER_MINOR__) "." QB_STR(__CUDACC_VER_BUILD__)
+           " fmad=off lineinfo=on src=" QB_SRC_HASH;
+}
+
 int qb_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -579,3 +579,13 @@ def test_bench_clock_sampler_degrades_without_a_gpu():
     s.start()
     out = s.stop()
     assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples", "source"} and out["reasons"] == []
+
+
+def test_loaded_library_was_built_from_this_source_tree():
+    """The shared library is git-ignored and travels prebuilt: its embedded source hash (qb_build_info) must equal the hash of the
+    CUDA / C++ sources next to it, so a stale or foreign .so cannot pass for the committed code."""
+    import quits_b200 as qbm
+    from quits_b200 import build as qbuild
+    info = qbm.build_info()
+    assert "arch=sm_100a" in info and "fmad=off" in info
+    assert ("src=" + qbuild.source_hash()) in info, info
