@@ -362,6 +362,49 @@ def test_lsd_higher_order_equals_the_literal_per_cluster_restatement(method, ord
     assert n_lsd > 150 and n_better > 5
 
 
+def test_lsd_exhaustive_order_reaches_the_minimum_weight_inside_every_cluster():
+    """Semantic anchor for the higher-order sweep, independent of any elimination detail: with lsd_e and an order that covers all
+    non-pivot columns of a cluster, the solution's weight inside the cluster is the minimum over ALL solutions supported on the
+    cluster's columns (brute force over 2^bits)."""
+    import itertools
+    import math
+    rng = np.random.default_rng(23)
+    checked = 0
+    for trial in range(80):
+        m = int(rng.integers(4, 16)); n = int(rng.integers(m, 2 * m + 4))
+        H = (rng.random((m, n)) < min(0.5, 2.5 / m)).astype(np.uint8)
+        for j in range(n):
+            if not H[:, j].any():
+                H[rng.integers(m), j] = 1
+        p = rng.uniform(0.01, 0.3, n)
+        dec = cref.BpOsd(sp.csc_matrix(H), p, max_iter=1, bp_method="minimum_sum", osd_method="lsd_e", osd_order=20)
+        for t in range(3):
+            err = (rng.random(n) < 0.2).astype(np.uint8)
+            syn = (H @ err % 2).astype(np.uint8)
+            e, llr, it, conv = dec.decode(syn)
+            if conv:
+                continue
+            clusters = []
+            _lsd0_literal(H, syn, llr, clusters)
+            for bits, checks in clusters:
+                if not bits or len(bits) > 14:
+                    continue
+                A = H[np.ix_(checks, bits)].astype(np.uint8)
+                sl = syn[checks].astype(np.uint8)
+                wt = np.array([math.log(1.0 / p[j]) for j in bits])
+                best = None
+                for x in itertools.product((0, 1), repeat=len(bits)):
+                    xv = np.array(x, dtype=np.uint8)
+                    if np.array_equal(A @ xv % 2, sl):
+                        w = float(wt[xv.astype(bool)].sum())
+                        best = w if best is None or w < best else best
+                assert best is not None
+                got = float(wt[e[bits].astype(bool)].sum())
+                assert abs(got - best) < 1e-9, (trial, t, bits, got, best)
+                checked += 1
+    assert checked > 60
+
+
 def test_lsd0_on_a_decoding_window():
     """On a real window (gross code, p = 3e-3) LSD-0 satisfies the syndrome and stays local: far fewer columns than OSD-0's
     rank-many pivots."""
