@@ -593,3 +593,15 @@ def test_bp_equals_the_literal_restatement(method, schedule, alpha):
             elif it == it2:
                 fin = np.isfinite(llr) & np.isfinite(llr2)
                 assert np.allclose(llr[fin], llr2[fin], rtol=1e-9, atol=1e-9), (trial, t)
+
+
+def test_message_free_flooding_min_sum_prototype_equals_the_oracle():
+    """tools/proto_stateless_minsum.py: flooding min-sum from (m1, m2, parity) per row and two bits per edge, without a message
+    array -- the design DESIGN.md section 7 proposes for windows that do not fit in shared memory -- returns the oracle's
+    posteriors, iteration counts and hard decisions bit for bit."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("proto_stateless_minsum", os.path.join(root, "tools", "proto_stateless_minsum.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.self_check(trials=24, seed=7) == 72
